@@ -1,0 +1,194 @@
+/*
+ * mirres_b200.h -- C ABI of libmirres_b200.so, the sm_100a implementation of MIRReS's path tracer with
+ * screen-space ReSTIR (the hot path nerf/renderer_restir.py drives in the reference).
+ *
+ * Conventions
+ *   - every entry point is `extern "C" int fn(..., void *stream)`; `stream` is a cudaStream_t (NULL = legacy
+ *     default stream).  Return value 0 = enqueued, < 0 = error (MIRRES_ERR_*, or -100 - cudaError for a
+ *     launch failure).  Nothing allocates, synchronises, or touches the host after argument checks.
+ *   - all pointers are DEVICE pointers into dense row-major tensors owned by the caller (in the product the
+ *     caller is PyTorch: `tensor.data_ptr()`), with the shapes/dtypes of the reference tensors they replace;
+ *     `[N,k]` means N rows of k fp32/int32 values, N = framedim_x * framedim_y, pixelIndex = y * framedim_x + x.
+ *   - numerical contract: include/mirres_fpmath.h.  Integer outputs (BVH topology, hit flags, primitive ids,
+ *     light texels, reservoir sample choices) are bit-exact against the oracle; radiance, reservoir weights
+ *     and gradients are reproducible to the stated tolerance (float atomics in the env-gradient scatter).
+ *   - each declaration cites the reference interface it replaces (file:line under the reference root).
+ */
+#ifndef MIRRES_B200_H
+#define MIRRES_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIRRES_ABI_VERSION 1
+
+#define MIRRES_ERR_NULL (-1)    /* a required pointer is NULL */
+#define MIRRES_ERR_SHAPE (-2)   /* a size argument is out of range */
+#define MIRRES_ERR_ALIGN (-3)   /* a pointer that must be 16-byte (scratch: 256-byte) aligned is not */
+#define MIRRES_ERR_SCRATCH (-4) /* scratch buffer smaller than mirres_bvh_scratch_bytes() */
+#define MIRRES_ERR_ALIAS (-5)   /* input and output buffers that must differ are the same */
+
+int mirres_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * LBVH construction.  Replaces restirbvhWorker.update_bvh, nerf/renderer_restir.py:25-89, and the Slang
+ * kernels it launches (nerf/bvhworkers/{get_elements,lbvh_morton_codes,lbvh_single_radixsort,lbvh_hierarchy,
+ * lbvh_bounding_boxes}.slang).  vert [V,3] f32, tri [F,3] i32.  Outputs in the reference layout:
+ *   info [2F-1,3] i32 (left, right, primitive; leaf <=> left == right == 0), aabb [2F-1,6] f32 (min xyz, max xyz),
+ *   internal nodes [0,F-2] (root 0), leaves [F-1,2F-2] in sorted-Morton order  (renderer_restir.py:61-64).
+ * packed_nodes / packed_tris (optional, both or neither): traversal records consumed by every ray-casting
+ * entry point below; sizes from mirres_bvh_packed_{node,tri}_bytes, 16-byte aligned.
+ * sorted_codes (optional) [F,2] i32: (Morton code, element index) after the stable sort (renderer_restir.py:48-57).
+ * scratch: mirres_bvh_scratch_bytes(F) bytes, 256-byte aligned.
+ */
+size_t mirres_bvh_scratch_bytes(int F);
+size_t mirres_bvh_packed_node_bytes(int F);
+size_t mirres_bvh_packed_tri_bytes(int F);
+int mirres_bvh_build(const float *vert, int V, const int *tri, int F, int *info, float *aabb, void *packed_nodes,
+                     void *packed_tris, int *sorted_codes, void *scratch, size_t scratch_bytes, void *stream);
+
+/* Granular stages with the argument meaning of the individual reference kernels (used by the slangpy-protocol
+ * shim so that the reference's own update_bvh can run unchanged):
+ *   generateElements  nerf/bvhworkers/get_elements.slang:3-39          (renderer_restir.py:32-33)
+ *   morton_codes      nerf/bvhworkers/lbvh_morton_codes.slang:46-79    (renderer_restir.py:44-51)
+ *   radix_sort        nerf/bvhworkers/lbvh_single_radixsort.slang:28-138 (renderer_restir.py:55-57)
+ *   hierarchy + get_bvh_height + get_bbox* + set_root
+ *                     nerf/bvhworkers/lbvh_hierarchy.slang:111-245, lbvh_bounding_boxes.slang:151-390
+ *                                                                       (renderer_restir.py:61-87)            */
+int mirres_bvh_elements(const float *vert, const int *tri, int F, int *ele_primitiveIdx, float *ele_aabb, void *stream);
+int mirres_bvh_morton(const float *ele_aabb, int F, float min_x, float min_y, float min_z, float max_x, float max_y,
+                      float max_z, int *morton_codes_ele, void *stream);
+int mirres_bvh_sort(int *pairs, int F, void *scratch, size_t scratch_bytes, void *stream);
+int mirres_bvh_hierarchy_refit(const int *sorted_pairs, const float *ele_aabb, int F, int *info, float *aabb,
+                               void *scratch, size_t scratch_bytes, void *stream);
+/* traversal records from reference-layout tensors built elsewhere */
+int mirres_bvh_pack(const int *info, const float *aabb, const float *vert, const int *tri, int F, void *packed_nodes,
+                    void *packed_tris, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Standalone rays.  Semantics of bvh_hit / bvh_hit_with_normal, nerf/ScreenSpaceReSTIR/utils/helperDi.slang:197-274,
+ * 313-395, with t_min = 0, t_max = 1e7 (the only values any call site uses).  org/dir [n,3]; dir is normalised
+ * inside.  hit [n] i32; t [n], pos [n,3], normal [n,3], prim [n] i32 and visits [n,2] u32 (node records fetched x2,
+ * triangles tested) are optional.  `prim` and `visits` are extensions the reference does not output.
+ */
+int mirres_trace_closest(const void *packed_nodes, const void *packed_tris, const float *org, const float *dir, int n,
+                         int *hit, float *t, float *pos, float *normal, int *prim, unsigned int *visits, void *stream);
+int mirres_trace_any(const void *packed_nodes, const void *packed_tris, const float *org, const float *dir, int n,
+                     int *hit, unsigned int *visits, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Environment light.  env_tex [H*W,3] is the vertically flipped, flattened lgt.base (renderer_restir.py:305-311).
+ *   mirres_env_build_distribution  replaces make_sampleable(), nerf/ScreenSpaceReSTIR/GenerateLightTiles.py:4-29
+ *       (make_sampleable.slang:34-86 + torch sum/cumsum): pdf_ [H*W], cdf_ [H*(W+1)], mpdf_ [H], mcdf_ [H+1];
+ *       row_scratch [H].  Scans are sequential fp32 prefix sums (defined order).
+ *   mirres_env_weights / mirres_env_distribution2d  the two Slang kernels alone (GenerateLightTiles.py:7-8,20-21).
+ *   mirres_neighbor_offsets  createNeighborOffsetTexture, make_sampleable.slang:186-205 (renderer_restir.py:217-219);
+ *       out [2*sample_count] raw int8-range values (the host divides by 127).
+ *   mirres_light_tiles  process_GenerateLightTiles, GenerateLightTiles.slang:16-62 (GenerateLightTiles.py:42-50):
+ *       light_data [T,3] (valid, oct.u, oct.v), light_uv [T,2] i32, light_pdf [T] (the reference names it light_inv_pdf).
+ */
+int mirres_env_build_distribution(const float *env_tex, int W, int H, float *pdf_, float *cdf_, float *mpdf_,
+                                  float *mcdf_, float *row_scratch, void *stream);
+int mirres_env_weights(const float *env_tex, int W, int H, float *weight, void *stream);
+int mirres_env_distribution2d(int W, int H, float *pdf_, float *cdf_, void *stream);
+int mirres_neighbor_offsets(int sample_count, float *out, void *stream);
+int mirres_light_tiles(const float *env_tex, int W, int H, const float *pdf_, const float *cdf_, const float *mpdf_,
+                       const float *mcdf_, unsigned int frame_index, int tile_count, int tile_size, float *light_data,
+                       int *light_uv, float *light_pdf, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ReSTIR passes.  Reservoir = (light_data [N,3], light_pdf [N], M [N] i32, weight [N]), res.slang:5-11.
+ * G-buffer: occ [N], normal_depth [N,4] (16-byte aligned), brdf_map [N,3] (lum kd, metallic, alpha), ray_dir [N,3],
+ * pos_map [N,3]  (renderer_restir.py:279-287).
+ *   mirres_initial_resampling   process_InitialResampling_, InitialResampling.slang:151-295 (renderer_restir.py:96-114)
+ *   mirres_temporal_resampling  process_TemporalResampling, TemporalResampling.slang:23-135 (Resampling.py:28-44);
+ *                               motion [N,2] may be NULL (= zeros, as renderer_restir.py:487 passes)
+ *   mirres_spatial_resampling   process_SpatialResampling_, SpatialResampling.slang:178-322 (renderer_restir.py:116-131);
+ *                               reads prev_*, writes res_* (must differ); offset_count must be a power of two
+ *   mirres_final_visibility     process_EvaluateFinalSamples_get_vis, EvaluateFinalSamples.slang:84-124 (renderer_restir.py:133-146)
+ *   mirres_eval_final_fwd/bwd   process_EvaluateFinalSamples_di_ and its Slang-autodiff `.bwd`,
+ *                               EvaluateFinalSamples.slang:129-188 (Resampling.py:94-143); bwd ACCUMULATES into grad_env [He*We,3]
+ */
+int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris, const float *pos_map, float *res_ld,
+                              float *res_pdf, int *res_M, float *res_w, const float *env_tex, int env_w, int env_h,
+                              int fx, int fy, unsigned int frame_index, const float *occ, const float *normal_depth,
+                              const float *brdf_map, const float *ray_dir, const float *pdf_, const float *mpdf_,
+                              const float *light_data, const float *light_pdf, int tile_count, int tile_size,
+                              int screen_tile, int n_light, int n_brdf, void *stream);
+int mirres_temporal_resampling(float *res_ld, float *res_pdf, int *res_M, float *res_w, const float *prev_ld,
+                               const float *prev_pdf, const int *prev_M, const float *prev_w, const float *env_tex,
+                               int env_w, int env_h, int fx, int fy, unsigned int frame_index, const float *occ,
+                               const float *normal_depth, const float *brdf_map, const float *ray_dir,
+                               const float *prev_occ, const float *prev_normal_depth, const float *prev_brdf_map,
+                               const float *prev_ray_dir, const float *motion, int max_history, void *stream);
+int mirres_spatial_resampling(const void *packed_nodes, const void *packed_tris, const float *pos_map, float *res_ld,
+                              float *res_pdf, int *res_M, float *res_w, const float *prev_ld, const float *prev_pdf,
+                              const int *prev_M, const float *prev_w, const float *neighbor_offsets, const float *env_tex,
+                              int env_w, int env_h, int fx, int fy, unsigned int frame_index, const float *occ,
+                              const float *normal_depth, const float *brdf_map, const float *ray_dir, int offset_count,
+                              int neighbor_count, float gather_radius, void *stream);
+int mirres_final_visibility(const void *packed_nodes, const void *packed_tris, const float *res_ld, int fx, int fy,
+                            const float *pos_map, float *vis_map, void *stream);
+int mirres_eval_final_fwd(const float *res_ld, const float *res_pdf, const int *res_M, const float *res_w,
+                          const float *env_tex, int env_w, int env_h, int fx, int fy, float *fs_dir, float *fs_dist,
+                          float *fs_Li, const float *vis_map, void *stream);
+int mirres_eval_final_bwd(const float *res_ld, const float *res_pdf, const int *res_M, const float *res_w, int env_w,
+                          int env_h, int fx, int fy, const float *vis_map, const float *grad_Li, float *grad_env,
+                          void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Shading and the multi-bounce integrator.
+ *   mirres_final_shading_fwd/bwd  process_FinalShading and its `.bwd`, FinalShading.slang:14-109 (Resampling.py:145-214);
+ *        rough_metal [N,2] = (linear roughness, metallic).  bwd OVERWRITES grad_normal [N,3], grad_diffuse [N,3],
+ *        grad_rough_metal [N,2], grad_Li [N,3].
+ *   mirres_bounce_first   process_new_dir_for_pt, FinalShading.slang:113-265 (Resampling.py:216-232)
+ *   mirres_bounce_shade   process_path_tracing_divided_no_grad, FinalShading.slang:641-1009 (Resampling.py:254-272)
+ *        prd [N,5] (throughput rgb, specular flag, stop flag) is read and written; new_* must not alias the inputs.
+ *        max_bounce replaces the compile-time MAX_Bounce = 2 (FinalShading.slang:7).
+ */
+int mirres_final_shading_fwd(const float *fs_dir, const float *fs_dist, const float *fs_Li, const float *env_tex,
+                             int env_w, int env_h, int fx, int fy, const float *occ, const float *normal,
+                             const float *ray_dir, const float *diffuse_map, const float *rough_metal, float *color,
+                             float *diff_light, float *spec_light, void *stream);
+int mirres_final_shading_bwd(const float *fs_dir, const float *fs_dist, const float *fs_Li, int fx, int fy,
+                             const float *occ, const float *normal, const float *ray_dir, const float *diffuse_map,
+                             const float *rough_metal, const float *grad_color, const float *grad_diff_light,
+                             const float *grad_spec_light, float *grad_normal, float *grad_diffuse,
+                             float *grad_rough_metal, float *grad_Li, void *stream);
+int mirres_bounce_first(const void *packed_nodes, const void *packed_tris, unsigned int frame_index,
+                        unsigned int bounce_count, int max_bounce, int fx, int fy, const float *occ, const float *pos_map,
+                        const float *normal, const float *ray_dir, float *prd, const float *diffuse_map,
+                        const float *rough_metal, float *new_pos, float *new_ray_d, float *new_occ, float *new_normal,
+                        void *stream);
+int mirres_bounce_shade(const void *packed_nodes, const void *packed_tris, unsigned int frame_index,
+                        unsigned int bounce_count, int max_bounce, int fx, int fy, const float *env_tex, int env_w,
+                        int env_h, const float *pdf_, const float *cdf_, const float *mpdf_, const float *mcdf_,
+                        const float *occ, const float *pos_map, const float *normal, const float *ray_dir, float *prd,
+                        const float *diffuse_map, const float *rough_metal, float *color, float *diff_color,
+                        float *spec_color, float *new_pos, float *new_ray_d, float *new_occ, float *new_normal,
+                        void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Edge-avoiding a-trous denoiser and the normal-variation AO proxy.
+ *   mirres_eaw_fwd   process_EAWDenoise / process_EAWDenoise_no_di, nerf/ScreenSpaceReSTIR/EAWDenoise.slang:50-302
+ *                    (nerf/ScreenSpaceReSTIR/Denoising.py:10-61); PHI = (c_phi, n_phi, p_phi); step_width is truncated
+ *                    to int as Denoising.py:18 does; out_color must not alias color.
+ *   mirres_eaw_bwd   the Slang-autodiff `.bwd` of process_EAWDenoise (Denoising.py:30-48), as a deterministic
+ *                    gather; OVERWRITES grad_color / grad_normal / grad_pos [N,3]; cum_w_scratch [N].
+ *   mirres_normal_ao process_normal_ao, EAWDenoise.slang:591-647 (nerf/renderer.py:1153-1158); out_ao [N,3].
+ */
+int mirres_eaw_fwd(float c_phi, float n_phi, float p_phi, int fx, int fy, float step_width, const float *occ,
+                   const float *color, const float *normal, const float *pos, float *out_color, void *stream);
+int mirres_eaw_bwd(float c_phi, float n_phi, float p_phi, int fx, int fy, float step_width, const float *occ,
+                   const float *color, const float *normal, const float *pos, const float *out_color,
+                   const float *grad_out, float *grad_color, float *grad_normal, float *grad_pos, float *cum_w_scratch,
+                   void *stream);
+int mirres_normal_ao(int fx, int fy, const float *occ, const float *normal, float *out_ao, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIRRES_B200_H */

@@ -1,0 +1,211 @@
+// mirres-b200: edge-avoiding a-trous wavelet denoiser (forward + backward) and the normal-variation AO proxy.
+//
+// Replaces:
+//   nerf/ScreenSpaceReSTIR/EAWDenoise.slang:50-174    process_EAWDenoise (and :178-302 _no_di, same arithmetic)
+//   its Slang-autodiff `.bwd` (nerf/ScreenSpaceReSTIR/Denoising.py:30-48)
+//   nerf/ScreenSpaceReSTIR/EAWDenoise.slang:591-647   process_normal_ao (nerf/renderer.py:1153-1158)
+//
+// Backward design: Slang's reverse mode scatters 25 taps x 9 channels of atomics per pixel.  The edge-stopping
+// weight w(q,r) and the 5x5 kernel are symmetric in (q,r), so the same gradient is a GATHER: every pixel q visits its
+// 25 neighbours r once and collects (a) what it receives as the centre of its own filter footprint and (b) what it
+// receives as a tap of r's footprint.  No atomics, deterministic, one pass after a normalisation pre-pass.
+#include "mr_common.cuh"
+#include "../../include/mirres_b200.h"
+
+namespace mr {
+
+struct EawParams {
+    float c_phi, n_phi, p_phi;
+    int fx, fy, step;
+    const float *__restrict__ occ;    // [N]
+    const float *__restrict__ color;  // [N,3]
+    const float *__restrict__ normal; // [N,3]
+    const float *__restrict__ pos;    // [N,3]
+    float *__restrict__ out_color;    // [N,3] (forward: written; backward: read)
+    // backward
+    float *__restrict__ cum_w;        // [N] normalisation of each footprint (pre-pass output)
+    const float *__restrict__ g_out;  // [N,3]
+    float *__restrict__ g_color;      // [N,3]
+    float *__restrict__ g_normal;     // [N,3]
+    float *__restrict__ g_pos;        // [N,3]
+};
+
+MR_DEV float eaw_kernel(int i)
+{
+    // separable binomial-like 5x5: outer product of (1/16, 1/4, 3/8, 1/4, 1/16)
+    const int x = i % 5, y = i / 5;
+    const float k1[5] = {1.0f, 4.0f, 6.0f, 4.0f, 1.0f};
+    // the reference tabulates the products as exact binary fractions (EAWDenoise.slang:111-139)
+    return (k1[x] * k1[y]) / 256.0f;
+}
+
+MR_DEV float edge_weight(float3 a, float3 b, float phi, bool clamp_zero)
+{
+    float3 t = a - b;
+    float dist2 = dot(t, t);
+    if (clamp_zero) dist2 = fmaxf(dist2, 0.0f);
+    return fminf(mr_expf(-(dist2) / phi), 1.0f);
+}
+
+// forward footprint of pixel (px,py): returns sum and cum_w
+MR_DEV void eaw_footprint(const EawParams &p, int px, int py, float3 cval, float3 nval, float3 pval, float3 &sum, float &cum_w)
+{
+    sum = f3(0.f);
+    cum_w = 0.0f;
+#pragma unroll 5
+    for (int i = 0; i < 25; ++i) {
+        const int ux = px + (i % 5 - 2) * p.step, uy = py + (i / 5 - 2) * p.step;
+        if (!(ux >= 0 && ux < p.fx && uy >= 0 && uy < p.fy)) continue;
+        const size_t r = (size_t)uy * p.fx + ux;
+        const float3 ctmp = load3(p.color, r);
+        const float c_w = edge_weight(cval, ctmp, p.c_phi, false);
+        const float n_w = edge_weight(nval, load3(p.normal, r), p.n_phi, true);
+        const float p_w = edge_weight(pval, load3(p.pos, r), p.p_phi, true);
+        const float weight = c_w * n_w * p_w;
+        const float k = eaw_kernel(i);
+        sum += ctmp * weight * k;
+        cum_w += weight * k;
+    }
+}
+
+MR_DEV void eaw_fwd_px(const EawParams &p, int idx)
+{
+    const size_t q = (size_t)idx;
+    const float3 cval = load3(p.color, q);
+    if (MR_LDG(p.occ + q) < 0.1f) { store3(p.out_color, q, cval); return; }
+    float3 sum;
+    float cum_w;
+    eaw_footprint(p, idx % p.fx, idx / p.fx, cval, load3(p.normal, q), load3(p.pos, q), sum, cum_w);
+    store3(p.out_color, q, sum / cum_w);
+}
+
+// backward pre-pass: normalisation of every footprint
+MR_DEV void eaw_norm_px(const EawParams &p, int idx)
+{
+    const size_t q = (size_t)idx;
+    float cum_w = 0.f;
+    if (!(MR_LDG(p.occ + q) < 0.1f)) {
+        float3 sum;
+        eaw_footprint(p, idx % p.fx, idx / p.fx, load3(p.color, q), load3(p.normal, q), load3(p.pos, q), sum, cum_w);
+    }
+    p.cum_w[q] = cum_w;
+}
+
+MR_DEV void eaw_bwd_px(const EawParams &p, int idx)
+{
+    const size_t q = (size_t)idx;
+    const int px = idx % p.fx, py = idx / p.fx;
+    const float3 cq = load3(p.color, q), nq = load3(p.normal, q), pq = load3(p.pos, q);
+    const bool q_center = !(MR_LDG(p.occ + q) < 0.1f);
+    const float3 gq = load3(p.g_out, q), oq = load3(p.out_color, q);
+    const float Wq = p.cum_w[q];
+    float3 gc = f3(0.f), gn = f3(0.f), gp = f3(0.f);
+#pragma unroll 5
+    for (int i = 0; i < 25; ++i) {
+        const int ux = px + (i % 5 - 2) * p.step, uy = py + (i / 5 - 2) * p.step;
+        if (!(ux >= 0 && ux < p.fx && uy >= 0 && uy < p.fy)) continue;
+        const size_t r = (size_t)uy * p.fx + ux;
+        const float3 cr = load3(p.color, r), nr = load3(p.normal, r), pr = load3(p.pos, r);
+        const float w = edge_weight(cq, cr, p.c_phi, false) * edge_weight(nq, nr, p.n_phi, true) * edge_weight(pq, pr, p.p_phi, true);
+        const float k = eaw_kernel(i);
+        const float3 dc = cq - cr, dn = nq - nr, dp = pq - pr;
+        if (q_center) {
+            // q is the centre, r its tap:  d out_q / d w = k (c_r - out_q) / W_q ;  dw/d|t|^2 = -w/phi ; d|t|^2/d c_q = 2 t
+            const float gw = k * dot(gq, cr - oq) / Wq;
+            const float s = -gw * w * 2.0f;
+            gc += dc * (s / p.c_phi);
+            gn += dn * (s / p.n_phi);
+            gp += dp * (s / p.p_phi);
+        }
+        if (!(MR_LDG(p.occ + r) < 0.1f)) {
+            // r is the centre, q its tap (kernel and weight are symmetric)
+            const float3 gr = load3(p.g_out, r), orr = load3(p.out_color, r);
+            const float Wr = p.cum_w[r];
+            gc += gr * (w * k / Wr);
+            const float gw = k * dot(gr, cq - orr) / Wr;
+            const float s = -gw * w * 2.0f; // d|t|^2 / d c_q = -2 (c_r - c_q) = 2 (c_q - c_r)
+            gc += dc * (s / p.c_phi);
+            gn += dn * (s / p.n_phi);
+            gp += dp * (s / p.p_phi);
+        }
+    }
+    store3(p.g_color, q, gc);
+    store3(p.g_normal, q, gn);
+    store3(p.g_pos, q, gp);
+}
+
+struct AoParams {
+    int fx, fy;
+    const float *__restrict__ occ;
+    const float *__restrict__ normal;
+    float *__restrict__ out_ao;
+};
+MR_DEV void normal_ao_px(const AoParams &p, int idx)
+{
+    const size_t q = (size_t)idx;
+    if (MR_LDG(p.occ + q) < 0.1f) { store3(p.out_ao, q, f3(0.f)); return; }
+    const int px = idx % p.fx, py = idx / p.fx;
+    const float3 nval = load3(p.normal, q);
+    int count = 0;
+    float sum = 0.f;
+    const int width = 4;
+    for (int i = -width; i < width; i++)
+        for (int j = -width; j < width; j++) {
+            const int ux = px + i, uy = py + j;
+            if (!(ux >= 0 && ux < p.fx && uy >= 0 && uy < p.fy)) continue;
+            const size_t r = (size_t)uy * p.fx + ux;
+            if (MR_LDG(p.occ + r) < 0.1f) continue;
+            float d = fmaxf(dot(load3(p.normal, r), nval), 0.0f);
+            d = fminf(1.0f, d);
+            sum += d;
+            count++;
+        }
+    float normal_weight = 1 - sum / (float)count;
+    float v = clampf(normal_weight * 50, 0.f, 1.f);
+    store3(p.out_ao, q, f3(v));
+}
+
+} // namespace mr
+
+using namespace mr;
+
+extern "C" {
+
+int mirres_eaw_fwd(float c_phi, float n_phi, float p_phi, int fx, int fy, float step_width, const float *occ,
+                   const float *color, const float *normal, const float *pos, float *out_color, void *stream)
+{
+    if (!occ || !color || !normal || !pos || !out_color) return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1) return MIRRES_ERR_SHAPE;
+    if (out_color == color) return MIRRES_ERR_ALIAS;
+    EawParams p = {};
+    p.c_phi = c_phi; p.n_phi = n_phi; p.p_phi = p_phi; p.fx = fx; p.fy = fy; p.step = (int)step_width;
+    p.occ = occ; p.color = color; p.normal = normal; p.pos = pos; p.out_color = out_color;
+    return foreach_item<EawParams, eaw_fwd_px, 128>(p, fx * fy, (cudaStream_t)stream);
+}
+
+int mirres_eaw_bwd(float c_phi, float n_phi, float p_phi, int fx, int fy, float step_width, const float *occ,
+                   const float *color, const float *normal, const float *pos, const float *out_color,
+                   const float *grad_out, float *grad_color, float *grad_normal, float *grad_pos, float *cum_w_scratch,
+                   void *stream)
+{
+    if (!occ || !color || !normal || !pos || !out_color || !grad_out || !grad_color || !grad_normal || !grad_pos || !cum_w_scratch)
+        return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1) return MIRRES_ERR_SHAPE;
+    EawParams p = {};
+    p.c_phi = c_phi; p.n_phi = n_phi; p.p_phi = p_phi; p.fx = fx; p.fy = fy; p.step = (int)step_width;
+    p.occ = occ; p.color = color; p.normal = normal; p.pos = pos; p.out_color = (float *)out_color;
+    p.cum_w = cum_w_scratch; p.g_out = grad_out; p.g_color = grad_color; p.g_normal = grad_normal; p.g_pos = grad_pos;
+    int rc = foreach_item<EawParams, eaw_norm_px, 128>(p, fx * fy, (cudaStream_t)stream);
+    if (rc) return rc;
+    return foreach_item<EawParams, eaw_bwd_px, 128>(p, fx * fy, (cudaStream_t)stream);
+}
+
+int mirres_normal_ao(int fx, int fy, const float *occ, const float *normal, float *out_ao, void *stream)
+{
+    if (!occ || !normal || !out_ao) return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1) return MIRRES_ERR_SHAPE;
+    AoParams p = {fx, fy, occ, normal, out_ao};
+    return foreach_item<AoParams, normal_ao_px, 128>(p, fx * fy, (cudaStream_t)stream);
+}
+
+} // extern "C"

@@ -1,0 +1,576 @@
+// mirres-b200: screen-space ReSTIR kernels for sm_100a.
+//
+// One thread per pixel, pixelIndex = y * framedim_x + x, RNG keyed on the global pixel coordinate
+// (so any tiling / sharding of the frame reproduces the single-GPU image bit for bit).
+// Replaces:
+//   nerf/ScreenSpaceReSTIR/InitialResampling.slang:151-295     -> k_initial
+//   nerf/ScreenSpaceReSTIR/TemporalResampling.slang:23-135     -> k_temporal
+//   nerf/ScreenSpaceReSTIR/SpatialResampling.slang:178-322     -> k_spatial
+//   nerf/ScreenSpaceReSTIR/EvaluateFinalSamples.slang:84-124   -> k_final_visibility
+//   nerf/ScreenSpaceReSTIR/EvaluateFinalSamples.slang:129-188  -> k_eval_final_fwd / k_eval_final_bwd (hand-derived)
+//   nerf/ScreenSpaceReSTIR/utils/res.slang:53-232              -> the streaming RIS steps inlined below
+// Visibility rays use mr::any_hit (first-hit exit), see mr_bvh.cuh for why that is result-identical.
+#include "mr_bvh.cuh"
+#include "mr_light.cuh"
+#include "mr_brdf.cuh"
+#include "../../include/mirres_b200.h"
+
+namespace mr {
+
+struct ResView {
+    float *ld;  // [N,3] valid flag, oct.u, oct.v
+    float *pdf; // [N]
+    int *M;     // [N]
+    float *w;   // [N]
+};
+struct ResConst {
+    const float *__restrict__ ld;
+    const float *__restrict__ pdf;
+    const int *__restrict__ M;
+    const float *__restrict__ w;
+};
+struct Reservoir {
+    float3 ld;
+    float pdf;
+    int M;
+    float w;
+};
+struct Ris {
+    float3 ld;
+    float pdf;
+    float wsum, M, weight, canonical;
+};
+MR_DEV Ris ris_empty()
+{
+    Ris s;
+    s.ld = f3(0.f);
+    s.pdf = 0.f;
+    s.wsum = 0.f; s.M = 0.f; s.weight = 0.f; s.canonical = 0.f;
+    return s;
+}
+MR_DEV void res_zero(const ResView &r, size_t i)
+{
+    store3(r.ld, i, f3(0.f));
+    r.pdf[i] = 0.f; r.M[i] = 0; r.w[i] = 0.f;
+}
+MR_DEV void res_store(const ResView &r, size_t i, const Ris &s)
+{
+    if (isinf(s.weight) || isnan(s.weight)) { res_zero(r, i); return; }
+    store3(r.ld, i, s.ld);
+    r.pdf[i] = s.pdf;
+    r.M[i] = to_int(s.M);
+    r.w[i] = s.weight;
+}
+MR_DEV Reservoir res_load(const ResConst &r, size_t i)
+{
+    Reservoir o;
+    o.ld = load3(r.ld, i);
+    o.pdf = MR_LDG(r.pdf + i);
+    o.M = MR_LDG(r.M + i);
+    o.w = MR_LDG(r.w + i);
+    return o;
+}
+MR_DEV Reservoir res_load_rw(const ResView &r, size_t i)
+{
+    Reservoir o;
+    o.ld = load3_rw(r.ld, i);
+    o.pdf = r.pdf[i];
+    o.M = r.M[i];
+    o.w = r.w[i];
+    return o;
+}
+MR_DEV bool ris_step_reservoir(Ris &st, const Reservoir &r, float targetPdf, uint32_t &sg)
+{
+    float sampleWeight = targetPdf * r.w * (float)r.M;
+    st.wsum += sampleWeight;
+    st.M += (float)r.M;
+    bool sel = rnd(sg) * st.wsum < sampleWeight;
+    if (sel) { st.ld = r.ld; st.pdf = r.pdf; st.weight = targetPdf; }
+    return sel;
+}
+MR_DEV float m_factor(float q0, float q1) { return q0 == 0.f ? 1.f : clampf(mr_pow8f(fminf(q1 / q0, 1.f)), 0.f, 1.f); }
+MR_DEV float pairwise_mis(float q0, float q1, float N0, float N1) { return (q1 == 0.f) ? 0.f : (N0 * q0) / (q0 * N0 + q1 * N1); }
+MR_DEV bool neighbor_ok(float3 n0, float d0, float3 n1, float d1) { return dot(n0, n1) >= 0.5f && fabsf(d0 - d1) <= 0.1f * d0; }
+
+struct GBuf {
+    const float *__restrict__ occ;          // [N]
+    const float *__restrict__ normal_depth; // [N,4]
+    const float *__restrict__ brdf;         // [N,3]
+    const float *__restrict__ ray_dir;      // [N,3]
+};
+MR_DEV float4 load_nd(const float *__restrict__ nd, size_t i) { return MR_LDG(reinterpret_cast<const float4 *>(nd) + i); }
+
+#define VIS_NEAR 0.01f
+
+// ------------------------------------------------------------------------------------------------------------------
+struct InitialParams {
+    BvhView bvh;
+    EnvView env;
+    GBuf g;
+    const float *__restrict__ pos_map;
+    ResView res;
+    const float *__restrict__ light_data;
+    const float *__restrict__ light_pdf;
+    int fx, fy;
+    unsigned int frame;
+    unsigned int tile_count, tile_size, screen_tile, n_light, n_brdf;
+};
+
+MR_DEV void initial_px(const InitialParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
+    if (MR_LDG(p.g.occ + i) < 0.1f) { res_zero(p.res, i); return; }
+    uint32_t tileSg = seed_of(px / p.screen_tile, py / p.screen_tile, p.frame);
+    uint32_t tileIndex = minu(to_uint(rnd(tileSg) * (float)p.tile_count), p.tile_count - 1u);
+    const uint32_t tileOffset = tileIndex * p.tile_size;
+    uint32_t sg = seed_of(px, py, p.frame);
+    const uint32_t stride = (p.tile_size + p.n_light - 1u) / p.n_light;
+    const uint32_t offset = minu(to_uint(rnd(sg) * (float)stride), stride - 1u);
+    float4 nd = load_nd(p.g.normal_depth, i);
+    const float3 N = make_float3(nd.x, nd.y, nd.z);
+    const float3 rd = load3(p.g.ray_dir, i);
+    const float3 brdf = load3(p.g.brdf, i);
+    const RisSurface surf = ris_surface(N, rd, brdf);
+    const float ratio = (float)p.n_brdf / (float)(p.n_light + p.n_brdf);
+    Ris st = ris_empty();
+    for (uint32_t k = 0; k < p.n_light; ++k) {
+        const uint32_t slot = tileOffset + (offset + k * stride) % p.tile_size;
+        const float3 cand = load3(p.light_data, slot);
+        const float cand_pdf = MR_LDG(p.light_pdf + slot);
+        float3 Le, L;
+        light_of(p.env, cand.y, cand.z, Le, L);
+        float targetPdf = target_pdf(surf, Le, L);
+        float sourcePdf = lerpf(cand_pdf, ris_brdf_pdf(surf, L), ratio);
+        float sampleWeight = targetPdf / sourcePdf;
+        st.wsum += sampleWeight;
+        st.M += 1.f;
+        if (rnd(sg) * st.wsum < sampleWeight) { st.ld = cand; st.pdf = cand_pdf; st.weight = targetPdf; }
+    }
+    for (uint32_t k = 0; k < p.n_brdf; ++k) {
+        float x0 = rnd(sg), x1 = rnd(sg), x2 = rnd(sg);
+        float3 dir;
+        if (!ris_brdf_sample(surf, x0, x1, x2, dir)) { st.M += 1.f; continue; }
+        float cand_pdf = env_pdf(p.env, dir);
+        float2 o = oct_encode(dir);
+        float3 Le = env_radiance(p.env, ngp_dir(dir));
+        float targetPdf = target_pdf(surf, Le, dir);
+        float sourcePdf = lerpf(cand_pdf, ris_brdf_pdf(surf, dir), ratio);
+        float sampleWeight = targetPdf / sourcePdf;
+        st.wsum += sampleWeight;
+        st.M += 1.f;
+        if (rnd(sg) * st.wsum < sampleWeight) { st.ld = make_float3(1.0f, o.x, o.y); st.pdf = cand_pdf; st.weight = targetPdf; }
+    }
+    if (st.ld.x > 0.1f) {
+        float3 L = oct_decode(st.ld.y, st.ld.z);
+        float3 o = load3(p.pos_map, i) + VIS_NEAR * L;
+        if (any_hit<false>(p.bvh, o, L, nullptr)) st = ris_empty();
+    }
+    st.weight = st.weight > 0.f ? (st.wsum / st.M) / st.weight : 0.f;
+    st.M = 1.f;
+    res_store(p.res, i, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct TemporalParams {
+    EnvView env;
+    GBuf g, prev_g;
+    ResView res;
+    ResConst prev;
+    const float *__restrict__ motion; // [N,2] or null (zeros)
+    int fx, fy;
+    unsigned int frame;
+    unsigned int max_history;
+};
+
+MR_DEV void temporal_px(const TemporalParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
+    if (MR_LDG(p.g.occ + i) < 0.1f) return;
+    uint32_t sg = seed_of(px, py, p.frame);
+    float u0 = rnd(sg), u1 = rnd(sg);
+    float mvx = p.motion ? MR_LDG(p.motion + 2 * i) : 0.f, mvy = p.motion ? MR_LDG(p.motion + 2 * i + 1) : 0.f;
+    int ppx = to_int((float)px + mvx * (float)(uint32_t)p.fx + (u0 * 1.f - 0.f));
+    int ppy = to_int((float)py + mvy * (float)(uint32_t)p.fy + (u1 * 1.f - 0.f));
+    if (ppx >= p.fx || ppx < 0 || ppy >= p.fy || ppy < 0) return;
+    const size_t pi = (size_t)ppy * p.fx + ppx;
+    if (MR_LDG(p.prev_g.occ + pi) < 0.1f) return;
+    float4 nd = load_nd(p.g.normal_depth, i), pnd = load_nd(p.prev_g.normal_depth, pi);
+    const float3 N = make_float3(nd.x, nd.y, nd.z), pN = make_float3(pnd.x, pnd.y, pnd.z);
+    const RisSurface cur_s = ris_surface(N, load3(p.g.ray_dir, i), load3(p.g.brdf, i));
+    const RisSurface prev_s = ris_surface(pN, load3(p.prev_g.ray_dir, pi), load3(p.prev_g.brdf, pi));
+    Reservoir cur = res_load_rw(p.res, i);
+    Reservoir prev = res_load(p.prev, pi);
+    prev.M = (int)minu((uint32_t)prev.M, (uint32_t)cur.M * p.max_history);
+    if (!neighbor_ok(N, nd.w, pN, pnd.w)) return;
+    Ris st = ris_empty();
+    float3 Le, L;
+    light_of(p.env, cur.ld.y, cur.ld.z, Le, L);
+    ris_step_reservoir(st, cur, target_pdf(cur_s, Le, L), sg);
+    light_of(p.env, prev.ld.y, prev.ld.z, Le, L);
+    bool usedPrev = ris_step_reservoir(st, prev, target_pdf(cur_s, Le, L), sg);
+    light_of(p.env, st.ld.y, st.ld.z, Le, L);
+    float currentPdf = target_pdf(cur_s, Le, L);
+    float prevPdf = target_pdf(prev_s, Le, L);
+    float normalization = (usedPrev ? prevPdf : currentPdf) / ((float)cur.M * currentPdf + (float)prev.M * prevPdf);
+    st.weight = st.weight > 0.f ? (st.wsum * normalization) / st.weight : 0.f;
+    res_store(p.res, i, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct SpatialParams {
+    BvhView bvh;
+    EnvView env;
+    GBuf g;
+    const float *__restrict__ pos_map;
+    ResView res;
+    ResConst prev;
+    const float *__restrict__ offsets; // [count,2] in [-1,1]
+    int fx, fy;
+    unsigned int frame;
+    unsigned int offset_count, neighbor_count;
+    float radius;
+};
+
+MR_DEV void spatial_px(const SpatialParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
+    if (MR_LDG(p.g.occ + i) < 0.1f) { res_zero(p.res, i); return; }
+    uint32_t sg = seed_of(px, py, p.frame);
+    float4 nd = load_nd(p.g.normal_depth, i);
+    const float3 N = make_float3(nd.x, nd.y, nd.z);
+    const RisSurface cur_s = ris_surface(N, load3(p.g.ray_dir, i), load3(p.g.brdf, i));
+    Ris st = ris_empty();
+    const uint32_t startIndex = to_uint(rnd(sg) * (float)p.offset_count);
+    const Reservoir cur = res_load(p.prev, i);
+    float3 cLe, cL;
+    light_of(p.env, cur.ld.y, cur.ld.z, cLe, cL);
+    const float currentTargetPdf = target_pdf(cur_s, cLe, cL);
+    const float3 cur_pos = load3(p.pos_map, i);
+    st.canonical = 1.f;
+    uint32_t validNeighbors = 1;
+    const uint32_t mask = p.offset_count - 1u;
+    for (uint32_t k = 0; k < p.neighbor_count; ++k) {
+        const uint32_t ni = (startIndex + k) & mask;
+        int npx = (int)px + to_int(MR_LDG(p.offsets + 2 * (size_t)ni) * p.radius);
+        int npy = (int)py + to_int(MR_LDG(p.offsets + 2 * (size_t)ni + 1) * p.radius);
+        if (!(npx >= 0 && npx < p.fx && npy >= 0 && npy < p.fy)) continue;
+        const size_t n = (size_t)npy * p.fx + npx;
+        float4 nnd = load_nd(p.g.normal_depth, n);
+        const float3 nN = make_float3(nnd.x, nnd.y, nnd.z);
+        if (!neighbor_ok(N, nd.w, nN, nnd.w)) continue;
+        const Reservoir nr = res_load(p.prev, n);
+        if (nr.M == 0) continue;
+        if (MR_LDG(p.g.occ + n) < 0.1f) continue;
+        const RisSurface nb_s = ris_surface(nN, load3(p.g.ray_dir, n), load3(p.g.brdf, n));
+        ++validNeighbors;
+        float3 nLe, nL;
+        light_of(p.env, nr.ld.y, nr.ld.z, nLe, nL);
+        const float3 nb_pos = load3(p.pos_map, n);
+        bool canonical_hit = any_hit<false>(p.bvh, cur_pos + VIS_NEAR * nL, nL, nullptr);
+        bool candidate_hit = any_hit<false>(p.bvh, nb_pos + VIS_NEAR * cL, cL, nullptr);
+        float candidateVisibility = candidate_hit ? 0.f : 1.0f;
+        float canonicalVisibility = canonical_hit ? 0.f : 1.0f;
+        float candAtOwn = target_pdf(nb_s, nLe, nL);
+        float candAtCur = target_pdf(cur_s, nLe, nL);
+        float canonAtNb = target_pdf(nb_s, cLe, cL);
+        candAtCur *= canonicalVisibility;
+        canonAtNb *= candidateVisibility;
+        float N0 = (float)((uint32_t)nr.M * p.neighbor_count);
+        float N1 = (float)cur.M;
+        float m0 = pairwise_mis(candAtOwn, candAtCur, N0, N1);
+        float m1 = 1.f - pairwise_mis(canonAtNb, currentTargetPdf, N0, N1);
+        float sampleWeight = candAtCur * nr.w * m0;
+        st.M += (float)nr.M * fminf(m_factor(candAtOwn, candAtCur), m_factor(canonAtNb, currentTargetPdf));
+        st.wsum += sampleWeight;
+        st.canonical += m1;
+        if (rnd(sg) * st.wsum < sampleWeight) { st.ld = nr.ld; st.pdf = nr.pdf; st.weight = candAtCur; }
+    }
+    {
+        float sampleWeight = currentTargetPdf * cur.w * st.canonical;
+        st.M += (float)cur.M;
+        st.wsum += sampleWeight;
+        if (rnd(sg) * st.wsum < sampleWeight) { st.ld = cur.ld; st.pdf = cur.pdf; st.weight = currentTargetPdf; }
+    }
+    st.M = (float)cur.M;
+    st.weight = st.weight > 0.f ? (st.wsum / (float)validNeighbors) / st.weight : 0.f;
+    res_store(p.res, i, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct VisParams {
+    BvhView bvh;
+    const float *__restrict__ res_ld;
+    const float *__restrict__ pos_map;
+    float *__restrict__ vis;
+};
+MR_DEV void final_visibility_px(const VisParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    float3 ld = load3(p.res_ld, i);
+    float v = 1.0f;
+    if (ld.x > 0.1f) {
+        float3 L = oct_decode(ld.y, ld.z);
+        float3 o = load3(p.pos_map, i) + VIS_NEAR * L;
+        v = any_hit<false>(p.bvh, o, L, nullptr) ? 0.0f : 1.0f;
+    }
+    p.vis[i] = v;
+}
+
+struct EvalParams {
+    ResConst res;
+    EnvView env;
+    const float *__restrict__ vis;
+    float *__restrict__ fs_dir;
+    float *__restrict__ fs_dist;
+    float *__restrict__ fs_Li;
+    const float *__restrict__ grad_Li; // backward only
+    float *grad_env;                   // backward only
+};
+MR_DEV void eval_final_fwd_px(const EvalParams &p, int idx)
+{
+    const ResConst &res = p.res;
+    const EnvView &env = p.env;
+    const float *vis = p.vis;
+    float *fs_dir = p.fs_dir, *fs_dist = p.fs_dist, *fs_Li = p.fs_Li;
+    const size_t i = (size_t)idx;
+    float3 ld = load3(res.ld, i);
+    float3 dir = f3(0.f), Li = f3(0.f);
+    float dist = 0.f;
+    if (ld.x > 0.1f) {
+        float3 Le, L;
+        light_of(env, ld.y, ld.z, Le, L);
+        if (MR_LDG(vis + i) > 0.f) {
+            dir = L;
+            dist = 1e6f;
+            Li = MR_LDG(res.w + i) * Le;
+        }
+    }
+    store3(fs_dir, i, dir);
+    fs_dist[i] = dist;
+    store3(fs_Li, i, Li);
+}
+
+// Backward of Li = W * bilinear(env)(dir): grad_env[tap] += w_tap * W * grad_Li (4 taps x 3 channels).
+// Many pixels select the same bright texels, so lanes of a warp that hit the same tap quad are summed with a
+// shuffle tree first (__match_any_sync on the texel index) and a single lane issues the atomics.
+// per-pixel part shared by both builds: which quad, which weights
+MR_DEV bool eval_final_bwd_terms(const EvalParams &p, int idx, Taps &t, float vals[12])
+{
+    const size_t i = (size_t)idx;
+    float3 ld = load3(p.res.ld, i);
+    if (!(ld.x > 0.1f) || !(MR_LDG(p.vis + i) > 0.f)) return false;
+    float3 L = oct_decode(ld.y, ld.z);
+    float2 uv;
+    if (!env_uv_of(ngp_dir(L), uv)) return false;
+    t = bilinear_taps(uv, p.env.W, p.env.H);
+    float3 g = MR_LDG(p.res.w + i) * load3(p.grad_Li, i);
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f) return false;
+    float iu = 1.0f - t.u, iv = 1.0f - t.v;
+    float w00 = iu * iv, w10 = t.u * iv, w01 = iu * t.v, w11 = t.u * t.v;
+    vals[0] = w00 * g.x; vals[1] = w00 * g.y; vals[2] = w00 * g.z;
+    vals[3] = w10 * g.x; vals[4] = w10 * g.y; vals[5] = w10 * g.z;
+    vals[6] = w01 * g.x; vals[7] = w01 * g.y; vals[8] = w01 * g.z;
+    vals[9] = w11 * g.x; vals[10] = w11 * g.y; vals[11] = w11 * g.z;
+    return true;
+}
+
+#if !defined(MR_HOST_CHECK)
+__global__ void __launch_bounds__(256) k_eval_final_bwd(EvalParams p, int n)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    Taps t;
+    t.i00 = t.i10 = t.i01 = t.i11 = -1;
+    t.u = t.v = 0.f;
+    float vals[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) vals[q] = 0.f;
+    const bool active = idx < n && eval_final_bwd_terms(p, idx, t, vals);
+    float *grad_env = p.grad_env;
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int act_mask = __ballot_sync(0xffffffffu, active);
+    if (act_mask == 0u) return;
+    // lanes that address the same tap quad (i00 and i11 identify it) are summed first
+    unsigned int peers = __match_any_sync(0xffffffffu, active ? (long long)t.i00 * 0x100000000ll + (long long)(unsigned int)t.i11
+                                                               : -1ll - (long long)lane);
+    peers &= act_mask;
+    const bool leader = active && (__ffs(peers) - 1 == (int)lane);
+    const unsigned int leaders = __ballot_sync(0xffffffffu, leader);
+    if (__popc(leaders) > 8) {
+        // too many distinct quads in this warp: aggregation would cost more than it saves
+        if (active) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                atomicAdd(grad_env + 3 * (size_t)t.i00 + c, vals[c]);
+                atomicAdd(grad_env + 3 * (size_t)t.i10 + c, vals[3 + c]);
+                atomicAdd(grad_env + 3 * (size_t)t.i01 + c, vals[6 + c]);
+                atomicAdd(grad_env + 3 * (size_t)t.i11 + c, vals[9 + c]);
+            }
+        }
+        return;
+    }
+    unsigned int todo = leaders;
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const unsigned int grp = __shfl_sync(0xffffffffu, peers, src);
+        const bool member = active && ((grp >> lane) & 1u);
+        float acc[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            float x = member ? vals[q] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            acc[q] = x;
+        }
+        if ((int)lane == src) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                atomicAdd(grad_env + 3 * (size_t)t.i00 + c, acc[c]);
+                atomicAdd(grad_env + 3 * (size_t)t.i10 + c, acc[3 + c]);
+                atomicAdd(grad_env + 3 * (size_t)t.i01 + c, acc[6 + c]);
+                atomicAdd(grad_env + 3 * (size_t)t.i11 + c, acc[9 + c]);
+            }
+        }
+    }
+}
+static int eval_final_bwd_launch(const EvalParams &p, int n, cudaStream_t st)
+{
+    k_eval_final_bwd<<<(n + 255) / 256, 256, 0, st>>>(p, n);
+    MR_CUDA_CHECK_LAUNCH();
+    return 0;
+}
+#else
+static int eval_final_bwd_launch(const EvalParams &p, int n, cudaStream_t)
+{
+    for (int idx = 0; idx < n; ++idx) {
+        Taps t;
+        float vals[12];
+        if (!eval_final_bwd_terms(p, idx, t, vals)) continue;
+        for (int c = 0; c < 3; ++c) {
+            p.grad_env[3 * (size_t)t.i00 + c] += vals[c];
+            p.grad_env[3 * (size_t)t.i10 + c] += vals[3 + c];
+            p.grad_env[3 * (size_t)t.i01 + c] += vals[6 + c];
+            p.grad_env[3 * (size_t)t.i11 + c] += vals[9 + c];
+        }
+    }
+    return 0;
+}
+#endif
+
+} // namespace mr
+
+using namespace mr;
+
+extern "C" {
+
+int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris, const float *pos_map, float *res_ld,
+                              float *res_pdf, int *res_M, float *res_w, const float *env_tex, int env_w, int env_h,
+                              int fx, int fy, unsigned int frame_index, const float *occ, const float *normal_depth,
+                              const float *brdf_map, const float *ray_dir, const float *pdf_, const float *mpdf_,
+                              const float *light_data, const float *light_pdf, int tile_count, int tile_size,
+                              int screen_tile, int n_light, int n_brdf, void *stream)
+{
+    if (!packed_nodes || !packed_tris || !pos_map || !res_ld || !res_pdf || !res_M || !res_w || !env_tex || !occ ||
+        !normal_depth || !brdf_map || !ray_dir || !pdf_ || !mpdf_ || !light_data || !light_pdf)
+        return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1 || env_w < 1 || env_h < 1 || tile_count < 1 || tile_size < 1 || screen_tile < 1 || n_light < 1 || n_brdf < 0)
+        return MIRRES_ERR_SHAPE;
+    if ((uintptr_t)normal_depth & 15) return MIRRES_ERR_ALIGN;
+    InitialParams p;
+    p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
+    p.env = {env_tex, env_w, env_h, pdf_, nullptr, mpdf_, nullptr};
+    p.g = {occ, normal_depth, brdf_map, ray_dir};
+    p.pos_map = pos_map;
+    p.res = {res_ld, res_pdf, res_M, res_w};
+    p.light_data = light_data;
+    p.light_pdf = light_pdf;
+    p.fx = fx; p.fy = fy; p.frame = frame_index;
+    p.tile_count = tile_count; p.tile_size = tile_size; p.screen_tile = screen_tile; p.n_light = n_light; p.n_brdf = n_brdf;
+    return foreach_item<InitialParams, initial_px, 128>(p, fx * fy, (cudaStream_t)stream);
+}
+
+int mirres_temporal_resampling(float *res_ld, float *res_pdf, int *res_M, float *res_w, const float *prev_ld,
+                               const float *prev_pdf, const int *prev_M, const float *prev_w, const float *env_tex,
+                               int env_w, int env_h, int fx, int fy, unsigned int frame_index, const float *occ,
+                               const float *normal_depth, const float *brdf_map, const float *ray_dir,
+                               const float *prev_occ, const float *prev_normal_depth, const float *prev_brdf_map,
+                               const float *prev_ray_dir, const float *motion, int max_history, void *stream)
+{
+    if (!res_ld || !res_pdf || !res_M || !res_w || !prev_ld || !prev_pdf || !prev_M || !prev_w || !env_tex || !occ ||
+        !normal_depth || !brdf_map || !ray_dir || !prev_occ || !prev_normal_depth || !prev_brdf_map || !prev_ray_dir)
+        return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1 || env_w < 1 || env_h < 1 || max_history < 0) return MIRRES_ERR_SHAPE;
+    if (((uintptr_t)normal_depth & 15) || ((uintptr_t)prev_normal_depth & 15)) return MIRRES_ERR_ALIGN;
+    TemporalParams p;
+    p.env = {env_tex, env_w, env_h, nullptr, nullptr, nullptr, nullptr};
+    p.g = {occ, normal_depth, brdf_map, ray_dir};
+    p.prev_g = {prev_occ, prev_normal_depth, prev_brdf_map, prev_ray_dir};
+    p.res = {res_ld, res_pdf, res_M, res_w};
+    p.prev = {prev_ld, prev_pdf, prev_M, prev_w};
+    p.motion = motion;
+    p.fx = fx; p.fy = fy; p.frame = frame_index; p.max_history = max_history;
+    return foreach_item<TemporalParams, temporal_px, 128>(p, fx * fy, (cudaStream_t)stream);
+}
+
+int mirres_spatial_resampling(const void *packed_nodes, const void *packed_tris, const float *pos_map, float *res_ld,
+                              float *res_pdf, int *res_M, float *res_w, const float *prev_ld, const float *prev_pdf,
+                              const int *prev_M, const float *prev_w, const float *neighbor_offsets, const float *env_tex,
+                              int env_w, int env_h, int fx, int fy, unsigned int frame_index, const float *occ,
+                              const float *normal_depth, const float *brdf_map, const float *ray_dir, int offset_count,
+                              int neighbor_count, float gather_radius, void *stream)
+{
+    if (!packed_nodes || !packed_tris || !pos_map || !res_ld || !res_pdf || !res_M || !res_w || !prev_ld || !prev_pdf ||
+        !prev_M || !prev_w || !neighbor_offsets || !env_tex || !occ || !normal_depth || !brdf_map || !ray_dir)
+        return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1 || env_w < 1 || env_h < 1 || offset_count < 1 || (offset_count & (offset_count - 1)) || neighbor_count < 0)
+        return MIRRES_ERR_SHAPE;
+    if ((uintptr_t)normal_depth & 15) return MIRRES_ERR_ALIGN;
+    if (res_ld == prev_ld) return MIRRES_ERR_ALIAS;
+    SpatialParams p;
+    p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
+    p.env = {env_tex, env_w, env_h, nullptr, nullptr, nullptr, nullptr};
+    p.g = {occ, normal_depth, brdf_map, ray_dir};
+    p.pos_map = pos_map;
+    p.res = {res_ld, res_pdf, res_M, res_w};
+    p.prev = {prev_ld, prev_pdf, prev_M, prev_w};
+    p.offsets = neighbor_offsets;
+    p.fx = fx; p.fy = fy; p.frame = frame_index;
+    p.offset_count = offset_count; p.neighbor_count = neighbor_count; p.radius = gather_radius;
+    return foreach_item<SpatialParams, spatial_px, 128>(p, fx * fy, (cudaStream_t)stream);
+}
+
+int mirres_final_visibility(const void *packed_nodes, const void *packed_tris, const float *res_ld, int fx, int fy,
+                            const float *pos_map, float *vis_map, void *stream)
+{
+    if (!packed_nodes || !packed_tris || !res_ld || !pos_map || !vis_map) return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1) return MIRRES_ERR_SHAPE;
+    VisParams p = {{(const PackedNode *)packed_nodes, (const float4 *)packed_tris}, res_ld, pos_map, vis_map};
+    return foreach_item<VisParams, final_visibility_px, 128>(p, fx * fy, (cudaStream_t)stream);
+}
+
+int mirres_eval_final_fwd(const float *res_ld, const float *res_pdf, const int *res_M, const float *res_w,
+                          const float *env_tex, int env_w, int env_h, int fx, int fy, float *fs_dir, float *fs_dist,
+                          float *fs_Li, const float *vis_map, void *stream)
+{
+    if (!res_ld || !res_w || !env_tex || !fs_dir || !fs_dist || !fs_Li || !vis_map) return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1 || env_w < 1 || env_h < 1) return MIRRES_ERR_SHAPE;
+    EvalParams p = {{res_ld, res_pdf, res_M, res_w}, {env_tex, env_w, env_h, nullptr, nullptr, nullptr, nullptr},
+                    vis_map, fs_dir, fs_dist, fs_Li, nullptr, nullptr};
+    return foreach_item<EvalParams, eval_final_fwd_px, 256>(p, fx * fy, (cudaStream_t)stream);
+}
+
+int mirres_eval_final_bwd(const float *res_ld, const float *res_pdf, const int *res_M, const float *res_w, int env_w,
+                          int env_h, int fx, int fy, const float *vis_map, const float *grad_Li, float *grad_env,
+                          void *stream)
+{
+    if (!res_ld || !res_w || !vis_map || !grad_Li || !grad_env) return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1 || env_w < 1 || env_h < 1) return MIRRES_ERR_SHAPE;
+    EvalParams p = {{res_ld, res_pdf, res_M, res_w}, {nullptr, env_w, env_h, nullptr, nullptr, nullptr, nullptr},
+                    vis_map, nullptr, nullptr, nullptr, grad_Li, grad_env};
+    return eval_final_bwd_launch(p, fx * fy, (cudaStream_t)stream);
+}
+
+} // extern "C"

@@ -1,0 +1,476 @@
+// mirres-b200: final shading (forward + hand-derived backward) and the multi-bounce integrator for sm_100a.
+//
+// Replaces:
+//   nerf/ScreenSpaceReSTIR/FinalShading.slang:14-109    process_FinalShading      -> final_shading_px
+//   Slang autodiff of the same kernel (`.bwd`, called from nerf/ScreenSpaceReSTIR/Resampling.py:179-214)
+//                                                                                 -> final_shading_bwd_px
+//   nerf/ScreenSpaceReSTIR/FinalShading.slang:113-265   process_new_dir_for_pt    -> bounce_first_px
+//   nerf/ScreenSpaceReSTIR/FinalShading.slang:641-1009  process_path_tracing_divided_no_grad -> bounce_shade_px
+// `max_bounce` generalises the reference's compile-time MAX_Bounce = 2 (FinalShading.slang:7).
+#include "mr_bvh.cuh"
+#include "mr_light.cuh"
+#include "mr_brdf.cuh"
+#include "../../include/mirres_b200.h"
+
+namespace mr {
+
+#define VIS_NEAR 0.01f
+
+// ---------------------------------------------------------------------------------------------------------------
+struct ShadeParams {
+    const float *__restrict__ fs_dir;  // [N,3]
+    const float *__restrict__ fs_dist; // [N]
+    const float *__restrict__ fs_Li;   // [N,3]
+    EnvView env;
+    const float *__restrict__ occ;     // [N]
+    const float *__restrict__ normal;  // [N,3]
+    const float *__restrict__ ray_dir; // [N,3]
+    const float *__restrict__ kd;      // [N,3]
+    const float *__restrict__ rm;      // [N,2] roughness, metallic
+    float *__restrict__ color;
+    float *__restrict__ diff_light;
+    float *__restrict__ spec_light;
+    // backward only
+    const float *__restrict__ g_color;
+    const float *__restrict__ g_diff;
+    const float *__restrict__ g_spec;
+    float *__restrict__ g_normal; // [N,3]
+    float *__restrict__ g_kd;     // [N,3]
+    float *__restrict__ g_rm;     // [N,2]
+    float *__restrict__ g_Li;     // [N,3]
+};
+
+MR_DEV void final_shading_px(const ShadeParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    const float3 rd = load3(p.ray_dir, i);
+    float3 color_val = f3(0.f), light_diffuse = f3(0.f), light_spec = f3(0.f);
+    if (MR_LDG(p.occ + i) > 0.1f) {
+        const float3 kd = load3(p.kd, i);
+        const float metallic = MR_LDG(p.rm + 2 * i + 1);
+        float3 diffuse_val = f3(0.f), specular_val = f3(0.f);
+        if (MR_LDG(p.fs_dist + i) > 0.f) {
+            const Surface s = surface_of(load3(p.normal, i), rd, kd, MR_LDG(p.rm + 2 * i), metallic);
+            const float3 wi = to_frame(s.frame, load3(p.fs_dir, i));
+            const float3 Li = load3(p.fs_Li, i);
+            if (s.pD > 0.f) diffuse_val = f3(lambert_light(s.wo, wi)) * Li;
+            if (s.pS > 0.f) specular_val = specular_f(s.wo, wi, s.spec, s.alpha) * Li;
+        }
+        color_val += kd * (1.0f - metallic) * diffuse_val + specular_val;
+        light_diffuse += diffuse_val;
+        light_spec += specular_val;
+    } else {
+        color_val = env_radiance(p.env, ngp_dir(rd));
+    }
+    store3(p.color, i, color_val);
+    store3(p.diff_light, i, light_diffuse);
+    store3(p.spec_light, i, light_spec);
+}
+
+// Reverse mode of final_shading_px with respect to normal, kd, (roughness, metallic) and Li.  Branch predicates
+// (occupancy, distance, lobe probabilities, the 1e-6 / alpha == 0 gates, clamps) are frozen, as Slang's autodiff
+// does.  The lobe probabilities only gate branches, so no gradient flows through them.
+MR_DEV void final_shading_bwd_px(const ShadeParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    float3 gN = f3(0.f), gKd = f3(0.f), gLi = f3(0.f);
+    float gR = 0.f, gM = 0.f;
+    if (MR_LDG(p.occ + i) > 0.1f && MR_LDG(p.fs_dist + i) > 0.f) {
+        const float INV_PI = 0.31830988f;
+        const float PI = 3.141592653589793f;
+        const float F0 = 0.04f;
+        const float3 N = load3(p.normal, i), rd = load3(p.ray_dir, i), kd = load3(p.kd, i);
+        const float rough = MR_LDG(p.rm + 2 * i), metallic = MR_LDG(p.rm + 2 * i + 1);
+        const float3 L = load3(p.fs_dir, i), Li = load3(p.fs_Li, i);
+        const float3 gC = load3(p.g_color, i), gD = load3(p.g_diff, i), gS = load3(p.g_spec, i);
+        const Surface s = surface_of(N, rd, kd, rough, metallic);
+        const float3 V = -rd;
+        const float3 wo = s.wo;
+        const float3 wi = to_frame(s.frame, L);
+        // forward values
+        const bool gate = !(fminf(wo.z, wi.z) < 1e-6f);
+        float Dl = 0.f;
+        if (s.pD > 0.f && gate) Dl = fmaxf(INV_PI * wi.z, 0.0f);
+        const float3 diffuse_val = f3(Dl) * Li;
+        // upstream on diffuse_val / specular_val
+        const float3 gDv = gC * (kd * (1.0f - metallic)) + gD;
+        const float3 gSv = gC + gS;
+        // color = kd (1-m) diffuse_val + specular_val
+        gKd += gC * diffuse_val * (1.0f - metallic);
+        gM += -(gC.x * kd.x * diffuse_val.x + gC.y * kd.y * diffuse_val.y + gC.z * kd.z * diffuse_val.z);
+        gLi += gDv * Dl;
+        float3 gwo = f3(0.f), gwi = f3(0.f);
+        if (s.pD > 0.f && gate && INV_PI * wi.z > 0.0f) gwi.z += INV_PI * (gDv.x * Li.x + gDv.y * Li.y + gDv.z * Li.z);
+        if (s.pS > 0.f && gate && s.alpha != 0.f) {
+            const float alpha = s.alpha;
+            const float3 sum = wo + wi;
+            const float len = sqrtf(dot(sum, sum));
+            const float3 h = sum / len;
+            const float c = dot(wo, h);
+            const float a2 = alpha * alpha;
+            const float dd = ((h.z * a2 - h.z) * h.z + 1);
+            const float D = a2 / (dd * dd * PI);
+            const float lI = ggx_lambda(a2, wo.z), lO = ggx_lambda(a2, wi.z);
+            const float G = 1 / (1 + lI + lO);
+            const float om = fmaxf(1 - c, 0);
+            const float p5 = mr_pow5f(om);
+            const float3 F = make_float3(s.spec.x + (1 - s.spec.x) * p5, s.spec.y + (1 - s.spec.y) * p5, s.spec.z + (1 - s.spec.z) * p5);
+            const float sc = D * G * 0.25f / wo.z; // Fs = F * sc
+            gLi += gSv * (F * sc);
+            const float3 gFs = gSv * Li;
+            const float3 gF = gFs * sc;
+            const float gsc = gFs.x * F.x + gFs.y * F.y + gFs.z * F.z;
+            // F = spec + (1 - spec) p5
+            const float3 gspec = gF * (1 - p5);
+            const float gp5 = gF.x * (1 - s.spec.x) + gF.y * (1 - s.spec.y) + gF.z * (1 - s.spec.z);
+            float gc = 0.f;
+            if (1 - c > 0) gc = -gp5 * 5.0f * (om * om) * (om * om);
+            // sc = D G / (4 wo.z)
+            const float gD_ = gsc * G * 0.25f / wo.z;
+            const float gG = gsc * D * 0.25f / wo.z;
+            gwo.z += -gsc * sc / wo.z;
+            // D(a2, hz)
+            float ga2 = gD_ * (1 / (dd * dd * PI) - 2 * a2 * (h.z * h.z) / (dd * dd * dd * PI));
+            float ghz = gD_ * (-2 * a2 / (dd * dd * dd * PI)) * (2 * h.z * (a2 - 1));
+            // G = 1 / (1 + lI + lO)
+            const float gl = -gG * G * G;
+            {
+                const float cs[2] = {wo.z, wi.z};
+                float gcs[2] = {0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float cz = cs[k];
+                    if (cz > 0) {
+                        const float c2 = cz * cz;
+                        const float num = fmaxf(1 - c2, 0);
+                        const float t = num / c2;
+                        const float root = sqrtf(1 + a2 * t);
+                        ga2 += gl * 0.25f * t / root;
+                        if (1 - c2 > 0) gcs[k] = gl * (0.25f * a2 / root) * (-2.0f / (c2 * cz));
+                    }
+                }
+                gwo.z += gcs[0];
+                gwi.z += gcs[1];
+            }
+            // c = dot(wo, h), hz = h.z, h = normalize(wo + wi)
+            float3 gh = gc * wo;
+            gh.z += ghz;
+            gwo += gc * h;
+            const float3 gsum = (gh - h * dot(h, gh)) / len;
+            gwo += gsum;
+            gwi += gsum;
+            // alpha = rough^2 (frozen to 0 below the threshold, in which case this branch is not taken)
+            gR += ga2 * 2 * alpha * 2 * rough;
+            // spec = F0 (1-m) + kd m
+            gKd += gspec * metallic;
+            gM += gspec.x * (kd.x - F0) + gspec.y * (kd.y - F0) + gspec.z * (kd.z - F0);
+        }
+        // wo = frame(N)^T V, wi = frame(N)^T L
+        const float3 gfx = gwo.x * V + gwi.x * L;
+        const float3 gfy = gwo.y * V + gwi.y * L;
+        const float3 gfz = gwo.z * V + gwi.z * L;
+        gN += gfz;
+        {
+            const float sign = N.z > 0 ? 1.0f : -1.0f;
+            const float a = -1.0f / (sign + N.z);
+            const float gb = gfx.y * sign + gfy.x;
+            const float ga = gfx.x * sign * N.x * N.x + gfy.y * N.y * N.y + gb * N.x * N.y;
+            gN.x += gfx.x * sign * 2 * N.x * a + gb * N.y * a - gfx.z * sign;
+            gN.y += gfy.y * 2 * N.y * a + gb * N.x * a - gfy.z;
+            gN.z += ga * (a * a); // a = -1/(sign+nz)  =>  da/dnz = 1/(sign+nz)^2 = a^2
+        }
+    }
+    store3(p.g_normal, i, gN);
+    store3(p.g_kd, i, gKd);
+    p.g_rm[2 * i] = gR;
+    p.g_rm[2 * i + 1] = gM;
+    store3(p.g_Li, i, gLi);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct BounceParams {
+    BvhView bvh;
+    EnvView env;
+    unsigned int frame, bounce_count;
+    int max_bounce;
+    int fx, fy;
+    const float *__restrict__ occ;
+    const float *__restrict__ pos_map;
+    const float *__restrict__ normal;
+    const float *__restrict__ ray_dir;
+    float *prd; // [N,5] throughput rgb, specular flag, stop flag
+    const float *__restrict__ kd;
+    const float *__restrict__ rm;
+    float *__restrict__ color;      // shade only
+    float *__restrict__ diff_color; // shade only
+    float *__restrict__ spec_color; // shade only
+    float *__restrict__ new_pos;
+    float *__restrict__ new_ray_d;
+    float *__restrict__ new_occ;
+    float *__restrict__ new_normal;
+};
+
+// sample a continuation direction and trace it (FinalShading.slang:190-262 and :907-977)
+MR_DEV void continue_path(const BounceParams &p, size_t i, const Surface &s, float3 surf_pos, uint32_t &sg, float3 thr)
+{
+    float3 out_dir, out_weight;
+    float out_pdf;
+    uint32_t sampledSpecular;
+    bool valid = bsdf_sample<true>(s, sg, out_dir, out_pdf, sampledSpecular, out_weight);
+    if (!valid) return;
+    if (is_black(out_weight) || out_pdf == 0.f) {
+        p.prd[5 * i + 4] = 1.f;
+    } else if (p.bounce_count + 1u <= (unsigned int)p.max_bounce) {
+        out_dir = normalize(from_frame(s.frame, out_dir));
+        Hit hit;
+        bool found = closest_hit<false>(p.bvh, surf_pos + VIS_NEAR * out_dir, out_dir, hit, nullptr);
+        const float specularBounce = (float)sampledSpecular;
+        thr *= out_weight;
+        p.prd[5 * i + 0] = thr.x;
+        p.prd[5 * i + 1] = thr.y;
+        p.prd[5 * i + 2] = thr.z;
+        p.prd[5 * i + 3] = specularBounce;
+        store3(p.new_ray_d, i, out_dir);
+        if (found) {
+            p.prd[5 * i + 4] = 0.f;
+            store3(p.new_pos, i, hit.pos);
+            store3(p.new_normal, i, hit.normal);
+            p.new_occ[i] = 1.f;
+        } else if (specularBounce > 0.f) {
+            p.prd[5 * i + 4] = 0.f;
+        }
+    }
+}
+
+MR_DEV void bounce_first_px(const BounceParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
+    float3 thr = make_float3(p.prd[5 * i], p.prd[5 * i + 1], p.prd[5 * i + 2]);
+    float is_stop = p.prd[5 * i + 4];
+    p.new_occ[i] = 0.f;
+    p.prd[5 * i + 4] = 1.f;
+    if (p.bounce_count == 0) {
+        thr = f3(1.0f);
+        is_stop = 0.f;
+        p.prd[5 * i] = 1.f; p.prd[5 * i + 1] = 1.f; p.prd[5 * i + 2] = 1.f;
+        p.prd[5 * i + 3] = 0.f;
+    }
+    if (is_stop > 0.f) return;
+    if (!(MR_LDG(p.occ + i) > 0.1f)) return;
+    uint32_t sg = seed_of(px, py, p.frame);
+    const Surface s = surface_of(load3(p.normal, i), load3(p.ray_dir, i), load3(p.kd, i), MR_LDG(p.rm + 2 * i), MR_LDG(p.rm + 2 * i + 1));
+    continue_path(p, i, s, load3(p.pos_map, i), sg, thr);
+}
+
+MR_DEV void bounce_shade_px(const BounceParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
+    float3 thr = make_float3(p.prd[5 * i], p.prd[5 * i + 1], p.prd[5 * i + 2]);
+    float specularBounce = p.prd[5 * i + 3];
+    float is_stop = p.prd[5 * i + 4];
+    p.new_occ[i] = 0.f;
+    p.prd[5 * i + 4] = 1.f;
+    if (p.bounce_count == 0) {
+        thr = f3(1.0f);
+        specularBounce = 0.f;
+        is_stop = 0.f;
+        p.prd[5 * i] = 1.f; p.prd[5 * i + 1] = 1.f; p.prd[5 * i + 2] = 1.f;
+        p.prd[5 * i + 3] = 0.f;
+    }
+    float3 color_val = f3(0.f), diff_val = f3(0.f), spec_val = f3(0.f);
+    if (!(is_stop > 0.f)) {
+        const float3 rd = load3(p.ray_dir, i);
+        if (MR_LDG(p.occ + i) > 0.1f) {
+            uint32_t sg = seed_of(px, py, p.frame);
+            const float3 N = load3(p.normal, i);
+            const float3 P = load3(p.pos_map, i);
+            const Surface s = surface_of(N, rd, load3(p.kd, i), MR_LDG(p.rm + 2 * i), MR_LDG(p.rm + 2 * i + 1));
+            const bool has_normal = !is_black(N);
+            // ---- next-event estimation: one env sample, power heuristic against the BSDF pdf
+            float lightPdf = 0.0f, scatteringPdf = 0.0f;
+            float3 Li = f3(0.f);
+            {
+                float2 u;
+                u.x = rnd(sg);
+                u.y = rnd(sg);
+                float3 sdir = f3(0.f);
+                float spdf = 0.f;
+                float2 luv;
+                bool ok = sample_env(p.env, u, sdir, spdf, luv);
+                if (ok) {
+                    lightPdf = spdf;
+                    Li = env_radiance(p.env, ngp_dir(sdir)) / spdf;
+                }
+                if (ok && lightPdf > 0 && !is_black(Li)) {
+                    float3 diff_f = f3(0.f), spec_f = f3(0.f), total_f = f3(0.f);
+                    const float3 wi = to_frame(s.frame, sdir);
+                    if (has_normal) {
+                        if (s.pD > 0.f) diff_f = f3(lambert_light(s.wo, wi));
+                        if (s.pS > 0.f) spec_f = specular_f(s.wo, wi, s.spec, s.alpha);
+                        total_f = s.kd_diff * diff_f + spec_f;
+                        diff_f = s.kd_diff * diff_f;
+                        scatteringPdf = bsdf_pdf(s, wi);
+                    }
+                    if (!is_black(total_f)) {
+                        const float3 ldir = normalize(sdir);
+                        const float tr = any_hit<false>(p.bvh, P + VIS_NEAR * ldir, ldir, nullptr) ? 0.0f : 1.0f;
+                        Li = Li * f3(tr);
+                        if (!is_black(Li)) {
+                            const float mis = power_heuristic(lightPdf, scatteringPdf);
+                            color_val += thr * total_f * Li * mis;
+                            diff_val += thr * diff_f * Li * mis;
+                            spec_val += thr * spec_f * Li * mis;
+                        }
+                    }
+                }
+            }
+            // ---- BSDF sample with MIS against the light pdf
+            if (has_normal) {
+                float3 m_wi, unused_w;
+                float m_pdf;
+                uint32_t sampledSpecular;
+                bool valid = bsdf_sample<false>(s, sg, m_wi, m_pdf, sampledSpecular, unused_w);
+                if (valid) {
+                    float3 wd = f3(1.0f), ws = f3(1.0f);
+                    if (s.pD > 0.f) wd = f3(lambert_light(s.wo, m_wi));
+                    if (s.pS > 0.f) ws = specular_f(s.wo, m_wi, s.spec, s.alpha);
+                    const float3 wt = s.kd_diff * wd + ws;
+                    m_wi = from_frame(s.frame, m_wi);
+                    scatteringPdf = m_pdf;
+                    // the reference divides by the pdf and multiplies it back (FinalShading.slang:853-859); kept for rounding
+                    float3 f = wt / m_pdf, diff_f = s.kd_diff * wd / m_pdf, spec_f = ws / m_pdf;
+                    f *= m_pdf;
+                    diff_f *= m_pdf;
+                    spec_f *= m_pdf;
+                    const float3 dirw = normalize(m_wi);
+                    if (!is_black(f) && scatteringPdf > 0) {
+                        float weight = 1.0f;
+                        bool light_pdf_zero = false;
+                        if (sampledSpecular == 0) {
+                            lightPdf = env_pdf(p.env, dirw);
+                            if (lightPdf == 0.0f) light_pdf_zero = true;
+                            weight = power_heuristic(scatteringPdf, lightPdf);
+                        }
+                        const bool blocked = any_hit<false>(p.bvh, P + VIS_NEAR * dirw, dirw, nullptr);
+                        Li = f3(0.f);
+                        if (!blocked) Li = env_radiance(p.env, ngp_dir(dirw));
+                        if (!is_black(Li) && !light_pdf_zero) {
+                            const float3 Tr = f3(1.0f);
+                            color_val += thr * f * Li * Tr * weight / scatteringPdf;
+                            diff_val += thr * diff_f * Li * Tr * weight / scatteringPdf;
+                            spec_val += thr * spec_f * Li * Tr * weight / scatteringPdf;
+                        }
+                    }
+                }
+            }
+            // ---- continuation
+            continue_path(p, i, s, P, sg, thr);
+        } else {
+            if (p.bounce_count == 0) {
+                color_val += thr * env_radiance(p.env, ngp_dir(rd));
+            } else if (specularBounce > 0.f) {
+                const float3 Le = env_radiance(p.env, ngp_dir(rd));
+                color_val += thr * Le;
+                spec_val += thr * Le;
+            }
+            p.prd[5 * i + 4] = 1.f;
+        }
+    }
+    store3(p.color, i, color_val);
+    store3(p.diff_color, i, diff_val);
+    store3(p.spec_color, i, spec_val);
+}
+
+} // namespace mr
+
+using namespace mr;
+
+extern "C" {
+
+int mirres_final_shading_fwd(const float *fs_dir, const float *fs_dist, const float *fs_Li, const float *env_tex,
+                             int env_w, int env_h, int fx, int fy, const float *occ, const float *normal,
+                             const float *ray_dir, const float *diffuse_map, const float *rough_metal, float *color,
+                             float *diff_light, float *spec_light, void *stream)
+{
+    if (!fs_dir || !fs_dist || !fs_Li || !env_tex || !occ || !normal || !ray_dir || !diffuse_map || !rough_metal ||
+        !color || !diff_light || !spec_light)
+        return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1 || env_w < 1 || env_h < 1) return MIRRES_ERR_SHAPE;
+    ShadeParams p = {};
+    p.fs_dir = fs_dir; p.fs_dist = fs_dist; p.fs_Li = fs_Li;
+    p.env = {env_tex, env_w, env_h, nullptr, nullptr, nullptr, nullptr};
+    p.occ = occ; p.normal = normal; p.ray_dir = ray_dir; p.kd = diffuse_map; p.rm = rough_metal;
+    p.color = color; p.diff_light = diff_light; p.spec_light = spec_light;
+    return foreach_item<ShadeParams, final_shading_px, 256>(p, fx * fy, (cudaStream_t)stream);
+}
+
+int mirres_final_shading_bwd(const float *fs_dir, const float *fs_dist, const float *fs_Li, int fx, int fy,
+                             const float *occ, const float *normal, const float *ray_dir, const float *diffuse_map,
+                             const float *rough_metal, const float *grad_color, const float *grad_diff_light,
+                             const float *grad_spec_light, float *grad_normal, float *grad_diffuse,
+                             float *grad_rough_metal, float *grad_Li, void *stream)
+{
+    if (!fs_dir || !fs_dist || !fs_Li || !occ || !normal || !ray_dir || !diffuse_map || !rough_metal || !grad_color ||
+        !grad_diff_light || !grad_spec_light || !grad_normal || !grad_diffuse || !grad_rough_metal || !grad_Li)
+        return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1) return MIRRES_ERR_SHAPE;
+    ShadeParams p = {};
+    p.fs_dir = fs_dir; p.fs_dist = fs_dist; p.fs_Li = fs_Li;
+    p.occ = occ; p.normal = normal; p.ray_dir = ray_dir; p.kd = diffuse_map; p.rm = rough_metal;
+    p.g_color = grad_color; p.g_diff = grad_diff_light; p.g_spec = grad_spec_light;
+    p.g_normal = grad_normal; p.g_kd = grad_diffuse; p.g_rm = grad_rough_metal; p.g_Li = grad_Li;
+    return foreach_item<ShadeParams, final_shading_bwd_px, 256>(p, fx * fy, (cudaStream_t)stream);
+}
+
+static int fill_bounce(BounceParams &p, const void *packed_nodes, const void *packed_tris, unsigned int frame_index,
+                       unsigned int bounce_count, int max_bounce, int fx, int fy, const float *occ, const float *pos_map,
+                       const float *normal, const float *ray_dir, float *prd, const float *diffuse_map,
+                       const float *rough_metal, float *new_pos, float *new_ray_d, float *new_occ, float *new_normal)
+{
+    if (!packed_nodes || !packed_tris || !occ || !pos_map || !normal || !ray_dir || !prd || !diffuse_map || !rough_metal ||
+        !new_pos || !new_ray_d || !new_occ || !new_normal)
+        return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1 || max_bounce < 0) return MIRRES_ERR_SHAPE;
+    if (new_pos == pos_map || new_occ == occ || new_normal == normal || new_ray_d == ray_dir) return MIRRES_ERR_ALIAS;
+    p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
+    p.frame = frame_index; p.bounce_count = bounce_count; p.max_bounce = max_bounce; p.fx = fx; p.fy = fy;
+    p.occ = occ; p.pos_map = pos_map; p.normal = normal; p.ray_dir = ray_dir; p.prd = prd; p.kd = diffuse_map; p.rm = rough_metal;
+    p.new_pos = new_pos; p.new_ray_d = new_ray_d; p.new_occ = new_occ; p.new_normal = new_normal;
+    return 0;
+}
+
+int mirres_bounce_first(const void *packed_nodes, const void *packed_tris, unsigned int frame_index,
+                        unsigned int bounce_count, int max_bounce, int fx, int fy, const float *occ, const float *pos_map,
+                        const float *normal, const float *ray_dir, float *prd, const float *diffuse_map,
+                        const float *rough_metal, float *new_pos, float *new_ray_d, float *new_occ, float *new_normal,
+                        void *stream)
+{
+    BounceParams p = {};
+    int rc = fill_bounce(p, packed_nodes, packed_tris, frame_index, bounce_count, max_bounce, fx, fy, occ, pos_map, normal,
+                         ray_dir, prd, diffuse_map, rough_metal, new_pos, new_ray_d, new_occ, new_normal);
+    if (rc) return rc;
+    return foreach_item<BounceParams, bounce_first_px, 128>(p, fx * fy, (cudaStream_t)stream);
+}
+
+int mirres_bounce_shade(const void *packed_nodes, const void *packed_tris, unsigned int frame_index,
+                        unsigned int bounce_count, int max_bounce, int fx, int fy, const float *env_tex, int env_w,
+                        int env_h, const float *pdf_, const float *cdf_, const float *mpdf_, const float *mcdf_,
+                        const float *occ, const float *pos_map, const float *normal, const float *ray_dir, float *prd,
+                        const float *diffuse_map, const float *rough_metal, float *color, float *diff_color,
+                        float *spec_color, float *new_pos, float *new_ray_d, float *new_occ, float *new_normal,
+                        void *stream)
+{
+    if (!env_tex || !pdf_ || !cdf_ || !mpdf_ || !mcdf_ || !color || !diff_color || !spec_color) return MIRRES_ERR_NULL;
+    if (env_w < 1 || env_h < 1) return MIRRES_ERR_SHAPE;
+    BounceParams p = {};
+    int rc = fill_bounce(p, packed_nodes, packed_tris, frame_index, bounce_count, max_bounce, fx, fy, occ, pos_map, normal,
+                         ray_dir, prd, diffuse_map, rough_metal, new_pos, new_ray_d, new_occ, new_normal);
+    if (rc) return rc;
+    p.env = {env_tex, env_w, env_h, pdf_, cdf_, mpdf_, mcdf_};
+    p.color = color; p.diff_color = diff_color; p.spec_color = spec_color;
+    return foreach_item<BounceParams, bounce_shade_px, 128>(p, fx * fy, (cudaStream_t)stream);
+}
+
+} // extern "C"

@@ -1,0 +1,88 @@
+// mirres-b200: standalone ray queries and traversal-record packing (also the G-buffer producer of the
+// synthetic benchmark).  Semantics: nerf/ScreenSpaceReSTIR/utils/helperDi.slang:197-274 (bvh_hit) and
+// :313-395 (bvh_hit_with_normal) with t_min = 0, t_max = 1e7; the primitive id and visit counters are
+// extensions the reference does not output.
+#include "mr_bvh.cuh"
+#include "../../include/mirres_b200.h"
+
+namespace mr {
+
+struct TraceParams {
+    BvhView bvh;
+    const float *__restrict__ org; // [n,3]
+    const float *__restrict__ dir; // [n,3]
+    int *__restrict__ hit;         // [n]
+    float *__restrict__ t;         // [n] or null
+    float *__restrict__ pos;       // [n,3] or null
+    float *__restrict__ normal;    // [n,3] or null
+    int *__restrict__ prim;        // [n] or null
+    unsigned int *__restrict__ visits; // [n,2] nodes, triangles -- or null
+};
+
+MR_DEV void trace_closest_item(const TraceParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    Hit h;
+    h.t = 0.f;
+    h.pos = f3(0.f);
+    h.normal = f3(1.f);
+    h.prim = -1;
+    TraceStats st = {0u, 0u};
+    bool found = p.visits ? closest_hit<true>(p.bvh, load3(p.org, i), load3(p.dir, i), h, &st)
+                          : closest_hit<false>(p.bvh, load3(p.org, i), load3(p.dir, i), h, nullptr);
+    p.hit[i] = found ? 1 : 0;
+    if (p.t) p.t[i] = found ? h.t : 0.f;
+    if (p.pos) store3(p.pos, i, found ? h.pos : f3(0.f));
+    if (p.normal) store3(p.normal, i, found ? h.normal : f3(1.f));
+    if (p.prim) p.prim[i] = found ? h.prim : -1;
+    if (p.visits) { p.visits[2 * i] = st.nodes; p.visits[2 * i + 1] = st.tris; }
+}
+
+MR_DEV void trace_any_item(const TraceParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    TraceStats st = {0u, 0u};
+    bool found = p.visits ? any_hit<true>(p.bvh, load3(p.org, i), load3(p.dir, i), &st)
+                          : any_hit<false>(p.bvh, load3(p.org, i), load3(p.dir, i), nullptr);
+    p.hit[i] = found ? 1 : 0;
+    if (p.visits) { p.visits[2 * i] = st.nodes; p.visits[2 * i + 1] = st.tris; }
+}
+
+} // namespace mr
+
+using namespace mr;
+
+extern "C" {
+
+int mirres_trace_closest(const void *packed_nodes, const void *packed_tris, const float *org, const float *dir, int n,
+                         int *hit, float *t, float *pos, float *normal, int *prim, unsigned int *visits, void *stream)
+{
+    if (!packed_nodes || !packed_tris || !org || !dir || !hit) return MIRRES_ERR_NULL;
+    if (n < 0) return MIRRES_ERR_SHAPE;
+    if (n == 0) return 0;
+    TraceParams p = {{(const PackedNode *)packed_nodes, (const float4 *)packed_tris}, org, dir, hit, t, pos, normal, prim, visits};
+    return foreach_item<TraceParams, trace_closest_item, 128>(p, n, (cudaStream_t)stream);
+}
+
+int mirres_trace_any(const void *packed_nodes, const void *packed_tris, const float *org, const float *dir, int n,
+                     int *hit, unsigned int *visits, void *stream)
+{
+    if (!packed_nodes || !packed_tris || !org || !dir || !hit) return MIRRES_ERR_NULL;
+    if (n < 0) return MIRRES_ERR_SHAPE;
+    if (n == 0) return 0;
+    TraceParams p = {{(const PackedNode *)packed_nodes, (const float4 *)packed_tris}, org, dir, hit, nullptr, nullptr, nullptr, nullptr, visits};
+    return foreach_item<TraceParams, trace_any_item, 128>(p, n, (cudaStream_t)stream);
+}
+
+// Traversal records from reference-layout tensors (any LBVH with leaves at [F-1,2F-2], root 0).
+int mirres_bvh_pack(const int *info, const float *aabb, const float *vert, const int *tri, int F, void *packed_nodes,
+                    void *packed_tris, void *stream)
+{
+    if (!info || !aabb || !vert || !tri || !packed_nodes || !packed_tris) return MIRRES_ERR_NULL;
+    if (F < 1) return MIRRES_ERR_SHAPE;
+    if (((uintptr_t)packed_nodes & 15) || ((uintptr_t)packed_tris & 15)) return MIRRES_ERR_ALIGN;
+    PackParams pp = {F, info, aabb, vert, tri, (PackedNode *)packed_nodes, (float4 *)packed_tris};
+    return foreach_item<PackParams, pack_item, 256>(pp, F, (cudaStream_t)stream);
+}
+
+} // extern "C"

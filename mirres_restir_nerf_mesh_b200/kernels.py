@@ -1,0 +1,245 @@
+"""Typed Python front-end of the C ABI: torch tensors in, stream-ordered launches out.
+
+One method per entry point of include/mirres_b200.h.  Tensors must be dense, of the documented dtype, and live on
+the GPU; the launch goes to torch's current CUDA stream (the reference launches on the same stream through
+slangpy's launchRaw).  Nothing here computes anything: it validates and forwards.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+class AbiError(RuntimeError):
+    pass
+
+
+_ERR = {-1: "null pointer", -2: "bad shape/size argument", -3: "misaligned pointer", -4: "scratch too small",
+        -5: "input/output aliasing"}
+
+
+class Kernels:
+    """Binds a loaded library.  `require_cuda=False` exists only for the test-only host-check flavour."""
+
+    def __init__(self, lib=None, require_cuda=True):
+        self.lib = lib if lib is not None else _lib.load()
+        self.require_cuda = require_cuda
+
+    # -- helpers ---------------------------------------------------------------------------------------------
+    def _p(self, t, dtype=None, optional=False):
+        if t is None:
+            if optional:
+                return None
+            raise AbiError("required tensor is None")
+        if not isinstance(t, torch.Tensor):
+            raise AbiError("expected a torch.Tensor, got %r" % type(t))
+        if self.require_cuda and not t.is_cuda:
+            raise AbiError("mirres-b200 kernels need CUDA tensors (no CPU fallback)")
+        if dtype is not None and t.dtype != dtype:
+            raise AbiError("expected dtype %s, got %s" % (dtype, t.dtype))
+        if not t.is_contiguous():
+            raise AbiError("tensor must be contiguous (call .contiguous() at the boundary)")
+        return ctypes.c_void_p(t.data_ptr())
+
+    def _f(self, t, optional=False):
+        return self._p(t, torch.float32, optional)
+
+    def _i(self, t, optional=False):
+        return self._p(t, torch.int32, optional)
+
+    def _stream(self):
+        if not self.require_cuda:
+            return None
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _check(rc, name):
+        if rc != 0:
+            if rc <= -100:
+                raise AbiError("%s: CUDA launch error %d" % (name, -rc - 100))
+            raise AbiError("%s: %s (%d)" % (name, _ERR.get(rc, "error"), rc))
+
+    @staticmethod
+    def _u32(x):
+        return ctypes.c_uint(int(x) & 0xFFFFFFFF)
+
+    # -- BVH ---------------------------------------------------------------------------------------------------
+    def bvh_sizes(self, F):
+        return (self.lib.mirres_bvh_scratch_bytes(F), self.lib.mirres_bvh_packed_node_bytes(F),
+                self.lib.mirres_bvh_packed_tri_bytes(F))
+
+    def bvh_build(self, vert, tri, info, aabb, packed_nodes, packed_tris, scratch, sorted_codes=None):
+        F = tri.shape[0]
+        rc = self.lib.mirres_bvh_build(self._f(vert), vert.shape[0], self._i(tri), F, self._i(info), self._f(aabb),
+                                       self._p(packed_nodes, torch.uint8, True), self._p(packed_tris, torch.uint8, True),
+                                       self._i(sorted_codes, True), self._p(scratch, torch.uint8), scratch.numel(),
+                                       self._stream())
+        self._check(rc, "mirres_bvh_build")
+
+    def bvh_elements(self, vert, tri, ele_primitiveIdx, ele_aabb):
+        rc = self.lib.mirres_bvh_elements(self._f(vert), self._i(tri), tri.shape[0], self._i(ele_primitiveIdx, True),
+                                          self._f(ele_aabb), self._stream())
+        self._check(rc, "mirres_bvh_elements")
+
+    def bvh_morton(self, ele_aabb, extent, morton_codes_ele):
+        rc = self.lib.mirres_bvh_morton(self._f(ele_aabb), ele_aabb.shape[0], *[float(x) for x in extent],
+                                        self._i(morton_codes_ele), self._stream())
+        self._check(rc, "mirres_bvh_morton")
+
+    def bvh_sort(self, pairs, scratch):
+        rc = self.lib.mirres_bvh_sort(self._i(pairs), pairs.shape[0], self._p(scratch, torch.uint8), scratch.numel(),
+                                      self._stream())
+        self._check(rc, "mirres_bvh_sort")
+
+    def bvh_hierarchy_refit(self, sorted_pairs, ele_aabb, info, aabb, scratch):
+        rc = self.lib.mirres_bvh_hierarchy_refit(self._i(sorted_pairs), self._f(ele_aabb), sorted_pairs.shape[0],
+                                                 self._i(info), self._f(aabb), self._p(scratch, torch.uint8),
+                                                 scratch.numel(), self._stream())
+        self._check(rc, "mirres_bvh_hierarchy_refit")
+
+    def bvh_pack(self, info, aabb, vert, tri, packed_nodes, packed_tris):
+        rc = self.lib.mirres_bvh_pack(self._i(info), self._f(aabb), self._f(vert), self._i(tri), tri.shape[0],
+                                      self._p(packed_nodes, torch.uint8), self._p(packed_tris, torch.uint8),
+                                      self._stream())
+        self._check(rc, "mirres_bvh_pack")
+
+    # -- rays --------------------------------------------------------------------------------------------------
+    def trace_closest(self, packed, org, dirs, hit, t=None, pos=None, normal=None, prim=None, visits=None):
+        rc = self.lib.mirres_trace_closest(self._p(packed[0]), self._p(packed[1]), self._f(org), self._f(dirs),
+                                           org.shape[0], self._i(hit), self._f(t, True), self._f(pos, True),
+                                           self._f(normal, True), self._i(prim, True), self._i(visits, True),
+                                           self._stream())
+        self._check(rc, "mirres_trace_closest")
+
+    def trace_any(self, packed, org, dirs, hit, visits=None):
+        rc = self.lib.mirres_trace_any(self._p(packed[0]), self._p(packed[1]), self._f(org), self._f(dirs), org.shape[0],
+                                       self._i(hit), self._i(visits, True), self._stream())
+        self._check(rc, "mirres_trace_any")
+
+    # -- environment -------------------------------------------------------------------------------------------
+    def env_build_distribution(self, env_tex, W, H, pdf_, cdf_, mpdf_, mcdf_, row_scratch):
+        rc = self.lib.mirres_env_build_distribution(self._f(env_tex), W, H, self._f(pdf_), self._f(cdf_), self._f(mpdf_),
+                                                    self._f(mcdf_), self._f(row_scratch), self._stream())
+        self._check(rc, "mirres_env_build_distribution")
+
+    def env_weights(self, env_tex, W, H, weight):
+        self._check(self.lib.mirres_env_weights(self._f(env_tex), W, H, self._f(weight), self._stream()),
+                    "mirres_env_weights")
+
+    def env_distribution2d(self, W, H, pdf_, cdf_):
+        self._check(self.lib.mirres_env_distribution2d(W, H, self._f(pdf_), self._f(cdf_), self._stream()),
+                    "mirres_env_distribution2d")
+
+    def neighbor_offsets(self, count, out):
+        self._check(self.lib.mirres_neighbor_offsets(count, self._f(out), self._stream()), "mirres_neighbor_offsets")
+
+    def light_tiles(self, env_tex, W, H, dist, frame_index, tile_count, tile_size, light_data, light_uv, light_pdf):
+        rc = self.lib.mirres_light_tiles(self._f(env_tex), W, H, self._f(dist[0]), self._f(dist[1]), self._f(dist[2]),
+                                         self._f(dist[3]), self._u32(frame_index), tile_count, tile_size,
+                                         self._f(light_data), self._i(light_uv), self._f(light_pdf), self._stream())
+        self._check(rc, "mirres_light_tiles")
+
+    # -- ReSTIR ------------------------------------------------------------------------------------------------
+    def _res(self, r):
+        return (self._f(r[0]), self._f(r[1]), self._i(r[2]), self._f(r[3]))
+
+    def initial_resampling(self, packed, pos_map, res, env_tex, W, H, fx, fy, frame_index, occ, normal_depth, brdf_map,
+                           ray_dir, pdf_, mpdf_, light_data, light_pdf, tile_count=128, tile_size=1024, screen_tile=8,
+                           n_light=32, n_brdf=1):
+        rc = self.lib.mirres_initial_resampling(self._p(packed[0]), self._p(packed[1]), self._f(pos_map), *self._res(res),
+                                                self._f(env_tex), W, H, fx, fy, self._u32(frame_index), self._f(occ),
+                                                self._f(normal_depth), self._f(brdf_map), self._f(ray_dir), self._f(pdf_),
+                                                self._f(mpdf_), self._f(light_data), self._f(light_pdf), tile_count,
+                                                tile_size, screen_tile, n_light, n_brdf, self._stream())
+        self._check(rc, "mirres_initial_resampling")
+
+    def temporal_resampling(self, res, prev, env_tex, W, H, fx, fy, frame_index, occ, normal_depth, brdf_map, ray_dir,
+                            prev_occ, prev_normal_depth, prev_brdf_map, prev_ray_dir, motion=None, max_history=20):
+        rc = self.lib.mirres_temporal_resampling(*self._res(res), *self._res(prev), self._f(env_tex), W, H, fx, fy,
+                                                 self._u32(frame_index), self._f(occ), self._f(normal_depth),
+                                                 self._f(brdf_map), self._f(ray_dir), self._f(prev_occ),
+                                                 self._f(prev_normal_depth), self._f(prev_brdf_map),
+                                                 self._f(prev_ray_dir), self._f(motion, True), max_history,
+                                                 self._stream())
+        self._check(rc, "mirres_temporal_resampling")
+
+    def spatial_resampling(self, packed, pos_map, res, prev, neighbor_offsets, env_tex, W, H, fx, fy, frame_index, occ,
+                           normal_depth, brdf_map, ray_dir, offset_count=8192, neighbor_count=5, gather_radius=30.0):
+        rc = self.lib.mirres_spatial_resampling(self._p(packed[0]), self._p(packed[1]), self._f(pos_map), *self._res(res),
+                                                *self._res(prev), self._f(neighbor_offsets), self._f(env_tex), W, H, fx,
+                                                fy, self._u32(frame_index), self._f(occ), self._f(normal_depth),
+                                                self._f(brdf_map), self._f(ray_dir), offset_count, neighbor_count,
+                                                float(gather_radius), self._stream())
+        self._check(rc, "mirres_spatial_resampling")
+
+    def final_visibility(self, packed, res_ld, fx, fy, pos_map, vis_map):
+        rc = self.lib.mirres_final_visibility(self._p(packed[0]), self._p(packed[1]), self._f(res_ld), fx, fy,
+                                              self._f(pos_map), self._f(vis_map), self._stream())
+        self._check(rc, "mirres_final_visibility")
+
+    def eval_final_fwd(self, res, env_tex, W, H, fx, fy, fs_dir, fs_dist, fs_Li, vis_map):
+        rc = self.lib.mirres_eval_final_fwd(*self._res(res), self._f(env_tex), W, H, fx, fy, self._f(fs_dir),
+                                            self._f(fs_dist), self._f(fs_Li), self._f(vis_map), self._stream())
+        self._check(rc, "mirres_eval_final_fwd")
+
+    def eval_final_bwd(self, res, W, H, fx, fy, vis_map, grad_Li, grad_env):
+        rc = self.lib.mirres_eval_final_bwd(*self._res(res), W, H, fx, fy, self._f(vis_map), self._f(grad_Li),
+                                            self._f(grad_env), self._stream())
+        self._check(rc, "mirres_eval_final_bwd")
+
+    # -- shading -----------------------------------------------------------------------------------------------
+    def final_shading_fwd(self, fs_dir, fs_dist, fs_Li, env_tex, W, H, fx, fy, occ, normal, ray_dir, diffuse, rough_metal,
+                          color, diff_light, spec_light):
+        rc = self.lib.mirres_final_shading_fwd(self._f(fs_dir), self._f(fs_dist), self._f(fs_Li), self._f(env_tex), W, H,
+                                               fx, fy, self._f(occ), self._f(normal), self._f(ray_dir), self._f(diffuse),
+                                               self._f(rough_metal), self._f(color), self._f(diff_light),
+                                               self._f(spec_light), self._stream())
+        self._check(rc, "mirres_final_shading_fwd")
+
+    def final_shading_bwd(self, fs_dir, fs_dist, fs_Li, fx, fy, occ, normal, ray_dir, diffuse, rough_metal, g_color,
+                          g_diff, g_spec, g_normal, g_diffuse, g_rough_metal, g_Li):
+        rc = self.lib.mirres_final_shading_bwd(self._f(fs_dir), self._f(fs_dist), self._f(fs_Li), fx, fy, self._f(occ),
+                                               self._f(normal), self._f(ray_dir), self._f(diffuse), self._f(rough_metal),
+                                               self._f(g_color), self._f(g_diff), self._f(g_spec), self._f(g_normal),
+                                               self._f(g_diffuse), self._f(g_rough_metal), self._f(g_Li), self._stream())
+        self._check(rc, "mirres_final_shading_bwd")
+
+    def bounce_first(self, packed, frame_index, bounce_count, max_bounce, fx, fy, occ, pos_map, normal, ray_dir, prd,
+                     diffuse, rough_metal, new_pos, new_ray_d, new_occ, new_normal):
+        rc = self.lib.mirres_bounce_first(self._p(packed[0]), self._p(packed[1]), self._u32(frame_index),
+                                          self._u32(bounce_count), max_bounce, fx, fy, self._f(occ), self._f(pos_map),
+                                          self._f(normal), self._f(ray_dir), self._f(prd), self._f(diffuse),
+                                          self._f(rough_metal), self._f(new_pos), self._f(new_ray_d), self._f(new_occ),
+                                          self._f(new_normal), self._stream())
+        self._check(rc, "mirres_bounce_first")
+
+    def bounce_shade(self, packed, frame_index, bounce_count, max_bounce, fx, fy, env_tex, W, H, dist, occ, pos_map,
+                     normal, ray_dir, prd, diffuse, rough_metal, color, diff_color, spec_color, new_pos, new_ray_d,
+                     new_occ, new_normal):
+        rc = self.lib.mirres_bounce_shade(self._p(packed[0]), self._p(packed[1]), self._u32(frame_index),
+                                          self._u32(bounce_count), max_bounce, fx, fy, self._f(env_tex), W, H,
+                                          self._f(dist[0]), self._f(dist[1]), self._f(dist[2]), self._f(dist[3]),
+                                          self._f(occ), self._f(pos_map), self._f(normal), self._f(ray_dir), self._f(prd),
+                                          self._f(diffuse), self._f(rough_metal), self._f(color), self._f(diff_color),
+                                          self._f(spec_color), self._f(new_pos), self._f(new_ray_d), self._f(new_occ),
+                                          self._f(new_normal), self._stream())
+        self._check(rc, "mirres_bounce_shade")
+
+    # -- denoiser ----------------------------------------------------------------------------------------------
+    def eaw_fwd(self, c_phi, n_phi, p_phi, fx, fy, step_width, occ, color, normal, pos, out_color):
+        rc = self.lib.mirres_eaw_fwd(float(c_phi), float(n_phi), float(p_phi), fx, fy, float(step_width), self._f(occ),
+                                     self._f(color), self._f(normal), self._f(pos), self._f(out_color), self._stream())
+        self._check(rc, "mirres_eaw_fwd")
+
+    def eaw_bwd(self, c_phi, n_phi, p_phi, fx, fy, step_width, occ, color, normal, pos, out_color, g_out, g_color,
+                g_normal, g_pos, cum_w_scratch):
+        rc = self.lib.mirres_eaw_bwd(float(c_phi), float(n_phi), float(p_phi), fx, fy, float(step_width), self._f(occ),
+                                     self._f(color), self._f(normal), self._f(pos), self._f(out_color), self._f(g_out),
+                                     self._f(g_color), self._f(g_normal), self._f(g_pos), self._f(cum_w_scratch),
+                                     self._stream())
+        self._check(rc, "mirres_eaw_bwd")
+
+    def normal_ao(self, fx, fy, occ, normal, out_ao):
+        rc = self.lib.mirres_normal_ao(fx, fy, self._f(occ), self._f(normal), self._f(out_ao), self._stream())
+        self._check(rc, "mirres_normal_ao")

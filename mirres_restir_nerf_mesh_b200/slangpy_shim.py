@@ -1,0 +1,329 @@
+"""A stand-in for the `slangpy` module the reference imports (nerf/renderer_restir.py:5,19-23,150-187).
+
+`loadModule(path, defines=...)` returns an object that speaks the call protocol the reference's Python uses:
+
+    m.kernel(**kwargs).launchRaw(blockSize=(..), gridSize=(..))       forward launch
+    m.kernel.bwd(**kwargs).launchRaw(...)                              reverse-mode launch; differentiable tensors are
+                                                                       passed as (primal, grad) tuples
+    m.Reservoir(...), m.FinalSample(...), m.pushConstantsMortonCodes(...)   struct constructors (tuples also accepted)
+
+Every kernel name of SURVEY.md section 2.1 is served by the C ABI of libmirres_b200.so; block / grid sizes are ignored
+(the library picks its own launch shapes).  A maintainer of the reference makes it run on this library with
+
+    import mirres_restir_nerf_mesh_b200.slangpy_shim as slangpy        # instead of `import slangpy`
+
+(see INTEGRATION.md).  Kernels the reference never calls (SURVEY.md 2.1 "dead Slang kernels") raise AttributeError.
+"""
+import os
+
+import torch
+
+from . import kernels as _kernels
+
+_KERNELS = None
+
+
+def get_kernels():
+    global _KERNELS
+    if _KERNELS is None:
+        _KERNELS = _kernels.Kernels()
+    return _KERNELS
+
+
+def set_kernels(k):
+    """Test hook: lets the CPU test-suite bind the host-check flavour of the same kernels."""
+    global _KERNELS
+    _KERNELS = k
+
+
+def _c(t):
+    """Dense view of an input tensor (the reference hands over strided views)."""
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _primal(x):
+    return x[0] if isinstance(x, (tuple, list)) else x
+
+
+def _grad(x):
+    return x[1]
+
+
+class _Struct(tuple):
+    pass
+
+
+def _reservoir(x):
+    if isinstance(x, dict):
+        return (x["light_data"], x["light_pdf"], x["M"], x["weight"])
+    return tuple(x)
+
+
+def _final_sample(x):
+    if isinstance(x, dict):
+        return (x["dir"], x["distance"], x["Li"])
+    return tuple(x)
+
+
+def packed_bvh(info, aabb, vert, tri):
+    """Traversal records for reference-layout BVH tensors; cached on the `info` tensor object, which
+    restirbvhWorker.update_mesh replaces on every rebuild."""
+    cached = getattr(info, "_mirres_packed", None)
+    if cached is not None:
+        return cached
+    k = get_kernels()
+    F = tri.shape[0]
+    _, nb, tb = k.bvh_sizes(F)
+    nodes = torch.empty(nb, dtype=torch.uint8, device=info.device)
+    tris = torch.empty(tb, dtype=torch.uint8, device=info.device)
+    k.bvh_pack(_c(info), _c(aabb), _c(vert), _c(tri), nodes, tris)
+    info._mirres_packed = (nodes, tris)
+    return info._mirres_packed
+
+
+class _Launch:
+    def __init__(self, fn, kw):
+        self._fn, self._kw = fn, kw
+
+    def launchRaw(self, blockSize=None, gridSize=None):
+        self._fn(**self._kw)
+
+
+class _Kernel:
+    def __init__(self, module, fwd, bwd=None):
+        self._module, self._fwd, self._bwd = module, fwd, bwd
+
+    def __call__(self, **kw):
+        return _Launch(lambda **k: self._fwd(self._module, **k), kw)
+
+    def bwd(self, **kw):
+        if self._bwd is None:
+            raise NotImplementedError("this kernel is not differentiable in the reference either")
+        return _Launch(lambda **k: self._bwd(self._module, **k), kw)
+
+
+# ---- kernel bodies: reference keyword names -> C ABI ------------------------------------------------------------------
+def _generateElements(m, vert, v_indx, ele_primitiveIdx, ele_aabb):
+    get_kernels().bvh_elements(_c(vert), _c(v_indx), ele_primitiveIdx, ele_aabb)
+
+
+def _morton_codes(m, pc, ele_aabb, morton_codes_ele):
+    ext = [float(pc[k]) for k in ("g_min_x", "g_min_y", "g_min_z", "g_max_x", "g_max_y", "g_max_z")]
+    get_kernels().bvh_morton(ele_aabb, ext, morton_codes_ele)
+
+
+def _scratch(F, device):
+    k = get_kernels()
+    return torch.empty(k.bvh_sizes(F)[0], dtype=torch.uint8, device=device)
+
+
+def _radix_sort(m, g_num_elements, g_elements_in, g_elements_out):
+    get_kernels().bvh_sort(g_elements_in, _scratch(int(g_num_elements), g_elements_in.device))
+
+
+def _hierarchy(m, g_num_elements, ele_primitiveIdx, ele_aabb, g_sorted_morton_codes, g_lbvh_info, g_lbvh_aabb,
+               g_lbvh_construction_infos):
+    # builds the hierarchy AND the final bounding boxes (one bottom-up pass); the level-by-level kernels below
+    # therefore have nothing left to do
+    get_kernels().bvh_hierarchy_refit(g_sorted_morton_codes, ele_aabb, g_lbvh_info, g_lbvh_aabb,
+                                      _scratch(int(g_num_elements), g_lbvh_info.device))
+
+
+def _get_bvh_height(m, g_num_elements, g_lbvh_info, g_lbvh_aabb, g_lbvh_construction_infos, tree_heights):
+    tree_heights.zero_()  # => the reference's `for i in range(tree_height_max)` loop runs zero times
+
+
+def _noop(m, **kw):
+    pass
+
+
+def _make_sampleable(m, env_tex, weight, width, height):
+    get_kernels().env_weights(_c(env_tex), int(width), int(height), weight)
+
+
+def _Distribution2D(m, w, h, pdf_, cdf_):
+    get_kernels().env_distribution2d(int(w), int(h), pdf_, cdf_)
+
+
+def _createNeighborOffsetTexture(m, sampleCount, neighborOffsets):
+    get_kernels().neighbor_offsets(int(sampleCount), neighborOffsets)
+
+
+def _GenerateLightTiles(m, env_tex, pdf_, cdf_, mpdf_, mcdf_, width, height, frameIndex, light_data, light_uv,
+                        light_inv_pdf, debug_out=None):
+    get_kernels().light_tiles(_c(env_tex), int(width), int(height), (pdf_, cdf_, mpdf_, mcdf_), int(frameIndex),
+                              m.define("LIGHT_TILE_COUNT", 128), m.define("LIGHT_TILE_SIZE", 1024), light_data, light_uv,
+                              light_inv_pdf)
+
+
+def _InitialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reservoirs, env_tex, env_width, env_height,
+                       framedim_x, framedim_y, frameIndex, occ_map, normal_depth, brdf_map, ray_dir, pdf_, cdf_, mpdf_,
+                       mcdf_, light_data, light_uv, light_inv_pdf):
+    get_kernels().initial_resampling(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), _c(pos_map),
+                                     _reservoir(reservoirs), _c(env_tex), int(env_width), int(env_height),
+                                     int(framedim_x), int(framedim_y), int(frameIndex), _c(occ_map), _c(normal_depth),
+                                     _c(brdf_map), _c(ray_dir), pdf_, mpdf_, light_data, light_inv_pdf,
+                                     m.define("LIGHT_TILE_COUNT", 128), m.define("LIGHT_TILE_SIZE", 1024),
+                                     m.define("SCREEN_TILE_SIZE", 8), m.define("INITIAL_LIGHT_SAMPLE_COUNT", 32),
+                                     m.define("INITIAL_BRDF_SAMPLE_COUNT", 1))
+
+
+def _TemporalResampling(m, reservoirs, prevReservoirs, env_tex, env_width, env_height, framedim_x, framedim_y,
+                        frameIndex, occ_map, normal_depth, brdf_map, ray_dir, prev_occ_map, prev_normal_depth,
+                        prev_brdf_map, prev_ray_dir, motionVectors=None):
+    get_kernels().temporal_resampling(_reservoir(reservoirs), _reservoir(prevReservoirs), _c(env_tex), int(env_width),
+                                      int(env_height), int(framedim_x), int(framedim_y), int(frameIndex), _c(occ_map),
+                                      _c(normal_depth), _c(brdf_map), _c(ray_dir), _c(prev_occ_map),
+                                      _c(prev_normal_depth), _c(prev_brdf_map), _c(prev_ray_dir),
+                                      None if motionVectors is None else _c(motionVectors),
+                                      m.define("MAX_HISTORY_LENGTH", 20))
+
+
+def _SpatialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reservoirs, prevReservoirs, neighborOffsets,
+                       env_tex, env_width, env_height, framedim_x, framedim_y, frameIndex, occ_map, normal_depth,
+                       brdf_map, ray_dir):
+    get_kernels().spatial_resampling(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), _c(pos_map),
+                                     _reservoir(reservoirs), _reservoir(prevReservoirs), _c(neighborOffsets),
+                                     _c(env_tex), int(env_width), int(env_height), int(framedim_x), int(framedim_y),
+                                     int(frameIndex), _c(occ_map), _c(normal_depth), _c(brdf_map), _c(ray_dir),
+                                     m.define("NEIGHBOR_OFFSET_COUNT", 8192), m.define("NEIGHBOR_COUNT", 5),
+                                     float(m.define("GATHER_RADIUS", 30)))
+
+
+def _get_vis(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, reservoirs, framedim_x, framedim_y, pos_map, vis_map):
+    get_kernels().final_visibility(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), _reservoir(reservoirs)[0],
+                                   int(framedim_x), int(framedim_y), _c(pos_map), vis_map)
+
+
+def _eval_final_fwd(m, reservoirs, env_tex, env_width, env_height, framedim_x, framedim_y, finalSample, vis_map):
+    fs = _final_sample(finalSample)
+    get_kernels().eval_final_fwd(_reservoir(reservoirs), _c(_primal(env_tex)), int(env_width), int(env_height),
+                                 int(framedim_x), int(framedim_y), fs[0], fs[1], _primal(fs[2]), vis_map)
+
+
+def _eval_final_bwd(m, reservoirs, env_tex, env_width, env_height, framedim_x, framedim_y, finalSample, vis_map):
+    fs = _final_sample(finalSample)
+    get_kernels().eval_final_bwd(_reservoir(reservoirs), int(env_width), int(env_height), int(framedim_x),
+                                 int(framedim_y), vis_map, _c(_grad(fs[2])), _grad(env_tex))
+
+
+def _final_shading_fwd(m, finalSample, env_tex, env_width, env_height, framedim_x, framedim_y, occ_map, normal, ray_dir,
+                       diffuse_map, linearRoughness_specular_map, color, diff_light, spec_light):
+    fs = _final_sample(finalSample)
+    get_kernels().final_shading_fwd(fs[0], fs[1], _c(_primal(fs[2])), _c(env_tex), int(env_width), int(env_height),
+                                    int(framedim_x), int(framedim_y), _c(occ_map), _c(_primal(normal)), _c(ray_dir),
+                                    _c(_primal(diffuse_map)), _c(_primal(linearRoughness_specular_map)),
+                                    _primal(color), _primal(diff_light), _primal(spec_light))
+
+
+def _final_shading_bwd(m, finalSample, env_tex, env_width, env_height, framedim_x, framedim_y, occ_map, normal, ray_dir,
+                       diffuse_map, linearRoughness_specular_map, color, diff_light, spec_light):
+    fs = _final_sample(finalSample)
+    get_kernels().final_shading_bwd(fs[0], fs[1], _c(_primal(fs[2])), int(framedim_x), int(framedim_y), _c(occ_map),
+                                    _c(_primal(normal)), _c(ray_dir), _c(_primal(diffuse_map)),
+                                    _c(_primal(linearRoughness_specular_map)), _c(_grad(color)), _c(_grad(diff_light)),
+                                    _c(_grad(spec_light)), _grad(normal), _grad(diffuse_map),
+                                    _grad(linearRoughness_specular_map), _grad(fs[2]))
+
+
+def _new_dir(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, frameIndex, bounce_count, framedim_x, framedim_y, occ_map,
+             pos_map, normal, ray_dir, prd, diffuse_map, linearRoughness_specular_map, new_pos_map, new_ray_d,
+             new_occ_map, new_normal):
+    get_kernels().bounce_first(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), int(frameIndex), int(bounce_count),
+                               m.define("MAX_Bounce", 2), int(framedim_x), int(framedim_y), _c(occ_map), _c(pos_map),
+                               _c(normal), _c(ray_dir), prd, _c(diffuse_map), _c(linearRoughness_specular_map),
+                               new_pos_map, new_ray_d, new_occ_map, new_normal)
+
+
+def _path_tracing(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, frameIndex, bounce_count, framedim_x, framedim_y, env_tex,
+                  env_width, env_height, pdf_, cdf_, mpdf_, mcdf_, occ_map, pos_map, normal, ray_dir, prd, diffuse_map,
+                  linearRoughness_specular_map, color, diff_color, spec_color, new_pos_map, new_ray_d, new_occ_map,
+                  new_normal):
+    get_kernels().bounce_shade(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), int(frameIndex), int(bounce_count),
+                               m.define("MAX_Bounce", 2), int(framedim_x), int(framedim_y), _c(env_tex), int(env_width),
+                               int(env_height), (pdf_, cdf_, mpdf_, mcdf_), _c(occ_map), _c(pos_map), _c(normal),
+                               _c(ray_dir), prd, _c(diffuse_map), _c(linearRoughness_specular_map), color, diff_color,
+                               spec_color, new_pos_map, new_ray_d, new_occ_map, new_normal)
+
+
+def _phi(PHI):
+    if isinstance(PHI, dict):
+        PHI = (PHI["c_phi"], PHI["n_phi"], PHI["p_phi"])
+    return tuple(float(x) for x in PHI)
+
+
+def _eaw_fwd(m, PHI, framedim_x, framedim_y, stepWidth, occ_map, color, normal_map, pos_map, out_color):
+    c, n, p = _phi(PHI)
+    get_kernels().eaw_fwd(c, n, p, int(framedim_x), int(framedim_y), stepWidth, _c(occ_map), _c(_primal(color)),
+                          _c(_primal(normal_map)), _c(_primal(pos_map)), _primal(out_color))
+
+
+def _eaw_bwd(m, PHI, framedim_x, framedim_y, stepWidth, occ_map, color, normal_map, pos_map, out_color):
+    c, n, p = _phi(PHI)
+    occ = _c(occ_map)
+    scratch = torch.empty(occ.shape[0], dtype=torch.float32, device=occ.device)
+    get_kernels().eaw_bwd(c, n, p, int(framedim_x), int(framedim_y), stepWidth, occ, _c(_primal(color)),
+                          _c(_primal(normal_map)), _c(_primal(pos_map)), _c(_primal(out_color)), _c(_grad(out_color)),
+                          _grad(color), _grad(normal_map), _grad(pos_map), scratch)
+
+
+def _normal_ao(m, framedim_x, framedim_y, occ_map, normal_map, ray_dir, out_ao):
+    get_kernels().normal_ao(int(framedim_x), int(framedim_y), _c(occ_map), _c(normal_map), out_ao)
+
+
+_TABLE = {
+    "get_elements": {"generateElements": (_generateElements, None)},
+    "lbvh_morton_codes": {"morton_codes": (_morton_codes, None)},
+    "lbvh_single_radixsort": {"radix_sort": (_radix_sort, None)},
+    "lbvh_hierarchy": {"hierarchy": (_hierarchy, None)},
+    "lbvh_bounding_boxes": {"get_bvh_height": (_get_bvh_height, None), "get_bbox": (_noop, None),
+                            "set_root": (_noop, None)},
+    "make_sampleable": {"make_sampleable": (_make_sampleable, None), "Distribution2D": (_Distribution2D, None),
+                        "createNeighborOffsetTexture": (_createNeighborOffsetTexture, None)},
+    "GenerateLightTiles": {"process_GenerateLightTiles": (_GenerateLightTiles, None)},
+    "InitialResampling": {"process_InitialResampling_": (_InitialResampling, None)},
+    "TemporalResampling": {"process_TemporalResampling": (_TemporalResampling, None)},
+    "SpatialResampling": {"process_SpatialResampling_": (_SpatialResampling, None)},
+    "EvaluateFinalSamples": {"process_EvaluateFinalSamples_get_vis": (_get_vis, None),
+                             "process_EvaluateFinalSamples_di_": (_eval_final_fwd, _eval_final_bwd)},
+    "FinalShading": {"process_FinalShading": (_final_shading_fwd, _final_shading_bwd),
+                     "process_new_dir_for_pt": (_new_dir, None),
+                     "process_path_tracing_divided_no_grad": (_path_tracing, None)},
+    "EAWDenoise": {"process_EAWDenoise": (_eaw_fwd, _eaw_bwd), "process_EAWDenoise_no_di": (_eaw_fwd, None),
+                   "process_normal_ao": (_normal_ao, None)},
+}
+
+
+class Module:
+    def __init__(self, path, defines=None):
+        self.path = path
+        self.name = os.path.splitext(os.path.basename(path))[0]
+        self.defines = dict(defines or {})
+        if self.name not in _TABLE:
+            raise FileNotFoundError("mirres-b200 serves no kernels for %r" % path)
+        for kname, (fwd, bwd) in _TABLE[self.name].items():
+            setattr(self, kname, _Kernel(self, fwd, bwd))
+
+    def define(self, key, default):
+        return int(self.defines.get(key, default))
+
+    # struct constructors used by the reference wrappers (Resampling.py:132-137,198-205; renderer_restir.py:44-47)
+    @staticmethod
+    def Reservoir(light_data, light_pdf, M, weight):
+        return _Struct((light_data, light_pdf, M, weight))
+
+    @staticmethod
+    def FinalSample(dir, distance, Li):
+        return _Struct((dir, distance, Li))
+
+    @staticmethod
+    def pushConstantsMortonCodes(**kw):
+        return dict(kw)
+
+    @staticmethod
+    def phi(c_phi, n_phi, p_phi):
+        return (c_phi, n_phi, p_phi)
+
+
+def loadModule(path, defines=None, **unused):
+    return Module(path, defines)
