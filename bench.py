@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config, one JSON line on stdout (rank 0).
+
+Metric: path samples/s (one sample = one pixel x one spp iteration of the whole ReSTIR + path-tracing pipeline) and
+fwd+bwd ms/step of the stage-1 training step, config C2 (`configs[1]`): synthetic 500k-triangle mesh, 800x800 rays,
+spp 4, 3 bounces (direct + 2 indirect), ReSTIR temporal + spatial reuse, LBVH rebuilt every step, backward into the
+envmap, shading normals (-> vertices) and kd/ks (-> vertex texture).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C2]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (one view per rank, weak scaling,
+                                                                                   one NCCL allreduce of the gradients)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "path_samples_per_sec"
+UNIT = "samples/s"
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks sampler (recipe line of /opt/skills/guides/B200_PROFILING.md)
+# ----------------------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        ok = [s for s in self.samples if len(s) == 7]
+        if not ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in ok)
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for k, n in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in ok)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(ok[0][1]), "reasons": reasons,
+                "power_w_max": max(float(s[2]) for s in ok), "samples": len(ok)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle (the reference itself has no CPU implementation and cannot be built here)
+# ----------------------------------------------------------------------------------------------------------------------
+def oracle_sample(cfg_name, crop, spp, threads=None):
+    """One bounded sample of the workload on the host cores: LBVH build + forward spp loop on a crop x crop frame.
+    Returns (samples, seconds, counters)."""
+    from oracle import oracle as O, driver as D
+    from mirres_restir_nerf_mesh_b200 import synth
+    cfg = synth.CONFIGS[cfg_name]
+    st = _ORACLE_STATE
+    if "mesh" not in st:
+        st["mesh"] = synth.make_mesh(cfg)
+        st["env"] = synth.envmap(*cfg["env"])
+        v, f = st["mesh"]
+        b = O.Bvh(v, f)
+        ro, rd = synth.camera_rays(crop, crop)
+        hit, t, pos, nrm, prim = O.trace(b, ro, rd)
+        st["g"] = synth.gbuffer_from_hits(ro, rd, hit, t, pos, nrm)
+    v, f = st["mesh"]
+    counters = O.new_counters()
+    t0 = time.perf_counter()
+    b = O.Bvh(v, f)  # the reference rebuilds the LBVH every step (nerf/renderer.py:975)
+    D.run_no_denoise(b, st["env"], st["g"], spp, crop, crop, 4242, lambda p: synth.material(p), max_bounce=cfg["max_bounce"],
+                     counters=counters)
+    dt = time.perf_counter() - t0
+    return crop * crop * spp, dt, counters
+
+
+_ORACLE_STATE = {}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mirres_restir_nerf_mesh_b200 import synth
+    cfg = synth.CONFIGS[args.config]
+    crop = 400
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        oracle_sample(args.config, crop, cfg["spp"])
+    tot_s, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        s, dt, _ = oracle_sample(args.config, crop, cfg["spp"])
+        tot_s += s
+        tot_t += dt
+    value = tot_s / tot_t
+    sample = ("CPU oracle (oracle/, C++/OpenMP restatement of the Slang kernels; the reference has no CPU path): LBVH "
+              "rebuild of the %s mesh + forward spp loop (spp=%d, %d bounces) on a %dx%d frame, no backward" %
+              (args.config, cfg["spp"], cfg["max_bounce"] + 1, crop, crop))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": _workload_name(args.config, cfg), "sample": "%dx%d" % (crop, crop)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def _workload_name(name, cfg):
+    return ("%s: stage-1 training step, %s mesh, %dx%d rays, spp=%d, %d bounces (direct + %d indirect), ReSTIR initial + "
+            "temporal + spatial, LBVH rebuild, fwd+bwd" % (name, "x".join(str(x) for x in cfg["mesh"][1].values()), cfg["W"],
+                                                          cfg["H"], cfg["spp"], cfg["max_bounce"] + 1, cfg["max_bounce"]))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+class ProfiledKernels:
+    """Wraps Kernels: counts launches and (optionally) brackets every ABI call with CUDA events on the launching
+    stream, so per-kernel device time is measured live inside the timed region."""
+    LAUNCHES = {"bvh_build": 19, "env_build_distribution": 2, "eaw_bwd": 2}
+
+    def __init__(self, inner, torch):
+        self._inner, self._torch = inner, torch
+        self.launches, self.events, self.record = 0, [], False
+
+    def __getattr__(self, name):
+        fn = getattr(self._inner, name)
+        if not callable(fn) or name.startswith("_") or name in ("bvh_sizes",):
+            return fn
+
+        def wrapped(*a, **kw):
+            self.launches += self.LAUNCHES.get(name, 1)
+            if self.record:
+                e0 = self._torch.cuda.Event(enable_timing=True)
+                e1 = self._torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn(*a, **kw)
+                e1.record()
+                self.events.append((name, e0, e1))
+                return r
+            return fn(*a, **kw)
+        return wrapped
+
+    def per_kernel_ms(self):
+        out = {}
+        for name, e0, e1 in self.events:
+            d = out.setdefault(name, [0.0, 0])
+            d[0] += e0.elapsed_time(e1)
+            d[1] += 1
+        return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from mirres_restir_nerf_mesh_b200 import synth, renderer_restir as R, slangpy_shim, kernels as K
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = synth.CONFIGS[args.config]
+    W, H, spp, mb = cfg["W"], cfg["H"], cfg["spp"], cfg["max_bounce"]
+    n = W * H
+
+    pk = ProfiledKernels(K.Kernels(), torch)
+    slangpy_shim.set_kernels(pk)
+
+    # ---- synthetic scene; each rank renders its own training view (weak scaling over views) -------------------------
+    vert_np, tri_np = synth.make_mesh(cfg)
+    env_np = synth.envmap(*cfg["env"])
+    ro_np, rd_np = synth.camera_rays(W, H, view=rank * 7)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    host = dict(vert=pin(vert_np), tri=pin(tri_np), env=pin(env_np), rays_o=pin(ro_np), rays_d=pin(rd_np))
+    vert, tri = host["vert"].to(dev), host["tri"].to(dev)
+    worker = R.restirbvhWorker(vert, tri)
+    worker.update_mesh(vert, tri)
+    hit = torch.zeros(n, dtype=torch.int32, device=dev)
+    t = torch.zeros(n, device=dev)
+    pos = torch.zeros(n, 3, device=dev)
+    nrm = torch.zeros(n, 3, device=dev)
+    prim = torch.zeros(n, dtype=torch.int32, device=dev)
+    rays_o, rays_d = host["rays_o"].to(dev), host["rays_d"].to(dev)
+    pk.trace_closest(worker.packed, rays_o, rays_d, hit, t, pos, nrm, prim)
+    mat = synth.ProceduralMaterial(0.0)
+    hitm = (hit > 0)[:, None]
+    occ = hitm.float()
+    pos = torch.where(hitm, pos, torch.zeros_like(pos))
+    nrm = torch.where(hitm, nrm, torch.zeros_like(nrm))
+    depth = torch.where(hitm[:, 0], (pos - rays_o).norm(dim=1), torch.zeros_like(t))[:, None]
+    kdks = mat.sample_no_di(pos)
+    kd0 = torch.where(hitm, kdks[:, 0:3], torch.zeros_like(pos))
+    rs0 = torch.where(hitm, kdks[:, 4:6], torch.zeros_like(kdks[:, 4:6]))
+    gbuf_dev = dict(occ=occ, pos=pos, nrm=nrm, depth=depth, kd=kd0.contiguous(), rs=rs0.contiguous(), ray=rays_d)
+    gbuf_host = {k: v.cpu().pin_memory() for k, v in gbuf_dev.items()}
+    prim_l = prim.long().clamp(min=0)
+    tri_l = tri.long()
+    mods = R.load_m_for_restir(W, H, device=dev, max_bounce=mb)
+    V = vert.shape[0]
+    target = torch.full((n, 3), 0.5, device=dev)
+    flat_grad = torch.zeros(env_np.size + V * 3 + V * 5, device=dev)
+    ne = env_np.size
+
+    def step(from_host):
+        if from_host:
+            v_ = host["vert"].to(dev, non_blocking=True)
+            f_ = host["tri"].to(dev, non_blocking=True)
+            g = {k: v.to(dev, non_blocking=True) for k, v in gbuf_host.items()}
+            env = host["env"].to(dev, non_blocking=True)
+        else:
+            v_, f_ = vert, tri
+            g = {k: v.clone() for k, v in gbuf_dev.items()}
+            env = env_dev.detach().clone()
+        env.requires_grad_(True)
+        normal = g["nrm"].requires_grad_(True)
+        kd = g["kd"].requires_grad_(True)
+        rs = g["rs"].requires_grad_(True)
+        worker.update_mesh(v_, f_)  # LBVH rebuilt every step, as render_stage1 does (nerf/renderer.py:975)
+        outs = R.run_restir_di_with_pt(False, 1, 1, 1, mat, None, worker, *mods, env, g["occ"], normal, g["depth"], kd, rs,
+                                       g["ray"], g["pos"], None, None, None, None, W, H, spp, 2, 2, 2.0, 0.1, 0.001,
+                                       random_offset=1234 + 17 * rank, max_bounce=mb)
+        loss = ((outs[0] - target) ** 2).mean()
+        loss.backward()
+        # gradients leave the path as grad_env [He,We,3] and dense per-pixel grads; scatter the latter to vertices /
+        # vertex texture (the reference does this in nvdiffrast / tcnn backward) and reduce everything in ONE collective
+        flat_grad.zero_()
+        flat_grad[:ne] = env.grad.reshape(-1)
+        gv = flat_grad[ne:ne + 3 * V].view(V, 3)
+        gt = flat_grad[ne + 3 * V:].view(V, 5)
+        third = 1.0 / 3.0
+        gtex = torch.cat((kd.grad, rs.grad), dim=1) * occ * third
+        gnrm = normal.grad * occ * third
+        for c in range(3):
+            gv.index_add_(0, tri_l[prim_l, c], gnrm)
+            gt.index_add_(0, tri_l[prim_l, c], gtex)
+        if world > 1:
+            dist.all_reduce(flat_grad)
+        return loss
+
+    env_dev = host["env"].to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
+
+    def timed(k_steps, from_host, record=False):
+        total_ms = 0.0
+        d2h = 0
+        for _ in range(k_steps):
+            flush.fill_(1.0)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            pk.record = record
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss = step(from_host)
+            if from_host:
+                lh = loss.detach().to("cpu", non_blocking=True)
+                gh = flat_grad[:ne].to("cpu", non_blocking=True)
+                d2h = lh.numel() * 4 + gh.numel() * 4
+            e1.record()
+            torch.cuda.synchronize()
+            pk.record = False
+            total_ms += e0.elapsed_time(e1)
+        return total_ms, d2h
+
+    for _ in range(args.warmup):
+        step(False)
+    torch.cuda.synchronize()
+    pk.launches = 0
+    with Clocks(local) as clocks:
+        ms_dev, _ = timed(args.steps, False, record=True)
+    launches = pk.launches
+    per_kernel = pk.per_kernel_ms()
+    step(True)
+    torch.cuda.synchronize()
+    ms_e2e, d2h_bytes = timed(args.steps, True)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in gbuf_host.values()) + sum(
+        host[k].numel() * host[k].element_size() for k in ("vert", "tri", "env"))
+
+    tms = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(tms[0]), float(tms[1])
+    samples = n * spp * world * args.steps
+    value = samples / (ms_dev * 1e-3)
+    e2e = samples / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = _peaks()
+        peak = peaks["hbm_gbs"] if peaks else 6650.0
+        roof = roofline(args.config, cfg, per_kernel, args.steps, peak, "measured" if peaks else "fallback")
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": _workload_name(args.config, cfg), "l2": "256 MiB flush between timed steps",
+                           "parallelism": "one view per rank, 1 NCCL allreduce of env+vertex+texture grads per step"},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof,
+                "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])}}
+        if world == 1 and not args.no_cpu_baseline:
+            s, dt, _ = oracle_sample(args.config, 400, spp)
+            s2, dt2, _ = oracle_sample(args.config, 400, spp)
+            line["cpu_baseline"] = {"value": (s + s2) / (dt + dt2), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "CPU oracle: LBVH rebuild + forward spp loop on a 400x400 frame of the same scene, 2 repetitions, no backward"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline(cfg_name, cfg, per_kernel, steps, peak, peak_kind):
+    """Dominant kernel vs the HBM roofline.  Algorithmic bytes per launch = S_screen(stage) * N + 36 * V_n + 48 * V_t
+     with V_n / V_t the oracle's node-pop / triangle-test counts per launch under the contract schedule
+    (profiles/oracle_counters_<cfg>.json, produced by tools/oracle_counters.py)."""
+    if not per_kernel:
+        return None
+    name, (ms, count) = max(per_kernel.items(), key=lambda kv: kv[1][0])
+    n = cfg["W"] * cfg["H"]
+    path = os.path.join(ROOT, "profiles", "oracle_counters_%s.json" % cfg_name)
+    counters = json.load(open(path)) if os.path.exists(path) else {}
+    screen = {"spatial_resampling": 104, "initial_resampling": 80, "bounce_shade": 176, "bounce_first": 140,
+              "final_visibility": 28, "temporal_resampling": 168}.get(name, 0)
+    c = counters.get(name, {})
+    alg = screen * n + 36 * c.get("nodes_per_launch", 0) + 48 * c.get("tris_per_launch", 0)
+    dur = ms / count * 1e-3
+    achieved = alg / dur / 1e9 if alg else None
+    return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+            "frac": (achieved / peak) if achieved else None, "traffic": c.get("dram_bytes_per_launch"),
+            "launch_ms": ms / count, "launches_timed": count, "alg_bytes_per_launch": alg,
+            "share_of_step": ms / steps / max(sum(v[0] for v in per_kernel.values()) / steps, 1e-9)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mirres_b200")
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -115,26 +115,41 @@ def envmap(He=256, We=512, seed=0):
     return np.maximum(img, 0.01).astype(np.float32)
 
 
+def _tri_np(x):
+    # triangle wave in [0,1] from exactly-rounded elementwise ops only (identical in numpy, torch CPU and torch CUDA,
+    # unlike sin, whose last ulp differs between libraries and would break bit-exact parity of the bounce materials)
+    f = x - np.floor(x)
+    return np.abs(np.float32(2.0) * f - np.float32(1.0))
+
+
 def material(pos, metallic=0.0):
     """Procedural kd [M,3], roughness [M,1], metallic [M,1] of surface positions pos [M,3]."""
     pos = np.asarray(pos, np.float32)
-    kd = (0.5 + 0.4 * np.sin(11.0 * pos)).astype(np.float32)
-    rough = (0.08 + 0.92 * (0.5 + 0.5 * np.sin(5.0 * pos[:, 0:1] + 3.0 * pos[:, 1:2]))).astype(np.float32)
+    f = np.float32
+    kd = (f(0.1) + f(0.8) * _tri_np(pos * f(1.7))).astype(np.float32)
+    rough = (f(0.08) + f(0.92) * _tri_np(pos[:, 0:1] * f(0.8) + pos[:, 1:2] * f(0.5))).astype(np.float32)
     met = np.full_like(rough, metallic)
     return kd, rough, met
 
 
 class ProceduralMaterial:
     """Stand-in for the tiny-cuda-nn `mlp_mat` (out of scope): `.sample_no_di(x) -> [M,6]` with kd in 0:3,
-    roughness in 4, metallic in 5 (nerf/renderer_restir.py:399-402).  Works on torch tensors of any device."""
+    roughness in 4, metallic in 5 (nerf/renderer_restir.py:399-402).  Works on torch tensors of any device and
+    returns bit-identical values to `material()` (every op is a single exactly-rounded elementwise kernel)."""
 
     def __init__(self, metallic=0.0):
         self.metallic = float(metallic)
 
+    @staticmethod
+    def _tri(x):
+        import torch
+        f = x - torch.floor(x)
+        return torch.abs(2.0 * f - 1.0)
+
     def sample_no_di(self, x):
         import torch
-        kd = 0.5 + 0.4 * torch.sin(11.0 * x)
-        rough = 0.08 + 0.92 * (0.5 + 0.5 * torch.sin(5.0 * x[:, 0:1] + 3.0 * x[:, 1:2]))
+        kd = 0.1 + 0.8 * self._tri(x * 1.7)
+        rough = 0.08 + 0.92 * self._tri(x[:, 0:1] * 0.8 + x[:, 1:2] * 0.5)
         met = torch.full_like(rough, self.metallic)
         return torch.cat([kd, torch.zeros_like(rough), rough, met], dim=-1)
 

@@ -230,3 +230,13 @@ def normal_ao(fx, fy, occ, normal):
     out = np.zeros((fx * fy, 3), np.float32)
     assert lib().orc_normal_ao(int(fx), int(fy), _p(occ), _p(normal), _p(out)) == 0
     return out
+
+
+def eval_final_taps(res_ld, W, H):
+    res_ld = _f32(res_ld)
+    n = res_ld.shape[0]
+    taps = np.zeros((n, 4), np.int32)
+    uv = np.zeros((n, 2), np.float32)
+    valid = np.zeros(n, np.int32)
+    assert lib().orc_eval_final_taps(_p(res_ld), int(W), int(H), int(n), _p(taps), _p(uv), _p(valid)) == 0
+    return taps, uv, valid

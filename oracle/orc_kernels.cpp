@@ -803,3 +803,25 @@ extern "C" int orc_normal_ao(int fx, int fy, const float *occ, const float *norm
     }
     return 0;
 }
+
+// Bilinear tap addresses / weights of the Li lookup of EvaluateFinalSamples.slang:151-158 (get_light_info_di ->
+// env_le_di -> eval_bi_di, helper.slang:72-99) for the backward oracle (oracle/backward.py).
+extern "C" int orc_eval_final_taps(const float *res_ld, int env_w, int env_h, int n, int *taps /*[n,4]*/, float *uv /*[n,2]*/,
+                                   int *valid /*[n]*/)
+{
+    for (int i = 0; i < n; ++i) {
+        f3 L = oct_decode(mk2(res_ld[3 * (size_t)i + 1], res_ld[3 * (size_t)i + 2]));
+        f2 q;
+        bool ok = env_dir_to_uv(ngp_dir(L), q);
+        valid[i] = ok ? 1 : 0;
+        BiTaps t = {0, 0, 0, 0, 0.f, 0.f};
+        if (ok) t = eval_bi_taps(q, env_w, env_h);
+        taps[4 * (size_t)i + 0] = t.y0 * env_w + t.x0;
+        taps[4 * (size_t)i + 1] = t.y0 * env_w + t.x1;
+        taps[4 * (size_t)i + 2] = t.y1 * env_w + t.x0;
+        taps[4 * (size_t)i + 3] = t.y1 * env_w + t.x1;
+        uv[2 * (size_t)i] = t.u;
+        uv[2 * (size_t)i + 1] = t.v;
+    }
+    return 0;
+}

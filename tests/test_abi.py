@@ -1,0 +1,50 @@
+"""The C ABI: header <-> ctypes table <-> exported symbols (no compute calls, no GPU needed)."""
+import ctypes
+import os
+
+import pytest
+
+from abi_check import header_signatures
+from mirres_restir_nerf_mesh_b200 import _lib, build
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    return build.build()
+
+
+def test_header_matches_ctypes_table():
+    hdr = header_signatures(_lib.HEADER_PATH)
+    for name, (ret, kinds) in hdr.items():
+        if ret == "size_t":
+            assert name in _lib.SIZE_FUNCS
+            continue
+        assert _lib.SIGNATURES.get(name) == kinds, name
+    assert set(_lib.SIGNATURES) | set(_lib.SIZE_FUNCS) == set(hdr)
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    assert os.path.exists(lib_path)
+    assert _lib.check_exports(lib_path) == []
+    lib = _lib.bind(ctypes.CDLL(lib_path))
+    assert lib.mirres_abi_version() == 1
+    assert lib.mirres_bvh_scratch_bytes(0) == 0
+    assert lib.mirres_bvh_packed_node_bytes(500000) == 64 * 499999
+    assert lib.mirres_bvh_packed_tri_bytes(500000) == 48 * 500000
+    assert lib.mirres_bvh_scratch_bytes(500000) > 500000 * 6 * 4
+
+
+def test_argument_checks_do_not_need_a_gpu(lib_path):
+    lib = _lib.bind(ctypes.CDLL(lib_path))
+    # null pointers and bad sizes are rejected before anything is enqueued
+    assert lib.mirres_trace_any(None, None, None, None, 4, None, None, None) == -1
+    assert lib.mirres_neighbor_offsets(0, ctypes.c_void_p(16), None) == -2
+    assert lib.mirres_bvh_build(None, 1, None, 1, None, None, None, None, None, None, 0, None) == -1
+
+
+def test_product_has_no_cpu_path():
+    import torch
+    from mirres_restir_nerf_mesh_b200 import kernels
+    k = kernels.Kernels()
+    with pytest.raises(kernels.AbiError):
+        k.neighbor_offsets(8, torch.zeros(16))  # CPU tensor -> loud failure, never a fallback

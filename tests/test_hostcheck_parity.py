@@ -1,0 +1,90 @@
+"""CPU parity: the product's kernel source (host-check flavour) + the product's Python driver against the
+independently written oracle, bit for bit, on small synthetic scenes.  See tests/hostcheck.py."""
+import numpy as np
+import pytest
+import torch
+
+import hostcheck as H
+import parity as P
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _bind_hostcheck():
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim
+    H.activate()
+    yield
+    slangpy_shim.set_kernels(None)
+
+
+def _worker(sc):
+    w = H.OracleBvhWorker(H.t(sc["vert"]), H.t(sc["tri"]))
+    w.update_mesh(H.t(sc["vert"]), H.t(sc["tri"]))
+    return w
+
+
+@pytest.mark.parametrize("name,metallic", [("T0", 0.0), ("T1", 0.0), ("T2", 0.4)])
+def test_pipeline_bit_exact(name, metallic):
+    sc = P.scene(name, metallic)
+    ref = P.oracle_run(sc)
+    got = P.product_run(sc, _worker(sc), "cpu", ref["prepared"])
+    assert P.compare(ref, got) == []
+
+
+def test_three_and_one_indirect_bounces():
+    sc = P.scene("T0")
+    for mb in (1, 3):
+        ref = P.oracle_run(sc, max_bounce=mb)
+        got = P.product_run(sc, _worker(sc), "cpu", ref["prepared"], max_bounce=mb)
+        assert P.compare(ref, got) == []
+
+
+def test_rays_bit_exact_including_negative_t(oracle):
+    sc = P.scene("T1")
+    w = _worker(sc)
+    k = H.kernels()
+    rng = np.random.default_rng(3)
+    hitm = sc["hit"] > 0
+    d = rng.standard_normal((int(hitm.sum()), 3)).astype(np.float32)
+    o = (sc["pos"][hitm] + 0.01 * d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    n = len(o)
+    hit = torch.zeros(n, dtype=torch.int32)
+    t, pos, nrm = torch.zeros(n), torch.zeros(n, 3), torch.zeros(n, 3)
+    prim = torch.zeros(n, dtype=torch.int32)
+    k.trace_closest(w.packed, H.t(o), H.t(d), hit, t, pos, nrm, prim)
+    oh, ot, op, on, opr = oracle.trace(sc["bvh"], o, d)
+    assert (ot[oh > 0] < 0).any()  # the quirk is exercised
+    assert (hit.numpy() == oh).all() and (prim.numpy() == opr).all()
+    assert (t.numpy() == ot).all() and (pos.numpy() == op).all() and (nrm.numpy()[oh > 0] == on[oh > 0]).all()
+    anyh = torch.zeros(n, dtype=torch.int32)
+    k.trace_any(w.packed, H.t(o), H.t(d), anyh)
+    assert (anyh.numpy() == oh).all()
+
+
+def test_env_and_offsets_bit_exact(oracle):
+    from mirres_restir_nerf_mesh_b200 import synth, renderer_restir as R
+    env = synth.envmap(32, 64)
+    tex = np.ascontiguousarray(env[::-1].reshape(-1, 3))
+    want = oracle.env_build_distribution(tex, 64, 32)
+    got = R.make_sampleable(None, H.t(tex), 64, 32)
+    for a, b in zip(got, want):
+        assert (a.numpy() == b).all()
+    out = torch.zeros(8192 * 2, 1)
+    H.kernels().neighbor_offsets(8192, out)
+    assert (out.numpy() == oracle.neighbor_offsets(8192)).all()
+
+
+def test_eaw_and_ao_bit_exact(oracle):
+    sc = P.scene("T1")
+    g = sc["gbuffer"]
+    rng = np.random.default_rng(0)
+    color = (rng.random((sc["W"] * sc["H"], 3)) * g["occ_map"]).astype(np.float32)
+    k = H.kernels()
+    for step in (2, 1):
+        out = torch.zeros(color.shape)
+        k.eaw_fwd(2.0, 0.1, 0.001, sc["W"], sc["H"], step, H.t(g["occ_map"]), H.t(color), H.t(g["normal_map"]),
+                  H.t(g["pos_map"]), out)
+        want = oracle.eaw_fwd(2.0, 0.1, 0.001, sc["W"], sc["H"], step, g["occ_map"], color, g["normal_map"], g["pos_map"])
+        assert (out.numpy() == want).all()
+    ao = torch.zeros(color.shape)
+    k.normal_ao(sc["W"], sc["H"], H.t(g["occ_map"]), H.t(g["normal_map"]), ao)
+    assert (ao.numpy() == oracle.normal_ao(sc["W"], sc["H"], g["occ_map"], g["normal_map"])).all()
