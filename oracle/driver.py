@@ -41,6 +41,8 @@ def restir_di_with_pt(bvh, env_map, g, spp, fx, fy, random_offset, material, max
     """g: prepared G-buffer dict (prepare_gbuffer).  Returns dict of per-call sums and mFrameIndex."""
     n = fx * fy
     He, We = env_map.shape[0], env_map.shape[1]
+    # `counters` may be one array (everything accumulated) or a dict with one array per kernel
+    ctr = (lambda name: counters.setdefault(name, O.new_counters())) if isinstance(counters, dict) else (lambda name: counters)
     env = np.ascontiguousarray(env_map[::-1].reshape(-1, 3), np.float32)  # torch.flip(dims=[0]).reshape(-1,3)
     dist = O.env_build_distribution(env, We, He)
     offs = (O.neighbor_offsets(8192).reshape(-1, 2) / np.float32(127)).astype(np.float32)
@@ -65,7 +67,7 @@ def restir_di_with_pt(bvh, env_map, g, spp, fx, fy, random_offset, material, max
         tiles = O.light_tiles(env, We, He, dist, base + cur, tile_count, tile_size)
         cur += 2
         O.initial_resampling(bvh, pos, res, env, We, He, fx, fy, base + cur, occ, nd, brdf, ray, dist, tiles,
-                             tile_count, tile_size, counters=counters)
+                             tile_count, tile_size, counters=ctr("initial_resampling"))
         cur += 1
         if i > 0:
             O.temporal_resampling(res, prev, env, We, He, fx, fy, base + cur, occ, nd, brdf, ray, prev_occ, prev_nd,
@@ -73,9 +75,9 @@ def restir_di_with_pt(bvh, env_map, g, spp, fx, fy, random_offset, material, max
             cur += 1
         res, prev = prev, res
         O.spatial_resampling(bvh, pos, res, prev, offs, env, We, He, fx, fy, base + cur, occ, nd, brdf, ray,
-                             counters=counters)
+                             counters=ctr("spatial_resampling"))
         cur += 1
-        O.final_visibility(bvh, res, fx, fy, pos, vis, counters=counters)
+        O.final_visibility(bvh, res, fx, fy, pos, vis, counters=ctr("final_visibility"))
         O.eval_final_fwd(res, env, We, He, fx, fy, fs_dir, fs_dist, fs_Li, vis)
         color, cdiff, cspec = O.final_shading_fwd(fs_dir, fs_dist, fs_Li, env, We, He, fx, fy, occ, normal, ray, kd, rs)
         if snapshots is not None:
@@ -83,7 +85,7 @@ def restir_di_with_pt(bvh, env_map, g, spp, fx, fy, random_offset, material, max
                                   fs_dir=fs_dir.copy(), fs_dist=fs_dist.copy(), fs_Li=fs_Li.copy(),
                                   color=color.copy(), diff=cdiff.copy(), spec=cspec.copy(), tiles=tiles))
         O.bounce_first(bvh, base + cur, 0, max_bounce, fx, fy, occ, pos, normal, ray, prd, kd, rs, A["pos"], A["ray"],
-                       A["occ"], A["nrm"], counters=counters)
+                       A["occ"], A["nrm"], counters=ctr("bounce_first"))
         cur += 5
         src, dst = A, B
         for b in range(1, max_bounce + 1):
@@ -93,7 +95,7 @@ def restir_di_with_pt(bvh, env_map, g, spp, fx, fy, random_offset, material, max
             new_rs[idx] = np.concatenate([mr, mm], axis=1)
             O.bounce_shade(bvh, base + cur, b, max_bounce, fx, fy, env, We, He, dist, src["occ"], src["pos"],
                            src["nrm"], src["ray"], prd, new_diffuse, new_rs, color_1, cdiff_1, cspec_1, dst["pos"],
-                           dst["ray"], dst["occ"], dst["nrm"], counters=counters)
+                           dst["ray"], dst["occ"], dst["nrm"], counters=ctr("bounce_shade"))
             tot["color_1"] += color_1
             tot["diff_1"] += cdiff_1
             tot["spec_1"] += cspec_1
