@@ -146,7 +146,8 @@ def _workload_name(name, cfg):
 class ProfiledKernels:
     """Wraps Kernels: counts launches and (optionally) brackets every ABI call with CUDA events on the launching
     stream, so per-kernel device time is measured live inside the timed region."""
-    LAUNCHES = {"bvh_build": 19, "env_build_distribution": 2, "eaw_bwd": 2}
+    LAUNCHES = {"bvh_build": 19, "env_build_distribution": 2, "eaw_bwd": 2, "workspace_prepare": 3, "initial_resampling": 3,
+                "spatial_resampling": 3, "final_visibility": 3, "bounce_first": 4, "bounce_shade": 5}
 
     def __init__(self, inner, torch):
         self._inner, self._torch = inner, torch
@@ -225,8 +226,8 @@ def run_gpu(args):
     rs0 = torch.where(hitm, kdks[:, 4:6], torch.zeros_like(kdks[:, 4:6]))
     gbuf_dev = dict(occ=occ, pos=pos, nrm=nrm, depth=depth, kd=kd0.contiguous(), rs=rs0.contiguous(), ray=rays_d)
     gbuf_host = {k: v.cpu().pin_memory() for k, v in gbuf_dev.items()}
-    prim_l = prim.long().clamp(min=0)
-    tri_l = tri.long()
+    fg = torch.nonzero(hit > 0).reshape(-1)          # foreground pixels of this view (static: computed once)
+    fg_tri = tri.long()[prim.long()[fg]]             # [n_fg, 3] vertex ids of the triangle each one sees
     mods = R.load_m_for_restir(W, H, device=dev, max_bounce=mb)
     V = vert.shape[0]
     target = torch.full((n, 3), 0.5, device=dev)
@@ -260,11 +261,11 @@ def run_gpu(args):
         gv = flat_grad[ne:ne + 3 * V].view(V, 3)
         gt = flat_grad[ne + 3 * V:].view(V, 5)
         third = 1.0 / 3.0
-        gtex = torch.cat((kd.grad, rs.grad), dim=1) * occ * third
-        gnrm = normal.grad * occ * third
+        gtex = torch.cat((kd.grad, rs.grad), dim=1)[fg] * third
+        gnrm = normal.grad[fg] * third
         for c in range(3):
-            gv.index_add_(0, tri_l[prim_l, c], gnrm)
-            gt.index_add_(0, tri_l[prim_l, c], gtex)
+            gv.index_add_(0, fg_tri[:, c], gnrm)
+            gt.index_add_(0, fg_tri[:, c], gtex)
         if world > 1:
             dist.all_reduce(flat_grad)
         return loss

@@ -100,6 +100,17 @@ int mirres_light_tiles(const float *env_tex, int W, int H, const float *pdf_, co
                        int *light_uv, float *light_pdf, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Wavefront workspace.  Every ray-casting entry point below runs as  gen (one thread per foreground pixel) ->
+ * ray queue -> queue tracer -> resolve  and needs a caller-allocated workspace of mirres_workspace_bytes(N) bytes
+ * (256-byte aligned), N = framedim_x * framedim_y.  mirres_workspace_prepare builds the ordered list of foreground
+ * pixels (occ >= 0.1, the test every reference kernel starts with, e.g. InitialResampling.slang:166) and must be
+ * called whenever the PRIMARY occupancy map changes (once per frame); the bounce kernels, whose `occ` argument is the
+ * occupancy of the previous path vertex, reuse the same list (a path vertex only exists where the primary hit does).
+ */
+size_t mirres_workspace_bytes(int n_pixels);
+int mirres_workspace_prepare(const float *occ, int n_pixels, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * ReSTIR passes.  Reservoir = (light_data [N,3], light_pdf [N], M [N] i32, weight [N]), res.slang:5-11.
  * G-buffer: occ [N], normal_depth [N,4] (16-byte aligned), brdf_map [N,3] (lum kd, metallic, alpha), ray_dir [N,3],
  * pos_map [N,3]  (renderer_restir.py:279-287).
@@ -117,21 +128,21 @@ int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris,
                               int fx, int fy, unsigned int frame_index, const float *occ, const float *normal_depth,
                               const float *brdf_map, const float *ray_dir, const float *pdf_, const float *mpdf_,
                               const float *light_data, const float *light_pdf, int tile_count, int tile_size,
-                              int screen_tile, int n_light, int n_brdf, void *stream);
+                              int screen_tile, int n_light, int n_brdf, void *workspace, size_t workspace_bytes, void *stream);
 int mirres_temporal_resampling(float *res_ld, float *res_pdf, int *res_M, float *res_w, const float *prev_ld,
                                const float *prev_pdf, const int *prev_M, const float *prev_w, const float *env_tex,
                                int env_w, int env_h, int fx, int fy, unsigned int frame_index, const float *occ,
                                const float *normal_depth, const float *brdf_map, const float *ray_dir,
                                const float *prev_occ, const float *prev_normal_depth, const float *prev_brdf_map,
-                               const float *prev_ray_dir, const float *motion, int max_history, void *stream);
+                               const float *prev_ray_dir, const float *motion, int max_history, void *workspace, size_t workspace_bytes, void *stream);
 int mirres_spatial_resampling(const void *packed_nodes, const void *packed_tris, const float *pos_map, float *res_ld,
                               float *res_pdf, int *res_M, float *res_w, const float *prev_ld, const float *prev_pdf,
                               const int *prev_M, const float *prev_w, const float *neighbor_offsets, const float *env_tex,
                               int env_w, int env_h, int fx, int fy, unsigned int frame_index, const float *occ,
                               const float *normal_depth, const float *brdf_map, const float *ray_dir, int offset_count,
-                              int neighbor_count, float gather_radius, void *stream);
+                              int neighbor_count, float gather_radius, void *workspace, size_t workspace_bytes, void *stream);
 int mirres_final_visibility(const void *packed_nodes, const void *packed_tris, const float *res_ld, int fx, int fy,
-                            const float *pos_map, float *vis_map, void *stream);
+                            const float *pos_map, float *vis_map, void *workspace, size_t workspace_bytes, void *stream);
 int mirres_eval_final_fwd(const float *res_ld, const float *res_pdf, const int *res_M, const float *res_w,
                           const float *env_tex, int env_w, int env_h, int fx, int fy, float *fs_dir, float *fs_dist,
                           float *fs_Li, const float *vis_map, void *stream);
@@ -162,14 +173,14 @@ int mirres_bounce_first(const void *packed_nodes, const void *packed_tris, unsig
                         unsigned int bounce_count, int max_bounce, int fx, int fy, const float *occ, const float *pos_map,
                         const float *normal, const float *ray_dir, float *prd, const float *diffuse_map,
                         const float *rough_metal, float *new_pos, float *new_ray_d, float *new_occ, float *new_normal,
-                        void *stream);
+                        void *workspace, size_t workspace_bytes, void *stream);
 int mirres_bounce_shade(const void *packed_nodes, const void *packed_tris, unsigned int frame_index,
                         unsigned int bounce_count, int max_bounce, int fx, int fy, const float *env_tex, int env_w,
                         int env_h, const float *pdf_, const float *cdf_, const float *mpdf_, const float *mcdf_,
                         const float *occ, const float *pos_map, const float *normal, const float *ray_dir, float *prd,
                         const float *diffuse_map, const float *rough_metal, float *color, float *diff_color,
                         float *spec_color, float *new_pos, float *new_ray_d, float *new_occ, float *new_normal,
-                        void *stream);
+                        void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Edge-avoiding a-trous denoiser and the normal-variation AO proxy.

@@ -30,21 +30,23 @@ SIGNATURES = {
     "mirres_env_distribution2d": "iippp",
     "mirres_neighbor_offsets": "ipp",
     "mirres_light_tiles": "piippppuiipppp",
-    "mirres_initial_resampling": "ppp" + "pppp" + "pii" + "iiu" + "pppp" + "pp" + "pp" + "iiiii" + "p",
-    "mirres_temporal_resampling": "pppp" + "pppp" + "pii" + "iiu" + "pppp" + "pppp" + "p" + "i" + "p",
-    "mirres_spatial_resampling": "ppp" + "pppp" + "pppp" + "p" + "pii" + "iiu" + "pppp" + "iif" + "p",
-    "mirres_final_visibility": "pppiippp",
+    "mirres_workspace_prepare": "pipzp",
+    "mirres_initial_resampling": "ppp" + "pppp" + "pii" + "iiu" + "pppp" + "pp" + "pp" + "iiiii" + "pz" + "p",
+    "mirres_temporal_resampling": "pppp" + "pppp" + "pii" + "iiu" + "pppp" + "pppp" + "p" + "i" + "pz" + "p",
+    "mirres_spatial_resampling": "ppp" + "pppp" + "pppp" + "p" + "pii" + "iiu" + "pppp" + "iif" + "pz" + "p",
+    "mirres_final_visibility": "pppiipp" + "pz" + "p",
     "mirres_eval_final_fwd": "pppp" + "pii" + "ii" + "ppp" + "p" + "p",
     "mirres_eval_final_bwd": "pppp" + "ii" + "ii" + "ppp" + "p",
     "mirres_final_shading_fwd": "ppp" + "pii" + "ii" + "ppppp" + "ppp" + "p",
     "mirres_final_shading_bwd": "ppp" + "ii" + "ppppp" + "ppp" + "pppp" + "p",
-    "mirres_bounce_first": "pp" + "uui" + "ii" + "pppp" + "p" + "pp" + "pppp" + "p",
-    "mirres_bounce_shade": "pp" + "uui" + "ii" + "pii" + "pppp" + "pppp" + "p" + "pp" + "ppp" + "pppp" + "p",
+    "mirres_bounce_first": "pp" + "uui" + "ii" + "pppp" + "p" + "pp" + "pppp" + "pz" + "p",
+    "mirres_bounce_shade": "pp" + "uui" + "ii" + "pii" + "pppp" + "pppp" + "p" + "pp" + "ppp" + "pppp" + "pz" + "p",
     "mirres_eaw_fwd": "fffiif" + "ppppp" + "p",
     "mirres_eaw_bwd": "fffiif" + "ppppp" + "ppppp" + "p",
     "mirres_normal_ao": "iipppp",
 }
-SIZE_FUNCS = ("mirres_bvh_scratch_bytes", "mirres_bvh_packed_node_bytes", "mirres_bvh_packed_tri_bytes")
+SIZE_FUNCS = ("mirres_bvh_scratch_bytes", "mirres_bvh_packed_node_bytes", "mirres_bvh_packed_tri_bytes",
+              "mirres_workspace_bytes")
 
 
 def bind(lib, allow_missing=()):

@@ -187,4 +187,15 @@ static inline int foreach_item(const P &p, int n, cudaStream_t st)
 }
 #endif
 
+// zero-fill that is stream-ordered on the device and immediate in the host-check flavour
+static inline void zero_async(void *ptr, size_t bytes, cudaStream_t st)
+{
+#if defined(MR_HOST_CHECK)
+    (void)st;
+    memset(ptr, 0, bytes);
+#else
+    cudaMemsetAsync(ptr, 0, bytes, st);
+#endif
+}
+
 } // namespace mr

@@ -10,7 +10,7 @@
 //   nerf/ScreenSpaceReSTIR/EvaluateFinalSamples.slang:129-188  -> k_eval_final_fwd / k_eval_final_bwd (hand-derived)
 //   nerf/ScreenSpaceReSTIR/utils/res.slang:53-232              -> the streaming RIS steps inlined below
 // Visibility rays use mr::any_hit (first-hit exit), see mr_bvh.cuh for why that is result-identical.
-#include "mr_bvh.cuh"
+#include "mr_wave.cuh"
 #include "mr_light.cuh"
 #include "mr_brdf.cuh"
 #include "../../include/mirres_b200.h"
@@ -114,13 +114,17 @@ struct InitialParams {
     int fx, fy;
     unsigned int frame;
     unsigned int tile_count, tile_size, screen_tile, n_light, n_brdf;
+    Workspace ws;
 };
 
-MR_DEV void initial_px(const InitialParams &p, int idx)
+// gen: the whole RIS stream of one active pixel; stores the reservoir as if the sample were visible and queues the
+// visibility ray (InitialResampling.slang:255-270); initial_resolve_px applies the occlusion test result.
+MR_DEV void initial_gen_px(const InitialParams &p, int a)
 {
+    if (a >= p.ws.counters[0]) return;
+    const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
-    if (MR_LDG(p.g.occ + i) < 0.1f) { res_zero(p.res, i); return; }
     uint32_t tileSg = seed_of(px / p.screen_tile, py / p.screen_tile, p.frame);
     uint32_t tileIndex = minu(to_uint(rnd(tileSg) * (float)p.tile_count), p.tile_count - 1u);
     const uint32_t tileOffset = tileIndex * p.tile_size;
@@ -163,12 +167,25 @@ MR_DEV void initial_px(const InitialParams &p, int idx)
     }
     if (st.ld.x > 0.1f) {
         float3 L = oct_decode(st.ld.y, st.ld.z);
-        float3 o = load3(p.pos_map, i) + VIS_NEAR * L;
-        if (any_hit<false>(p.bvh, o, L, nullptr)) st = ris_empty();
+        queue_ray(p.ws, (size_t)a, load3(p.pos_map, i) + VIS_NEAR * L, L);
+    } else {
+        queue_empty(p.ws, (size_t)a);
     }
     st.weight = st.weight > 0.f ? (st.wsum / st.M) / st.weight : 0.f;
     st.M = 1.f;
     res_store(p.res, i, st);
+}
+
+// an occluded sample resets the RIS state before the final weight is formed: (0,0,0), pdf 0, M 1, W 0
+MR_DEV void initial_resolve_px(const InitialParams &p, int a)
+{
+    if (a >= p.ws.counters[0]) return;
+    if (p.ws.ray_o[a].w == 0.0f || p.ws.hit[a] == 0u) return;
+    const size_t i = (size_t)p.ws.active[a];
+    store3(p.res.ld, i, f3(0.f));
+    p.res.pdf[i] = 0.f;
+    p.res.M[i] = 1;
+    p.res.w[i] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -181,10 +198,13 @@ struct TemporalParams {
     int fx, fy;
     unsigned int frame;
     unsigned int max_history;
+    Workspace ws;
 };
 
-MR_DEV void temporal_px(const TemporalParams &p, int idx)
+MR_DEV void temporal_px(const TemporalParams &p, int a)
 {
+    if (a >= p.ws.counters[0]) return;
+    const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
     if (MR_LDG(p.g.occ + i) < 0.1f) return;
@@ -231,13 +251,64 @@ struct SpatialParams {
     unsigned int frame;
     unsigned int offset_count, neighbor_count;
     float radius;
+    Workspace ws;
 };
 
-MR_DEV void spatial_px(const SpatialParams &p, int idx)
+MR_DEV bool spatial_neighbor(const SpatialParams &p, uint32_t px, uint32_t py, uint32_t startIndex, uint32_t k, size_t &n)
 {
+    const uint32_t ni = (startIndex + k) & (p.offset_count - 1u);
+    int npx = (int)px + to_int(MR_LDG(p.offsets + 2 * (size_t)ni) * p.radius);
+    int npy = (int)py + to_int(MR_LDG(p.offsets + 2 * (size_t)ni + 1) * p.radius);
+    if (!(npx >= 0 && npx < p.fx && npy >= 0 && npy < p.fy)) return false;
+    n = (size_t)npy * p.fx + npx;
+    return true;
+}
+
+// gen: picks the neighbours, applies the reuse heuristics and queues the two visibility rays of every accepted one
+// (SpatialResampling.slang:229-277): slot 2k = own surface -> neighbour's light, slot 2k+1 = neighbour surface -> own light
+MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
+{
+    if (a >= p.ws.counters[0]) return;
+    const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
-    if (MR_LDG(p.g.occ + i) < 0.1f) { res_zero(p.res, i); return; }
+    uint32_t sg = seed_of(px, py, p.frame);
+    float4 nd = load_nd(p.g.normal_depth, i);
+    const float3 N = make_float3(nd.x, nd.y, nd.z);
+    const uint32_t startIndex = to_uint(rnd(sg) * (float)p.offset_count);
+    const float3 cur_ld = load3(p.prev.ld, i);
+    const float3 cL = oct_decode(cur_ld.y, cur_ld.z);
+    const float3 cur_pos = load3(p.pos_map, i);
+    const size_t base = (size_t)a * MR_MAX_RAYS_PER_PIXEL;
+    for (uint32_t k = 0; k < p.neighbor_count; ++k) {
+        size_t n;
+        bool ok = spatial_neighbor(p, px, py, startIndex, k, n);
+        float3 nld = f3(0.f);
+        if (ok) {
+            float4 nnd = load_nd(p.g.normal_depth, n);
+            ok = neighbor_ok(N, nd.w, make_float3(nnd.x, nnd.y, nnd.z), nnd.w);
+        }
+        if (ok) ok = MR_LDG(p.prev.M + n) != 0;
+        if (ok) ok = !(MR_LDG(p.g.occ + n) < 0.1f);
+        if (ok) {
+            nld = load3(p.prev.ld, n);
+            const float3 nL = oct_decode(nld.y, nld.z);
+            queue_ray(p.ws, base + 2 * k, cur_pos + VIS_NEAR * nL, nL);
+            queue_ray(p.ws, base + 2 * k + 1, load3(p.pos_map, n) + VIS_NEAR * cL, cL);
+        } else {
+            queue_empty(p.ws, base + 2 * k);
+            queue_empty(p.ws, base + 2 * k + 1);
+        }
+    }
+}
+
+// resolve: the pairwise-MIS streaming pass with the traced visibilities (res.slang:173-232)
+MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
+{
+    if (a >= p.ws.counters[0]) return;
+    const int idx = p.ws.active[a];
+    const size_t i = (size_t)idx;
+    const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
     uint32_t sg = seed_of(px, py, p.frame);
     float4 nd = load_nd(p.g.normal_depth, i);
     const float3 N = make_float3(nd.x, nd.y, nd.z);
@@ -248,29 +319,22 @@ MR_DEV void spatial_px(const SpatialParams &p, int idx)
     float3 cLe, cL;
     light_of(p.env, cur.ld.y, cur.ld.z, cLe, cL);
     const float currentTargetPdf = target_pdf(cur_s, cLe, cL);
-    const float3 cur_pos = load3(p.pos_map, i);
     st.canonical = 1.f;
     uint32_t validNeighbors = 1;
-    const uint32_t mask = p.offset_count - 1u;
+    const size_t base = (size_t)a * MR_MAX_RAYS_PER_PIXEL;
     for (uint32_t k = 0; k < p.neighbor_count; ++k) {
-        const uint32_t ni = (startIndex + k) & mask;
-        int npx = (int)px + to_int(MR_LDG(p.offsets + 2 * (size_t)ni) * p.radius);
-        int npy = (int)py + to_int(MR_LDG(p.offsets + 2 * (size_t)ni + 1) * p.radius);
-        if (!(npx >= 0 && npx < p.fx && npy >= 0 && npy < p.fy)) continue;
-        const size_t n = (size_t)npy * p.fx + npx;
+        if (p.ws.ray_o[base + 2 * k].w == 0.0f) continue;
+        size_t n;
+        spatial_neighbor(p, px, py, startIndex, k, n);
         float4 nnd = load_nd(p.g.normal_depth, n);
         const float3 nN = make_float3(nnd.x, nnd.y, nnd.z);
-        if (!neighbor_ok(N, nd.w, nN, nnd.w)) continue;
         const Reservoir nr = res_load(p.prev, n);
-        if (nr.M == 0) continue;
-        if (MR_LDG(p.g.occ + n) < 0.1f) continue;
         const RisSurface nb_s = ris_surface(nN, load3(p.g.ray_dir, n), load3(p.g.brdf, n));
         ++validNeighbors;
         float3 nLe, nL;
         light_of(p.env, nr.ld.y, nr.ld.z, nLe, nL);
-        const float3 nb_pos = load3(p.pos_map, n);
-        bool canonical_hit = any_hit<false>(p.bvh, cur_pos + VIS_NEAR * nL, nL, nullptr);
-        bool candidate_hit = any_hit<false>(p.bvh, nb_pos + VIS_NEAR * cL, cL, nullptr);
+        const bool canonical_hit = p.ws.hit[base + 2 * k] != 0u;
+        const bool candidate_hit = p.ws.hit[base + 2 * k + 1] != 0u;
         float candidateVisibility = candidate_hit ? 0.f : 1.0f;
         float canonicalVisibility = canonical_hit ? 0.f : 1.0f;
         float candAtOwn = target_pdf(nb_s, nLe, nL);
@@ -305,20 +369,29 @@ struct VisParams {
     const float *__restrict__ res_ld;
     const float *__restrict__ pos_map;
     float *__restrict__ vis;
+    int n;
+    Workspace ws;
 };
-MR_DEV void final_visibility_px(const VisParams &p, int idx)
+// thread t: vis[t] = 1 for every pixel (EvaluateFinalSamples.slang:103); the first n_active threads also queue a ray
+MR_DEV void final_visibility_gen_px(const VisParams &p, int t)
 {
-    const size_t i = (size_t)idx;
+    p.vis[t] = 1.0f;
+    if (t >= p.ws.counters[0]) return;
+    const size_t i = (size_t)p.ws.active[t];
     float3 ld = load3(p.res_ld, i);
-    float v = 1.0f;
     if (ld.x > 0.1f) {
         float3 L = oct_decode(ld.y, ld.z);
-        float3 o = load3(p.pos_map, i) + VIS_NEAR * L;
-        v = any_hit<false>(p.bvh, o, L, nullptr) ? 0.0f : 1.0f;
+        queue_ray(p.ws, (size_t)t, load3(p.pos_map, i) + VIS_NEAR * L, L);
+    } else {
+        queue_empty(p.ws, (size_t)t);
     }
-    p.vis[i] = v;
 }
-
+MR_DEV void final_visibility_resolve_px(const VisParams &p, int a)
+{
+    if (a >= p.ws.counters[0]) return;
+    if (p.ws.ray_o[a].w == 0.0f) return;
+    p.vis[p.ws.active[a]] = p.ws.hit[a] != 0u ? 0.0f : 1.0f;
+}
 struct EvalParams {
     ResConst res;
     EnvView env;
@@ -466,12 +539,29 @@ using namespace mr;
 
 extern "C" {
 
+#define MR_WS_ARGS void *workspace, size_t workspace_bytes
+static int ws_open(Workspace &ws, int n, void *workspace, size_t workspace_bytes)
+{
+    if (!workspace) return MIRRES_ERR_NULL;
+    if ((uintptr_t)workspace & 255) return MIRRES_ERR_ALIGN;
+    if (workspace_bytes < workspace_carve(nullptr, n, nullptr)) return MIRRES_ERR_SCRATCH;
+    workspace_carve(&ws, n, (char *)workspace);
+    return 0;
+}
+static void res_zero_all(const ResView &r, int n, cudaStream_t st)
+{
+    zero_async(r.ld, sizeof(float) * 3 * (size_t)n, st);
+    zero_async(r.pdf, sizeof(float) * (size_t)n, st);
+    zero_async(r.M, sizeof(int) * (size_t)n, st);
+    zero_async(r.w, sizeof(float) * (size_t)n, st);
+}
+
 int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris, const float *pos_map, float *res_ld,
                               float *res_pdf, int *res_M, float *res_w, const float *env_tex, int env_w, int env_h,
                               int fx, int fy, unsigned int frame_index, const float *occ, const float *normal_depth,
                               const float *brdf_map, const float *ray_dir, const float *pdf_, const float *mpdf_,
                               const float *light_data, const float *light_pdf, int tile_count, int tile_size,
-                              int screen_tile, int n_light, int n_brdf, void *stream)
+                              int screen_tile, int n_light, int n_brdf, MR_WS_ARGS, void *stream)
 {
     if (!packed_nodes || !packed_tris || !pos_map || !res_ld || !res_pdf || !res_M || !res_w || !env_tex || !occ ||
         !normal_depth || !brdf_map || !ray_dir || !pdf_ || !mpdf_ || !light_data || !light_pdf)
@@ -479,7 +569,11 @@ int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris,
     if (fx < 1 || fy < 1 || env_w < 1 || env_h < 1 || tile_count < 1 || tile_size < 1 || screen_tile < 1 || n_light < 1 || n_brdf < 0)
         return MIRRES_ERR_SHAPE;
     if ((uintptr_t)normal_depth & 15) return MIRRES_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = fx * fy;
     InitialParams p;
+    int rc = ws_open(p.ws, n, workspace, workspace_bytes);
+    if (rc) return rc;
     p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
     p.env = {env_tex, env_w, env_h, pdf_, nullptr, mpdf_, nullptr};
     p.g = {occ, normal_depth, brdf_map, ray_dir};
@@ -489,7 +583,10 @@ int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris,
     p.light_pdf = light_pdf;
     p.fx = fx; p.fy = fy; p.frame = frame_index;
     p.tile_count = tile_count; p.tile_size = tile_size; p.screen_tile = screen_tile; p.n_light = n_light; p.n_brdf = n_brdf;
-    return foreach_item<InitialParams, initial_px, 128>(p, fx * fy, (cudaStream_t)stream);
+    res_zero_all(p.res, n, st); // background pixels (InitialResampling.slang:166-176)
+    if ((rc = foreach_item<InitialParams, initial_gen_px, 128>(p, n, st))) return rc;
+    if ((rc = trace_queue_any(p.bvh, p.ws, 1, device_sm_count(), st))) return rc;
+    return foreach_item<InitialParams, initial_resolve_px, 256>(p, n, st);
 }
 
 int mirres_temporal_resampling(float *res_ld, float *res_pdf, int *res_M, float *res_w, const float *prev_ld,
@@ -497,7 +594,7 @@ int mirres_temporal_resampling(float *res_ld, float *res_pdf, int *res_M, float 
                                int env_w, int env_h, int fx, int fy, unsigned int frame_index, const float *occ,
                                const float *normal_depth, const float *brdf_map, const float *ray_dir,
                                const float *prev_occ, const float *prev_normal_depth, const float *prev_brdf_map,
-                               const float *prev_ray_dir, const float *motion, int max_history, void *stream)
+                               const float *prev_ray_dir, const float *motion, int max_history, MR_WS_ARGS, void *stream)
 {
     if (!res_ld || !res_pdf || !res_M || !res_w || !prev_ld || !prev_pdf || !prev_M || !prev_w || !env_tex || !occ ||
         !normal_depth || !brdf_map || !ray_dir || !prev_occ || !prev_normal_depth || !prev_brdf_map || !prev_ray_dir)
@@ -505,6 +602,8 @@ int mirres_temporal_resampling(float *res_ld, float *res_pdf, int *res_M, float 
     if (fx < 1 || fy < 1 || env_w < 1 || env_h < 1 || max_history < 0) return MIRRES_ERR_SHAPE;
     if (((uintptr_t)normal_depth & 15) || ((uintptr_t)prev_normal_depth & 15)) return MIRRES_ERR_ALIGN;
     TemporalParams p;
+    int rc = ws_open(p.ws, fx * fy, workspace, workspace_bytes);
+    if (rc) return rc;
     p.env = {env_tex, env_w, env_h, nullptr, nullptr, nullptr, nullptr};
     p.g = {occ, normal_depth, brdf_map, ray_dir};
     p.prev_g = {prev_occ, prev_normal_depth, prev_brdf_map, prev_ray_dir};
@@ -520,16 +619,21 @@ int mirres_spatial_resampling(const void *packed_nodes, const void *packed_tris,
                               const int *prev_M, const float *prev_w, const float *neighbor_offsets, const float *env_tex,
                               int env_w, int env_h, int fx, int fy, unsigned int frame_index, const float *occ,
                               const float *normal_depth, const float *brdf_map, const float *ray_dir, int offset_count,
-                              int neighbor_count, float gather_radius, void *stream)
+                              int neighbor_count, float gather_radius, MR_WS_ARGS, void *stream)
 {
     if (!packed_nodes || !packed_tris || !pos_map || !res_ld || !res_pdf || !res_M || !res_w || !prev_ld || !prev_pdf ||
         !prev_M || !prev_w || !neighbor_offsets || !env_tex || !occ || !normal_depth || !brdf_map || !ray_dir)
         return MIRRES_ERR_NULL;
-    if (fx < 1 || fy < 1 || env_w < 1 || env_h < 1 || offset_count < 1 || (offset_count & (offset_count - 1)) || neighbor_count < 0)
+    if (fx < 1 || fy < 1 || env_w < 1 || env_h < 1 || offset_count < 1 || (offset_count & (offset_count - 1)) ||
+        neighbor_count < 0 || 2 * neighbor_count > MR_MAX_RAYS_PER_PIXEL)
         return MIRRES_ERR_SHAPE;
     if ((uintptr_t)normal_depth & 15) return MIRRES_ERR_ALIGN;
     if (res_ld == prev_ld) return MIRRES_ERR_ALIAS;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = fx * fy;
     SpatialParams p;
+    int rc = ws_open(p.ws, n, workspace, workspace_bytes);
+    if (rc) return rc;
     p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
     p.env = {env_tex, env_w, env_h, nullptr, nullptr, nullptr, nullptr};
     p.g = {occ, normal_depth, brdf_map, ray_dir};
@@ -539,16 +643,27 @@ int mirres_spatial_resampling(const void *packed_nodes, const void *packed_tris,
     p.offsets = neighbor_offsets;
     p.fx = fx; p.fy = fy; p.frame = frame_index;
     p.offset_count = offset_count; p.neighbor_count = neighbor_count; p.radius = gather_radius;
-    return foreach_item<SpatialParams, spatial_px, 128>(p, fx * fy, (cudaStream_t)stream);
+    res_zero_all(p.res, n, st); // background pixels (SpatialResampling.slang:192-201)
+    if ((rc = foreach_item<SpatialParams, spatial_gen_px, 128>(p, n, st))) return rc;
+    if ((rc = trace_queue_any(p.bvh, p.ws, MR_MAX_RAYS_PER_PIXEL, device_sm_count(), st))) return rc;
+    return foreach_item<SpatialParams, spatial_resolve_px, 128>(p, n, st);
 }
 
 int mirres_final_visibility(const void *packed_nodes, const void *packed_tris, const float *res_ld, int fx, int fy,
-                            const float *pos_map, float *vis_map, void *stream)
+                            const float *pos_map, float *vis_map, MR_WS_ARGS, void *stream)
 {
     if (!packed_nodes || !packed_tris || !res_ld || !pos_map || !vis_map) return MIRRES_ERR_NULL;
     if (fx < 1 || fy < 1) return MIRRES_ERR_SHAPE;
-    VisParams p = {{(const PackedNode *)packed_nodes, (const float4 *)packed_tris}, res_ld, pos_map, vis_map};
-    return foreach_item<VisParams, final_visibility_px, 128>(p, fx * fy, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = fx * fy;
+    VisParams p;
+    int rc = ws_open(p.ws, n, workspace, workspace_bytes);
+    if (rc) return rc;
+    p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
+    p.res_ld = res_ld; p.pos_map = pos_map; p.vis = vis_map; p.n = n;
+    if ((rc = foreach_item<VisParams, final_visibility_gen_px, 256>(p, n, st))) return rc;
+    if ((rc = trace_queue_any(p.bvh, p.ws, 1, device_sm_count(), st))) return rc;
+    return foreach_item<VisParams, final_visibility_resolve_px, 256>(p, n, st);
 }
 
 int mirres_eval_final_fwd(const float *res_ld, const float *res_pdf, const int *res_M, const float *res_w,

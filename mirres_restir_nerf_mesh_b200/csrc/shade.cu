@@ -7,7 +7,7 @@
 //   nerf/ScreenSpaceReSTIR/FinalShading.slang:113-265   process_new_dir_for_pt    -> bounce_first_px
 //   nerf/ScreenSpaceReSTIR/FinalShading.slang:641-1009  process_path_tracing_divided_no_grad -> bounce_shade_px
 // `max_bounce` generalises the reference's compile-time MAX_Bounce = 2 (FinalShading.slang:7).
-#include "mr_bvh.cuh"
+#include "mr_wave.cuh"
 #include "mr_light.cuh"
 #include "mr_brdf.cuh"
 #include "../../include/mirres_b200.h"
@@ -208,10 +208,31 @@ struct BounceParams {
     float *__restrict__ new_ray_d;
     float *__restrict__ new_occ;
     float *__restrict__ new_normal;
+    Workspace ws;   // shadow-ray queue (2 slots per active pixel) and per-pixel scratch
+    Workspace wsc;  // continuation-ray queue (1 slot per active pixel): same workspace, ray arrays offset by 2N
 };
 
-// sample a continuation direction and trace it (FinalShading.slang:190-262 and :907-977)
-MR_DEV void continue_path(const BounceParams &p, size_t i, const Surface &s, float3 surf_pos, uint32_t &sg, float3 thr)
+// Entry sequence of both bounce kernels for EVERY pixel of the frame (FinalShading.slang:132-148, 657-690): remember
+// the incoming stop flag, clear new_occ, raise the stop flag, reset the path state at bounce 0, zero the outputs.
+MR_DEV void bounce_prologue_px(const BounceParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    p.ws.stop_in[i] = p.bounce_count == 0 ? 0.f : p.prd[5 * i + 4];
+    p.new_occ[i] = 0.f;
+    p.prd[5 * i + 4] = 1.f;
+    if (p.bounce_count == 0) {
+        p.prd[5 * i] = 1.f; p.prd[5 * i + 1] = 1.f; p.prd[5 * i + 2] = 1.f;
+        p.prd[5 * i + 3] = 0.f;
+    }
+    if (p.color) {
+        store3(p.color, i, f3(0.f));
+        store3(p.diff_color, i, f3(0.f));
+        store3(p.spec_color, i, f3(0.f));
+    }
+}
+
+// sample a continuation direction and queue its closest-hit ray (FinalShading.slang:190-262 and :907-977)
+MR_DEV void continue_path_gen(const BounceParams &p, int a, size_t i, const Surface &s, float3 surf_pos, uint32_t &sg, float3 thr)
 {
     float3 out_dir, out_weight;
     float out_pdf;
@@ -222,165 +243,186 @@ MR_DEV void continue_path(const BounceParams &p, size_t i, const Surface &s, flo
         p.prd[5 * i + 4] = 1.f;
     } else if (p.bounce_count + 1u <= (unsigned int)p.max_bounce) {
         out_dir = normalize(from_frame(s.frame, out_dir));
-        Hit hit;
-        bool found = closest_hit<false>(p.bvh, surf_pos + VIS_NEAR * out_dir, out_dir, hit, nullptr);
-        const float specularBounce = (float)sampledSpecular;
+        queue_ray(p.wsc, (size_t)a, surf_pos + VIS_NEAR * out_dir, out_dir);
         thr *= out_weight;
         p.prd[5 * i + 0] = thr.x;
         p.prd[5 * i + 1] = thr.y;
         p.prd[5 * i + 2] = thr.z;
-        p.prd[5 * i + 3] = specularBounce;
+        p.prd[5 * i + 3] = (float)sampledSpecular;
         store3(p.new_ray_d, i, out_dir);
-        if (found) {
-            p.prd[5 * i + 4] = 0.f;
-            store3(p.new_pos, i, hit.pos);
-            store3(p.new_normal, i, hit.normal);
-            p.new_occ[i] = 1.f;
-        } else if (specularBounce > 0.f) {
-            p.prd[5 * i + 4] = 0.f;
-        }
     }
 }
 
-MR_DEV void bounce_first_px(const BounceParams &p, int idx)
+MR_DEV void continue_path_resolve(const BounceParams &p, int a)
 {
+    if (p.wsc.ray_o[a].w == 0.0f) return;
+    const size_t i = (size_t)p.wsc.active[a];
+    const float4 h0 = p.wsc.chit[2 * (size_t)a], h1 = p.wsc.chit[2 * (size_t)a + 1];
+    if (h0.w != 0.0f) {
+        p.prd[5 * i + 4] = 0.f;
+        store3(p.new_pos, i, make_float3(h0.x, h0.y, h0.z));
+        store3(p.new_normal, i, make_float3(h1.x, h1.y, h1.z));
+        p.new_occ[i] = 1.f;
+    } else if (p.prd[5 * i + 3] > 0.f) {
+        p.prd[5 * i + 4] = 0.f; // a specular bounce that leaves the scene picks up the envmap in the next kernel
+    }
+}
+
+MR_DEV void bounce_first_gen_px(const BounceParams &p, int a)
+{
+    if (a >= p.ws.counters[0]) return;
+    const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
-    float3 thr = make_float3(p.prd[5 * i], p.prd[5 * i + 1], p.prd[5 * i + 2]);
-    float is_stop = p.prd[5 * i + 4];
-    p.new_occ[i] = 0.f;
-    p.prd[5 * i + 4] = 1.f;
-    if (p.bounce_count == 0) {
-        thr = f3(1.0f);
-        is_stop = 0.f;
-        p.prd[5 * i] = 1.f; p.prd[5 * i + 1] = 1.f; p.prd[5 * i + 2] = 1.f;
-        p.prd[5 * i + 3] = 0.f;
-    }
-    if (is_stop > 0.f) return;
+    queue_empty(p.wsc, (size_t)a);
+    if (p.ws.stop_in[i] > 0.f) return;
     if (!(MR_LDG(p.occ + i) > 0.1f)) return;
+    const float3 thr = make_float3(p.prd[5 * i], p.prd[5 * i + 1], p.prd[5 * i + 2]);
     uint32_t sg = seed_of(px, py, p.frame);
     const Surface s = surface_of(load3(p.normal, i), load3(p.ray_dir, i), load3(p.kd, i), MR_LDG(p.rm + 2 * i), MR_LDG(p.rm + 2 * i + 1));
-    continue_path(p, i, s, load3(p.pos_map, i), sg, thr);
+    continue_path_gen(p, a, i, s, load3(p.pos_map, i), sg, thr);
 }
 
-MR_DEV void bounce_shade_px(const BounceParams &p, int idx)
+MR_DEV void bounce_first_resolve_px(const BounceParams &p, int a)
 {
+    if (a >= p.ws.counters[0]) return;
+    continue_path_resolve(p, a);
+}
+
+// per-active-pixel scratch of the shade kernel (floats): [0..8] contributions that need no ray (colour, diffuse, specular),
+// [9..17] the light sample's contribution, [18..26] the BSDF sample's contribution, both pending their shadow ray
+MR_DEV void put9(float *q, float3 a, float3 b, float3 c)
+{
+    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = b.x; q[4] = b.y; q[5] = b.z; q[6] = c.x; q[7] = c.y; q[8] = c.z;
+}
+
+MR_DEV void bounce_shade_gen_px(const BounceParams &p, int a)
+{
+    if (a >= p.ws.counters[0]) return;
+    const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
-    float3 thr = make_float3(p.prd[5 * i], p.prd[5 * i + 1], p.prd[5 * i + 2]);
-    float specularBounce = p.prd[5 * i + 3];
-    float is_stop = p.prd[5 * i + 4];
-    p.new_occ[i] = 0.f;
-    p.prd[5 * i + 4] = 1.f;
-    if (p.bounce_count == 0) {
-        thr = f3(1.0f);
-        specularBounce = 0.f;
-        is_stop = 0.f;
-        p.prd[5 * i] = 1.f; p.prd[5 * i + 1] = 1.f; p.prd[5 * i + 2] = 1.f;
-        p.prd[5 * i + 3] = 0.f;
+    float *scratch = p.ws.px + (size_t)a * MR_PX_SCRATCH_FLOATS;
+    queue_empty(p.ws, 2 * (size_t)a);
+    queue_empty(p.ws, 2 * (size_t)a + 1);
+    queue_empty(p.wsc, (size_t)a);
+    put9(scratch, f3(0.f), f3(0.f), f3(0.f));
+    if (p.ws.stop_in[i] > 0.f) return;
+    const float3 thr = make_float3(p.prd[5 * i], p.prd[5 * i + 1], p.prd[5 * i + 2]);
+    const float specularBounce = p.prd[5 * i + 3];
+    const float3 rd = load3(p.ray_dir, i);
+    if (!(MR_LDG(p.occ + i) > 0.1f)) {
+        // the path left the scene: primary misses and specular chains collect the envmap (FinalShading.slang:979-996)
+        if (p.bounce_count == 0) {
+            put9(scratch, thr * env_radiance(p.env, ngp_dir(rd)), f3(0.f), f3(0.f));
+        } else if (specularBounce > 0.f) {
+            const float3 Le = env_radiance(p.env, ngp_dir(rd));
+            put9(scratch, thr * Le, f3(0.f), thr * Le);
+        }
+        p.prd[5 * i + 4] = 1.f;
+        return;
     }
-    float3 color_val = f3(0.f), diff_val = f3(0.f), spec_val = f3(0.f);
-    if (!(is_stop > 0.f)) {
-        const float3 rd = load3(p.ray_dir, i);
-        if (MR_LDG(p.occ + i) > 0.1f) {
-            uint32_t sg = seed_of(px, py, p.frame);
-            const float3 N = load3(p.normal, i);
-            const float3 P = load3(p.pos_map, i);
-            const Surface s = surface_of(N, rd, load3(p.kd, i), MR_LDG(p.rm + 2 * i), MR_LDG(p.rm + 2 * i + 1));
-            const bool has_normal = !is_black(N);
-            // ---- next-event estimation: one env sample, power heuristic against the BSDF pdf
-            float lightPdf = 0.0f, scatteringPdf = 0.0f;
-            float3 Li = f3(0.f);
-            {
-                float2 u;
-                u.x = rnd(sg);
-                u.y = rnd(sg);
-                float3 sdir = f3(0.f);
-                float spdf = 0.f;
-                float2 luv;
-                bool ok = sample_env(p.env, u, sdir, spdf, luv);
-                if (ok) {
-                    lightPdf = spdf;
-                    Li = env_radiance(p.env, ngp_dir(sdir)) / spdf;
-                }
-                if (ok && lightPdf > 0 && !is_black(Li)) {
-                    float3 diff_f = f3(0.f), spec_f = f3(0.f), total_f = f3(0.f);
-                    const float3 wi = to_frame(s.frame, sdir);
-                    if (has_normal) {
-                        if (s.pD > 0.f) diff_f = f3(lambert_light(s.wo, wi));
-                        if (s.pS > 0.f) spec_f = specular_f(s.wo, wi, s.spec, s.alpha);
-                        total_f = s.kd_diff * diff_f + spec_f;
-                        diff_f = s.kd_diff * diff_f;
-                        scatteringPdf = bsdf_pdf(s, wi);
-                    }
-                    if (!is_black(total_f)) {
-                        const float3 ldir = normalize(sdir);
-                        const float tr = any_hit<false>(p.bvh, P + VIS_NEAR * ldir, ldir, nullptr) ? 0.0f : 1.0f;
-                        Li = Li * f3(tr);
-                        if (!is_black(Li)) {
-                            const float mis = power_heuristic(lightPdf, scatteringPdf);
-                            color_val += thr * total_f * Li * mis;
-                            diff_val += thr * diff_f * Li * mis;
-                            spec_val += thr * spec_f * Li * mis;
-                        }
-                    }
-                }
-            }
-            // ---- BSDF sample with MIS against the light pdf
+    uint32_t sg = seed_of(px, py, p.frame);
+    const float3 N = load3(p.normal, i);
+    const float3 P = load3(p.pos_map, i);
+    const Surface s = surface_of(N, rd, load3(p.kd, i), MR_LDG(p.rm + 2 * i), MR_LDG(p.rm + 2 * i + 1));
+    const bool has_normal = !is_black(N);
+    // ---- next-event estimation: one env sample, power heuristic against the BSDF pdf
+    float lightPdf = 0.0f, scatteringPdf = 0.0f;
+    {
+        float2 u;
+        u.x = rnd(sg);
+        u.y = rnd(sg);
+        float3 sdir = f3(0.f), Li = f3(0.f);
+        float spdf = 0.f;
+        float2 luv;
+        bool ok = sample_env(p.env, u, sdir, spdf, luv);
+        if (ok) {
+            lightPdf = spdf;
+            Li = env_radiance(p.env, ngp_dir(sdir)) / spdf;
+        }
+        if (ok && lightPdf > 0 && !is_black(Li)) {
+            float3 diff_f = f3(0.f), spec_f = f3(0.f), total_f = f3(0.f);
+            const float3 wi = to_frame(s.frame, sdir);
             if (has_normal) {
-                float3 m_wi, unused_w;
-                float m_pdf;
-                uint32_t sampledSpecular;
-                bool valid = bsdf_sample<false>(s, sg, m_wi, m_pdf, sampledSpecular, unused_w);
-                if (valid) {
-                    float3 wd = f3(1.0f), ws = f3(1.0f);
-                    if (s.pD > 0.f) wd = f3(lambert_light(s.wo, m_wi));
-                    if (s.pS > 0.f) ws = specular_f(s.wo, m_wi, s.spec, s.alpha);
-                    const float3 wt = s.kd_diff * wd + ws;
-                    m_wi = from_frame(s.frame, m_wi);
-                    scatteringPdf = m_pdf;
-                    // the reference divides by the pdf and multiplies it back (FinalShading.slang:853-859); kept for rounding
-                    float3 f = wt / m_pdf, diff_f = s.kd_diff * wd / m_pdf, spec_f = ws / m_pdf;
-                    f *= m_pdf;
-                    diff_f *= m_pdf;
-                    spec_f *= m_pdf;
-                    const float3 dirw = normalize(m_wi);
-                    if (!is_black(f) && scatteringPdf > 0) {
-                        float weight = 1.0f;
-                        bool light_pdf_zero = false;
-                        if (sampledSpecular == 0) {
-                            lightPdf = env_pdf(p.env, dirw);
-                            if (lightPdf == 0.0f) light_pdf_zero = true;
-                            weight = power_heuristic(scatteringPdf, lightPdf);
-                        }
-                        const bool blocked = any_hit<false>(p.bvh, P + VIS_NEAR * dirw, dirw, nullptr);
-                        Li = f3(0.f);
-                        if (!blocked) Li = env_radiance(p.env, ngp_dir(dirw));
-                        if (!is_black(Li) && !light_pdf_zero) {
-                            const float3 Tr = f3(1.0f);
-                            color_val += thr * f * Li * Tr * weight / scatteringPdf;
-                            diff_val += thr * diff_f * Li * Tr * weight / scatteringPdf;
-                            spec_val += thr * spec_f * Li * Tr * weight / scatteringPdf;
-                        }
-                    }
-                }
+                if (s.pD > 0.f) diff_f = f3(lambert_light(s.wo, wi));
+                if (s.pS > 0.f) spec_f = specular_f(s.wo, wi, s.spec, s.alpha);
+                total_f = s.kd_diff * diff_f + spec_f;
+                diff_f = s.kd_diff * diff_f;
+                scatteringPdf = bsdf_pdf(s, wi);
             }
-            // ---- continuation
-            continue_path(p, i, s, P, sg, thr);
-        } else {
-            if (p.bounce_count == 0) {
-                color_val += thr * env_radiance(p.env, ngp_dir(rd));
-            } else if (specularBounce > 0.f) {
-                const float3 Le = env_radiance(p.env, ngp_dir(rd));
-                color_val += thr * Le;
-                spec_val += thr * Le;
+            if (!is_black(total_f)) {
+                const float3 ldir = normalize(sdir);
+                queue_ray(p.ws, 2 * (size_t)a, P + VIS_NEAR * ldir, ldir);
+                // the reference multiplies Li by the transmittance (1 when unoccluded) before using it
+                Li = Li * f3(1.0f);
+                const float mis = power_heuristic(lightPdf, scatteringPdf);
+                put9(scratch + 9, thr * total_f * Li * mis, thr * diff_f * Li * mis, thr * spec_f * Li * mis);
             }
-            p.prd[5 * i + 4] = 1.f;
         }
     }
-    store3(p.color, i, color_val);
-    store3(p.diff_color, i, diff_val);
-    store3(p.spec_color, i, spec_val);
+    // ---- BSDF sample with MIS against the light pdf
+    if (has_normal) {
+        float3 m_wi, unused_w;
+        float m_pdf;
+        uint32_t sampledSpecular;
+        bool valid = bsdf_sample<false>(s, sg, m_wi, m_pdf, sampledSpecular, unused_w);
+        if (valid) {
+            float3 wd = f3(1.0f), wsp = f3(1.0f);
+            if (s.pD > 0.f) wd = f3(lambert_light(s.wo, m_wi));
+            if (s.pS > 0.f) wsp = specular_f(s.wo, m_wi, s.spec, s.alpha);
+            const float3 wt = s.kd_diff * wd + wsp;
+            m_wi = from_frame(s.frame, m_wi);
+            scatteringPdf = m_pdf;
+            // the reference divides by the pdf and multiplies it back (FinalShading.slang:853-859); kept for rounding
+            float3 f = wt / m_pdf, diff_f = s.kd_diff * wd / m_pdf, spec_f = wsp / m_pdf;
+            f *= m_pdf;
+            diff_f *= m_pdf;
+            spec_f *= m_pdf;
+            const float3 dirw = normalize(m_wi);
+            if (!is_black(f) && scatteringPdf > 0) {
+                float weight = 1.0f;
+                bool light_pdf_zero = false;
+                if (sampledSpecular == 0) {
+                    lightPdf = env_pdf(p.env, dirw);
+                    if (lightPdf == 0.0f) light_pdf_zero = true;
+                    weight = power_heuristic(scatteringPdf, lightPdf);
+                }
+                // the radiance that arrives if the ray escapes is looked up now; it only counts if the ray does escape
+                const float3 Li = env_radiance(p.env, ngp_dir(dirw));
+                if (!is_black(Li) && !light_pdf_zero) {
+                    queue_ray(p.ws, 2 * (size_t)a + 1, P + VIS_NEAR * dirw, dirw);
+                    const float3 Tr = f3(1.0f);
+                    put9(scratch + 18, thr * f * Li * Tr * weight / scatteringPdf, thr * diff_f * Li * Tr * weight / scatteringPdf,
+                         thr * spec_f * Li * Tr * weight / scatteringPdf);
+                }
+            }
+        }
+    }
+    // ---- continuation
+    continue_path_gen(p, a, i, s, P, sg, thr);
+}
+
+MR_DEV void bounce_shade_resolve_px(const BounceParams &p, int a)
+{
+    if (a >= p.ws.counters[0]) return;
+    const size_t i = (size_t)p.ws.active[a];
+    const float *q = p.ws.px + (size_t)a * MR_PX_SCRATCH_FLOATS;
+    float3 c = make_float3(q[0], q[1], q[2]), d = make_float3(q[3], q[4], q[5]), sp = make_float3(q[6], q[7], q[8]);
+    if (p.ws.ray_o[2 * (size_t)a].w != 0.0f && p.ws.hit[2 * (size_t)a] == 0u) {
+        c += make_float3(q[9], q[10], q[11]);
+        d += make_float3(q[12], q[13], q[14]);
+        sp += make_float3(q[15], q[16], q[17]);
+    }
+    if (p.ws.ray_o[2 * (size_t)a + 1].w != 0.0f && p.ws.hit[2 * (size_t)a + 1] == 0u) {
+        c += make_float3(q[18], q[19], q[20]);
+        d += make_float3(q[21], q[22], q[23]);
+        sp += make_float3(q[24], q[25], q[26]);
+    }
+    store3(p.color, i, c);
+    store3(p.diff_color, i, d);
+    store3(p.spec_color, i, sp);
+    continue_path_resolve(p, a);
 }
 
 } // namespace mr
@@ -427,13 +469,21 @@ int mirres_final_shading_bwd(const float *fs_dir, const float *fs_dist, const fl
 static int fill_bounce(BounceParams &p, const void *packed_nodes, const void *packed_tris, unsigned int frame_index,
                        unsigned int bounce_count, int max_bounce, int fx, int fy, const float *occ, const float *pos_map,
                        const float *normal, const float *ray_dir, float *prd, const float *diffuse_map,
-                       const float *rough_metal, float *new_pos, float *new_ray_d, float *new_occ, float *new_normal)
+                       const float *rough_metal, float *new_pos, float *new_ray_d, float *new_occ, float *new_normal,
+                       void *workspace, size_t workspace_bytes)
 {
     if (!packed_nodes || !packed_tris || !occ || !pos_map || !normal || !ray_dir || !prd || !diffuse_map || !rough_metal ||
-        !new_pos || !new_ray_d || !new_occ || !new_normal)
+        !new_pos || !new_ray_d || !new_occ || !new_normal || !workspace)
         return MIRRES_ERR_NULL;
     if (fx < 1 || fy < 1 || max_bounce < 0) return MIRRES_ERR_SHAPE;
     if (new_pos == pos_map || new_occ == occ || new_normal == normal || new_ray_d == ray_dir) return MIRRES_ERR_ALIAS;
+    if ((uintptr_t)workspace & 255) return MIRRES_ERR_ALIGN;
+    const int n = fx * fy;
+    if (workspace_bytes < workspace_carve(nullptr, n, nullptr)) return MIRRES_ERR_SCRATCH;
+    workspace_carve(&p.ws, n, (char *)workspace);
+    p.wsc = p.ws;
+    p.wsc.ray_o += 2 * (size_t)n;
+    p.wsc.ray_d += 2 * (size_t)n;
     p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
     p.frame = frame_index; p.bounce_count = bounce_count; p.max_bounce = max_bounce; p.fx = fx; p.fy = fy;
     p.occ = occ; p.pos_map = pos_map; p.normal = normal; p.ray_dir = ray_dir; p.prd = prd; p.kd = diffuse_map; p.rm = rough_metal;
@@ -445,13 +495,19 @@ int mirres_bounce_first(const void *packed_nodes, const void *packed_tris, unsig
                         unsigned int bounce_count, int max_bounce, int fx, int fy, const float *occ, const float *pos_map,
                         const float *normal, const float *ray_dir, float *prd, const float *diffuse_map,
                         const float *rough_metal, float *new_pos, float *new_ray_d, float *new_occ, float *new_normal,
-                        void *stream)
+                        void *workspace, size_t workspace_bytes, void *stream)
 {
     BounceParams p = {};
     int rc = fill_bounce(p, packed_nodes, packed_tris, frame_index, bounce_count, max_bounce, fx, fy, occ, pos_map, normal,
-                         ray_dir, prd, diffuse_map, rough_metal, new_pos, new_ray_d, new_occ, new_normal);
+                         ray_dir, prd, diffuse_map, rough_metal, new_pos, new_ray_d, new_occ, new_normal, workspace,
+                         workspace_bytes);
     if (rc) return rc;
-    return foreach_item<BounceParams, bounce_first_px, 128>(p, fx * fy, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = fx * fy;
+    if ((rc = foreach_item<BounceParams, bounce_prologue_px, 256>(p, n, st))) return rc;
+    if ((rc = foreach_item<BounceParams, bounce_first_gen_px, 128>(p, n, st))) return rc;
+    if ((rc = trace_queue_closest(p.bvh, p.wsc, st))) return rc;
+    return foreach_item<BounceParams, bounce_first_resolve_px, 256>(p, n, st);
 }
 
 int mirres_bounce_shade(const void *packed_nodes, const void *packed_tris, unsigned int frame_index,
@@ -460,17 +516,24 @@ int mirres_bounce_shade(const void *packed_nodes, const void *packed_tris, unsig
                         const float *occ, const float *pos_map, const float *normal, const float *ray_dir, float *prd,
                         const float *diffuse_map, const float *rough_metal, float *color, float *diff_color,
                         float *spec_color, float *new_pos, float *new_ray_d, float *new_occ, float *new_normal,
-                        void *stream)
+                        void *workspace, size_t workspace_bytes, void *stream)
 {
     if (!env_tex || !pdf_ || !cdf_ || !mpdf_ || !mcdf_ || !color || !diff_color || !spec_color) return MIRRES_ERR_NULL;
     if (env_w < 1 || env_h < 1) return MIRRES_ERR_SHAPE;
     BounceParams p = {};
     int rc = fill_bounce(p, packed_nodes, packed_tris, frame_index, bounce_count, max_bounce, fx, fy, occ, pos_map, normal,
-                         ray_dir, prd, diffuse_map, rough_metal, new_pos, new_ray_d, new_occ, new_normal);
+                         ray_dir, prd, diffuse_map, rough_metal, new_pos, new_ray_d, new_occ, new_normal, workspace,
+                         workspace_bytes);
     if (rc) return rc;
     p.env = {env_tex, env_w, env_h, pdf_, cdf_, mpdf_, mcdf_};
     p.color = color; p.diff_color = diff_color; p.spec_color = spec_color;
-    return foreach_item<BounceParams, bounce_shade_px, 128>(p, fx * fy, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = fx * fy;
+    if ((rc = foreach_item<BounceParams, bounce_prologue_px, 256>(p, n, st))) return rc;
+    if ((rc = foreach_item<BounceParams, bounce_shade_gen_px, 128>(p, n, st))) return rc;
+    if ((rc = trace_queue_any(p.bvh, p.ws, 2, device_sm_count(), st))) return rc;
+    if ((rc = trace_queue_closest(p.bvh, p.wsc, st))) return rc;
+    return foreach_item<BounceParams, bounce_shade_resolve_px, 256>(p, n, st);
 }
 
 } // extern "C"

@@ -140,42 +140,54 @@ class Kernels:
                                          self._f(light_data), self._i(light_uv), self._f(light_pdf), self._stream())
         self._check(rc, "mirres_light_tiles")
 
+    # -- wavefront workspace -----------------------------------------------------------------------------------
+    def workspace_bytes(self, n_pixels):
+        return self.lib.mirres_workspace_bytes(int(n_pixels))
+
+    def workspace_prepare(self, occ, ws):
+        rc = self.lib.mirres_workspace_prepare(self._f(occ), occ.shape[0], self._p(ws, torch.uint8), ws.numel(),
+                                               self._stream())
+        self._check(rc, "mirres_workspace_prepare")
+
+    def _ws(self, ws):
+        return (self._p(ws, torch.uint8), ws.numel())
+
     # -- ReSTIR ------------------------------------------------------------------------------------------------
     def _res(self, r):
         return (self._f(r[0]), self._f(r[1]), self._i(r[2]), self._f(r[3]))
 
     def initial_resampling(self, packed, pos_map, res, env_tex, W, H, fx, fy, frame_index, occ, normal_depth, brdf_map,
-                           ray_dir, pdf_, mpdf_, light_data, light_pdf, tile_count=128, tile_size=1024, screen_tile=8,
+                           ray_dir, pdf_, mpdf_, light_data, light_pdf, ws, tile_count=128, tile_size=1024, screen_tile=8,
                            n_light=32, n_brdf=1):
         rc = self.lib.mirres_initial_resampling(self._p(packed[0]), self._p(packed[1]), self._f(pos_map), *self._res(res),
                                                 self._f(env_tex), W, H, fx, fy, self._u32(frame_index), self._f(occ),
                                                 self._f(normal_depth), self._f(brdf_map), self._f(ray_dir), self._f(pdf_),
                                                 self._f(mpdf_), self._f(light_data), self._f(light_pdf), tile_count,
-                                                tile_size, screen_tile, n_light, n_brdf, self._stream())
+                                                tile_size, screen_tile, n_light, n_brdf, *self._ws(ws), self._stream())
         self._check(rc, "mirres_initial_resampling")
 
     def temporal_resampling(self, res, prev, env_tex, W, H, fx, fy, frame_index, occ, normal_depth, brdf_map, ray_dir,
-                            prev_occ, prev_normal_depth, prev_brdf_map, prev_ray_dir, motion=None, max_history=20):
+                            prev_occ, prev_normal_depth, prev_brdf_map, prev_ray_dir, ws, motion=None, max_history=20):
         rc = self.lib.mirres_temporal_resampling(*self._res(res), *self._res(prev), self._f(env_tex), W, H, fx, fy,
                                                  self._u32(frame_index), self._f(occ), self._f(normal_depth),
                                                  self._f(brdf_map), self._f(ray_dir), self._f(prev_occ),
                                                  self._f(prev_normal_depth), self._f(prev_brdf_map),
                                                  self._f(prev_ray_dir), self._f(motion, True), max_history,
-                                                 self._stream())
+                                                 *self._ws(ws), self._stream())
         self._check(rc, "mirres_temporal_resampling")
 
     def spatial_resampling(self, packed, pos_map, res, prev, neighbor_offsets, env_tex, W, H, fx, fy, frame_index, occ,
-                           normal_depth, brdf_map, ray_dir, offset_count=8192, neighbor_count=5, gather_radius=30.0):
+                           normal_depth, brdf_map, ray_dir, ws, offset_count=8192, neighbor_count=5, gather_radius=30.0):
         rc = self.lib.mirres_spatial_resampling(self._p(packed[0]), self._p(packed[1]), self._f(pos_map), *self._res(res),
                                                 *self._res(prev), self._f(neighbor_offsets), self._f(env_tex), W, H, fx,
                                                 fy, self._u32(frame_index), self._f(occ), self._f(normal_depth),
                                                 self._f(brdf_map), self._f(ray_dir), offset_count, neighbor_count,
-                                                float(gather_radius), self._stream())
+                                                float(gather_radius), *self._ws(ws), self._stream())
         self._check(rc, "mirres_spatial_resampling")
 
-    def final_visibility(self, packed, res_ld, fx, fy, pos_map, vis_map):
+    def final_visibility(self, packed, res_ld, fx, fy, pos_map, vis_map, ws):
         rc = self.lib.mirres_final_visibility(self._p(packed[0]), self._p(packed[1]), self._f(res_ld), fx, fy,
-                                              self._f(pos_map), self._f(vis_map), self._stream())
+                                              self._f(pos_map), self._f(vis_map), *self._ws(ws), self._stream())
         self._check(rc, "mirres_final_visibility")
 
     def eval_final_fwd(self, res, env_tex, W, H, fx, fy, fs_dir, fs_dist, fs_Li, vis_map):
@@ -206,24 +218,24 @@ class Kernels:
         self._check(rc, "mirres_final_shading_bwd")
 
     def bounce_first(self, packed, frame_index, bounce_count, max_bounce, fx, fy, occ, pos_map, normal, ray_dir, prd,
-                     diffuse, rough_metal, new_pos, new_ray_d, new_occ, new_normal):
+                     diffuse, rough_metal, new_pos, new_ray_d, new_occ, new_normal, ws):
         rc = self.lib.mirres_bounce_first(self._p(packed[0]), self._p(packed[1]), self._u32(frame_index),
                                           self._u32(bounce_count), max_bounce, fx, fy, self._f(occ), self._f(pos_map),
                                           self._f(normal), self._f(ray_dir), self._f(prd), self._f(diffuse),
                                           self._f(rough_metal), self._f(new_pos), self._f(new_ray_d), self._f(new_occ),
-                                          self._f(new_normal), self._stream())
+                                          self._f(new_normal), *self._ws(ws), self._stream())
         self._check(rc, "mirres_bounce_first")
 
     def bounce_shade(self, packed, frame_index, bounce_count, max_bounce, fx, fy, env_tex, W, H, dist, occ, pos_map,
                      normal, ray_dir, prd, diffuse, rough_metal, color, diff_color, spec_color, new_pos, new_ray_d,
-                     new_occ, new_normal):
+                     new_occ, new_normal, ws):
         rc = self.lib.mirres_bounce_shade(self._p(packed[0]), self._p(packed[1]), self._u32(frame_index),
                                           self._u32(bounce_count), max_bounce, fx, fy, self._f(env_tex), W, H,
                                           self._f(dist[0]), self._f(dist[1]), self._f(dist[2]), self._f(dist[3]),
                                           self._f(occ), self._f(pos_map), self._f(normal), self._f(ray_dir), self._f(prd),
                                           self._f(diffuse), self._f(rough_metal), self._f(color), self._f(diff_color),
                                           self._f(spec_color), self._f(new_pos), self._f(new_ray_d), self._f(new_occ),
-                                          self._f(new_normal), self._stream())
+                                          self._f(new_normal), *self._ws(ws), self._stream())
         self._check(rc, "mirres_bounce_shade")
 
     # -- denoiser ----------------------------------------------------------------------------------------------

@@ -34,6 +34,7 @@ def set_kernels(k):
     """Test hook: lets the CPU test-suite bind the host-check flavour of the same kernels."""
     global _KERNELS
     _KERNELS = k
+    _WORKSPACES.clear()
 
 
 def _c(t):
@@ -79,6 +80,22 @@ def packed_bvh(info, aabb, vert, tri):
     k.bvh_pack(_c(info), _c(aabb), _c(vert), _c(tri), nodes, tris)
     info._mirres_packed = (nodes, tris)
     return info._mirres_packed
+
+
+_WORKSPACES = {}
+
+
+def workspace(device, n_pixels):
+    """Wavefront workspace (include/mirres_b200.h) for frames of n_pixels on `device`, allocated once and reused."""
+    key = (str(device), int(n_pixels))
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        nbytes = get_kernels().workspace_bytes(n_pixels)
+        buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        off = (-buf.data_ptr()) % 256  # CUDA allocations are already 512-byte aligned; host ones are not
+        ws = buf[off:off + nbytes]
+        _WORKSPACES[key] = ws
+    return ws
 
 
 class _Launch:
@@ -159,10 +176,14 @@ def _GenerateLightTiles(m, env_tex, pdf_, cdf_, mpdf_, mcdf_, width, height, fra
 def _InitialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reservoirs, env_tex, env_width, env_height,
                        framedim_x, framedim_y, frameIndex, occ_map, normal_depth, brdf_map, ray_dir, pdf_, cdf_, mpdf_,
                        mcdf_, light_data, light_uv, light_inv_pdf):
+    # first kernel of every spp iteration that sees the primary occupancy: (re)build the foreground-pixel list here
+    occ = _c(occ_map)
+    ws = workspace(occ.device, occ.shape[0])
+    get_kernels().workspace_prepare(occ, ws)
     get_kernels().initial_resampling(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), _c(pos_map),
                                      _reservoir(reservoirs), _c(env_tex), int(env_width), int(env_height),
-                                     int(framedim_x), int(framedim_y), int(frameIndex), _c(occ_map), _c(normal_depth),
-                                     _c(brdf_map), _c(ray_dir), pdf_, mpdf_, light_data, light_inv_pdf,
+                                     int(framedim_x), int(framedim_y), int(frameIndex), occ, _c(normal_depth),
+                                     _c(brdf_map), _c(ray_dir), pdf_, mpdf_, light_data, light_inv_pdf, ws,
                                      m.define("LIGHT_TILE_COUNT", 128), m.define("LIGHT_TILE_SIZE", 1024),
                                      m.define("SCREEN_TILE_SIZE", 8), m.define("INITIAL_LIGHT_SAMPLE_COUNT", 32),
                                      m.define("INITIAL_BRDF_SAMPLE_COUNT", 1))
@@ -175,6 +196,7 @@ def _TemporalResampling(m, reservoirs, prevReservoirs, env_tex, env_width, env_h
                                       int(env_height), int(framedim_x), int(framedim_y), int(frameIndex), _c(occ_map),
                                       _c(normal_depth), _c(brdf_map), _c(ray_dir), _c(prev_occ_map),
                                       _c(prev_normal_depth), _c(prev_brdf_map), _c(prev_ray_dir),
+                                      workspace(occ_map.device, occ_map.shape[0]),
                                       None if motionVectors is None else _c(motionVectors),
                                       m.define("MAX_HISTORY_LENGTH", 20))
 
@@ -186,13 +208,14 @@ def _SpatialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reser
                                      _reservoir(reservoirs), _reservoir(prevReservoirs), _c(neighborOffsets),
                                      _c(env_tex), int(env_width), int(env_height), int(framedim_x), int(framedim_y),
                                      int(frameIndex), _c(occ_map), _c(normal_depth), _c(brdf_map), _c(ray_dir),
-                                     m.define("NEIGHBOR_OFFSET_COUNT", 8192), m.define("NEIGHBOR_COUNT", 5),
+                                     workspace(occ_map.device, occ_map.shape[0]), m.define("NEIGHBOR_OFFSET_COUNT", 8192), m.define("NEIGHBOR_COUNT", 5),
                                      float(m.define("GATHER_RADIUS", 30)))
 
 
 def _get_vis(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, reservoirs, framedim_x, framedim_y, pos_map, vis_map):
     get_kernels().final_visibility(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), _reservoir(reservoirs)[0],
-                                   int(framedim_x), int(framedim_y), _c(pos_map), vis_map)
+                                   int(framedim_x), int(framedim_y), _c(pos_map), vis_map,
+                                   workspace(vis_map.device, vis_map.shape[0]))
 
 
 def _eval_final_fwd(m, reservoirs, env_tex, env_width, env_height, framedim_x, framedim_y, finalSample, vis_map):
@@ -232,7 +255,7 @@ def _new_dir(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, frameIndex, bounce_count
     get_kernels().bounce_first(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), int(frameIndex), int(bounce_count),
                                m.define("MAX_Bounce", 2), int(framedim_x), int(framedim_y), _c(occ_map), _c(pos_map),
                                _c(normal), _c(ray_dir), prd, _c(diffuse_map), _c(linearRoughness_specular_map),
-                               new_pos_map, new_ray_d, new_occ_map, new_normal)
+                               new_pos_map, new_ray_d, new_occ_map, new_normal, workspace(prd.device, prd.shape[0]))
 
 
 def _path_tracing(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, frameIndex, bounce_count, framedim_x, framedim_y, env_tex,
@@ -243,7 +266,8 @@ def _path_tracing(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, frameIndex, bounce_
                                m.define("MAX_Bounce", 2), int(framedim_x), int(framedim_y), _c(env_tex), int(env_width),
                                int(env_height), (pdf_, cdf_, mpdf_, mcdf_), _c(occ_map), _c(pos_map), _c(normal),
                                _c(ray_dir), prd, _c(diffuse_map), _c(linearRoughness_specular_map), color, diff_color,
-                               spec_color, new_pos_map, new_ray_d, new_occ_map, new_normal)
+                               spec_color, new_pos_map, new_ray_d, new_occ_map, new_normal,
+                               workspace(prd.device, prd.shape[0]))
 
 
 def _phi(PHI):

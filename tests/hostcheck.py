@@ -24,6 +24,7 @@ _MISSING = ("mirres_abi_version", "mirres_bvh_build", "mirres_bvh_elements", "mi
             "mirres_bvh_packed_tri_bytes")
 
 
+
 class HostKernels(_kernels.Kernels):
     def __init__(self):
         path = _build.build_hostcheck()

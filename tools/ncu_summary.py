@@ -1,0 +1,51 @@
+"""Summarise an .ncu-rep (read here, no GPU needed): key metrics of the first kernel in the report.
+
+    python tools/ncu_summary.py gpurun_out/prof_spatial_px.ncu-rep [out.txt]
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+    "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
+    "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "sm__inst_executed_pipe_fp64.sum",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.sum",
+]
+
+
+def main(path, out=None):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    lines = ["# %s" % path, "kernel: %s" % vals[hdr.index("Kernel Name")][:120]]
+    for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            lines.append("%-80s %s %s" % (k, vals[i], units[i]))
+    # anything with 'stalled' and a notable value
+    text = "\n".join(lines)
+    print(text)
+    if out:
+        open(out, "w").write(text + "\n")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
