@@ -89,6 +89,9 @@ int mirres_trace_any(const void *packed_nodes, const void *packed_tris, const fl
  *       out [2*sample_count] raw int8-range values (the host divides by 127).
  *   mirres_light_tiles  process_GenerateLightTiles, GenerateLightTiles.slang:16-62 (GenerateLightTiles.py:42-50):
  *       light_data [T,3] (valid, oct.u, oct.v), light_uv [T,2] i32, light_pdf [T] (the reference names it light_inv_pdf).
+ *       light_cache (optional, [T,8] f32, 16-byte aligned): world direction and emitted radiance of every slot, i.e.
+ *       what get_light_info (lightDi.slang:291-298) returns for it; mirres_initial_resampling reads it instead of
+ *       re-deriving both for each of the 32 candidates of every pixel (identical values, computed once per slot).
  */
 int mirres_env_build_distribution(const float *env_tex, int W, int H, float *pdf_, float *cdf_, float *mpdf_,
                                   float *mcdf_, float *row_scratch, void *stream);
@@ -97,7 +100,7 @@ int mirres_env_distribution2d(int W, int H, float *pdf_, float *cdf_, void *stre
 int mirres_neighbor_offsets(int sample_count, float *out, void *stream);
 int mirres_light_tiles(const float *env_tex, int W, int H, const float *pdf_, const float *cdf_, const float *mpdf_,
                        const float *mcdf_, unsigned int frame_index, int tile_count, int tile_size, float *light_data,
-                       int *light_uv, float *light_pdf, void *stream);
+                       int *light_uv, float *light_pdf, float *light_cache, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Wavefront workspace.  Every ray-casting entry point below runs as  gen (one thread per foreground pixel) ->
@@ -127,8 +130,9 @@ int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris,
                               float *res_pdf, int *res_M, float *res_w, const float *env_tex, int env_w, int env_h,
                               int fx, int fy, unsigned int frame_index, const float *occ, const float *normal_depth,
                               const float *brdf_map, const float *ray_dir, const float *pdf_, const float *mpdf_,
-                              const float *light_data, const float *light_pdf, int tile_count, int tile_size,
-                              int screen_tile, int n_light, int n_brdf, void *workspace, size_t workspace_bytes, void *stream);
+                              const float *light_data, const float *light_pdf, const float *light_cache,
+                              int tile_count, int tile_size, int screen_tile, int n_light, int n_brdf, void *workspace,
+                              size_t workspace_bytes, void *stream);
 int mirres_temporal_resampling(float *res_ld, float *res_pdf, int *res_M, float *res_w, const float *prev_ld,
                                const float *prev_pdf, const int *prev_M, const float *prev_w, const float *env_tex,
                                int env_w, int env_h, int fx, int fy, unsigned int frame_index, const float *occ,

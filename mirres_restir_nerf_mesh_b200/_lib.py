@@ -29,9 +29,9 @@ SIGNATURES = {
     "mirres_env_weights": "piipp",
     "mirres_env_distribution2d": "iippp",
     "mirres_neighbor_offsets": "ipp",
-    "mirres_light_tiles": "piippppuiipppp",
+    "mirres_light_tiles": "piippppuiippppp",
     "mirres_workspace_prepare": "pipzp",
-    "mirres_initial_resampling": "ppp" + "pppp" + "pii" + "iiu" + "pppp" + "pp" + "pp" + "iiiii" + "pz" + "p",
+    "mirres_initial_resampling": "ppp" + "pppp" + "pii" + "iiu" + "pppp" + "pp" + "ppp" + "iiiii" + "pz" + "p",
     "mirres_temporal_resampling": "pppp" + "pppp" + "pii" + "iiu" + "pppp" + "pppp" + "p" + "i" + "pz" + "p",
     "mirres_spatial_resampling": "ppp" + "pppp" + "pppp" + "p" + "pii" + "iiu" + "pppp" + "iif" + "pz" + "p",
     "mirres_final_visibility": "pppiipp" + "pz" + "p",

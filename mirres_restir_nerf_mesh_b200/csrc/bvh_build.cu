@@ -134,41 +134,29 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const unsigned int *
     hist[threadIdx.x * num_blocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of hist[256*num_blocks] in place (bin-major), single block of 1024 threads
-__global__ void __launch_bounds__(1024) k_sort_scan(unsigned int *hist, int total)
+// exclusive scan of hist[256][num_blocks] in place (bin-major order): thread b walks the row of bin b, the 256 row
+// totals are scanned in shared memory, then every row is shifted by the total of the bins before it
+__global__ void __launch_bounds__(256) k_sort_scan(unsigned int *hist, int num_blocks)
 {
-    __shared__ unsigned int warp_sums[32];
-    __shared__ unsigned int carry;
-    if (threadIdx.x == 0) carry = 0;
+    __shared__ unsigned int totals[256];
+    unsigned int *row = hist + (size_t)threadIdx.x * num_blocks;
+    unsigned int acc = 0;
+    for (int i = 0; i < num_blocks; ++i) {
+        unsigned int v = row[i];
+        row[i] = acc;
+        acc += v;
+    }
+    totals[threadIdx.x] = acc;
     __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < total; base += 1024) {
-        int i = base + threadIdx.x;
-        unsigned int v = i < total ? hist[i] : 0u;
-        unsigned int x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) warp_sums[wid] = x;
+    // inclusive Hillis-Steele scan over 256 totals
+    for (int o = 1; o < 256; o <<= 1) {
+        unsigned int y = threadIdx.x >= (unsigned int)o ? totals[threadIdx.x - o] : 0u;
         __syncthreads();
-        if (wid == 0) {
-            unsigned int w = warp_sums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned int y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            warp_sums[lane] = w;
-        }
-        __syncthreads();
-        unsigned int prefix = carry + (wid > 0 ? warp_sums[wid - 1] : 0u) + x - v;
-        if (i < total) hist[i] = prefix;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = prefix + v;
+        totals[threadIdx.x] += y;
         __syncthreads();
     }
+    const unsigned int base = threadIdx.x > 0 ? totals[threadIdx.x - 1] : 0u;
+    for (int i = 0; i < num_blocks; ++i) row[i] += base;
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const unsigned int *__restrict__ keys_in,
@@ -343,7 +331,7 @@ static int sort_pairs(BuildScratch &s, int F, cudaStream_t st)
     for (int pass = 0; pass < 4; ++pass) {
         int in = pass & 1, out = in ^ 1;
         k_sort_hist<<<s.num_blocks, SORT_THREADS, 0, st>>>(s.keys[in], F, 8 * pass, s.hist, s.num_blocks);
-        k_sort_scan<<<1, 1024, 0, st>>>(s.hist, 256 * s.num_blocks);
+        k_sort_scan<<<1, 256, 0, st>>>(s.hist, s.num_blocks);
         k_sort_scatter<<<s.num_blocks, SORT_THREADS, 0, st>>>(s.keys[in], s.vals[in], F, 8 * pass, s.hist, s.num_blocks,
                                                              s.keys[out], s.vals[out]);
     }

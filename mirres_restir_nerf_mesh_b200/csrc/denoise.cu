@@ -105,6 +105,8 @@ MR_DEV void eaw_bwd_px(const EawParams &p, int idx)
         const int ux = px + (i % 5 - 2) * p.step, uy = py + (i / 5 - 2) * p.step;
         if (!(ux >= 0 && ux < p.fx && uy >= 0 && uy < p.fy)) continue;
         const size_t r = (size_t)uy * p.fx + ux;
+        const bool r_center = !(MR_LDG(p.occ + r) < 0.1f);
+        if (!q_center && !r_center) continue; // neither footprint exists: nothing flows between q and r
         const float3 cr = load3(p.color, r), nr = load3(p.normal, r), pr = load3(p.pos, r);
         const float w = edge_weight(cq, cr, p.c_phi, false) * edge_weight(nq, nr, p.n_phi, true) * edge_weight(pq, pr, p.p_phi, true);
         const float k = eaw_kernel(i);
@@ -117,7 +119,7 @@ MR_DEV void eaw_bwd_px(const EawParams &p, int idx)
             gn += dn * (s / p.n_phi);
             gp += dp * (s / p.p_phi);
         }
-        if (!(MR_LDG(p.occ + r) < 0.1f)) {
+        if (r_center) {
             // r is the centre, q its tap (kernel and weight are symmetric)
             const float3 gr = load3(p.g_out, r), orr = load3(p.out_color, r);
             const float Wr = p.cum_w[r];

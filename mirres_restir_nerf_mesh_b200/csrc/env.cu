@@ -171,6 +171,7 @@ struct TileParams {
     float *__restrict__ light_data;
     int *__restrict__ light_uv;
     float *__restrict__ light_pdf;
+    float4 *__restrict__ cache; // optional [T,2]: world direction and emitted radiance of every slot
 };
 MR_DEV void light_tile_px(const TileParams &p, int b)
 {
@@ -200,6 +201,13 @@ MR_DEV void light_tile_px(const TileParams &p, int b)
     light_uv[2 * (size_t)b] = xy.x;
     light_uv[2 * (size_t)b + 1] = xy.y;
     light_pdf[b] = ip;
+    if (p.cache) {
+        // what every pixel that draws this slot would compute from it (InitialResampling.slang:208-209)
+        float3 Le, L;
+        light_of(e, ld.y, ld.z, Le, L);
+        p.cache[2 * (size_t)b] = make_float4(L.x, L.y, L.z, 0.f);
+        p.cache[2 * (size_t)b + 1] = make_float4(Le.x, Le.y, Le.z, 0.f);
+    }
 }
 
 } // namespace mr
@@ -256,11 +264,12 @@ int mirres_neighbor_offsets(int sample_count, float *out, void *stream)
 
 int mirres_light_tiles(const float *env_tex, int W, int H, const float *pdf_, const float *cdf_, const float *mpdf_,
                        const float *mcdf_, unsigned int frame_index, int tile_count, int tile_size, float *light_data,
-                       int *light_uv, float *light_pdf, void *stream)
+                       int *light_uv, float *light_pdf, float *light_cache, void *stream)
 {
     if (!env_tex || !pdf_ || !cdf_ || !mpdf_ || !mcdf_ || !light_data || !light_uv || !light_pdf) return MIRRES_ERR_NULL;
     if (W < 1 || H < 1 || tile_count < 1 || tile_size < 1) return MIRRES_ERR_SHAPE;
-    TileParams p = {{env_tex, W, H, pdf_, cdf_, mpdf_, mcdf_}, frame_index, light_data, light_uv, light_pdf};
+    if ((uintptr_t)light_cache & 15) return MIRRES_ERR_ALIGN;
+    TileParams p = {{env_tex, W, H, pdf_, cdf_, mpdf_, mcdf_}, frame_index, light_data, light_uv, light_pdf, (float4 *)light_cache};
     return foreach_item<TileParams, light_tile_px, 256>(p, tile_count * tile_size, (cudaStream_t)stream);
 }
 

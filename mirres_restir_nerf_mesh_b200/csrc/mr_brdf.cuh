@@ -111,6 +111,11 @@ struct RisSurface {
     float alpha;       // brdf_map.z  (clamped roughness squared)
     float kd_w, ks_w;  // brdf_map.x, brdf_map.y
     float mix;         // kd_w / (kd_w + ks_w) or 1
+    // per-surface terms the reference re-derives for every candidate; hoisted here (same operations, same values)
+    Basis basis;       // perp_stark frame of N
+    float3 Vlocal;     // V in that frame
+    float NdotV;       // saturate(N.V)
+    float lambdaV;     // Smith lambda of the view direction
 };
 MR_DEV RisSurface ris_surface(float3 N, float3 ray_dir, float3 brdf)
 {
@@ -122,18 +127,22 @@ MR_DEV RisSurface ris_surface(float3 N, float3 ray_dir, float3 brdf)
     s.ks_w = brdf.y;
     float sum = brdf.x + brdf.y;
     s.mix = sum > 1e-7f ? (brdf.x / sum) : 1.f;
+    s.basis = basis_of(N);
+    s.Vlocal = to_local(s.basis, s.V);
+    s.NdotV = saturate(dot(N, s.V));
+    s.lambdaV = ggx_lambda(s.alpha * s.alpha, s.NdotV);
     return s;
 }
 MR_DEV float ris_brdf(const RisSurface &s, float3 L)
 {
     const float INV_PI = 0.31830988f;
-    float NdotV = saturate(dot(s.N, s.V));
+    const float NdotV = s.NdotV;
     float NdotL = saturate(dot(s.N, L));
     float3 H = normalize(s.V + L);
     float NdotH = saturate(dot(s.N, H));
     float LdotH = saturate(dot(L, H));
     float D = ggx_ndf(s.alpha, NdotH);
-    float G = smith_separable(s.alpha, NdotV, NdotL);
+    float G = 1 / ((1 + s.lambdaV) * (1 + ggx_lambda(s.alpha * s.alpha, NdotL))); // separable Smith
     float F = s.ks_w < 1e-8f ? 0.f : schlick(s.ks_w, 1.f, LdotH) / s.ks_w;
     float diffuse = NdotL * INV_PI;
     float specular = fmaxf(0.f, D * G * F / (4.f * NdotV));
@@ -147,15 +156,14 @@ MR_DEV float ris_brdf_pdf(const RisSurface &s, float3 dir)
     const float INV_PI = 0.31830988f;
     float cosTheta = saturate(dot(s.N, dir));
     float diffusePdf = cosTheta * INV_PI;
-    Basis b = basis_of(s.N);
-    float3 h = normalize(to_local(b, dir + s.V));
-    float specularPdf = ggx_ndf_pdf(s.alpha, h.z) / (4.f * saturate(dot(h, to_local(b, s.V))));
+    float3 h = normalize(to_local(s.basis, dir + s.V));
+    float specularPdf = ggx_ndf_pdf(s.alpha, h.z) / (4.f * saturate(dot(h, s.Vlocal)));
     return cosTheta > 0.f ? lerpf(specularPdf, diffusePdf, s.mix) : 0.f;
 }
 MR_DEV bool ris_brdf_sample(const RisSurface &s, float x0, float x1, float x2, float3 &dir)
 {
     float pdf;
-    Basis b = basis_of(s.N);
+    const Basis &b = s.basis;
     if (x0 < s.mix) {
         dir = to_global(b, cosine_hemisphere(x1, x2, pdf));
     } else {

@@ -89,7 +89,7 @@ MR_DEV void queue_closest_item(const QueueTraceParams &p, int slot)
 
 // queue tracers and device query: defined once, in wave.cu
 int trace_queue_any(const BvhView &bvh, const Workspace &ws, int rays_per_item, int sm_count, cudaStream_t st);
-int trace_queue_closest(const BvhView &bvh, const Workspace &ws, cudaStream_t st);
+int trace_queue_closest(const BvhView &bvh, const Workspace &ws, int sm_count, cudaStream_t st);
 int device_sm_count();
 
 } // namespace mr

@@ -111,6 +111,7 @@ struct InitialParams {
     ResView res;
     const float *__restrict__ light_data;
     const float *__restrict__ light_pdf;
+    const float4 *__restrict__ light_cache; // optional (direction, radiance) per tile slot, see mirres_light_tiles
     int fx, fy;
     unsigned int frame;
     unsigned int tile_count, tile_size, screen_tile, n_light, n_brdf;
@@ -143,7 +144,13 @@ MR_DEV void initial_gen_px(const InitialParams &p, int a)
         const float3 cand = load3(p.light_data, slot);
         const float cand_pdf = MR_LDG(p.light_pdf + slot);
         float3 Le, L;
-        light_of(p.env, cand.y, cand.z, Le, L);
+        if (p.light_cache) {
+            const float4 c0 = MR_LDG(p.light_cache + 2 * (size_t)slot), c1 = MR_LDG(p.light_cache + 2 * (size_t)slot + 1);
+            L = make_float3(c0.x, c0.y, c0.z);
+            Le = make_float3(c1.x, c1.y, c1.z);
+        } else {
+            light_of(p.env, cand.y, cand.z, Le, L);
+        }
         float targetPdf = target_pdf(surf, Le, L);
         float sourcePdf = lerpf(cand_pdf, ris_brdf_pdf(surf, L), ratio);
         float sampleWeight = targetPdf / sourcePdf;
@@ -560,15 +567,16 @@ int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris,
                               float *res_pdf, int *res_M, float *res_w, const float *env_tex, int env_w, int env_h,
                               int fx, int fy, unsigned int frame_index, const float *occ, const float *normal_depth,
                               const float *brdf_map, const float *ray_dir, const float *pdf_, const float *mpdf_,
-                              const float *light_data, const float *light_pdf, int tile_count, int tile_size,
-                              int screen_tile, int n_light, int n_brdf, MR_WS_ARGS, void *stream)
+                              const float *light_data, const float *light_pdf, const float *light_cache,
+                              int tile_count, int tile_size, int screen_tile, int n_light, int n_brdf, MR_WS_ARGS,
+                              void *stream)
 {
     if (!packed_nodes || !packed_tris || !pos_map || !res_ld || !res_pdf || !res_M || !res_w || !env_tex || !occ ||
         !normal_depth || !brdf_map || !ray_dir || !pdf_ || !mpdf_ || !light_data || !light_pdf)
         return MIRRES_ERR_NULL;
     if (fx < 1 || fy < 1 || env_w < 1 || env_h < 1 || tile_count < 1 || tile_size < 1 || screen_tile < 1 || n_light < 1 || n_brdf < 0)
         return MIRRES_ERR_SHAPE;
-    if ((uintptr_t)normal_depth & 15) return MIRRES_ERR_ALIGN;
+    if (((uintptr_t)normal_depth & 15) || ((uintptr_t)light_cache & 15)) return MIRRES_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const int n = fx * fy;
     InitialParams p;
@@ -581,6 +589,7 @@ int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris,
     p.res = {res_ld, res_pdf, res_M, res_w};
     p.light_data = light_data;
     p.light_pdf = light_pdf;
+    p.light_cache = (const float4 *)light_cache;
     p.fx = fx; p.fy = fy; p.frame = frame_index;
     p.tile_count = tile_count; p.tile_size = tile_size; p.screen_tile = screen_tile; p.n_light = n_light; p.n_brdf = n_brdf;
     res_zero_all(p.res, n, st); // background pixels (InitialResampling.slang:166-176)

@@ -506,7 +506,7 @@ int mirres_bounce_first(const void *packed_nodes, const void *packed_tris, unsig
     const int n = fx * fy;
     if ((rc = foreach_item<BounceParams, bounce_prologue_px, 256>(p, n, st))) return rc;
     if ((rc = foreach_item<BounceParams, bounce_first_gen_px, 128>(p, n, st))) return rc;
-    if ((rc = trace_queue_closest(p.bvh, p.wsc, st))) return rc;
+    if ((rc = trace_queue_closest(p.bvh, p.wsc, device_sm_count(), st))) return rc;
     return foreach_item<BounceParams, bounce_first_resolve_px, 256>(p, n, st);
 }
 
@@ -532,7 +532,7 @@ int mirres_bounce_shade(const void *packed_nodes, const void *packed_tris, unsig
     if ((rc = foreach_item<BounceParams, bounce_prologue_px, 256>(p, n, st))) return rc;
     if ((rc = foreach_item<BounceParams, bounce_shade_gen_px, 128>(p, n, st))) return rc;
     if ((rc = trace_queue_any(p.bvh, p.ws, 2, device_sm_count(), st))) return rc;
-    if ((rc = trace_queue_closest(p.bvh, p.wsc, st))) return rc;
+    if ((rc = trace_queue_closest(p.bvh, p.wsc, device_sm_count(), st))) return rc;
     return foreach_item<BounceParams, bounce_shade_resolve_px, 256>(p, n, st);
 }
 

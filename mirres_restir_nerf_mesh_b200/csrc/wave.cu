@@ -211,10 +211,139 @@ int trace_queue_any(const BvhView &bvh, const Workspace &ws, int rays_per_item, 
 #endif
 }
 
-int trace_queue_closest(const BvhView &bvh, const Workspace &ws, cudaStream_t st)
+#if !defined(MR_HOST_CHECK)
+// ---- persistent closest-hit tracer: same refill scheme, reference visit order (see closest_hit in mr_bvh.cuh) --------
+__global__ void __launch_bounds__(MR_TRACE_BLOCK) k_trace_closest_persistent(BvhView bvh, Workspace ws)
 {
+    const unsigned int FULL = 0xffffffffu;
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const int total = ws.counters[0];
+    int *work = ws.counters + 1;
+    int stack_ref[MR_STACK];
+    float stack_t[MR_STACK];
+    int sp = 0, cur = 0, slot = -1, best_slot = -1;
+    float closest = 1e7f;
+    bool any = false, have = false, exhausted = false;
+    Ray r;
+    r.o = r.d = r.inv = f3(0.f);
+    for (;;) {
+        const unsigned int need = __ballot_sync(FULL, !have);
+        if (need != 0u && !exhausted) {
+            const int n_need = __popc(need);
+            const int leader = __ffs(need) - 1;
+            int base = 0;
+            if ((int)lane == leader) base = atomicAdd(work, n_need);
+            base = __shfl_sync(FULL, base, leader);
+            if (!have) {
+                const int s = base + __popc(need & lt_mask);
+                if (s < total) {
+                    const float4 o = __ldg(ws.ray_o + s);
+                    if (o.w != 0.0f) {
+                        const float4 d = __ldg(ws.ray_d + s);
+                        r = make_ray(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z));
+                        slot = s;
+                        sp = 0;
+                        cur = 0;
+                        closest = 1e7f;
+                        any = false;
+                        best_slot = -1;
+                        have = true;
+                    }
+                }
+            }
+            if (base + n_need >= total) exhausted = true;
+        }
+        if (!__any_sync(FULL, have)) {
+            if (exhausted) break;
+            continue;
+        }
+#pragma unroll 1
+        for (int it = 0; it < MR_TRACE_STEPS; ++it) {
+            if (!have) break;
+            bool pop = false;
+            if (cur >= 0) {
+                const PackedNode *pn = bvh.nodes + cur;
+                const float4 a = __ldg(&pn->a), b = __ldg(&pn->b), c = __ldg(&pn->c);
+                const int4 d = __ldg(&pn->d);
+                float ln, lf, rn, rf;
+                slab(r, a.x, a.y, a.z, a.w, b.x, b.y, ln, lf);
+                slab(r, b.z, b.w, c.x, c.y, c.z, c.w, rn, rf);
+                const bool passL = fminf(closest, lf) > ln;
+                const bool passR = fminf(closest, rf) > rn;
+                if (passR) {
+                    cur = d.y;
+                    if (passL) {
+                        stack_ref[sp] = d.x;
+                        stack_t[sp] = ln;
+                        ++sp;
+                    }
+                } else if (passL) {
+                    cur = d.x;
+                } else {
+                    pop = true;
+                }
+            } else {
+                const int leaf = ~cur;
+                const float4 *tp = bvh.tris + 3 * (size_t)leaf;
+                float t, u, v;
+                if (tri_test(r, __ldg(tp), __ldg(tp + 1), __ldg(tp + 2), t, u, v)) {
+                    if (t <= closest) best_slot = leaf;
+                    closest = fminf(t, closest);
+                    any = true;
+                }
+                pop = true;
+            }
+            if (pop) {
+                bool found = false;
+                while (sp > 0) {
+                    --sp;
+                    if (closest > stack_t[sp]) {
+                        cur = stack_ref[sp];
+                        found = true;
+                        break;
+                    }
+                }
+                if (!found) {
+                    float3 pos = f3(0.f), n = f3(1.0f);
+                    if (any) {
+                        pos = r.o + closest * r.d;
+                        if (best_slot >= 0) {
+                            const float4 *tp = bvh.tris + 3 * (size_t)best_slot;
+                            const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+                            float t, u, v;
+                            tri_test(r, q0, q1, q2, t, u, v);
+                            const float3 fn = normalize(cross(make_float3(q1.x, q1.y, q1.z), make_float3(q2.x, q2.y, q2.z)));
+                            const float w = 1.0f - u - v;
+                            n = u * fn + v * fn + w * fn;
+                            if (dot(-r.d, n) < 0) n = -n;
+                            n = normalize(n);
+                        }
+                    }
+                    ws.chit[2 * (size_t)slot] = make_float4(pos.x, pos.y, pos.z, any ? 1.0f : 0.0f);
+                    ws.chit[2 * (size_t)slot + 1] = make_float4(n.x, n.y, n.z, any ? closest : 0.f);
+                    have = false;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+#endif
+
+int trace_queue_closest(const BvhView &bvh, const Workspace &ws, int sm_count, cudaStream_t st)
+{
+#if defined(MR_HOST_CHECK)
+    (void)sm_count;
     QueueTraceParams p = {bvh, ws, 1};
     return foreach_item<QueueTraceParams, queue_closest_item, 128>(p, ws.capacity, st);
+#else
+    cudaMemsetAsync(ws.counters + 1, 0, sizeof(int), st);
+    const int blocks = sm_count * (1024 / MR_TRACE_BLOCK);
+    k_trace_closest_persistent<<<blocks, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -100 - (int)e;
+#endif
 }
 
 int device_sm_count()

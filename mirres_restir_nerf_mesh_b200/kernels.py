@@ -134,10 +134,12 @@ class Kernels:
     def neighbor_offsets(self, count, out):
         self._check(self.lib.mirres_neighbor_offsets(count, self._f(out), self._stream()), "mirres_neighbor_offsets")
 
-    def light_tiles(self, env_tex, W, H, dist, frame_index, tile_count, tile_size, light_data, light_uv, light_pdf):
+    def light_tiles(self, env_tex, W, H, dist, frame_index, tile_count, tile_size, light_data, light_uv, light_pdf,
+                    light_cache=None):
         rc = self.lib.mirres_light_tiles(self._f(env_tex), W, H, self._f(dist[0]), self._f(dist[1]), self._f(dist[2]),
                                          self._f(dist[3]), self._u32(frame_index), tile_count, tile_size,
-                                         self._f(light_data), self._i(light_uv), self._f(light_pdf), self._stream())
+                                         self._f(light_data), self._i(light_uv), self._f(light_pdf), self._f(light_cache, True),
+                                         self._stream())
         self._check(rc, "mirres_light_tiles")
 
     # -- wavefront workspace -----------------------------------------------------------------------------------
@@ -158,11 +160,12 @@ class Kernels:
 
     def initial_resampling(self, packed, pos_map, res, env_tex, W, H, fx, fy, frame_index, occ, normal_depth, brdf_map,
                            ray_dir, pdf_, mpdf_, light_data, light_pdf, ws, tile_count=128, tile_size=1024, screen_tile=8,
-                           n_light=32, n_brdf=1):
+                           n_light=32, n_brdf=1, light_cache=None):
         rc = self.lib.mirres_initial_resampling(self._p(packed[0]), self._p(packed[1]), self._f(pos_map), *self._res(res),
                                                 self._f(env_tex), W, H, fx, fy, self._u32(frame_index), self._f(occ),
                                                 self._f(normal_depth), self._f(brdf_map), self._f(ray_dir), self._f(pdf_),
-                                                self._f(mpdf_), self._f(light_data), self._f(light_pdf), tile_count,
+                                                self._f(mpdf_), self._f(light_data), self._f(light_pdf),
+                                                self._f(light_cache, True), tile_count,
                                                 tile_size, screen_tile, n_light, n_brdf, *self._ws(ws), self._stream())
         self._check(rc, "mirres_initial_resampling")
 

@@ -168,9 +168,14 @@ def _createNeighborOffsetTexture(m, sampleCount, neighborOffsets):
 
 def _GenerateLightTiles(m, env_tex, pdf_, cdf_, mpdf_, mcdf_, width, height, frameIndex, light_data, light_uv,
                         light_inv_pdf, debug_out=None):
+    # per-slot (direction, radiance) cache, kept on the light_data tensor it describes; rewritten on every call
+    cache = getattr(light_data, "_mirres_cache", None)
+    if cache is None or cache.shape[0] != light_data.shape[0] or cache.device != light_data.device:
+        cache = torch.empty((light_data.shape[0], 8), dtype=torch.float32, device=light_data.device)
+        light_data._mirres_cache = cache
     get_kernels().light_tiles(_c(env_tex), int(width), int(height), (pdf_, cdf_, mpdf_, mcdf_), int(frameIndex),
                               m.define("LIGHT_TILE_COUNT", 128), m.define("LIGHT_TILE_SIZE", 1024), light_data, light_uv,
-                              light_inv_pdf)
+                              light_inv_pdf, cache)
 
 
 def _InitialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reservoirs, env_tex, env_width, env_height,
@@ -186,7 +191,8 @@ def _InitialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reser
                                      _c(brdf_map), _c(ray_dir), pdf_, mpdf_, light_data, light_inv_pdf, ws,
                                      m.define("LIGHT_TILE_COUNT", 128), m.define("LIGHT_TILE_SIZE", 1024),
                                      m.define("SCREEN_TILE_SIZE", 8), m.define("INITIAL_LIGHT_SAMPLE_COUNT", 32),
-                                     m.define("INITIAL_BRDF_SAMPLE_COUNT", 1))
+                                     m.define("INITIAL_BRDF_SAMPLE_COUNT", 1),
+                                     light_cache=getattr(light_data, "_mirres_cache", None))
 
 
 def _TemporalResampling(m, reservoirs, prevReservoirs, env_tex, env_width, env_height, framedim_x, framedim_y,
