@@ -298,6 +298,8 @@ def run_gpu(args):
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
+    if args.timeline:
+        _timeline(torch, step, args.timeline)
     pk.launches = 0
     with Clocks(local) as clocks:
         ms_dev, _ = timed(args.steps, False, record=True)
@@ -340,6 +342,30 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def _timeline(torch, step, path):
+    """Diagnostics (not a bench number): one warm step under torch.profiler (CUPTI); writes every device kernel with its
+    start and duration, plus the idle gaps between kernels, so launch-bound stretches of the step can be seen."""
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        step(False)
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    t0 = evs[0].time_range.start
+    rows, busy, last_end = [], 0.0, t0
+    for e in evs:
+        s, d = e.time_range.start - t0, e.time_range.end - e.time_range.start
+        gap = max(0.0, e.time_range.start - last_end)
+        last_end = max(last_end, e.time_range.end)
+        busy += d
+        rows.append((s, d, gap, e.name))
+    with open(path, "w") as f:
+        f.write("# start_us dur_us gap_before_us name ; span %.1f us, busy %.1f us, kernels %d\n" % (last_end - t0, busy, len(rows)))
+        for s, d, gap, name in rows:
+            f.write("%10.1f %9.1f %8.1f  %s\n" % (s, d, gap, name[:110]))
+
+
 def roofline(cfg_name, cfg, per_kernel, steps, peak, peak_kind):
     """Dominant kernel vs the HBM roofline.  Algorithmic bytes per launch = S_screen(stage) * N + 36 * V_n + 48 * V_t
      with V_n / V_t the oracle's node-pop / triangle-test counts per launch under the contract schedule
@@ -370,6 +396,7 @@ def main():
     ap.add_argument("--impl", default="mirres_b200")
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline", default=None, help="diagnostics: write a per-kernel device timeline of one warm step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
