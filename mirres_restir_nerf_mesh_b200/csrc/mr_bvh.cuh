@@ -2,19 +2,28 @@
 //
 // The reference walks its LBVH with one 16-byte stack record per node, six scalar AABB loads per
 // pop and no early-out for boolean rays (nerf/ScreenSpaceReSTIR/utils/helperDi.slang:136-395).
-// Here the hierarchy is re-packed at build time into 64-byte "two children per record" nodes
-// (four LDG.128) and 48-byte leaf-ordered triangle records (three LDG.128, edges pre-subtracted),
-// and two traversals are provided:
+// Here the hierarchy is re-packed at build time into 128-byte WIDE records -- for every internal
+// node the boxes of its (up to four) GRANDCHILDREN, listed in the order the reference would visit
+// them -- and 48-byte leaf-ordered triangle records (edges pre-subtracted).  One record fetch
+// (seven independent LDG.128) replaces up to three dependent fetches of the binary walk, which
+// halves the chain of dependent L2 loads that bounds a ray's latency.  Two traversals:
 //
 //   any_hit      boolean rays (shadow / visibility).  helperDi.slang:197-274 returns any_hit = "some
 //                leaf triangle was line-hit before pruning could start", which is independent of the
 //                visit order, so the walk stops at the first hit.
 //   closest_hit  rays whose t / normal are consumed (helperDi.slang:313-395).  The result depends on the
-//                visit order (negative-t hits, ties), so the walk keeps the reference order: the right
-//                child is visited before the left one, a popped subtree is re-tested against the
-//                current closest distance.  The slab test of a child is done when its parent is
-//                visited (entry distance kept on the stack) -- identical to testing it when popped,
-//                because the entry distance does not depend on the closest distance.
+//                visit order (negative-t hits, ties), so the walk keeps the reference order: right
+//                subtree before left subtree at every level, a deferred subtree is re-tested against
+//                the current closest distance when it is popped.
+//
+// Why skipping a level is exact.  The reference enters a node iff min(closest, t_far) > t_near for the
+// node's box.  A child box is contained in its parent's box (refit takes exact min/max), and the slab
+// arithmetic (subtract, multiply by the same 1/d, min/max) is monotone in fp32, so t_near(child) >=
+// t_near(parent) and t_far(child) <= t_far(parent): a grandchild that passes implies its parent passes,
+// a parent that fails implies its children fail.  `closest` does not change between the visit of a node
+// and the visit of its right child, and a deferred entry is re-tested with the closest distance at pop
+// time exactly as the reference re-tests a popped node.  Entry distances do not depend on `closest`, so
+// they are computed once, when the record is fetched, and kept on the stack.
 //
 // Bug-compatible details kept on purpose: no t-range test on triangles, `t_max <= t_min` rejects,
 // zero direction components become 1e-6, the direction is re-normalised on entry.
@@ -23,11 +32,12 @@
 
 namespace mr {
 
+// entries in reference visit order: expand(right child) then expand(left child), expand(X) = [X] if X is a leaf,
+// else [right(X), left(X)].  Unused entries hold an empty box (+inf, -inf) and can never pass the slab test.
 struct alignas(16) PackedNode {
-    float4 a; // L.min.x L.min.y L.min.z L.max.x
-    float4 b; // L.max.y L.max.z R.min.x R.min.y
-    float4 c; // R.min.z R.max.x R.max.y R.max.z
-    int4 d;   // left ref, right ref, -, -      ref >= 0: internal node index; ref < 0: ~leaf slot
+    float4 b[6]; // entry k: floats [6k, 6k+5] = min.xyz max.xyz
+    int4 ref;    // entry refs: >= 0 internal node index, < 0: ~leaf slot
+    float4 pad;  // 128-byte stride (never loaded)
 };
 
 struct BvhView {
@@ -57,26 +67,39 @@ MR_DEV void pack_item(const PackParams &p, int gid)
         p.tris[3 * (size_t)gid + 1] = make_float4(e1.x, e1.y, e1.z, 0.f);
         p.tris[3 * (size_t)gid + 2] = make_float4(e2.x, e2.y, e2.z, 0.f);
     }
-    if (F == 1) {
-        // a single triangle: node 0 holds the leaf on the left and an empty box on the right
-        const float *b = p.aabb;
-        const float inf = bits_float(0x7f800000);
-        PackedNode n;
-        n.a = make_float4(b[0], b[1], b[2], b[3]);
-        n.b = make_float4(b[4], b[5], inf, inf);
-        n.c = make_float4(inf, -inf, -inf, -inf);
-        n.d = make_int4(~0, ~0, 0, 0);
-        p.nodes[0] = n;
-        return;
+    if (gid >= F - 1 && !(F == 1 && gid == 0)) return;
+    const float inf = bits_float(0x7f800000);
+    float box[24];
+    int ref[4] = {0, 0, 0, 0};
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        box[6 * k] = inf; box[6 * k + 1] = inf; box[6 * k + 2] = inf;
+        box[6 * k + 3] = -inf; box[6 * k + 4] = -inf; box[6 * k + 5] = -inf;
     }
-    if (gid >= F - 1) return;
-    int l = MR_LDG(p.info + 3 * (size_t)gid), r = MR_LDG(p.info + 3 * (size_t)gid + 1);
-    const float *bl = p.aabb + 6 * (size_t)l, *br = p.aabb + 6 * (size_t)r;
+    auto put = [&](int node) {
+        const float *b = p.aabb + 6 * (size_t)node;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) box[6 * cnt + k] = MR_LDG(b + k);
+        ref[cnt] = node < LEAF ? node : ~(node - LEAF);
+        ++cnt;
+    };
+    auto expand = [&](int node) {
+        if (node >= LEAF) { put(node); return; }
+        put(MR_LDG(p.info + 3 * (size_t)node + 1)); // right child is visited first
+        put(MR_LDG(p.info + 3 * (size_t)node));
+    };
+    if (F == 1) {
+        put(LEAF); // a single triangle: the root is the leaf
+    } else {
+        expand(MR_LDG(p.info + 3 * (size_t)gid + 1));
+        expand(MR_LDG(p.info + 3 * (size_t)gid));
+    }
     PackedNode n;
-    n.a = make_float4(MR_LDG(bl), MR_LDG(bl + 1), MR_LDG(bl + 2), MR_LDG(bl + 3));
-    n.b = make_float4(MR_LDG(bl + 4), MR_LDG(bl + 5), MR_LDG(br), MR_LDG(br + 1));
-    n.c = make_float4(MR_LDG(br + 2), MR_LDG(br + 3), MR_LDG(br + 4), MR_LDG(br + 5));
-    n.d = make_int4(l < LEAF ? l : ~(l - LEAF), r < LEAF ? r : ~(r - LEAF), 0, 0);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) n.b[k] = make_float4(box[4 * k], box[4 * k + 1], box[4 * k + 2], box[4 * k + 3]);
+    n.ref = make_int4(ref[0], ref[1], ref[2], ref[3]);
+    n.pad = make_float4(0.f, 0.f, 0.f, 0.f);
     p.nodes[gid] = n;
 }
 
@@ -134,8 +157,24 @@ MR_DEV bool tri_test(const Ray &r, float4 q0, float4 q1, float4 q2, float &t, fl
 }
 
 struct TraceStats {
-    unsigned int nodes, tris;
+    unsigned int nodes, tris; // wide records fetched, triangles tested
 };
+
+// one wide record: entry distances of its four entries
+struct WideHit {
+    float tn[4], tf[4];
+    int4 ref;
+};
+MR_DEV void wide_fetch(const Ray &r, const PackedNode *pn, WideHit &w)
+{
+    const float4 q0 = MR_LDG(&pn->b[0]), q1 = MR_LDG(&pn->b[1]), q2 = MR_LDG(&pn->b[2]);
+    const float4 q3 = MR_LDG(&pn->b[3]), q4 = MR_LDG(&pn->b[4]), q5 = MR_LDG(&pn->b[5]);
+    w.ref = MR_LDG(&pn->ref);
+    slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, w.tn[0], w.tf[0]);
+    slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, w.tn[1], w.tf[1]);
+    slab(r, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, w.tn[2], w.tf[2]);
+    slab(r, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, w.tn[3], w.tf[3]);
+}
 
 // Boolean query: true iff the reference's bvh_hit(rayo, rayd, 0, 1e7) returns true.
 template <bool STATS>
@@ -147,24 +186,19 @@ MR_DEV bool any_hit(const BvhView &bvh, float3 origin, float3 dir, TraceStats *s
     int sp = 0;
     int node = 0;
     for (;;) {
-        const PackedNode *pn = bvh.nodes + node;
-        float4 a = MR_LDG(&pn->a), b = MR_LDG(&pn->b), c = MR_LDG(&pn->c);
-        int4 d = MR_LDG(&pn->d);
-        if (STATS) st->nodes += 2;
-        float ln, lf, rn, rf;
-        slab(r, a.x, a.y, a.z, a.w, b.x, b.y, ln, lf);
-        slab(r, b.z, b.w, c.x, c.y, c.z, c.w, rn, rf);
-        bool passL = fminf(t_max, lf) > ln;
-        bool passR = fminf(t_max, rf) > rn;
-        int next;
+        WideHit w;
+        wide_fetch(r, bvh.nodes + node, w);
+        if (STATS) st->nodes += 1;
+        const int refs[4] = {w.ref.x, w.ref.y, w.ref.z, w.ref.w};
+        int next = 0;
         bool have = false;
-        if (passR) {
-            next = d.y;
-            have = true;
-            if (passL) stack[sp++] = d.x;
-        } else if (passL) {
-            next = d.x;
-            have = true;
+#pragma unroll
+        for (int k = 3; k >= 0; --k) {
+            if (fminf(t_max, w.tf[k]) > w.tn[k]) {
+                if (have) stack[sp++] = next;
+                next = refs[k];
+                have = true;
+            }
         }
         for (;;) {
             if (!have) {
@@ -189,6 +223,26 @@ struct Hit {
     int prim;
 };
 
+// face normal of the recorded triangle, flipped towards the ray origin (helperDi.slang:299-307).
+// best_slot can only stay -1 when every hit returned NaN; the reference then keeps float3(1).
+MR_DEV void closest_finish(const BvhView &bvh, const Ray &r, int best_slot, float3 &n, int &prim)
+{
+    n = f3(1.0f);
+    prim = -1;
+    if (best_slot >= 0) {
+        const float4 *tp = bvh.tris + 3 * (size_t)best_slot;
+        float4 q0 = MR_LDG(tp), q1 = MR_LDG(tp + 1), q2 = MR_LDG(tp + 2);
+        float t, u, v;
+        tri_test(r, q0, q1, q2, t, u, v);
+        float3 fn = normalize(cross(make_float3(q1.x, q1.y, q1.z), make_float3(q2.x, q2.y, q2.z)));
+        float w = 1.0f - u - v;
+        n = u * fn + v * fn + w * fn;
+        if (dot(-r.d, n) < 0) n = -n;
+        n = normalize(n);
+        prim = float_bits(q0.w);
+    }
+}
+
 // Closest-hit with the reference's visit order and update rules (helperDi.slang:313-395).
 template <bool STATS>
 MR_DEV bool closest_hit(const BvhView &bvh, float3 origin, float3 dir, Hit &out, TraceStats *st)
@@ -202,28 +256,26 @@ MR_DEV bool closest_hit(const BvhView &bvh, float3 origin, float3 dir, Hit &out,
     int sp = 0;
     int node = 0;
     for (;;) {
-        const PackedNode *pn = bvh.nodes + node;
-        float4 a = MR_LDG(&pn->a), b = MR_LDG(&pn->b), c = MR_LDG(&pn->c);
-        int4 d = MR_LDG(&pn->d);
-        if (STATS) st->nodes += 2;
-        float ln, lf, rn, rf;
-        slab(r, a.x, a.y, a.z, a.w, b.x, b.y, ln, lf);
-        slab(r, b.z, b.w, c.x, c.y, c.z, c.w, rn, rf);
-        bool passL = fminf(closest, lf) > ln;
-        bool passR = fminf(closest, rf) > rn;
-        int next;
+        WideHit w;
+        wide_fetch(r, bvh.nodes + node, w);
+        if (STATS) st->nodes += 1;
+        const int refs[4] = {w.ref.x, w.ref.y, w.ref.z, w.ref.w};
+        int next = 0;
+        float next_t = 0.f;
         bool have = false;
-        if (passR) {
-            next = d.y;
-            have = true;
-            if (passL) {
-                stack_ref[sp] = d.x;
-                stack_t[sp] = ln;
-                ++sp;
+        // entries that pass now, lowest index = visited next, the others deferred so that they pop in index order
+#pragma unroll
+        for (int k = 3; k >= 0; --k) {
+            if (fminf(closest, w.tf[k]) > w.tn[k]) {
+                if (have) {
+                    stack_ref[sp] = next;
+                    stack_t[sp] = next_t;
+                    ++sp;
+                }
+                next = refs[k];
+                next_t = w.tn[k];
+                have = true;
             }
-        } else if (passL) {
-            next = d.x;
-            have = true;
         }
         for (;;) {
             if (!have) {
@@ -261,26 +313,7 @@ done:
     }
     out.t = closest;
     out.pos = r.o + closest * r.d;
-    {
-        // face normal of the recorded triangle, flipped towards the ray origin (helperDi.slang:299-307).
-        // best_slot can only stay -1 when every hit returned NaN; the reference then keeps float3(1).
-        float3 n = f3(1.0f);
-        int prim = -1;
-        if (best_slot >= 0) {
-            const float4 *tp = bvh.tris + 3 * (size_t)best_slot;
-            float4 q0 = MR_LDG(tp), q1 = MR_LDG(tp + 1), q2 = MR_LDG(tp + 2);
-            float t, u, v;
-            tri_test(r, q0, q1, q2, t, u, v);
-            float3 fn = normalize(cross(make_float3(q1.x, q1.y, q1.z), make_float3(q2.x, q2.y, q2.z)));
-            float w = 1.0f - u - v;
-            n = u * fn + v * fn + w * fn;
-            if (dot(-r.d, n) < 0) n = -n;
-            n = normalize(n);
-            prim = float_bits(q0.w);
-        }
-        out.normal = n;
-        out.prim = prim;
-    }
+    closest_finish(bvh, r, best_slot, out.normal, out.prim);
     return true;
 }
 

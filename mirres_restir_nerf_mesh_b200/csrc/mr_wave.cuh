@@ -1,15 +1,19 @@
-// mirres-b200 wavefront machinery: compacted foreground pixels, ray queues, queue tracers.
+// mirres-b200 wavefront machinery: compacted foreground pixels, dense ray queues, persistent queue tracers.
 //
 // The reference casts rays from inside its per-pixel kernels (one thread = one pixel, up to ten sequential rays in
 // process_SpatialResampling_, nerf/ScreenSpaceReSTIR/SpatialResampling.slang:258-284).  On a 21 %-covered 800x800
 // frame ncu measured 4.8 of 32 lanes active per instruction for that shape.  Here every ray-casting entry point is a
 // wavefront instead:
-//     gen kernel      (one thread per ACTIVE pixel)  -> ray queue, fixed R slots per active pixel, SoA float4 o / d
-//     queue tracer    (any-hit: persistent warps that refill idle lanes from the queue; closest-hit: one thread/slot)
-//     resolve kernel  (one thread per active pixel)  -> consumes hit flags / hit records
+//     gen kernel      (one thread per ACTIVE pixel)  -> appends its rays to a DENSE queue (warp-aggregated ticket);
+//                                                       every ray carries the id of the result slot it belongs to
+//     queue tracer    persistent warps: idle lanes are refilled from the queue; once the queue runs dry, idle lanes
+//                     of an any-hit warp STEAL deferred subtrees from the traversal stacks of busy lanes (a boolean
+//                     query is an OR over subtrees, so the split cannot change the result); closest-hit rays keep the
+//                     reference visit order, one lane per ray
+//     resolve kernel  (one thread per active pixel)  -> consumes hit flags / hit records by slot
 // Arithmetic per pixel and per ray is unchanged, so results stay bit-identical to the per-pixel formulation.
 //
-// Workspace (caller-allocated, mirres_workspace_bytes(N)): active pixel list, queue, results, per-pixel scratch.
+// Workspace (caller-allocated, mirres_workspace_bytes(N)): active pixel list, queues, results, per-pixel scratch.
 #pragma once
 #include "mr_bvh.cuh"
 
@@ -18,14 +22,28 @@ namespace mr {
 #define MR_MAX_RAYS_PER_PIXEL 10
 #define MR_PX_SCRATCH_FLOATS 32
 
+// per-slot state of a boolean ray
+#define MR_HIT_MISS 0u
+#define MR_HIT_HIT 1u
+#define MR_HIT_NONE 2u // no ray was queued for this slot
+
+// counters[]: [0] active pixels  [1] any-hit ticket  [2] any-hit queue size  [3] closest ticket  [4] closest queue size
+#define MR_CTR_ACTIVE 0
+#define MR_CTR_ANY_TICKET 1
+#define MR_CTR_ANY_SIZE 2
+#define MR_CTR_CLOSEST_TICKET 3
+#define MR_CTR_CLOSEST_SIZE 4
+
 struct Workspace {
-    int *counters;     // [0] number of active pixels, [1] work counter of the running tracer, [2..15] spare
+    int *counters;     // [64] see MR_CTR_*
     int *active;       // [N] pixel indices with occ >= 0.1, ascending
     int *block_counts; // [ceil(N/1024) + 1] compaction scratch
-    float4 *ray_o;     // [N * 10] origin.xyz, w = 1 valid / 0 empty slot
+    float4 *ray_o;     // [N * 10] dense any-hit queue: origin.xyz, w = result slot (int bits)
     float4 *ray_d;     // [N * 10] direction.xyz (normalised again by the tracer, as bvh_hit does)
-    unsigned int *hit; // [N * 10] any-hit result per slot
-    float4 *chit;      // [N * 2]  closest-hit record per active pixel: (pos.xyz, found) (normal.xyz, t)
+    unsigned int *hit; // [N * 10] per SLOT: MR_HIT_*
+    float4 *cray_o;    // [N] dense closest-hit queue: origin.xyz, w = result slot (int bits)
+    float4 *cray_d;    // [N]
+    float4 *chit;      // [N * 2] per SLOT (= active pixel): (pos.xyz, -1 no ray / 0 miss / 1 hit) (normal.xyz, t)
     float *px;         // [N * MR_PX_SCRATCH_FLOATS] per-active-pixel state carried from gen to resolve
     float *stop_in;    // [N] stop flag of every pixel as it was on entry to a bounce kernel
     int capacity;      // N
@@ -43,6 +61,8 @@ static inline size_t workspace_carve(Workspace *w, int N, char *base)
     p = take((size_t)N * MR_MAX_RAYS_PER_PIXEL * sizeof(float4)); if (w) w->ray_o = (float4 *)p;
     p = take((size_t)N * MR_MAX_RAYS_PER_PIXEL * sizeof(float4)); if (w) w->ray_d = (float4 *)p;
     p = take((size_t)N * MR_MAX_RAYS_PER_PIXEL * sizeof(unsigned int)); if (w) w->hit = (unsigned int *)p;
+    p = take((size_t)N * sizeof(float4)); if (w) w->cray_o = (float4 *)p;
+    p = take((size_t)N * sizeof(float4)); if (w) w->cray_d = (float4 *)p;
     p = take((size_t)N * 2 * sizeof(float4)); if (w) w->chit = (float4 *)p;
     p = take((size_t)N * MR_PX_SCRATCH_FLOATS * sizeof(float)); if (w) w->px = (float *)p;
     p = take((size_t)N * sizeof(float)); if (w) w->stop_in = (float *)p;
@@ -50,46 +70,71 @@ static inline size_t workspace_carve(Workspace *w, int N, char *base)
     return off;
 }
 
+// one ticket of a queue; lanes of a warp that arrive together share one atomic
+MR_DEV int queue_alloc(int *ctr)
+{
+#if defined(__CUDA_ARCH__)
+    const unsigned int m = __activemask();
+    const unsigned int lane = threadIdx.x & 31u;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(ctr, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+#else
+    int q;
+#pragma omp atomic capture
+    q = (*ctr)++;
+    return q;
+#endif
+}
+
 MR_DEV void queue_ray(const Workspace &w, size_t slot, float3 o, float3 d)
 {
-    w.ray_o[slot] = make_float4(o.x, o.y, o.z, 1.0f);
-    w.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
+    w.hit[slot] = MR_HIT_MISS;
+    const int q = queue_alloc(w.counters + MR_CTR_ANY_SIZE);
+    w.ray_o[q] = make_float4(o.x, o.y, o.z, bits_float((int)slot));
+    w.ray_d[q] = make_float4(d.x, d.y, d.z, 0.0f);
 }
-MR_DEV void queue_empty(const Workspace &w, size_t slot) { w.ray_o[slot] = make_float4(0.f, 0.f, 0.f, 0.0f); }
+MR_DEV void queue_empty(const Workspace &w, size_t slot) { w.hit[slot] = MR_HIT_NONE; }
 
-// ---- one-thread-per-slot tracers (closest-hit; also the host-check flavour of any-hit) ---------------------------
+MR_DEV void queue_closest_ray(const Workspace &w, size_t slot, float3 o, float3 d)
+{
+    const int q = queue_alloc(w.counters + MR_CTR_CLOSEST_SIZE);
+    w.cray_o[q] = make_float4(o.x, o.y, o.z, bits_float((int)slot));
+    w.cray_d[q] = make_float4(d.x, d.y, d.z, 0.0f);
+}
+MR_DEV void queue_closest_empty(const Workspace &w, size_t slot) { w.chit[2 * slot] = make_float4(0.f, 0.f, 0.f, -1.0f); }
+
+// ---- one-thread-per-entry tracers: the host-check flavour of the queue tracers ------------------------------------
 struct QueueTraceParams {
     BvhView bvh;
     Workspace ws;
-    int rays_per_item;
 };
-MR_DEV void queue_any_item(const QueueTraceParams &p, int slot)
+MR_DEV void queue_any_item(const QueueTraceParams &p, int q)
 {
-    if (slot >= p.ws.counters[0] * p.rays_per_item) return;
-    float4 o = p.ws.ray_o[slot];
-    if (o.w == 0.0f) return;
-    float4 d = p.ws.ray_d[slot];
-    p.ws.hit[slot] = any_hit<false>(p.bvh, make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), nullptr) ? 1u : 0u;
+    if (q >= p.ws.counters[MR_CTR_ANY_SIZE]) return;
+    const float4 o = p.ws.ray_o[q], d = p.ws.ray_d[q];
+    if (any_hit<false>(p.bvh, make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), nullptr)) p.ws.hit[float_bits(o.w)] = MR_HIT_HIT;
 }
-// closest-hit queue: one slot per active pixel, record in chit
-MR_DEV void queue_closest_item(const QueueTraceParams &p, int slot)
+MR_DEV void queue_closest_item(const QueueTraceParams &p, int q)
 {
-    if (slot >= p.ws.counters[0]) return;
-    float4 o = p.ws.ray_o[slot];
-    if (o.w == 0.0f) return;
-    float4 d = p.ws.ray_d[slot];
+    if (q >= p.ws.counters[MR_CTR_CLOSEST_SIZE]) return;
+    const float4 o = p.ws.cray_o[q], d = p.ws.cray_d[q];
+    const size_t slot = (size_t)float_bits(o.w);
     Hit h;
     h.t = 0.f;
     h.pos = f3(0.f);
     h.normal = f3(1.f);
     bool found = closest_hit<false>(p.bvh, make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), h, nullptr);
-    p.ws.chit[2 * (size_t)slot] = make_float4(h.pos.x, h.pos.y, h.pos.z, found ? 1.0f : 0.0f);
-    p.ws.chit[2 * (size_t)slot + 1] = make_float4(h.normal.x, h.normal.y, h.normal.z, h.t);
+    p.ws.chit[2 * slot] = make_float4(h.pos.x, h.pos.y, h.pos.z, found ? 1.0f : 0.0f);
+    p.ws.chit[2 * slot + 1] = make_float4(h.normal.x, h.normal.y, h.normal.z, h.t);
 }
 
-// queue tracers and device query: defined once, in wave.cu
-int trace_queue_any(const BvhView &bvh, const Workspace &ws, int rays_per_item, int sm_count, cudaStream_t st);
-int trace_queue_closest(const BvhView &bvh, const Workspace &ws, int sm_count, cudaStream_t st);
+// queue tracers and device query: defined once, in wave.cu.  queue_reset must be enqueued before the gen kernel of
+// every ray-casting entry point; trace_queues walks the any-hit queue, the closest-hit queue, or both concurrently.
+void queue_reset(const Workspace &ws, cudaStream_t st);
+int trace_queues(const BvhView &bvh, const Workspace &ws, bool any, bool closest, int sm_count, cudaStream_t st);
 int device_sm_count();
 
 } // namespace mr

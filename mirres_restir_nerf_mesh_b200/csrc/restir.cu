@@ -187,7 +187,7 @@ MR_DEV void initial_gen_px(const InitialParams &p, int a)
 MR_DEV void initial_resolve_px(const InitialParams &p, int a)
 {
     if (a >= p.ws.counters[0]) return;
-    if (p.ws.ray_o[a].w == 0.0f || p.ws.hit[a] == 0u) return;
+    if (p.ws.hit[a] != MR_HIT_HIT) return;
     const size_t i = (size_t)p.ws.active[a];
     store3(p.res.ld, i, f3(0.f));
     p.res.pdf[i] = 0.f;
@@ -330,7 +330,7 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
     uint32_t validNeighbors = 1;
     const size_t base = (size_t)a * MR_MAX_RAYS_PER_PIXEL;
     for (uint32_t k = 0; k < p.neighbor_count; ++k) {
-        if (p.ws.ray_o[base + 2 * k].w == 0.0f) continue;
+        if (p.ws.hit[base + 2 * k] == MR_HIT_NONE) continue;
         size_t n;
         spatial_neighbor(p, px, py, startIndex, k, n);
         float4 nnd = load_nd(p.g.normal_depth, n);
@@ -340,8 +340,8 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
         ++validNeighbors;
         float3 nLe, nL;
         light_of(p.env, nr.ld.y, nr.ld.z, nLe, nL);
-        const bool canonical_hit = p.ws.hit[base + 2 * k] != 0u;
-        const bool candidate_hit = p.ws.hit[base + 2 * k + 1] != 0u;
+        const bool canonical_hit = p.ws.hit[base + 2 * k] == MR_HIT_HIT;
+        const bool candidate_hit = p.ws.hit[base + 2 * k + 1] == MR_HIT_HIT;
         float candidateVisibility = candidate_hit ? 0.f : 1.0f;
         float canonicalVisibility = canonical_hit ? 0.f : 1.0f;
         float candAtOwn = target_pdf(nb_s, nLe, nL);
@@ -396,8 +396,8 @@ MR_DEV void final_visibility_gen_px(const VisParams &p, int t)
 MR_DEV void final_visibility_resolve_px(const VisParams &p, int a)
 {
     if (a >= p.ws.counters[0]) return;
-    if (p.ws.ray_o[a].w == 0.0f) return;
-    p.vis[p.ws.active[a]] = p.ws.hit[a] != 0u ? 0.0f : 1.0f;
+    if (p.ws.hit[a] == MR_HIT_NONE) return;
+    p.vis[p.ws.active[a]] = p.ws.hit[a] == MR_HIT_HIT ? 0.0f : 1.0f;
 }
 struct EvalParams {
     ResConst res;
@@ -593,8 +593,9 @@ int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris,
     p.fx = fx; p.fy = fy; p.frame = frame_index;
     p.tile_count = tile_count; p.tile_size = tile_size; p.screen_tile = screen_tile; p.n_light = n_light; p.n_brdf = n_brdf;
     res_zero_all(p.res, n, st); // background pixels (InitialResampling.slang:166-176)
+    queue_reset(p.ws, st);
     if ((rc = foreach_item<InitialParams, initial_gen_px, 128>(p, n, st))) return rc;
-    if ((rc = trace_queue_any(p.bvh, p.ws, 1, device_sm_count(), st))) return rc;
+    if ((rc = trace_queues(p.bvh, p.ws, true, false, device_sm_count(), st))) return rc;
     return foreach_item<InitialParams, initial_resolve_px, 256>(p, n, st);
 }
 
@@ -653,8 +654,9 @@ int mirres_spatial_resampling(const void *packed_nodes, const void *packed_tris,
     p.fx = fx; p.fy = fy; p.frame = frame_index;
     p.offset_count = offset_count; p.neighbor_count = neighbor_count; p.radius = gather_radius;
     res_zero_all(p.res, n, st); // background pixels (SpatialResampling.slang:192-201)
+    queue_reset(p.ws, st);
     if ((rc = foreach_item<SpatialParams, spatial_gen_px, 128>(p, n, st))) return rc;
-    if ((rc = trace_queue_any(p.bvh, p.ws, MR_MAX_RAYS_PER_PIXEL, device_sm_count(), st))) return rc;
+    if ((rc = trace_queues(p.bvh, p.ws, true, false, device_sm_count(), st))) return rc;
     return foreach_item<SpatialParams, spatial_resolve_px, 128>(p, n, st);
 }
 
@@ -670,8 +672,9 @@ int mirres_final_visibility(const void *packed_nodes, const void *packed_tris, c
     if (rc) return rc;
     p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
     p.res_ld = res_ld; p.pos_map = pos_map; p.vis = vis_map; p.n = n;
+    queue_reset(p.ws, st);
     if ((rc = foreach_item<VisParams, final_visibility_gen_px, 256>(p, n, st))) return rc;
-    if ((rc = trace_queue_any(p.bvh, p.ws, 1, device_sm_count(), st))) return rc;
+    if ((rc = trace_queues(p.bvh, p.ws, true, false, device_sm_count(), st))) return rc;
     return foreach_item<VisParams, final_visibility_resolve_px, 256>(p, n, st);
 }
 

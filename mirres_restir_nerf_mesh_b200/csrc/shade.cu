@@ -208,8 +208,7 @@ struct BounceParams {
     float *__restrict__ new_ray_d;
     float *__restrict__ new_occ;
     float *__restrict__ new_normal;
-    Workspace ws;   // shadow-ray queue (2 slots per active pixel) and per-pixel scratch
-    Workspace wsc;  // continuation-ray queue (1 slot per active pixel): same workspace, ray arrays offset by 2N
+    Workspace ws;   // shadow-ray slots (2 per active pixel), continuation-ray slot (1 per active pixel), per-pixel scratch
 };
 
 // Entry sequence of both bounce kernels for EVERY pixel of the frame (FinalShading.slang:132-148, 657-690): remember
@@ -243,7 +242,7 @@ MR_DEV void continue_path_gen(const BounceParams &p, int a, size_t i, const Surf
         p.prd[5 * i + 4] = 1.f;
     } else if (p.bounce_count + 1u <= (unsigned int)p.max_bounce) {
         out_dir = normalize(from_frame(s.frame, out_dir));
-        queue_ray(p.wsc, (size_t)a, surf_pos + VIS_NEAR * out_dir, out_dir);
+        queue_closest_ray(p.ws, (size_t)a, surf_pos + VIS_NEAR * out_dir, out_dir);
         thr *= out_weight;
         p.prd[5 * i + 0] = thr.x;
         p.prd[5 * i + 1] = thr.y;
@@ -255,9 +254,10 @@ MR_DEV void continue_path_gen(const BounceParams &p, int a, size_t i, const Surf
 
 MR_DEV void continue_path_resolve(const BounceParams &p, int a)
 {
-    if (p.wsc.ray_o[a].w == 0.0f) return;
-    const size_t i = (size_t)p.wsc.active[a];
-    const float4 h0 = p.wsc.chit[2 * (size_t)a], h1 = p.wsc.chit[2 * (size_t)a + 1];
+    const float4 h0 = p.ws.chit[2 * (size_t)a];
+    if (h0.w < 0.0f) return; // no continuation ray
+    const size_t i = (size_t)p.ws.active[a];
+    const float4 h1 = p.ws.chit[2 * (size_t)a + 1];
     if (h0.w != 0.0f) {
         p.prd[5 * i + 4] = 0.f;
         store3(p.new_pos, i, make_float3(h0.x, h0.y, h0.z));
@@ -274,7 +274,7 @@ MR_DEV void bounce_first_gen_px(const BounceParams &p, int a)
     const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
-    queue_empty(p.wsc, (size_t)a);
+    queue_closest_empty(p.ws, (size_t)a);
     if (p.ws.stop_in[i] > 0.f) return;
     if (!(MR_LDG(p.occ + i) > 0.1f)) return;
     const float3 thr = make_float3(p.prd[5 * i], p.prd[5 * i + 1], p.prd[5 * i + 2]);
@@ -305,7 +305,7 @@ MR_DEV void bounce_shade_gen_px(const BounceParams &p, int a)
     float *scratch = p.ws.px + (size_t)a * MR_PX_SCRATCH_FLOATS;
     queue_empty(p.ws, 2 * (size_t)a);
     queue_empty(p.ws, 2 * (size_t)a + 1);
-    queue_empty(p.wsc, (size_t)a);
+    queue_closest_empty(p.ws, (size_t)a);
     put9(scratch, f3(0.f), f3(0.f), f3(0.f));
     if (p.ws.stop_in[i] > 0.f) return;
     const float3 thr = make_float3(p.prd[5 * i], p.prd[5 * i + 1], p.prd[5 * i + 2]);
@@ -409,12 +409,12 @@ MR_DEV void bounce_shade_resolve_px(const BounceParams &p, int a)
     const size_t i = (size_t)p.ws.active[a];
     const float *q = p.ws.px + (size_t)a * MR_PX_SCRATCH_FLOATS;
     float3 c = make_float3(q[0], q[1], q[2]), d = make_float3(q[3], q[4], q[5]), sp = make_float3(q[6], q[7], q[8]);
-    if (p.ws.ray_o[2 * (size_t)a].w != 0.0f && p.ws.hit[2 * (size_t)a] == 0u) {
+    if (p.ws.hit[2 * (size_t)a] == MR_HIT_MISS) {
         c += make_float3(q[9], q[10], q[11]);
         d += make_float3(q[12], q[13], q[14]);
         sp += make_float3(q[15], q[16], q[17]);
     }
-    if (p.ws.ray_o[2 * (size_t)a + 1].w != 0.0f && p.ws.hit[2 * (size_t)a + 1] == 0u) {
+    if (p.ws.hit[2 * (size_t)a + 1] == MR_HIT_MISS) {
         c += make_float3(q[18], q[19], q[20]);
         d += make_float3(q[21], q[22], q[23]);
         sp += make_float3(q[24], q[25], q[26]);
@@ -481,9 +481,6 @@ static int fill_bounce(BounceParams &p, const void *packed_nodes, const void *pa
     const int n = fx * fy;
     if (workspace_bytes < workspace_carve(nullptr, n, nullptr)) return MIRRES_ERR_SCRATCH;
     workspace_carve(&p.ws, n, (char *)workspace);
-    p.wsc = p.ws;
-    p.wsc.ray_o += 2 * (size_t)n;
-    p.wsc.ray_d += 2 * (size_t)n;
     p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
     p.frame = frame_index; p.bounce_count = bounce_count; p.max_bounce = max_bounce; p.fx = fx; p.fy = fy;
     p.occ = occ; p.pos_map = pos_map; p.normal = normal; p.ray_dir = ray_dir; p.prd = prd; p.kd = diffuse_map; p.rm = rough_metal;
@@ -504,9 +501,10 @@ int mirres_bounce_first(const void *packed_nodes, const void *packed_tris, unsig
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int n = fx * fy;
+    queue_reset(p.ws, st);
     if ((rc = foreach_item<BounceParams, bounce_prologue_px, 256>(p, n, st))) return rc;
     if ((rc = foreach_item<BounceParams, bounce_first_gen_px, 128>(p, n, st))) return rc;
-    if ((rc = trace_queue_closest(p.bvh, p.wsc, device_sm_count(), st))) return rc;
+    if ((rc = trace_queues(p.bvh, p.ws, false, true, device_sm_count(), st))) return rc;
     return foreach_item<BounceParams, bounce_first_resolve_px, 256>(p, n, st);
 }
 
@@ -529,10 +527,10 @@ int mirres_bounce_shade(const void *packed_nodes, const void *packed_tris, unsig
     p.color = color; p.diff_color = diff_color; p.spec_color = spec_color;
     cudaStream_t st = (cudaStream_t)stream;
     const int n = fx * fy;
+    queue_reset(p.ws, st);
     if ((rc = foreach_item<BounceParams, bounce_prologue_px, 256>(p, n, st))) return rc;
     if ((rc = foreach_item<BounceParams, bounce_shade_gen_px, 128>(p, n, st))) return rc;
-    if ((rc = trace_queue_any(p.bvh, p.ws, 2, device_sm_count(), st))) return rc;
-    if ((rc = trace_queue_closest(p.bvh, p.wsc, device_sm_count(), st))) return rc;
+    if ((rc = trace_queues(p.bvh, p.ws, true, true, device_sm_count(), st))) return rc;
     return foreach_item<BounceParams, bounce_shade_resolve_px, 256>(p, n, st);
 }
 

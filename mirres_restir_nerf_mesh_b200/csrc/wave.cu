@@ -105,121 +105,156 @@ __global__ void __launch_bounds__(CP_BLOCK) k_compact_write(const float *__restr
 #endif
 
 #if !defined(MR_HOST_CHECK)
-// ---- persistent any-hit tracer ----------------------------------------------------------------------------------------
-// Warps pull ray slots from the queue with one atomic per refill; a lane whose ray terminates (first hit, or stack
-// empty) is refilled at the next check point, so the SIMD lanes stay busy although path lengths vary by > 10x.
+// ---- persistent queue tracers ------------------------------------------------------------------------------------------
+// Warps pull rays from a dense queue with one atomic per refill; a lane whose ray terminates (first hit, or stack empty)
+// is refilled at the next check point, so the SIMD lanes stay busy although path lengths vary by > 10x.
 #define MR_TRACE_BLOCK 256
 #define MR_TRACE_STEPS 6
+#define MR_TRACE_STEPS_SHARED 4
 
-__global__ void __launch_bounds__(MR_TRACE_BLOCK) k_trace_any_persistent(BvhView bvh, Workspace ws, int rays_per_item)
+// Any-hit.  When a warp cannot refill all of its idle lanes (queue dry, or -- for small queues -- the per-warp grab limit
+// is reached) the idle lanes take over the OLDEST deferred subtree of busy lanes.  bvh_hit's boolean result is the OR over
+// all leaf tests (mr_bvh.cuh), so walking the subtrees of one ray on several lanes returns the same flag while the
+// longest ray of a launch stops being a serial chain of ~10^3 dependent L2 loads.
+__device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Workspace &ws, int grab)
 {
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    const int total = ws.counters[0] * rays_per_item;
-    int *work = ws.counters + 1;
+    const int total = ws.counters[MR_CTR_ANY_SIZE];
+    int *ticket = ws.counters + MR_CTR_ANY_TICKET;
     int stack[MR_STACK];
-    int sp = 0;
+    int sp = 0, bot = 0;   // live entries: [bot, sp)
     int cur = 0;           // node reference being processed: >= 0 internal, < 0 leaf
     int slot = -1;
-    bool have = false;     // this lane owns a live ray
+    bool have = false;      // this lane owns a live (ray, subtree)
+    bool found = false;     // this lane has just resolved its ray with a hit
     bool exhausted = false; // warp-uniform: the queue has been drained
+    bool shared = false;    // warp-uniform: some ray of this warp is being walked by more than one lane
     Ray r;
     r.o = r.d = r.inv = f3(0.f);
     for (;;) {
-        const unsigned int need = __ballot_sync(FULL, !have);
+        unsigned int need = __ballot_sync(FULL, !have);
         if (need != 0u && !exhausted) {
-            const int n_need = __popc(need);
+            const int n_take = min(__popc(need), grab);
             const int leader = __ffs(need) - 1;
             int base = 0;
-            if ((int)lane == leader) base = atomicAdd(work, n_need);
+            if ((int)lane == leader) base = atomicAdd(ticket, n_take);
             base = __shfl_sync(FULL, base, leader);
-            if (!have) {
-                const int s = base + __popc(need & lt_mask);
+            const int rank = __popc(need & lt_mask);
+            if (!have && rank < n_take) {
+                const int s = base + rank;
                 if (s < total) {
                     const float4 o = __ldg(ws.ray_o + s);
-                    if (o.w != 0.0f) {
-                        const float4 d = __ldg(ws.ray_d + s);
-                        r = make_ray(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z));
-                        slot = s;
-                        sp = 0;
-                        cur = 0;
-                        have = true;
-                    }
+                    const float4 d = __ldg(ws.ray_d + s);
+                    r = make_ray(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z));
+                    slot = __float_as_int(o.w);
+                    sp = bot = 0;
+                    cur = 0;
+                    have = true;
                 }
             }
-            if (base + n_need >= total) exhausted = true;
+            if (base + n_take >= total) exhausted = true;
         }
-        if (!__any_sync(FULL, have)) {
+        const unsigned int busy = __ballot_sync(FULL, have);
+        if (busy == 0u) {
             if (exhausted) break;
             continue;
         }
+        if (busy != FULL) {
+            // ---- steal: the k-th idle lane takes the oldest deferred subtree of the k-th lane that has one
+            const unsigned int donors = __ballot_sync(FULL, have && sp > bot);
+            if (donors != 0u) {
+                const unsigned int idle = ~busy;
+                const int n_pairs = min(__popc(donors), __popc(idle));
+                const bool robbed = have && sp > bot && __popc(donors & lt_mask) < n_pairs;
+                int give = 0;
+                if (robbed) give = stack[bot++];
+                const int my_rank = __popc(idle & lt_mask);
+                const bool thief = !have && my_rank < n_pairs;
+                int src = (int)lane;
+                if (thief) {
+                    unsigned int m = donors;
+                    for (int j = 0; j < my_rank; ++j) m &= m - 1u;
+                    src = __ffs(m) - 1;
+                }
+                const int g_node = __shfl_sync(FULL, give, src);
+                const int g_slot = __shfl_sync(FULL, slot, src);
+                const float ox = __shfl_sync(FULL, r.o.x, src), oy = __shfl_sync(FULL, r.o.y, src), oz = __shfl_sync(FULL, r.o.z, src);
+                const float dx = __shfl_sync(FULL, r.d.x, src), dy = __shfl_sync(FULL, r.d.y, src), dz = __shfl_sync(FULL, r.d.z, src);
+                const float ix = __shfl_sync(FULL, r.inv.x, src), iy = __shfl_sync(FULL, r.inv.y, src), iz = __shfl_sync(FULL, r.inv.z, src);
+                if (thief) {
+                    r.o = make_float3(ox, oy, oz);
+                    r.d = make_float3(dx, dy, dz);
+                    r.inv = make_float3(ix, iy, iz);
+                    slot = g_slot;
+                    cur = g_node;
+                    sp = bot = 0;
+                    have = true;
+                }
+                shared = true;
+            }
+        }
+        const int steps = shared ? MR_TRACE_STEPS_SHARED : MR_TRACE_STEPS;
 #pragma unroll 1
-        for (int it = 0; it < MR_TRACE_STEPS; ++it) {
+        for (int it = 0; it < steps; ++it) {
             if (!have) break;
             if (cur >= 0) {
-                const PackedNode *pn = bvh.nodes + cur;
-                const float4 a = __ldg(&pn->a), b = __ldg(&pn->b), c = __ldg(&pn->c);
-                const int4 d = __ldg(&pn->d);
-                float ln, lf, rn, rf;
-                slab(r, a.x, a.y, a.z, a.w, b.x, b.y, ln, lf);
-                slab(r, b.z, b.w, c.x, c.y, c.z, c.w, rn, rf);
-                const bool passL = fminf(1e7f, lf) > ln;
-                const bool passR = fminf(1e7f, rf) > rn;
-                if (passR) {
-                    cur = d.y;
-                    if (passL) stack[sp++] = d.x;
-                } else if (passL) {
-                    cur = d.x;
-                } else if (sp > 0) {
+                WideHit w;
+                wide_fetch(r, bvh.nodes + cur, w);
+                const int refs[4] = {w.ref.x, w.ref.y, w.ref.z, w.ref.w};
+                int next = 0;
+                bool got = false;
+#pragma unroll
+                for (int k = 3; k >= 0; --k) {
+                    if (fminf(1e7f, w.tf[k]) > w.tn[k]) {
+                        if (got) stack[sp++] = next;
+                        next = refs[k];
+                        got = true;
+                    }
+                }
+                if (got) {
+                    cur = next;
+                } else if (sp > bot) {
                     cur = stack[--sp];
                 } else {
-                    ws.hit[slot] = 0u;
                     have = false;
                 }
             } else {
                 const float4 *tp = bvh.tris + 3 * (size_t)(~cur);
                 float t, u, v;
                 if (tri_test(r, __ldg(tp), __ldg(tp + 1), __ldg(tp + 2), t, u, v)) {
-                    ws.hit[slot] = 1u;
+                    ws.hit[slot] = MR_HIT_HIT;
                     have = false;
-                } else if (sp > 0) {
+                    found = true;
+                } else if (sp > bot) {
                     cur = stack[--sp];
                 } else {
-                    ws.hit[slot] = 0u;
                     have = false;
                 }
             }
         }
+        if (shared) {
+            // a hit found by one lane resolves the ray for every lane that walks a piece of it
+            const unsigned int fmask = __ballot_sync(FULL, found);
+            if (fmask != 0u) {
+                const unsigned int peers = __match_any_sync(FULL, (have || found) ? slot : -1 - (int)lane);
+                if (have && (peers & fmask) != 0u) have = false;
+            }
+        }
+        found = false;
         __syncwarp();
     }
 }
-#endif
 
-int trace_queue_any(const BvhView &bvh, const Workspace &ws, int rays_per_item, int sm_count, cudaStream_t st)
-{
-#if defined(MR_HOST_CHECK)
-    (void)sm_count;
-    QueueTraceParams p = {bvh, ws, rays_per_item};
-    return foreach_item<QueueTraceParams, queue_any_item, 128>(p, ws.capacity * rays_per_item, st);
-#else
-    cudaMemsetAsync(ws.counters + 1, 0, sizeof(int), st);
-    const int blocks = sm_count * (2048 / MR_TRACE_BLOCK);
-    k_trace_any_persistent<<<blocks, MR_TRACE_BLOCK, 0, st>>>(bvh, ws, rays_per_item);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : -100 - (int)e;
-#endif
-}
-
-#if !defined(MR_HOST_CHECK)
-// ---- persistent closest-hit tracer: same refill scheme, reference visit order (see closest_hit in mr_bvh.cuh) --------
-__global__ void __launch_bounds__(MR_TRACE_BLOCK) k_trace_closest_persistent(BvhView bvh, Workspace ws)
+// Closest-hit: same refill scheme, reference visit order (see closest_hit in mr_bvh.cuh), one lane per ray.
+__device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const Workspace &ws)
 {
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    const int total = ws.counters[0];
-    int *work = ws.counters + 1;
+    const int total = ws.counters[MR_CTR_CLOSEST_SIZE];
+    int *ticket = ws.counters + MR_CTR_CLOSEST_TICKET;
     int stack_ref[MR_STACK];
     float stack_t[MR_STACK];
     int sp = 0, cur = 0, slot = -1, best_slot = -1;
@@ -233,23 +268,21 @@ __global__ void __launch_bounds__(MR_TRACE_BLOCK) k_trace_closest_persistent(Bvh
             const int n_need = __popc(need);
             const int leader = __ffs(need) - 1;
             int base = 0;
-            if ((int)lane == leader) base = atomicAdd(work, n_need);
+            if ((int)lane == leader) base = atomicAdd(ticket, n_need);
             base = __shfl_sync(FULL, base, leader);
             if (!have) {
                 const int s = base + __popc(need & lt_mask);
                 if (s < total) {
-                    const float4 o = __ldg(ws.ray_o + s);
-                    if (o.w != 0.0f) {
-                        const float4 d = __ldg(ws.ray_d + s);
-                        r = make_ray(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z));
-                        slot = s;
-                        sp = 0;
-                        cur = 0;
-                        closest = 1e7f;
-                        any = false;
-                        best_slot = -1;
-                        have = true;
-                    }
+                    const float4 o = __ldg(ws.cray_o + s);
+                    const float4 d = __ldg(ws.cray_d + s);
+                    r = make_ray(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z));
+                    slot = __float_as_int(o.w);
+                    sp = 0;
+                    cur = 0;
+                    closest = 1e7f;
+                    any = false;
+                    best_slot = -1;
+                    have = true;
                 }
             }
             if (base + n_need >= total) exhausted = true;
@@ -263,26 +296,27 @@ __global__ void __launch_bounds__(MR_TRACE_BLOCK) k_trace_closest_persistent(Bvh
             if (!have) break;
             bool pop = false;
             if (cur >= 0) {
-                const PackedNode *pn = bvh.nodes + cur;
-                const float4 a = __ldg(&pn->a), b = __ldg(&pn->b), c = __ldg(&pn->c);
-                const int4 d = __ldg(&pn->d);
-                float ln, lf, rn, rf;
-                slab(r, a.x, a.y, a.z, a.w, b.x, b.y, ln, lf);
-                slab(r, b.z, b.w, c.x, c.y, c.z, c.w, rn, rf);
-                const bool passL = fminf(closest, lf) > ln;
-                const bool passR = fminf(closest, rf) > rn;
-                if (passR) {
-                    cur = d.y;
-                    if (passL) {
-                        stack_ref[sp] = d.x;
-                        stack_t[sp] = ln;
-                        ++sp;
+                WideHit w;
+                wide_fetch(r, bvh.nodes + cur, w);
+                const int refs[4] = {w.ref.x, w.ref.y, w.ref.z, w.ref.w};
+                int next = 0;
+                float next_t = 0.f;
+                bool got = false;
+#pragma unroll
+                for (int k = 3; k >= 0; --k) {
+                    if (fminf(closest, w.tf[k]) > w.tn[k]) {
+                        if (got) {
+                            stack_ref[sp] = next;
+                            stack_t[sp] = next_t;
+                            ++sp;
+                        }
+                        next = refs[k];
+                        next_t = w.tn[k];
+                        got = true;
                     }
-                } else if (passL) {
-                    cur = d.x;
-                } else {
-                    pop = true;
                 }
+                if (got) cur = next;
+                else pop = true;
             } else {
                 const int leaf = ~cur;
                 const float4 *tp = bvh.tris + 3 * (size_t)leaf;
@@ -307,18 +341,9 @@ __global__ void __launch_bounds__(MR_TRACE_BLOCK) k_trace_closest_persistent(Bvh
                 if (!found) {
                     float3 pos = f3(0.f), n = f3(1.0f);
                     if (any) {
+                        int prim_unused;
                         pos = r.o + closest * r.d;
-                        if (best_slot >= 0) {
-                            const float4 *tp = bvh.tris + 3 * (size_t)best_slot;
-                            const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-                            float t, u, v;
-                            tri_test(r, q0, q1, q2, t, u, v);
-                            const float3 fn = normalize(cross(make_float3(q1.x, q1.y, q1.z), make_float3(q2.x, q2.y, q2.z)));
-                            const float w = 1.0f - u - v;
-                            n = u * fn + v * fn + w * fn;
-                            if (dot(-r.d, n) < 0) n = -n;
-                            n = normalize(n);
-                        }
+                        closest_finish(bvh, r, best_slot, n, prim_unused);
                     }
                     ws.chit[2 * (size_t)slot] = make_float4(pos.x, pos.y, pos.z, any ? 1.0f : 0.0f);
                     ws.chit[2 * (size_t)slot + 1] = make_float4(n.x, n.y, n.z, any ? closest : 0.f);
@@ -329,18 +354,59 @@ __global__ void __launch_bounds__(MR_TRACE_BLOCK) k_trace_closest_persistent(Bvh
         __syncwarp();
     }
 }
+
+// small queues: give every warp a few rays and let stealing spread each of them over the lanes
+__device__ __forceinline__ int any_grab_limit(const Workspace &ws, int warps)
+{
+    const int total = ws.counters[MR_CTR_ANY_SIZE];
+    return max(2, min(32, (total + warps - 1) / warps));
+}
+
+__global__ void __launch_bounds__(MR_TRACE_BLOCK) k_trace_any_persistent(BvhView bvh, Workspace ws)
+{
+    trace_any_worker(bvh, ws, any_grab_limit(ws, gridDim.x * (MR_TRACE_BLOCK / 32)));
+}
+__global__ void __launch_bounds__(MR_TRACE_BLOCK, 4) k_trace_closest_persistent(BvhView bvh, Workspace ws)
+{
+    trace_closest_worker(bvh, ws);
+}
+// both queues in one launch: even blocks walk the boolean rays, odd blocks the closest-hit rays (the two queues of
+// process_path_tracing_divided_no_grad are independent, FinalShading.slang:745-977)
+__global__ void __launch_bounds__(MR_TRACE_BLOCK, 4) k_trace_mixed_persistent(BvhView bvh, Workspace ws)
+{
+    if ((blockIdx.x & 1u) == 0u) trace_any_worker(bvh, ws, any_grab_limit(ws, (gridDim.x / 2) * (MR_TRACE_BLOCK / 32)));
+    else trace_closest_worker(bvh, ws);
+}
 #endif
 
-int trace_queue_closest(const BvhView &bvh, const Workspace &ws, int sm_count, cudaStream_t st)
+void queue_reset(const Workspace &ws, cudaStream_t st)
+{
+    zero_async(ws.counters + 1, 4 * sizeof(int), st);
+}
+
+int trace_queues(const BvhView &bvh, const Workspace &ws, bool any, bool closest, int sm_count, cudaStream_t st)
 {
 #if defined(MR_HOST_CHECK)
     (void)sm_count;
-    QueueTraceParams p = {bvh, ws, 1};
-    return foreach_item<QueueTraceParams, queue_closest_item, 128>(p, ws.capacity, st);
+    QueueTraceParams p = {bvh, ws};
+    int rc = 0;
+    if (any) rc = foreach_item<QueueTraceParams, queue_any_item, 128>(p, ws.capacity * MR_MAX_RAYS_PER_PIXEL, st);
+    if (!rc && closest) rc = foreach_item<QueueTraceParams, queue_closest_item, 128>(p, ws.capacity, st);
+    return rc;
 #else
-    cudaMemsetAsync(ws.counters + 1, 0, sizeof(int), st);
-    const int blocks = sm_count * (1024 / MR_TRACE_BLOCK);
-    k_trace_closest_persistent<<<blocks, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+    // persistent grids: exactly the number of blocks that are resident at once
+    static int occ_any = 0, occ_closest = 0, occ_mixed = 0;
+    if (!occ_any) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_any, k_trace_any_persistent, MR_TRACE_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_closest, k_trace_closest_persistent, MR_TRACE_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mixed, k_trace_mixed_persistent, MR_TRACE_BLOCK, 0);
+        if (occ_any < 1) occ_any = 4;
+        if (occ_closest < 1) occ_closest = 4;
+        if (occ_mixed < 2) occ_mixed = 4;
+    }
+    if (any && closest) k_trace_mixed_persistent<<<sm_count * (occ_mixed & ~1), MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+    else if (any) k_trace_any_persistent<<<sm_count * occ_any, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+    else if (closest) k_trace_closest_persistent<<<sm_count * occ_closest, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -100 - (int)e;
 #endif
@@ -385,7 +451,7 @@ int mirres_workspace_prepare(const float *occ, int n_pixels, void *workspace, si
     for (int i = 0; i < n_pixels; ++i)
         if (!(occ[i] < 0.1f)) ws.active[c++] = i;
     ws.counters[0] = c;
-    ws.counters[1] = 0;
+    for (int k = 1; k < 8; ++k) ws.counters[k] = 0;
     return 0;
 #else
     cudaStream_t st = (cudaStream_t)stream;
