@@ -165,15 +165,24 @@ struct WideHit {
     float tn[4], tf[4];
     int4 ref;
 };
+MR_DEV void wide_slabs(const Ray &r, float4 q0, float4 q1, float4 q2, float4 q3, float4 q4, float4 q5, WideHit &w)
+{
+    slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, w.tn[0], w.tf[0]);
+    slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, w.tn[1], w.tf[1]);
+    slab(r, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, w.tn[2], w.tf[2]);
+    slab(r, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, w.tn[3], w.tf[3]);
+}
 MR_DEV void wide_fetch(const Ray &r, const PackedNode *pn, WideHit &w)
 {
     const float4 q0 = MR_LDG(&pn->b[0]), q1 = MR_LDG(&pn->b[1]), q2 = MR_LDG(&pn->b[2]);
     const float4 q3 = MR_LDG(&pn->b[3]), q4 = MR_LDG(&pn->b[4]), q5 = MR_LDG(&pn->b[5]);
     w.ref = MR_LDG(&pn->ref);
-    slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, w.tn[0], w.tf[0]);
-    slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, w.tn[1], w.tf[1]);
-    slab(r, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, w.tn[2], w.tf[2]);
-    slab(r, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, w.tn[3], w.tf[3]);
+    wide_slabs(r, q0, q1, q2, q3, q4, q5, w);
+}
+// record address of a traversal reference: wide node (>= 0) or packed triangle (< 0)
+MR_DEV const float4 *ref_address(const BvhView &bvh, int ref)
+{
+    return ref >= 0 ? reinterpret_cast<const float4 *>(bvh.nodes + ref) : bvh.tris + 3 * (size_t)(~ref);
 }
 
 // Boolean query: true iff the reference's bvh_hit(rayo, rayd, 0, 1e7) returns true.

@@ -4,6 +4,7 @@
 // SpatialResampling.slang:192, FinalShading.slang:166,760).  The list of pixels that survive that test is built
 // once per frame here and shared by all wavefront stages (mr_wave.cuh); ascending pixel order keeps neighbouring
 // lanes on neighbouring surface points.
+#include <stdlib.h>
 #include "mr_wave.cuh"
 #include "../../include/mirres_b200.h"
 
@@ -116,6 +117,12 @@ __global__ void __launch_bounds__(CP_BLOCK) k_compact_write(const float *__restr
 // is reached) the idle lanes take over the OLDEST deferred subtree of busy lanes.  bvh_hit's boolean result is the OR over
 // all leaf tests (mr_bvh.cuh), so walking the subtrees of one ray on several lanes returns the same flag while the
 // longest ray of a launch stops being a serial chain of ~10^3 dependent L2 loads.
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+template <bool PREFETCH>
 __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Workspace &ws, int grab)
 {
     const unsigned int FULL = 0xffffffffu;
@@ -199,16 +206,25 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
 #pragma unroll 1
         for (int it = 0; it < steps; ++it) {
             if (!have) break;
+            // load phase common to both record kinds, so that node lanes and leaf lanes of a diverged warp wait for
+            // their L2 round trip at the same time
+            const float4 *rec = ref_address(bvh, cur);
+            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
             if (cur >= 0) {
+                const float4 q3 = __ldg(rec + 3), q4 = __ldg(rec + 4), q5 = __ldg(rec + 5);
+                const int4 ref = __ldg(reinterpret_cast<const int4 *>(rec + 6));
                 WideHit w;
-                wide_fetch(r, bvh.nodes + cur, w);
-                const int refs[4] = {w.ref.x, w.ref.y, w.ref.z, w.ref.w};
+                wide_slabs(r, q0, q1, q2, q3, q4, q5, w);
+                const int refs[4] = {ref.x, ref.y, ref.z, ref.w};
                 int next = 0;
                 bool got = false;
 #pragma unroll
                 for (int k = 3; k >= 0; --k) {
                     if (fminf(1e7f, w.tf[k]) > w.tn[k]) {
-                        if (got) stack[sp++] = next;
+                        if (got) {
+                            if (PREFETCH) prefetch_l1(ref_address(bvh, next));
+                            stack[sp++] = next;
+                        }
                         next = refs[k];
                         got = true;
                     }
@@ -221,9 +237,8 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
                     have = false;
                 }
             } else {
-                const float4 *tp = bvh.tris + 3 * (size_t)(~cur);
                 float t, u, v;
-                if (tri_test(r, __ldg(tp), __ldg(tp + 1), __ldg(tp + 2), t, u, v)) {
+                if (tri_test(r, q0, q1, q2, t, u, v)) {
                     ws.hit[slot] = MR_HIT_HIT;
                     have = false;
                     found = true;
@@ -248,6 +263,7 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
 }
 
 // Closest-hit: same refill scheme, reference visit order (see closest_hit in mr_bvh.cuh), one lane per ray.
+template <bool PREFETCH>
 __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const Workspace &ws)
 {
     const unsigned int FULL = 0xffffffffu;
@@ -295,10 +311,14 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
         for (int it = 0; it < MR_TRACE_STEPS; ++it) {
             if (!have) break;
             bool pop = false;
+            const float4 *rec = ref_address(bvh, cur);
+            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
             if (cur >= 0) {
+                const float4 q3 = __ldg(rec + 3), q4 = __ldg(rec + 4), q5 = __ldg(rec + 5);
+                const int4 ref = __ldg(reinterpret_cast<const int4 *>(rec + 6));
                 WideHit w;
-                wide_fetch(r, bvh.nodes + cur, w);
-                const int refs[4] = {w.ref.x, w.ref.y, w.ref.z, w.ref.w};
+                wide_slabs(r, q0, q1, q2, q3, q4, q5, w);
+                const int refs[4] = {ref.x, ref.y, ref.z, ref.w};
                 int next = 0;
                 float next_t = 0.f;
                 bool got = false;
@@ -306,6 +326,7 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
                 for (int k = 3; k >= 0; --k) {
                     if (fminf(closest, w.tf[k]) > w.tn[k]) {
                         if (got) {
+                            if (PREFETCH) prefetch_l1(ref_address(bvh, next));
                             stack_ref[sp] = next;
                             stack_t[sp] = next_t;
                             ++sp;
@@ -319,9 +340,8 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
                 else pop = true;
             } else {
                 const int leaf = ~cur;
-                const float4 *tp = bvh.tris + 3 * (size_t)leaf;
                 float t, u, v;
-                if (tri_test(r, __ldg(tp), __ldg(tp + 1), __ldg(tp + 2), t, u, v)) {
+                if (tri_test(r, q0, q1, q2, t, u, v)) {
                     if (t <= closest) best_slot = leaf;
                     closest = fminf(t, closest);
                     any = true;
@@ -362,20 +382,23 @@ __device__ __forceinline__ int any_grab_limit(const Workspace &ws, int warps)
     return max(2, min(32, (total + warps - 1) / warps));
 }
 
+template <bool PREFETCH>
 __global__ void __launch_bounds__(MR_TRACE_BLOCK) k_trace_any_persistent(BvhView bvh, Workspace ws)
 {
-    trace_any_worker(bvh, ws, any_grab_limit(ws, gridDim.x * (MR_TRACE_BLOCK / 32)));
+    trace_any_worker<PREFETCH>(bvh, ws, any_grab_limit(ws, gridDim.x * (MR_TRACE_BLOCK / 32)));
 }
+template <bool PREFETCH>
 __global__ void __launch_bounds__(MR_TRACE_BLOCK, 4) k_trace_closest_persistent(BvhView bvh, Workspace ws)
 {
-    trace_closest_worker(bvh, ws);
+    trace_closest_worker<PREFETCH>(bvh, ws);
 }
 // both queues in one launch: even blocks walk the boolean rays, odd blocks the closest-hit rays (the two queues of
 // process_path_tracing_divided_no_grad are independent, FinalShading.slang:745-977)
+template <bool PREFETCH>
 __global__ void __launch_bounds__(MR_TRACE_BLOCK, 4) k_trace_mixed_persistent(BvhView bvh, Workspace ws)
 {
-    if ((blockIdx.x & 1u) == 0u) trace_any_worker(bvh, ws, any_grab_limit(ws, (gridDim.x / 2) * (MR_TRACE_BLOCK / 32)));
-    else trace_closest_worker(bvh, ws);
+    if ((blockIdx.x & 1u) == 0u) trace_any_worker<PREFETCH>(bvh, ws, any_grab_limit(ws, (gridDim.x / 2) * (MR_TRACE_BLOCK / 32)));
+    else trace_closest_worker<PREFETCH>(bvh, ws);
 }
 #endif
 
@@ -395,18 +418,27 @@ int trace_queues(const BvhView &bvh, const Workspace &ws, bool any, bool closest
     return rc;
 #else
     // persistent grids: exactly the number of blocks that are resident at once
-    static int occ_any = 0, occ_closest = 0, occ_mixed = 0;
+    static int occ_any = 0, occ_closest = 0, occ_mixed = 0, prefetch = 0;
     if (!occ_any) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_any, k_trace_any_persistent, MR_TRACE_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_closest, k_trace_closest_persistent, MR_TRACE_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mixed, k_trace_mixed_persistent, MR_TRACE_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_any, k_trace_any_persistent<false>, MR_TRACE_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_closest, k_trace_closest_persistent<false>, MR_TRACE_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mixed, k_trace_mixed_persistent<false>, MR_TRACE_BLOCK, 0);
         if (occ_any < 1) occ_any = 4;
         if (occ_closest < 1) occ_closest = 4;
         if (occ_mixed < 2) occ_mixed = 4;
+        const char *e = getenv("MIRRES_PREFETCH");
+        prefetch = e ? atoi(e) : 0;
     }
-    if (any && closest) k_trace_mixed_persistent<<<sm_count * (occ_mixed & ~1), MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
-    else if (any) k_trace_any_persistent<<<sm_count * occ_any, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
-    else if (closest) k_trace_closest_persistent<<<sm_count * occ_closest, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+    const int g_mixed = sm_count * (occ_mixed & ~1), g_any = sm_count * occ_any, g_closest = sm_count * occ_closest;
+    if (prefetch) {
+        if (any && closest) k_trace_mixed_persistent<true><<<g_mixed, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+        else if (any) k_trace_any_persistent<true><<<g_any, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+        else if (closest) k_trace_closest_persistent<true><<<g_closest, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+    } else {
+        if (any && closest) k_trace_mixed_persistent<false><<<g_mixed, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+        else if (any) k_trace_any_persistent<false><<<g_any, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+        else if (closest) k_trace_closest_persistent<false><<<g_closest, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+    }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -100 - (int)e;
 #endif

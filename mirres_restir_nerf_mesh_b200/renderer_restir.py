@@ -27,6 +27,17 @@ from .slangpy_shim import get_kernels
 
 TOTAL_RIS_PASSES = 5 + 15  # frame-index stride per spp iteration (nerf/renderer_restir.py:242)
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One extra CUDA stream per device for the indirect-path chain (see restir_di_with_pt)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
+
 
 # =====================================================================================================================
 # LBVH worker
@@ -388,7 +399,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                       reservoirs, prev_reservoirs, final_samples, neighborOffsets, light_tile_count, light_tile_size,
                       env_map_init, occ_map, pos_map, normal_map, depth_map, diffuse_map, roughness_specular,
                       ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors, color,
-                      *, random_offset=None, max_bounce=None, hooks=None):
+                      *, random_offset=None, max_bounce=None, hooks=None, overlap=None):
     n = framedim_x * framedim_y
     dev = pos_map.device
     if random_offset is None:
@@ -433,8 +444,56 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
 
     frame = 0
     scale = (scale_x, scale_y, scale_z)
+
+    # The indirect path of an spp iteration (continuation ray + `max_bounce` shaded vertices) reads only the G-buffer
+    # and its own path state, never the reservoirs, so it is independent of the direct-light chain of every iteration.
+    # With `overlap` it is enqueued on a second CUDA stream with its own ray-queue workspace: the two chains then fill
+    # each other's latency tails (a traversal launch ends with a few long rays on an otherwise idle GPU).
+    if overlap is None:
+        overlap = hooks is None and pos_map.is_cuda
+    main_stream = side_stream = None
+    keepalive = []
+    if overlap:
+        main_stream = torch.cuda.current_stream()
+        side_stream = _side_stream(dev)
+        side_stream.wait_stream(main_stream)
+    state = dict(kd=new_diffuse_map, rs=new_roughness_specular)
+
+    def indirect_chain(i, first_pass):
+        base = random_offset + TOTAL_RIS_PASSES * i
+        ris_pass = first_pass
+        process_new_dir_for_pt(FinalShading_m, *bvh, base + ris_pass, 0, framedim_x, framedim_y, occ_map, pos_map,
+                               normal_detached, ray_dir_map, prd, kd, rs, ping["pos"], ping["ray"], ping["occ"],
+                               ping["nrm"])
+        ris_pass += 5
+        src, dst = ping, pong
+        for bounce in range(1, max_bounce + 1):
+            keepalive.extend((state["kd"], state["rs"]))
+            state["kd"], state["rs"] = _query_material(mlp_mat, src["occ"], src["pos"], state["kd"], state["rs"],
+                                                       use_scale, scale)
+            indirect_one_hit_divided_no_grad(FinalShading_m, *bvh, base + ris_pass, bounce, framedim_x, framedim_y,
+                                             env_map, width, height, pdf_, cdf_, mpdf_, mcdf_, src["occ"], src["pos"],
+                                             src["nrm"], src["ray"], prd, state["kd"], state["rs"],
+                                             color_1, color_diff_1, color_spec_1, dst["pos"], dst["ray"], dst["occ"],
+                                             dst["nrm"])
+            sums["color_1"] += color_1
+            sums["diff_1"] += color_diff_1
+            sums["spec_1"] += color_spec_1
+            if hooks is not None:
+                hooks("bounce", (i, bounce), dict(color=color_1, diff=color_diff_1, spec=color_spec_1, prd=prd,
+                                                  occ=dst["occ"], pos=dst["pos"]))
+            ris_pass += 5
+            src, dst = dst, src
+
+    normal_detached = normal_map.detach()
     for i in range(spp):
         base = random_offset + TOTAL_RIS_PASSES * frame
+        # frame-index schedule of the reference (nerf/renderer_restir.py:314-459): tiles +0 (+1 inside), initial +2,
+        # temporal +3 (i > 0), spatial next, new_dir = spatial + 1, shaded vertices +5 each
+        first_indirect_pass = 4 if i == 0 else 5
+        if overlap:
+            with torch.cuda.stream(side_stream), slangpy.workspace_tag("indirect"):
+                indirect_chain(i, first_indirect_pass)
         ris_pass = 0
         GenerateLightTiles(generateLightTiles_m, None, env_map, pdf_, cdf_, mpdf_, mcdf_, width, height,
                            base + ris_pass, light_data, light_uv, light_inv_pdf, light_tile_count, light_tile_size)
@@ -466,34 +525,18 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                                     final_samples=final_samples, final_Li=final_Li, color=color, diff=color_diff,
                                     spec=color_spec, light_data=light_data, light_uv=light_uv,
                                     light_pdf=light_inv_pdf))
-        # indirect light: one continuation ray from the primary hit, then `max_bounce` shaded vertices
-        process_new_dir_for_pt(FinalShading_m, *bvh, base + ris_pass, 0, framedim_x, framedim_y, occ_map, pos_map,
-                               normal_map.detach(), ray_dir_map, prd, kd, rs, ping["pos"], ping["ray"], ping["occ"],
-                               ping["nrm"])
-        ris_pass += 5
-        src, dst = ping, pong
-        for bounce in range(1, max_bounce + 1):
-            new_diffuse_map, new_roughness_specular = _query_material(mlp_mat, src["occ"], src["pos"], new_diffuse_map,
-                                                                      new_roughness_specular, use_scale, scale)
-            indirect_one_hit_divided_no_grad(FinalShading_m, *bvh, base + ris_pass, bounce, framedim_x, framedim_y,
-                                             env_map, width, height, pdf_, cdf_, mpdf_, mcdf_, src["occ"], src["pos"],
-                                             src["nrm"], src["ray"], prd, new_diffuse_map, new_roughness_specular,
-                                             color_1, color_diff_1, color_spec_1, dst["pos"], dst["ray"], dst["occ"],
-                                             dst["nrm"])
-            sums["color_1"] += color_1
-            sums["diff_1"] += color_diff_1
-            sums["spec_1"] += color_spec_1
-            if hooks is not None:
-                hooks("bounce", (i, bounce), dict(color=color_1, diff=color_diff_1, spec=color_spec_1, prd=prd,
-                                                  occ=dst["occ"], pos=dst["pos"]))
-            ris_pass += 5
-            src, dst = dst, src
+        assert ris_pass == first_indirect_pass
+        if not overlap:
+            indirect_chain(i, first_indirect_pass)
         frame += 1
         reservoirs, prev_reservoirs = prev_reservoirs, reservoirs
         prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir = occ_map, normal_depth, brdf_map, ray_dir_map
         sums["color"] += color
         sums["diff"] += color_diff
         sums["spec"] += color_spec
+    if overlap:
+        main_stream.wait_stream(side_stream)
+    keepalive.clear()
     return (sums["color"], sums["color_1"], sums["diff"], sums["spec"], sums["diff_1"], sums["spec_1"],
             total_indirect_light, frame)
 
@@ -505,7 +548,8 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
                           light_tile_size, env_map, occ_map, normal_map, depth_map, diffuse_map, roughness_specular,
                           ray_dir_map, pos_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir,
                           framedim_x, framedim_y, spp, denoise_iter, stepWidth, c_phi_scale=1.0, n_phi_scale=0.1,
-                          p_phi_scale=0.1, *, random_offset=None, max_bounce=None, hooks=None, bilateral=None):
+                          p_phi_scale=0.1, *, random_offset=None, max_bounce=None, hooks=None, bilateral=None,
+                          overlap=None):
     occ_map.masked_fill_(occ_map <= 0.5, 0)  # in place, as the reference does (:484-485), but without a host sync
     ray_dir_map = _normalize_rows(ray_dir_map)
     n, dev = framedim_x * framedim_y, pos_map.device
@@ -518,7 +562,8 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
         EvaluateFinalSamples_m, FinalShading_m, light_data, light_uv, light_inv_pdf, reservoirs, prev_reservoirs,
         final_samples, neighborOffsets, light_tile_count, light_tile_size, env_map, occ_map, pos_map, normal_map,
         depth_map, diffuse_map, roughness_specular, ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map,
-        prev_ray_dir, motionVectors, color, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks)
+        prev_ray_dir, motionVectors, color, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks,
+        overlap=overlap)
     total_color = total_color / mFrameIndex
     total_diff_light = total_diff_light / mFrameIndex
     total_spec_light = total_spec_light / mFrameIndex

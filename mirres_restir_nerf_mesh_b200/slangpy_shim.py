@@ -83,15 +83,31 @@ def packed_bvh(info, aabb, vert, tri):
 
 
 _WORKSPACES = {}
+_WS_TAG = ["main"]
+
+
+class workspace_tag:
+    """Selects which wavefront workspace the ray-casting kernels launched inside the `with` block use.  Kernels that
+    run concurrently on different CUDA streams (the direct-light chain and the indirect path of one spp iteration, see
+    renderer_restir.restir_di_with_pt) must not share ray queues, so each chain gets its own workspace."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        _WS_TAG.append(self.tag)
+
+    def __exit__(self, *a):
+        _WS_TAG.pop()
 
 
 def workspace(device, n_pixels):
     """Wavefront workspace (include/mirres_b200.h) for frames of n_pixels on `device`, allocated once and reused."""
-    key = (str(device), int(n_pixels))
+    key = (str(device), int(n_pixels), _WS_TAG[-1])
     ws = _WORKSPACES.get(key)
     if ws is None:
         nbytes = get_kernels().workspace_bytes(n_pixels)
-        buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        buf = torch.zeros(nbytes + 256, dtype=torch.uint8, device=device)
         off = (-buf.data_ptr()) % 256  # CUDA allocations are already 512-byte aligned; host ones are not
         ws = buf[off:off + nbytes]
         _WORKSPACES[key] = ws
@@ -258,6 +274,9 @@ def _final_shading_bwd(m, finalSample, env_tex, env_width, env_height, framedim_
 def _new_dir(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, frameIndex, bounce_count, framedim_x, framedim_y, occ_map,
              pos_map, normal, ray_dir, prd, diffuse_map, linearRoughness_specular_map, new_pos_map, new_ray_d,
              new_occ_map, new_normal):
+    if _WS_TAG[-1] != "main" and int(bounce_count) == 0:
+        # a chain with its own workspace builds its own foreground-pixel list from the primary occupancy
+        get_kernels().workspace_prepare(_c(occ_map), workspace(prd.device, prd.shape[0]))
     get_kernels().bounce_first(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), int(frameIndex), int(bounce_count),
                                m.define("MAX_Bounce", 2), int(framedim_x), int(framedim_y), _c(occ_map), _c(pos_map),
                                _c(normal), _c(ray_dir), prd, _c(diffuse_map), _c(linearRoughness_specular_map),
