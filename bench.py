@@ -147,7 +147,7 @@ class ProfiledKernels:
     """Wraps Kernels: counts launches and (optionally) brackets every ABI call with CUDA events on the launching
     stream, so per-kernel device time is measured live inside the timed region."""
     LAUNCHES = {"bvh_build": 19, "env_build_distribution": 2, "eaw_bwd": 2, "workspace_prepare": 3, "initial_resampling": 3,
-                "spatial_resampling": 3, "final_visibility": 3, "bounce_first": 4, "bounce_shade": 5}
+                "spatial_resampling": 3, "final_visibility": 3, "bounce_first": 4, "bounce_shade": 4}
 
     def __init__(self, inner, torch):
         self._inner, self._torch = inner, torch
@@ -184,6 +184,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from mirres_restir_nerf_mesh_b200 import synth, renderer_restir as R, slangpy_shim, kernels as K
+    from mirres_restir_nerf_mesh_b200.graphed import CapturedStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -205,111 +206,114 @@ def run_gpu(args):
     ro_np, rd_np = synth.camera_rays(W, H, view=rank * 7)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     host = dict(vert=pin(vert_np), tri=pin(tri_np), env=pin(env_np), rays_o=pin(ro_np), rays_d=pin(rd_np))
-    vert, tri = host["vert"].to(dev), host["tri"].to(dev)
-    worker = R.restirbvhWorker(vert, tri)
-    worker.update_mesh(vert, tri)
-    hit = torch.zeros(n, dtype=torch.int32, device=dev)
-    t = torch.zeros(n, device=dev)
-    pos = torch.zeros(n, 3, device=dev)
-    nrm = torch.zeros(n, 3, device=dev)
-    prim = torch.zeros(n, dtype=torch.int32, device=dev)
-    rays_o, rays_d = host["rays_o"].to(dev), host["rays_d"].to(dev)
-    pk.trace_closest(worker.packed, rays_o, rays_d, hit, t, pos, nrm, prim)
+    device_in = {k: v.to(dev) for k, v in host.items()}
+    worker = R.restirbvhWorker(device_in["vert"], device_in["tri"])
     mat = synth.ProceduralMaterial(0.0)
-    hitm = (hit > 0)[:, None]
-    occ = hitm.float()
-    pos = torch.where(hitm, pos, torch.zeros_like(pos))
-    nrm = torch.where(hitm, nrm, torch.zeros_like(nrm))
-    depth = torch.where(hitm[:, 0], (pos - rays_o).norm(dim=1), torch.zeros_like(t))[:, None]
-    kdks = mat.sample_no_di(pos)
-    kd0 = torch.where(hitm, kdks[:, 0:3], torch.zeros_like(pos))
-    rs0 = torch.where(hitm, kdks[:, 4:6], torch.zeros_like(kdks[:, 4:6]))
-    gbuf_dev = dict(occ=occ, pos=pos, nrm=nrm, depth=depth, kd=kd0.contiguous(), rs=rs0.contiguous(), ray=rays_d)
-    gbuf_host = {k: v.cpu().pin_memory() for k, v in gbuf_dev.items()}
-    fg = torch.nonzero(hit > 0).reshape(-1)          # foreground pixels of this view (static: computed once)
-    fg_tri = tri.long()[prim.long()[fg]]             # [n_fg, 3] vertex ids of the triangle each one sees
     mods = R.load_m_for_restir(W, H, device=dev, max_bounce=mb)
-    V = vert.shape[0]
+    V, ne = vert_np.shape[0], env_np.size
     target = torch.full((n, 3), 0.5, device=dev)
-    flat_grad = torch.zeros(env_np.size + V * 3 + V * 5, device=dev)
-    ne = env_np.size
+    flat_grad = torch.zeros(ne + V * 3 + V * 5, device=dev)  # env | vertex-normal | vertex-texture (kd, rough, metal)
+    opts = dict(overlap=not args.no_overlap)
 
-    def step(from_host):
-        if from_host:
-            v_ = host["vert"].to(dev, non_blocking=True)
-            f_ = host["tri"].to(dev, non_blocking=True)
-            g = {k: v.to(dev, non_blocking=True) for k, v in gbuf_host.items()}
-            env = host["env"].to(dev, non_blocking=True)
-        else:
-            v_, f_ = vert, tri
-            g = {k: v.clone() for k, v in gbuf_dev.items()}
-            env = env_dev.detach().clone()
-        env.requires_grad_(True)
-        normal = g["nrm"].requires_grad_(True)
-        kd = g["kd"].requires_grad_(True)
-        rs = g["rs"].requires_grad_(True)
-        worker.update_mesh(v_, f_)  # LBVH rebuilt every step, as render_stage1 does (nerf/renderer.py:975)
-        outs = R.run_restir_di_with_pt(False, 1, 1, 1, mat, None, worker, *mods, env, g["occ"], normal, g["depth"], kd, rs,
-                                       g["ray"], g["pos"], None, None, None, None, W, H, spp, 2, 2, 2.0, 0.1, 0.001,
-                                       random_offset=1234 + 17 * rank, max_bounce=mb)
+    def full_step(vert, tri, env, rays_o, rays_d):
+        """One stage-1 training step of one view: LBVH rebuild (nerf/renderer.py:975), G-buffer, ReSTIR + path tracer,
+        denoise + composite, loss, backward into env / normals / kd / ks, scatter to vertices and vertex texture."""
+        worker.update_mesh(vert, tri)
+        occ, depth = torch.empty(n, 1, device=dev), torch.empty(n, 1, device=dev)
+        pos, nrm = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
+        prim, bary = torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, 2, device=dev)
+        pk.gbuffer_primary(worker.packed, rays_o, rays_d, occ, pos, nrm, depth, prim, bary)
+        kdks = mat.sample_no_di_dense(pos) * occ   # stand-in for the tiny-cuda-nn material MLP (out of scope)
+        env_l = env.detach().clone().requires_grad_(True)
+        normal = nrm.requires_grad_(True)
+        kd = kdks[:, 0:3].contiguous().requires_grad_(True)
+        rs = kdks[:, 4:6].contiguous().requires_grad_(True)
+        outs = R.run_restir_di_with_pt(False, 1, 1, 1, mat, None, worker, *mods, env_l, occ, normal, depth, kd, rs, rays_d,
+                                       pos, None, None, None, None, W, H, spp, 2, 2, 2.0, 0.1, 0.001,
+                                       random_offset=1234 + 17 * rank, max_bounce=mb, **opts)
         loss = ((outs[0] - target) ** 2).mean()
         loss.backward()
-        # gradients leave the path as grad_env [He,We,3] and dense per-pixel grads; scatter the latter to vertices /
-        # vertex texture (the reference does this in nvdiffrast / tcnn backward) and reduce everything in ONE collective
+        # gradients leave the path as grad_env [He,We,3] and dense per-pixel grads; the latter are scattered to vertices /
+        # vertex texture here (the reference: nvdiffrast / tcnn backward), everything lands in ONE flat buffer
         flat_grad.zero_()
-        flat_grad[:ne] = env.grad.reshape(-1)
-        gv = flat_grad[ne:ne + 3 * V].view(V, 3)
-        gt = flat_grad[ne + 3 * V:].view(V, 5)
-        third = 1.0 / 3.0
-        gtex = torch.cat((kd.grad, rs.grad), dim=1)[fg] * third
-        gnrm = normal.grad[fg] * third
-        for c in range(3):
-            gv.index_add_(0, fg_tri[:, c], gnrm)
-            gt.index_add_(0, fg_tri[:, c], gtex)
-        if world > 1:
-            dist.all_reduce(flat_grad)
-        return loss
+        flat_grad[:ne].copy_(env_l.grad.reshape(-1))
+        pk.interpolate_bwd(normal.grad, prim, bary, tri, flat_grad[ne:ne + 3 * V].view(V, 3))
+        pk.interpolate_bwd(torch.cat((kd.grad, rs.grad), dim=1), prim, bary, tri, flat_grad[ne + 3 * V:].view(V, 5))
+        return loss.detach(), flat_grad
 
-    env_dev = host["env"].to(dev)
+    def finish():
+        if world > 1:
+            dist.all_reduce(flat_grad)  # the per-step collective: texture, envmap and vertex gradients
+
+    for _ in range(max(args.warmup, 3)):
+        full_step(**device_in)
+        finish()
+    torch.cuda.synchronize()
+    captured = None
+    if not args.no_graph:
+        captured = CapturedStep(full_step, device_in, warmup=1)
+
+    def run_step(from_host):
+        if captured is not None:
+            if from_host:
+                captured.load(**host)
+            out = captured.replay()
+        else:
+            src = {k: v.to(dev, non_blocking=True) for k, v in host.items()} if from_host else device_in
+            out = full_step(**src)
+        finish()
+        return out
+
+    if args.timeline:
+        _timeline(torch, lambda _: run_step(False), args.timeline)
+
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
 
-    def timed(k_steps, from_host, record=False):
-        total_ms = 0.0
-        d2h = 0
+    def timed(k_steps, from_host):
+        total_ms, d2h = 0.0, 0
         for _ in range(k_steps):
             flush.fill_(1.0)
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
-            pk.record = record
+                torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            loss = step(from_host)
+            loss, fg = run_step(from_host)
             if from_host:
-                lh = loss.detach().to("cpu", non_blocking=True)
-                gh = flat_grad[:ne].to("cpu", non_blocking=True)
+                lh = loss.to("cpu", non_blocking=True)
+                gh = fg[:ne].to("cpu", non_blocking=True)
                 d2h = lh.numel() * 4 + gh.numel() * 4
             e1.record()
             torch.cuda.synchronize()
-            pk.record = False
             total_ms += e0.elapsed_time(e1)
         return total_ms, d2h
 
     for _ in range(args.warmup):
-        step(False)
+        run_step(False)
     torch.cuda.synchronize()
-    if args.timeline:
-        _timeline(torch, step, args.timeline)
-    pk.launches = 0
     with Clocks(local) as clocks:
-        ms_dev, _ = timed(args.steps, False, record=True)
-    launches = pk.launches
-    per_kernel = pk.per_kernel_ms()
-    step(True)
+        ms_dev, _ = timed(args.steps, False)
+    run_step(True)
     torch.cuda.synchronize()
     ms_e2e, d2h_bytes = timed(args.steps, True)
-    h2d_bytes = sum(v.numel() * v.element_size() for v in gbuf_host.values()) + sum(
-        host[k].numel() * host[k].element_size() for k in ("vert", "tri", "env"))
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    # per-kernel device times: an eager pass with the chains serialised (events bracket every C-ABI call on the stream
+    # it is launched on; with the two chains overlapped the brackets of concurrent kernels would not be comparable)
+    opts["overlap"] = False
+    per_kernel, launches = {}, 0
+    if rank == 0:
+        full_step(**device_in)
+        torch.cuda.synchronize()
+        pk.launches, pk.events, pk.record = 0, [], True
+        k_steps = 2
+        for _ in range(k_steps):
+            flush.fill_(1.0)
+            full_step(**device_in)
+        torch.cuda.synchronize()
+        pk.record = False
+        per_kernel, launches = pk.per_kernel_ms(), pk.launches // k_steps
 
     tms = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -322,16 +326,22 @@ def run_gpu(args):
     if rank == 0:
         peaks = _peaks()
         peak = peaks["hbm_gbs"] if peaks else 6650.0
-        roof = roofline(args.config, cfg, per_kernel, args.steps, peak, "measured" if peaks else "fallback")
+        roof = roofline(args.config, cfg, per_kernel, 2, peak, "measured" if peaks else "fallback")
+        step_alg = step_algorithmic_bytes(args.config, cfg, spp)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": _workload_name(args.config, cfg), "l2": "256 MiB flush between timed steps",
-                           "parallelism": "one view per rank, 1 NCCL allreduce of env+vertex+texture grads per step"},
+                           "parallelism": "one view per rank, 1 NCCL allreduce of env+vertex+texture grads per step",
+                           "execution": ("CUDA graph replay of the whole step" if captured is not None else "eager") +
+                                        (", direct and indirect chains on two streams" if not args.no_overlap else "")},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof,
-                "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])}}
+                "gpu_launches": launches * args.steps, "clocks": clocks.summary(), "roofline": roof,
+                "step_roofline": None if step_alg is None else {
+                    "alg_bytes_per_step": step_alg, "achieved": step_alg / (ms_dev / args.steps * 1e-3) / 1e9,
+                    "peak": peak, "unit": "GB/s", "frac": step_alg / (ms_dev / args.steps * 1e-3) / 1e9 / peak},
+                "kernel_ms_per_step": {k: round(v[0] / 2, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])}}
         if world == 1 and not args.no_cpu_baseline:
             s, dt, _ = oracle_sample(args.config, 400, spp)
             s2, dt2, _ = oracle_sample(args.config, 400, spp)
@@ -339,7 +349,21 @@ def run_gpu(args):
                                     "sample": "CPU oracle: LBVH rebuild + forward spp loop on a 400x400 frame of the same scene, 2 repetitions, no backward"}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def step_algorithmic_bytes(cfg_name, cfg, spp):
+    """Algorithmic bytes of one whole step: sum over samples of S_screen + 36 V_n + 48 V_t, forward
+    (872 B first spp iteration, 1040 B after) + backward (280 B), plus 424 B per rebuilt triangle."""
+    path = os.path.join(ROOT, "profiles", "oracle_counters_%s.json" % cfg_name)
+    if not os.path.exists(path):
+        return None
+    c = json.load(open(path))
+    n = cfg["W"] * cfg["H"]
+    trav = c["per_sample"]["B_alg_traversal_bytes"] * n * spp
+    screen = n * (872 + 1040 * (spp - 1) + 280 * spp)
+    return trav + screen + 424 * c["triangles"]
 
 
 def _timeline(torch, step, path):
@@ -347,7 +371,7 @@ def _timeline(torch, step, path):
     start and duration, plus the idle gaps between kernels, so launch-bound stretches of the step can be seen."""
     from torch.profiler import profile, ProfilerActivity
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
         step(False)
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
@@ -396,6 +420,8 @@ def main():
     ap.add_argument("--impl", default="mirres_b200")
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-overlap", action="store_true", help="direct and indirect chains on one stream")
     ap.add_argument("--timeline", default=None, help="diagnostics: write a per-kernel device timeline of one warm step")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -203,6 +203,27 @@ int mirres_eaw_bwd(float c_phi, float n_phi, float p_phi, int fx, int fy, float 
                    void *stream);
 int mirres_normal_ao(int fx, int fy, const float *occ, const float *normal, float *out_ao, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * G-buffer producer and gradient scatter.
+ *   mirres_gbuffer_primary   stands in for the nvdiffrast rasterise + interpolate stage that feeds
+ *        run_restir_di_with_pt (nerf/renderer.py:979-1030, 1092-1096): one closest-hit ray per pixel with the
+ *        semantics of bvh_hit_with_normal (helperDi.slang:313-395).  org/dir [n,3]; outputs occ [n] (1 hit / 0),
+ *        pos [n,3], normal [n,3] (face normal flipped towards the ray, or -- when vnormal [V,3] and tri [F,3] are
+ *        given -- the barycentric interpolation of the vertex normals, the role of dr.interpolate over
+ *        auto_normals, nerf/meshutils.py:14-39), depth [n] = |pos - org|, prim [n] i32 (-1 miss), bary [n,2] = (u, v)
+ *        weights of the triangle's 2nd / 3rd vertex.  prim and bary are optional.
+ *   mirres_interpolate_bwd   reverse of that interpolation, i.e. the scatter nvdiffrast / the texture backward do
+ *        for the per-pixel gradients the path emits (Resampling.py:193-214):
+ *            out[tri[prim[i]][k], c] += w_k(i) * grad[i, c],   w = (1-u-v, u, v)   (bary NULL: 1/3 each)
+ *        grad [n,C], C <= 8; out [V,C] is ACCUMULATED into.  Lanes of a warp that see the same triangle are summed
+ *        with shuffles first (__match_any_sync on prim), one lane issues the atomics.
+ */
+int mirres_gbuffer_primary(const void *packed_nodes, const void *packed_tris, const float *org, const float *dir, int n,
+                           const float *vnormal, const int *tri, float *occ, float *pos, float *normal, float *depth,
+                           int *prim, float *bary, void *stream);
+int mirres_interpolate_bwd(const float *grad, int n, int C, const int *prim, const float *bary, const int *tri, int F,
+                           float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

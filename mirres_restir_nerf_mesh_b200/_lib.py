@@ -44,6 +44,8 @@ SIGNATURES = {
     "mirres_eaw_fwd": "fffiif" + "ppppp" + "p",
     "mirres_eaw_bwd": "fffiif" + "ppppp" + "ppppp" + "p",
     "mirres_normal_ao": "iipppp",
+    "mirres_gbuffer_primary": "ppppi" + "pp" + "pppppp" + "p",
+    "mirres_interpolate_bwd": "piipppipp",
 }
 SIZE_FUNCS = ("mirres_bvh_scratch_bytes", "mirres_bvh_packed_node_bytes", "mirres_bvh_packed_tri_bytes",
               "mirres_workspace_bytes")

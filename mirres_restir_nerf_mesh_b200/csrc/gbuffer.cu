@@ -1,0 +1,224 @@
+// mirres-b200: G-buffer producer and the gradient scatter that closes the backward pass.
+//
+// In the reference the G-buffer comes from nvdiffrast (rasterise + interpolate, nerf/renderer.py:979-1030) and the
+// per-pixel gradients the path emits (grad_normal / grad_diffuse / grad_ks, nerf/ScreenSpaceReSTIR/Resampling.py:193-214)
+// are scattered to mesh vertices and texels by nvdiffrast's / tiny-cuda-nn's own backward.  Here:
+//   mirres_gbuffer_primary   one closest-hit ray per pixel through the same LBVH (bvh_hit_with_normal semantics,
+//                            helperDi.slang:313-395): occupancy, position, normal, depth and -- what rasterisation
+//                            gives the reference -- the triangle id and barycentrics of every pixel; with per-vertex
+//                            normals the shading normal is their barycentric interpolation (the role of
+//                            dr.interpolate over auto_normals, nerf/meshutils.py:14-39)
+//   mirres_interpolate_bwd   reverse of barycentric interpolation: out[tri[prim][k], c] += w_k * grad[pixel, c].
+//                            Neighbouring pixels see the same triangle, so lanes of a warp with the same triangle id
+//                            are summed with a shuffle tree (__match_any_sync) and one lane issues the atomics.
+#include "mr_bvh.cuh"
+#include "../../include/mirres_b200.h"
+
+namespace mr {
+
+struct GbufParams {
+    BvhView bvh;
+    const float *__restrict__ org;     // [n,3]
+    const float *__restrict__ dir;     // [n,3]
+    const float *__restrict__ vnormal; // [V,3] or null
+    const int *__restrict__ tri;       // [F,3] (only with vnormal)
+    float *__restrict__ occ;           // [n]
+    float *__restrict__ pos;           // [n,3]
+    float *__restrict__ normal;        // [n,3]
+    float *__restrict__ depth;         // [n]
+    int *__restrict__ prim;            // [n]
+    float *__restrict__ bary;          // [n,2]
+};
+
+MR_DEV void gbuffer_item(const GbufParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    Hit h;
+    h.t = 0.f;
+    h.pos = f3(0.f);
+    h.normal = f3(1.f);
+    h.prim = -1;
+    h.bary[0] = h.bary[1] = 0.f;
+    const float3 o = load3(p.org, i);
+    const bool found = closest_hit<false>(p.bvh, o, load3(p.dir, i), h, nullptr);
+    float3 n = f3(0.f), x = f3(0.f);
+    float d = 0.f;
+    if (found) {
+        x = h.pos;
+        n = h.normal;
+        const float3 dv = x - o;
+        d = sqrtf(dot(dv, dv));
+        if (p.vnormal && h.prim >= 0) {
+            const int i0 = MR_LDG(p.tri + 3 * (size_t)h.prim), i1 = MR_LDG(p.tri + 3 * (size_t)h.prim + 1), i2 = MR_LDG(p.tri + 3 * (size_t)h.prim + 2);
+            const float w = 1.0f - h.bary[0] - h.bary[1];
+            n = w * load3(p.vnormal, (size_t)i0) + h.bary[0] * load3(p.vnormal, (size_t)i1) + h.bary[1] * load3(p.vnormal, (size_t)i2);
+        }
+    }
+    p.occ[i] = found ? 1.0f : 0.0f;
+    store3(p.pos, i, x);
+    store3(p.normal, i, n);
+    p.depth[i] = d;
+    if (p.prim) p.prim[i] = found ? h.prim : -1;
+    if (p.bary) { p.bary[2 * i] = found ? h.bary[0] : 0.f; p.bary[2 * i + 1] = found ? h.bary[1] : 0.f; }
+}
+
+#define MR_SCATTER_MAX_C 8
+
+struct ScatterParams {
+    const float *__restrict__ grad; // [n,C]
+    const int *__restrict__ prim;   // [n], -1 = background
+    const float *__restrict__ bary; // [n,2] or null (null: 1/3 each)
+    const int *__restrict__ tri;    // [F,3]
+    float *out;                     // [V,C]
+    int n, C, F;
+};
+
+// per-pixel part shared by both builds
+MR_DEV bool scatter_terms(const ScatterParams &p, int idx, int &prim, float w[3], float g[MR_SCATTER_MAX_C])
+{
+    prim = MR_LDG(p.prim + idx);
+    if (prim < 0 || prim >= p.F) return false;
+    bool nz = false;
+    for (int c = 0; c < p.C; ++c) {
+        g[c] = MR_LDG(p.grad + (size_t)idx * p.C + c);
+        nz = nz || g[c] != 0.f;
+    }
+    if (!nz) return false;
+    if (p.bary) {
+        const float u = MR_LDG(p.bary + 2 * (size_t)idx), v = MR_LDG(p.bary + 2 * (size_t)idx + 1);
+        w[0] = 1.0f - u - v; w[1] = u; w[2] = v;
+    } else {
+        w[0] = w[1] = w[2] = 1.0f / 3.0f;
+    }
+    return true;
+}
+
+#if !defined(MR_HOST_CHECK)
+template <int C>
+__global__ void __launch_bounds__(256) k_interpolate_bwd(ScatterParams p)
+{
+    const unsigned int FULL = 0xffffffffu;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int lane = threadIdx.x & 31u;
+    int prim = -1;
+    float w[3] = {0.f, 0.f, 0.f}, g[MR_SCATTER_MAX_C];
+#pragma unroll
+    for (int c = 0; c < MR_SCATTER_MAX_C; ++c) g[c] = 0.f;
+    const bool active = idx < p.n && scatter_terms(p, idx, prim, w, g);
+    const unsigned int act = __ballot_sync(FULL, active);
+    if (act == 0u) return;
+    // lanes that see the same triangle form a group; its first lane is the leader
+    const unsigned int peers = __match_any_sync(FULL, active ? prim : -1 - (int)lane) & act;
+    const bool leader = active && (__ffs(peers) - 1 == (int)lane);
+    const unsigned int leaders = __ballot_sync(FULL, leader);
+    int v[3] = {0, 0, 0};
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = __ldg(p.tri + 3 * (size_t)prim + k);
+    }
+    if (__popc(leaders) == __popc(act)) {
+        // every lane has its own triangle: nothing to aggregate
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int c = 0; c < C; ++c) atomicAdd(p.out + (size_t)v[k] * C + c, w[k] * g[c]);
+        }
+        return;
+    }
+    // sum inside each group by walking the group mask
+    float acc[3][C];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[k][c] = active ? w[k] * g[c] : 0.f;
+    // every lane pulls the contributions of the other members of ITS group; after the loop the leader holds the
+    // group total (members hold the same total, which they discard)
+    unsigned int rest = peers & ~(1u << lane);
+    const int rounds = (int)__reduce_max_sync(FULL, (unsigned int)__popc(peers)) - 1; // largest group of this warp
+    float mine[3][C];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int c = 0; c < C; ++c) mine[k][c] = acc[k][c];
+    for (int r = 0; r < rounds; ++r) {
+        const int src = rest ? __ffs(rest) - 1 : (int)lane;
+        const bool take = rest != 0u;
+        rest &= rest - 1u;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float x = __shfl_sync(FULL, mine[k][c], src);
+                if (take) acc[k][c] += x;
+            }
+    }
+    if (leader) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int c = 0; c < C; ++c) atomicAdd(p.out + (size_t)v[k] * C + c, acc[k][c]);
+    }
+}
+#endif
+
+static int interpolate_bwd_launch(const ScatterParams &p, cudaStream_t st)
+{
+#if defined(MR_HOST_CHECK)
+    (void)st;
+    for (int idx = 0; idx < p.n; ++idx) {
+        int prim;
+        float w[3], g[MR_SCATTER_MAX_C];
+        if (!scatter_terms(p, idx, prim, w, g)) continue;
+        for (int k = 0; k < 3; ++k) {
+            const int v = p.tri[3 * (size_t)prim + k];
+            for (int c = 0; c < p.C; ++c) p.out[(size_t)v * p.C + c] += w[k] * g[c];
+        }
+    }
+    return 0;
+#else
+    const int grid = (p.n + 255) / 256;
+    switch (p.C) {
+    case 1: k_interpolate_bwd<1><<<grid, 256, 0, st>>>(p); break;
+    case 2: k_interpolate_bwd<2><<<grid, 256, 0, st>>>(p); break;
+    case 3: k_interpolate_bwd<3><<<grid, 256, 0, st>>>(p); break;
+    case 4: k_interpolate_bwd<4><<<grid, 256, 0, st>>>(p); break;
+    case 5: k_interpolate_bwd<5><<<grid, 256, 0, st>>>(p); break;
+    case 6: k_interpolate_bwd<6><<<grid, 256, 0, st>>>(p); break;
+    case 7: k_interpolate_bwd<7><<<grid, 256, 0, st>>>(p); break;
+    default: k_interpolate_bwd<8><<<grid, 256, 0, st>>>(p); break;
+    }
+    MR_CUDA_CHECK_LAUNCH();
+    return 0;
+#endif
+}
+
+} // namespace mr
+
+using namespace mr;
+
+extern "C" {
+
+int mirres_gbuffer_primary(const void *packed_nodes, const void *packed_tris, const float *org, const float *dir, int n,
+                           const float *vnormal, const int *tri, float *occ, float *pos, float *normal, float *depth,
+                           int *prim, float *bary, void *stream)
+{
+    if (!packed_nodes || !packed_tris || !org || !dir || !occ || !pos || !normal || !depth) return MIRRES_ERR_NULL;
+    if (vnormal && !tri) return MIRRES_ERR_NULL;
+    if (n < 0) return MIRRES_ERR_SHAPE;
+    if (n == 0) return 0;
+    GbufParams p = {{(const PackedNode *)packed_nodes, (const float4 *)packed_tris}, org, dir, vnormal, tri, occ, pos, normal, depth, prim, bary};
+    return foreach_item<GbufParams, gbuffer_item, 128>(p, n, (cudaStream_t)stream);
+}
+
+int mirres_interpolate_bwd(const float *grad, int n, int C, const int *prim, const float *bary, const int *tri, int F,
+                           float *out, void *stream)
+{
+    if (!grad || !prim || !tri || !out) return MIRRES_ERR_NULL;
+    if (n < 0 || C < 1 || C > MR_SCATTER_MAX_C || F < 1) return MIRRES_ERR_SHAPE;
+    if (n == 0) return 0;
+    ScatterParams p = {grad, prim, bary, tri, out, n, C, F};
+    return interpolate_bwd_launch(p, (cudaStream_t)stream);
+}
+
+} // extern "C"

@@ -230,14 +230,16 @@ struct Hit {
     float3 pos;
     float3 normal;
     int prim;
+    float bary[2]; // (u, v): weights of the triangle's 2nd and 3rd vertex; the 1st has 1 - u - v
 };
 
 // face normal of the recorded triangle, flipped towards the ray origin (helperDi.slang:299-307).
 // best_slot can only stay -1 when every hit returned NaN; the reference then keeps float3(1).
-MR_DEV void closest_finish(const BvhView &bvh, const Ray &r, int best_slot, float3 &n, int &prim)
+MR_DEV void closest_finish(const BvhView &bvh, const Ray &r, int best_slot, float3 &n, int &prim, float *bary_uv = nullptr)
 {
     n = f3(1.0f);
     prim = -1;
+    if (bary_uv) { bary_uv[0] = 0.f; bary_uv[1] = 0.f; }
     if (best_slot >= 0) {
         const float4 *tp = bvh.tris + 3 * (size_t)best_slot;
         float4 q0 = MR_LDG(tp), q1 = MR_LDG(tp + 1), q2 = MR_LDG(tp + 2);
@@ -249,6 +251,7 @@ MR_DEV void closest_finish(const BvhView &bvh, const Ray &r, int best_slot, floa
         if (dot(-r.d, n) < 0) n = -n;
         n = normalize(n);
         prim = float_bits(q0.w);
+        if (bary_uv) { bary_uv[0] = u; bary_uv[1] = v; }
     }
 }
 
@@ -322,7 +325,7 @@ done:
     }
     out.t = closest;
     out.pos = r.o + closest * r.d;
-    closest_finish(bvh, r, best_slot, out.normal, out.prim);
+    closest_finish(bvh, r, best_slot, out.normal, out.prim, out.bary);
     return true;
 }
 

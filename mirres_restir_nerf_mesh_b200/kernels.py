@@ -258,3 +258,17 @@ class Kernels:
     def normal_ao(self, fx, fy, occ, normal, out_ao):
         rc = self.lib.mirres_normal_ao(fx, fy, self._f(occ), self._f(normal), self._f(out_ao), self._stream())
         self._check(rc, "mirres_normal_ao")
+
+    # -- G-buffer producer / gradient scatter ------------------------------------------------------------------------
+    def gbuffer_primary(self, packed, org, dirs, occ, pos, normal, depth, prim=None, bary=None, vnormal=None, tri=None):
+        rc = self.lib.mirres_gbuffer_primary(self._p(packed[0]), self._p(packed[1]), self._f(org), self._f(dirs),
+                                             org.shape[0], self._f(vnormal, True), self._i(tri, True), self._f(occ),
+                                             self._f(pos), self._f(normal), self._f(depth), self._i(prim, True),
+                                             self._f(bary, True), self._stream())
+        self._check(rc, "mirres_gbuffer_primary")
+
+    def interpolate_bwd(self, grad, prim, bary, tri, out):
+        rc = self.lib.mirres_interpolate_bwd(self._f(grad), grad.shape[0], grad.shape[1], self._i(prim),
+                                             self._f(bary, True), self._i(tri), tri.shape[0], self._f(out),
+                                             self._stream())
+        self._check(rc, "mirres_interpolate_bwd")

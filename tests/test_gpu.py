@@ -123,6 +123,39 @@ def test_rays_bit_exact(kernels, oracle):
     assert (ot[oh > 0] < 0).any()  # negative-t quirk exercised
 
 
+def test_gbuffer_primary_and_gradient_scatter(kernels, oracle):
+    """SURVEY.md 8f-2 through the C ABI: primary G-buffer bit-exact against the oracle's closest-hit; the warp-aggregated
+    reverse scatter against a float64 index_add (tolerance: float atomics are order-nondeterministic)."""
+    sc = P.scene("C1")
+    w = make_worker(sc)
+    n = len(sc["rays_o"])
+    occ, depth = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    pos, nrm = torch.zeros(n, 3, device=DEV), torch.zeros(n, 3, device=DEV)
+    prim, bary = torch.zeros(n, dtype=torch.int32, device=DEV), torch.zeros(n, 2, device=DEV)
+    kernels.gbuffer_primary(w.packed, tt(sc["rays_o"]), tt(sc["rays_d"]), occ, pos, nrm, depth, prim, bary)
+    oh, ot, op, on, opr = oracle.trace(sc["bvh"], sc["rays_o"], sc["rays_d"])
+    m = oh > 0
+    assert (occ.cpu().numpy() == oh).all() and (prim.cpu().numpy() == opr).all()
+    assert (pos.cpu().numpy()[m] == op[m]).all() and (nrm.cpu().numpy()[m] == on[m]).all()
+    tri = tt(sc["tri"])
+    V = len(sc["vert"])
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for C, use_bary, contended in ((3, True, False), (8, True, False), (5, False, False), (8, True, True)):
+        grad = torch.randn(n, C, generator=g).to(DEV)
+        pr = prim.clone()
+        if contended:  # every foreground pixel sees one of four triangles: exercises the aggregation path
+            pr = torch.where(prim >= 0, prim % 4, prim)
+        out = torch.zeros(V, C, device=DEV)
+        kernels.interpolate_bwd(grad, pr, bary if use_bary else None, tri, out)
+        b = bary.double() if use_bary else torch.full((n, 2), 1 / 3, device=DEV, dtype=torch.float64)
+        wts = torch.stack((1 - b[:, 0] - b[:, 1], b[:, 0], b[:, 1]), 1)
+        fg = pr >= 0
+        want = torch.zeros(V, C, device=DEV, dtype=torch.float64)
+        for kk in range(3):
+            want.index_add_(0, tri[pr[fg].long(), kk].long(), wts[fg, kk:kk + 1] * grad[fg].double())
+        torch.testing.assert_close(out.double(), want, rtol=GRAD_RTOL, atol=1e-3 if contended else 1e-5)
+
+
 @pytest.mark.parametrize("name,metallic", [("T0", 0.0), ("T1", 0.0), ("T2", 0.4), ("C1", 0.0)])
 def test_pipeline_parity(kernels, name, metallic):
     sc = P.scene(name, metallic)

@@ -88,3 +88,53 @@ def test_eaw_and_ao_bit_exact(oracle):
     ao = torch.zeros(color.shape)
     k.normal_ao(sc["W"], sc["H"], H.t(g["occ_map"]), H.t(g["normal_map"]), ao)
     assert (ao.numpy() == oracle.normal_ao(sc["W"], sc["H"], g["occ_map"], g["normal_map"])).all()
+
+
+def _scatter_reference(grad, prim, bary, tri, V):
+    out = np.zeros((V, grad.shape[1]), np.float64)
+    for i in np.nonzero(prim >= 0)[0]:
+        u, v = (bary[i] if bary is not None else (1 / 3, 1 / 3))
+        w = (1 - u - v, u, v) if bary is not None else (1 / 3, 1 / 3, 1 / 3)
+        for k in range(3):
+            out[tri[prim[i], k]] += w[k] * grad[i].astype(np.float64)
+    return out
+
+
+def test_gbuffer_primary_and_interpolate_bwd(oracle):
+    """primary-ray G-buffer (bit-exact against the oracle's closest-hit) and its reverse scatter."""
+    sc = P.scene("T2")
+    w = _worker(sc)
+    k = H.kernels()
+    n = len(sc["rays_o"])
+    occ, pos, nrm, depth = torch.zeros(n), torch.zeros(n, 3), torch.zeros(n, 3), torch.zeros(n)
+    prim, bary = torch.zeros(n, dtype=torch.int32), torch.zeros(n, 2)
+    k.gbuffer_primary(w.packed, H.t(sc["rays_o"]), H.t(sc["rays_d"]), occ, pos, nrm, depth, prim, bary)
+    oh, ot, op, on, opr = oracle.trace(sc["bvh"], sc["rays_o"], sc["rays_d"])
+    m = oh > 0
+    assert m.any() and (~m).any()
+    assert (occ.numpy() == oh).all() and (prim.numpy() == opr).all()
+    assert (pos.numpy()[m] == op[m]).all() and (nrm.numpy()[m] == on[m]).all()
+    assert (pos.numpy()[~m] == 0).all() and (nrm.numpy()[~m] == 0).all() and (prim.numpy()[~m] == -1).all()
+    np.testing.assert_allclose(depth.numpy()[m], np.linalg.norm(op[m] - sc["rays_o"][m], axis=1), rtol=1e-6)
+    # barycentrics reproduce the hit point
+    tri, vert = sc["tri"], sc["vert"]
+    b = bary.numpy()[m]
+    pv = vert[tri[opr[m]]]
+    rec = (1 - b[:, 0:1] - b[:, 1:2]) * pv[:, 0] + b[:, 0:1] * pv[:, 1] + b[:, 1:2] * pv[:, 2]
+    np.testing.assert_allclose(rec, op[m], atol=2e-5)
+    # interpolated vertex normals
+    vn = vert / np.linalg.norm(vert, axis=1, keepdims=True)
+    nrm2 = torch.zeros(n, 3)
+    k.gbuffer_primary(w.packed, H.t(sc["rays_o"]), H.t(sc["rays_d"]), occ, pos, nrm2, depth, prim, bary, H.t(vn.astype(np.float32)), H.t(tri))
+    vv = vn.astype(np.float32)[tri[opr[m]]]
+    want = (1 - b[:, 0:1] - b[:, 1:2]) * vv[:, 0] + b[:, 0:1] * vv[:, 1] + b[:, 1:2] * vv[:, 2]
+    np.testing.assert_allclose(nrm2.numpy()[m], want, atol=1e-6)
+    # reverse scatter, with and without barycentric weights, C = 3 and C = 8
+    rng = np.random.default_rng(0)
+    for C, use_bary in ((3, True), (8, True), (5, False)):
+        grad = rng.standard_normal((n, C)).astype(np.float32)
+        grad[~m] = 7.0  # background gradients must be ignored
+        out = torch.zeros(len(vert), C)
+        k.interpolate_bwd(H.t(grad), prim, bary if use_bary else None, H.t(tri), out)
+        want = _scatter_reference(grad, prim.numpy(), bary.numpy() if use_bary else None, tri, len(vert))
+        np.testing.assert_allclose(out.numpy(), want, rtol=1e-4, atol=1e-5)
