@@ -222,7 +222,7 @@ def run_gpu(args):
         occ, depth = torch.empty(n, 1, device=dev), torch.empty(n, 1, device=dev)
         pos, nrm = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
         prim, bary = torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, 2, device=dev)
-        pk.gbuffer_primary(worker.packed, rays_o, rays_d, occ, pos, nrm, depth, prim, bary)
+        pk.gbuffer_primary(worker.packed, rays_o, rays_d, occ, pos, nrm, depth, prim, bary, ws=slangpy_shim.workspace(dev, n))
         kdks = mat.sample_no_di_dense(pos) * occ   # stand-in for the tiny-cuda-nn material MLP (out of scope)
         env_l = env.detach().clone().requires_grad_(True)
         normal = nrm.requires_grad_(True)

@@ -27,7 +27,7 @@ extern "C" {
 
 #define MIRRES_ERR_NULL (-1)    /* a required pointer is NULL */
 #define MIRRES_ERR_SHAPE (-2)   /* a size argument is out of range */
-#define MIRRES_ERR_ALIGN (-3)   /* a pointer that must be 16-byte (scratch: 256-byte) aligned is not */
+#define MIRRES_ERR_ALIGN (-3)   /* a pointer that must be 16-byte (BVH records: 32-byte, scratch: 256-byte) aligned is not */
 #define MIRRES_ERR_SCRATCH (-4) /* scratch buffer smaller than mirres_bvh_scratch_bytes() */
 #define MIRRES_ERR_ALIAS (-5)   /* input and output buffers that must differ are the same */
 
@@ -40,7 +40,7 @@ int mirres_abi_version(void);
  *   info [2F-1,3] i32 (left, right, primitive; leaf <=> left == right == 0), aabb [2F-1,6] f32 (min xyz, max xyz),
  *   internal nodes [0,F-2] (root 0), leaves [F-1,2F-2] in sorted-Morton order  (renderer_restir.py:61-64).
  * packed_nodes / packed_tris (optional, both or neither): traversal records consumed by every ray-casting
- * entry point below; sizes from mirres_bvh_packed_{node,tri}_bytes, 16-byte aligned.
+ * entry point below; sizes from mirres_bvh_packed_{node,tri}_bytes, 32-byte aligned (256-bit loads).
  * sorted_codes (optional) [F,2] i32: (Morton code, element index) after the stable sort (renderer_restir.py:48-57).
  * scratch: mirres_bvh_scratch_bytes(F) bytes, 256-byte aligned.
  */
@@ -202,6 +202,19 @@ int mirres_eaw_bwd(float c_phi, float n_phi, float p_phi, int fx, int fy, float 
                    const float *grad_out, float *grad_color, float *grad_normal, float *grad_pos, float *cum_w_scratch,
                    void *stream);
 int mirres_normal_ao(int fx, int fy, const float *occ, const float *normal, float *out_ao, void *stream);
+/* Batched a-trous level: n_images (<= 8) colour images filtered over the same occ / normal / pos in one pass -- the five
+ * images run_restir_di_with_pt denoises per level (nerf/renderer_restir.py:517-541).  colors / out_colors / ... are HOST
+ * arrays of n_images device pointers (read at launch).  Per-image results are bit-identical to mirres_eaw_fwd / _bwd;
+ * the guide-buffer loads and the normal / position edge weights are shared.  cum_w (optional in forward, [N] per image)
+ * receives the normalisation of every footprint, which mirres_eaw_bwd_multi consumes instead of recomputing it.
+ * Backward OVERWRITES grad_colors[m], grad_normals[m], grad_pos[m] ([N,3] each, one set per image). */
+int mirres_eaw_fwd_multi(float c_phi, float n_phi, float p_phi, int fx, int fy, float step_width, const float *occ,
+                         const float *normal, const float *pos, int n_images, const float *const *colors,
+                         float *const *out_colors, float *const *cum_w, void *stream);
+int mirres_eaw_bwd_multi(float c_phi, float n_phi, float p_phi, int fx, int fy, float step_width, const float *occ,
+                         const float *normal, const float *pos, int n_images, const float *const *colors,
+                         const float *const *out_colors, const float *const *cum_w, const float *const *grad_outs,
+                         float *const *grad_colors, float *const *grad_normals, float *const *grad_pos, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * G-buffer producer and gradient scatter.
@@ -211,7 +224,8 @@ int mirres_normal_ao(int fx, int fy, const float *occ, const float *normal, floa
  *        pos [n,3], normal [n,3] (face normal flipped towards the ray, or -- when vnormal [V,3] and tri [F,3] are
  *        given -- the barycentric interpolation of the vertex normals, the role of dr.interpolate over
  *        auto_normals, nerf/meshutils.py:14-39), depth [n] = |pos - org|, prim [n] i32 (-1 miss), bary [n,2] = (u, v)
- *        weights of the triangle's 2nd / 3rd vertex.  prim and bary are optional.
+ *        weights of the triangle's 2nd / 3rd vertex.  prim and bary are optional.  workspace (optional, sized by
+ *        mirres_workspace_bytes(n)): the rays go through the persistent queue tracer instead of one thread per ray.
  *   mirres_interpolate_bwd   reverse of that interpolation, i.e. the scatter nvdiffrast / the texture backward do
  *        for the per-pixel gradients the path emits (Resampling.py:193-214):
  *            out[tri[prim[i]][k], c] += w_k(i) * grad[i, c],   w = (1-u-v, u, v)   (bary NULL: 1/3 each)
@@ -220,7 +234,7 @@ int mirres_normal_ao(int fx, int fy, const float *occ, const float *normal, floa
  */
 int mirres_gbuffer_primary(const void *packed_nodes, const void *packed_tris, const float *org, const float *dir, int n,
                            const float *vnormal, const int *tri, float *occ, float *pos, float *normal, float *depth,
-                           int *prim, float *bary, void *stream);
+                           int *prim, float *bary, void *workspace, size_t workspace_bytes, void *stream);
 int mirres_interpolate_bwd(const float *grad, int n, int C, const int *prim, const float *bary, const int *tri, int F,
                            float *out, void *stream);
 

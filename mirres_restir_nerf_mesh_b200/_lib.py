@@ -44,7 +44,9 @@ SIGNATURES = {
     "mirres_eaw_fwd": "fffiif" + "ppppp" + "p",
     "mirres_eaw_bwd": "fffiif" + "ppppp" + "ppppp" + "p",
     "mirres_normal_ao": "iipppp",
-    "mirres_gbuffer_primary": "ppppi" + "pp" + "pppppp" + "p",
+    "mirres_eaw_fwd_multi": "fffiif" + "ppp" + "i" + "ppp" + "p",
+    "mirres_eaw_bwd_multi": "fffiif" + "ppp" + "i" + "ppppppp" + "p",
+    "mirres_gbuffer_primary": "ppppi" + "pp" + "pppppp" + "pz" + "p",
     "mirres_interpolate_bwd": "piipppipp",
 }
 SIZE_FUNCS = ("mirres_bvh_scratch_bytes", "mirres_bvh_packed_node_bytes", "mirres_bvh_packed_tri_bytes",

@@ -134,29 +134,56 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const unsigned int *
     hist[threadIdx.x * num_blocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of hist[256][num_blocks] in place (bin-major order): thread b walks the row of bin b, the 256 row
-// totals are scanned in shared memory, then every row is shifted by the total of the bins before it
-__global__ void __launch_bounds__(256) k_sort_scan(unsigned int *hist, int num_blocks)
+// exclusive scan of hist[256][num_blocks] in place (bin-major order), one block of 32 warps: warp w owns bins
+// [8w, 8w+8); it scans each of its rows with coalesced 32-wide chunks, the 256 row totals are scanned in shared memory,
+// then every row is shifted by the total of the bins before it
+__global__ void __launch_bounds__(1024) k_sort_scan(unsigned int *hist, int num_blocks)
 {
     __shared__ unsigned int totals[256];
-    unsigned int *row = hist + (size_t)threadIdx.x * num_blocks;
-    unsigned int acc = 0;
-    for (int i = 0; i < num_blocks; ++i) {
-        unsigned int v = row[i];
-        row[i] = acc;
-        acc += v;
+    const unsigned int FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int b = 0; b < 8; ++b) {
+        const int bin = wid * 8 + b;
+        unsigned int *row = hist + (size_t)bin * num_blocks;
+        unsigned int carry = 0;
+        for (int base = 0; base < num_blocks; base += 32) {
+            const int i = base + lane;
+            const unsigned int v = i < num_blocks ? row[i] : 0u;
+            unsigned int x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int y = __shfl_up_sync(FULL, x, o);
+                if (lane >= o) x += y;
+            }
+            if (i < num_blocks) row[i] = carry + x - v;
+            carry += __shfl_sync(FULL, x, 31);
+        }
+        if (lane == 0) totals[bin] = carry;
     }
-    totals[threadIdx.x] = acc;
     __syncthreads();
-    // inclusive Hillis-Steele scan over 256 totals
-    for (int o = 1; o < 256; o <<= 1) {
-        unsigned int y = threadIdx.x >= (unsigned int)o ? totals[threadIdx.x - o] : 0u;
-        __syncthreads();
-        totals[threadIdx.x] += y;
-        __syncthreads();
+    if (wid == 0) {
+        // exclusive scan of the 256 totals: 8 per lane
+        unsigned int loc[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { loc[k] = sum; sum += totals[lane * 8 + k]; }
+        unsigned int x = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        const unsigned int before = x - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) totals[lane * 8 + k] = before + loc[k];
     }
-    const unsigned int base = threadIdx.x > 0 ? totals[threadIdx.x - 1] : 0u;
-    for (int i = 0; i < num_blocks; ++i) row[i] += base;
+    __syncthreads();
+    for (int b = 0; b < 8; ++b) {
+        const int bin = wid * 8 + b;
+        const unsigned int add = totals[bin];
+        if (add == 0u) continue;
+        unsigned int *row = hist + (size_t)bin * num_blocks;
+        for (int i = lane; i < num_blocks; i += 32) row[i] += add;
+    }
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const unsigned int *__restrict__ keys_in,
@@ -331,7 +358,7 @@ static int sort_pairs(BuildScratch &s, int F, cudaStream_t st)
     for (int pass = 0; pass < 4; ++pass) {
         int in = pass & 1, out = in ^ 1;
         k_sort_hist<<<s.num_blocks, SORT_THREADS, 0, st>>>(s.keys[in], F, 8 * pass, s.hist, s.num_blocks);
-        k_sort_scan<<<1, 256, 0, st>>>(s.hist, s.num_blocks);
+        k_sort_scan<<<1, 1024, 0, st>>>(s.hist, s.num_blocks);
         k_sort_scatter<<<s.num_blocks, SORT_THREADS, 0, st>>>(s.keys[in], s.vals[in], F, 8 * pass, s.hist, s.num_blocks,
                                                              s.keys[out], s.vals[out]);
     }
@@ -349,7 +376,7 @@ int mirres_abi_version(void) { return MIRRES_ABI_VERSION; }
 
 size_t mirres_bvh_scratch_bytes(int F) { return F < 1 ? 0 : carve(nullptr, F, nullptr); }
 size_t mirres_bvh_packed_node_bytes(int F) { return F < 1 ? 0 : sizeof(PackedNode) * (size_t)(F > 1 ? F - 1 : 1); }
-size_t mirres_bvh_packed_tri_bytes(int F) { return F < 1 ? 0 : sizeof(float4) * 3 * (size_t)F; }
+size_t mirres_bvh_packed_tri_bytes(int F) { return F < 1 ? 0 : sizeof(PackedTri) * (size_t)F; }
 
 int mirres_bvh_build(const float *vert, int V, const int *tri, int F, int *info, float *aabb, void *packed_nodes,
                      void *packed_tris, int *sorted_codes, void *scratch, size_t scratch_bytes, void *stream)
@@ -357,7 +384,7 @@ int mirres_bvh_build(const float *vert, int V, const int *tri, int F, int *info,
     if (!vert || !tri || !info || !aabb || !scratch) return MIRRES_ERR_NULL;
     if (F < 1 || V < 1) return MIRRES_ERR_SHAPE;
     if (scratch_bytes < carve(nullptr, F, nullptr)) return MIRRES_ERR_SCRATCH;
-    if (((uintptr_t)scratch & 255) || ((uintptr_t)packed_nodes & 15) || ((uintptr_t)packed_tris & 15)) return MIRRES_ERR_ALIGN;
+    if (((uintptr_t)scratch & 255) || ((uintptr_t)packed_nodes & 31) || ((uintptr_t)packed_tris & 31)) return MIRRES_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     BuildScratch s;
     carve(&s, F, (char *)scratch);
@@ -373,7 +400,7 @@ int mirres_bvh_build(const float *vert, int V, const int *tri, int F, int *info,
     k_refit<<<grid, 256, 0, st>>>(F, info, aabb, s.parent, s.visits);
     MR_CUDA_CHECK_LAUNCH();
     if (packed_nodes && packed_tris) {
-        PackParams pp = {F, info, aabb, vert, tri, (PackedNode *)packed_nodes, (float4 *)packed_tris};
+        PackParams pp = {F, info, aabb, vert, tri, (PackedNode *)packed_nodes, (PackedTri *)packed_tris};
         return foreach_item<PackParams, pack_item, 256>(pp, F, st);
     }
     return 0;

@@ -136,6 +136,152 @@ MR_DEV void eaw_bwd_px(const EawParams &p, int idx)
     store3(p.g_pos, q, gp);
 }
 
+// ---- batched variants: several colour images filtered over the SAME guide buffers in one pass --------------------------
+// run_restir_di_with_pt denoises five images per a-trous level (diffuse, specular, indirect, indirect diffuse,
+// indirect specular; nerf/renderer_restir.py:517-541) with identical occ / normal / pos.  The normal and position
+// edge-stopping weights (two of the three exps per tap) and the guide loads are shared; per-image arithmetic and its
+// order are unchanged, so every output is bit-identical to the single-image entry point.
+#define MR_EAW_MAX_IMAGES 8
+struct EawMultiParams {
+    float c_phi, n_phi, p_phi;
+    int fx, fy, step, n_images;
+    const float *__restrict__ occ;
+    const float *__restrict__ normal;
+    const float *__restrict__ pos;
+    const float *color[MR_EAW_MAX_IMAGES];
+    float *out_color[MR_EAW_MAX_IMAGES]; // forward: written; backward: read
+    float *cum_w[MR_EAW_MAX_IMAGES];     // forward: optional output; backward: input (normalisation of each footprint)
+    const float *g_out[MR_EAW_MAX_IMAGES];
+    float *g_color[MR_EAW_MAX_IMAGES];
+    float *g_normal[MR_EAW_MAX_IMAGES];
+    float *g_pos[MR_EAW_MAX_IMAGES];
+};
+
+template <int NI>
+MR_DEV void eaw_fwd_multi_px(const EawMultiParams &p, int idx)
+{
+    const size_t q = (size_t)idx;
+    float3 cval[NI];
+#pragma unroll
+    for (int m = 0; m < NI; ++m) cval[m] = load3(p.color[m], q);
+    if (MR_LDG(p.occ + q) < 0.1f) {
+#pragma unroll
+        for (int m = 0; m < NI; ++m) {
+            store3(p.out_color[m], q, cval[m]);
+            if (p.cum_w[m]) p.cum_w[m][q] = 0.f;
+        }
+        return;
+    }
+    const int px = idx % p.fx, py = idx / p.fx;
+    const float3 nval = load3(p.normal, q), pval = load3(p.pos, q);
+    float3 sum[NI];
+    float cum[NI];
+#pragma unroll
+    for (int m = 0; m < NI; ++m) { sum[m] = f3(0.f); cum[m] = 0.f; }
+#pragma unroll 5
+    for (int i = 0; i < 25; ++i) {
+        const int ux = px + (i % 5 - 2) * p.step, uy = py + (i / 5 - 2) * p.step;
+        if (!(ux >= 0 && ux < p.fx && uy >= 0 && uy < p.fy)) continue;
+        const size_t r = (size_t)uy * p.fx + ux;
+        const float n_w = edge_weight(nval, load3(p.normal, r), p.n_phi, true);
+        const float p_w = edge_weight(pval, load3(p.pos, r), p.p_phi, true);
+        const float k = eaw_kernel(i);
+#pragma unroll
+        for (int m = 0; m < NI; ++m) {
+            const float3 ctmp = load3(p.color[m], r);
+            const float c_w = edge_weight(cval[m], ctmp, p.c_phi, false);
+            const float weight = c_w * n_w * p_w;
+            sum[m] += ctmp * weight * k;
+            cum[m] += weight * k;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NI; ++m) {
+        store3(p.out_color[m], q, sum[m] / cum[m]);
+        if (p.cum_w[m]) p.cum_w[m][q] = cum[m];
+    }
+}
+
+template <int NI>
+MR_DEV void eaw_bwd_multi_px(const EawMultiParams &p, int idx)
+{
+    const size_t q = (size_t)idx;
+    const int px = idx % p.fx, py = idx / p.fx;
+    const float3 nq = load3(p.normal, q), pq = load3(p.pos, q);
+    const bool q_center = !(MR_LDG(p.occ + q) < 0.1f);
+    float3 cq[NI], gq[NI], oq[NI], gc[NI], gn[NI], gp[NI];
+    float Wq[NI];
+#pragma unroll
+    for (int m = 0; m < NI; ++m) {
+        cq[m] = load3(p.color[m], q);
+        gq[m] = load3(p.g_out[m], q);
+        oq[m] = load3(p.out_color[m], q);
+        Wq[m] = p.cum_w[m][q];
+        gc[m] = gn[m] = gp[m] = f3(0.f);
+    }
+#pragma unroll 5
+    for (int i = 0; i < 25; ++i) {
+        const int ux = px + (i % 5 - 2) * p.step, uy = py + (i / 5 - 2) * p.step;
+        if (!(ux >= 0 && ux < p.fx && uy >= 0 && uy < p.fy)) continue;
+        const size_t r = (size_t)uy * p.fx + ux;
+        const bool r_center = !(MR_LDG(p.occ + r) < 0.1f);
+        if (!q_center && !r_center) continue;
+        const float3 nr = load3(p.normal, r), pr = load3(p.pos, r);
+        const float n_w = edge_weight(nq, nr, p.n_phi, true), p_w = edge_weight(pq, pr, p.p_phi, true);
+        const float k = eaw_kernel(i);
+        const float3 dn = nq - nr, dp = pq - pr;
+#pragma unroll
+        for (int m = 0; m < NI; ++m) {
+            const float3 cr = load3(p.color[m], r);
+            const float w = edge_weight(cq[m], cr, p.c_phi, false) * n_w * p_w;
+            const float3 dc = cq[m] - cr;
+            if (q_center) {
+                const float gw = k * dot(gq[m], cr - oq[m]) / Wq[m];
+                const float s = -gw * w * 2.0f;
+                gc[m] += dc * (s / p.c_phi);
+                gn[m] += dn * (s / p.n_phi);
+                gp[m] += dp * (s / p.p_phi);
+            }
+            if (r_center) {
+                const float3 gr = load3(p.g_out[m], r), orr = load3(p.out_color[m], r);
+                const float Wr = p.cum_w[m][r];
+                gc[m] += gr * (w * k / Wr);
+                const float gw = k * dot(gr, cq[m] - orr) / Wr;
+                const float s = -gw * w * 2.0f;
+                gc[m] += dc * (s / p.c_phi);
+                gn[m] += dn * (s / p.n_phi);
+                gp[m] += dp * (s / p.p_phi);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NI; ++m) {
+        store3(p.g_color[m], q, gc[m]);
+        store3(p.g_normal[m], q, gn[m]);
+        store3(p.g_pos[m], q, gp[m]);
+    }
+}
+
+template <int NI>
+static int eaw_multi_launch(const EawMultiParams &p, bool backward, cudaStream_t st)
+{
+    if (backward) return foreach_item<EawMultiParams, eaw_bwd_multi_px<NI>, 128>(p, p.fx * p.fy, st);
+    return foreach_item<EawMultiParams, eaw_fwd_multi_px<NI>, 128>(p, p.fx * p.fy, st);
+}
+static int eaw_multi_dispatch(const EawMultiParams &p, bool backward, cudaStream_t st)
+{
+    switch (p.n_images) {
+    case 1: return eaw_multi_launch<1>(p, backward, st);
+    case 2: return eaw_multi_launch<2>(p, backward, st);
+    case 3: return eaw_multi_launch<3>(p, backward, st);
+    case 4: return eaw_multi_launch<4>(p, backward, st);
+    case 5: return eaw_multi_launch<5>(p, backward, st);
+    case 6: return eaw_multi_launch<6>(p, backward, st);
+    case 7: return eaw_multi_launch<7>(p, backward, st);
+    default: return eaw_multi_launch<8>(p, backward, st);
+    }
+}
+
 struct AoParams {
     int fx, fy;
     const float *__restrict__ occ;
@@ -200,6 +346,51 @@ int mirres_eaw_bwd(float c_phi, float n_phi, float p_phi, int fx, int fy, float 
     int rc = foreach_item<EawParams, eaw_norm_px, 128>(p, fx * fy, (cudaStream_t)stream);
     if (rc) return rc;
     return foreach_item<EawParams, eaw_bwd_px, 128>(p, fx * fy, (cudaStream_t)stream);
+}
+
+int mirres_eaw_fwd_multi(float c_phi, float n_phi, float p_phi, int fx, int fy, float step_width, const float *occ,
+                         const float *normal, const float *pos, int n_images, const float *const *colors,
+                         float *const *out_colors, float *const *cum_w, void *stream)
+{
+    if (!occ || !normal || !pos || !colors || !out_colors) return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1 || n_images < 1 || n_images > MR_EAW_MAX_IMAGES) return MIRRES_ERR_SHAPE;
+    EawMultiParams p = {};
+    p.c_phi = c_phi; p.n_phi = n_phi; p.p_phi = p_phi; p.fx = fx; p.fy = fy; p.step = (int)step_width; p.n_images = n_images;
+    p.occ = occ; p.normal = normal; p.pos = pos;
+    for (int m = 0; m < n_images; ++m) {
+        if (!colors[m] || !out_colors[m]) return MIRRES_ERR_NULL;
+        for (int j = 0; j < n_images; ++j)
+            if (out_colors[m] == colors[j]) return MIRRES_ERR_ALIAS;
+        p.color[m] = colors[m];
+        p.out_color[m] = out_colors[m];
+        p.cum_w[m] = cum_w ? cum_w[m] : nullptr;
+    }
+    return eaw_multi_dispatch(p, false, (cudaStream_t)stream);
+}
+
+int mirres_eaw_bwd_multi(float c_phi, float n_phi, float p_phi, int fx, int fy, float step_width, const float *occ,
+                         const float *normal, const float *pos, int n_images, const float *const *colors,
+                         const float *const *out_colors, const float *const *cum_w, const float *const *grad_outs,
+                         float *const *grad_colors, float *const *grad_normals, float *const *grad_pos, void *stream)
+{
+    if (!occ || !normal || !pos || !colors || !out_colors || !cum_w || !grad_outs || !grad_colors || !grad_normals || !grad_pos)
+        return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1 || n_images < 1 || n_images > MR_EAW_MAX_IMAGES) return MIRRES_ERR_SHAPE;
+    EawMultiParams p = {};
+    p.c_phi = c_phi; p.n_phi = n_phi; p.p_phi = p_phi; p.fx = fx; p.fy = fy; p.step = (int)step_width; p.n_images = n_images;
+    p.occ = occ; p.normal = normal; p.pos = pos;
+    for (int m = 0; m < n_images; ++m) {
+        if (!colors[m] || !out_colors[m] || !cum_w[m] || !grad_outs[m] || !grad_colors[m] || !grad_normals[m] || !grad_pos[m])
+            return MIRRES_ERR_NULL;
+        p.color[m] = colors[m];
+        p.out_color[m] = (float *)out_colors[m];
+        p.cum_w[m] = (float *)cum_w[m];
+        p.g_out[m] = grad_outs[m];
+        p.g_color[m] = grad_colors[m];
+        p.g_normal[m] = grad_normals[m];
+        p.g_pos[m] = grad_pos[m];
+    }
+    return eaw_multi_dispatch(p, true, (cudaStream_t)stream);
 }
 
 int mirres_normal_ao(int fx, int fy, const float *occ, const float *normal, float *out_ao, void *stream)

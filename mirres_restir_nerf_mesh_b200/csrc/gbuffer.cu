@@ -11,7 +11,7 @@
 //   mirres_interpolate_bwd   reverse of barycentric interpolation: out[tri[prim][k], c] += w_k * grad[pixel, c].
 //                            Neighbouring pixels see the same triangle, so lanes of a warp with the same triangle id
 //                            are summed with a shuffle tree (__match_any_sync) and one lane issues the atomics.
-#include "mr_bvh.cuh"
+#include "mr_wave.cuh"
 #include "../../include/mirres_b200.h"
 
 namespace mr {
@@ -30,6 +30,49 @@ struct GbufParams {
     float *__restrict__ bary;          // [n,2]
 };
 
+// shared tail of both launch shapes
+MR_DEV void gbuffer_write(const GbufParams &p, size_t i, bool found, float3 o, float3 x, float3 n, int prim, float u, float v)
+{
+    float d = 0.f;
+    if (found) {
+        const float3 dv = x - o;
+        d = sqrtf(dot(dv, dv));
+        if (p.vnormal && prim >= 0) {
+            const int i0 = MR_LDG(p.tri + 3 * (size_t)prim), i1 = MR_LDG(p.tri + 3 * (size_t)prim + 1), i2 = MR_LDG(p.tri + 3 * (size_t)prim + 2);
+            const float w = 1.0f - u - v;
+            n = w * load3(p.vnormal, (size_t)i0) + u * load3(p.vnormal, (size_t)i1) + v * load3(p.vnormal, (size_t)i2);
+        }
+    } else {
+        x = f3(0.f);
+        n = f3(0.f);
+    }
+    p.occ[i] = found ? 1.0f : 0.0f;
+    store3(p.pos, i, x);
+    store3(p.normal, i, n);
+    p.depth[i] = d;
+    if (p.prim) p.prim[i] = found ? prim : -1;
+    if (p.bary) { p.bary[2 * i] = found ? u : 0.f; p.bary[2 * i + 1] = found ? v : 0.f; }
+}
+
+// wavefront shape: every pixel queues its primary ray (slot = pixel), the persistent closest-hit tracer walks the queue,
+// the resolve kernel assembles the maps
+struct GbufWaveParams {
+    GbufParams g;
+    Workspace ws;
+    int n;
+};
+MR_DEV void gbuffer_gen_px(const GbufWaveParams &p, int idx)
+{
+    queue_closest_ray(p.ws, (size_t)idx, load3(p.g.org, (size_t)idx), load3(p.g.dir, (size_t)idx));
+}
+MR_DEV void gbuffer_resolve_px(const GbufWaveParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    const float4 h0 = p.ws.chit[3 * i], h1 = p.ws.chit[3 * i + 1], h2 = p.ws.chit[3 * i + 2];
+    gbuffer_write(p.g, i, h0.w > 0.5f, load3(p.g.org, i), make_float3(h0.x, h0.y, h0.z), make_float3(h1.x, h1.y, h1.z),
+                  float_bits(h2.x), h2.y, h2.z);
+}
+
 MR_DEV void gbuffer_item(const GbufParams &p, int idx)
 {
     const size_t i = (size_t)idx;
@@ -41,25 +84,7 @@ MR_DEV void gbuffer_item(const GbufParams &p, int idx)
     h.bary[0] = h.bary[1] = 0.f;
     const float3 o = load3(p.org, i);
     const bool found = closest_hit<false>(p.bvh, o, load3(p.dir, i), h, nullptr);
-    float3 n = f3(0.f), x = f3(0.f);
-    float d = 0.f;
-    if (found) {
-        x = h.pos;
-        n = h.normal;
-        const float3 dv = x - o;
-        d = sqrtf(dot(dv, dv));
-        if (p.vnormal && h.prim >= 0) {
-            const int i0 = MR_LDG(p.tri + 3 * (size_t)h.prim), i1 = MR_LDG(p.tri + 3 * (size_t)h.prim + 1), i2 = MR_LDG(p.tri + 3 * (size_t)h.prim + 2);
-            const float w = 1.0f - h.bary[0] - h.bary[1];
-            n = w * load3(p.vnormal, (size_t)i0) + h.bary[0] * load3(p.vnormal, (size_t)i1) + h.bary[1] * load3(p.vnormal, (size_t)i2);
-        }
-    }
-    p.occ[i] = found ? 1.0f : 0.0f;
-    store3(p.pos, i, x);
-    store3(p.normal, i, n);
-    p.depth[i] = d;
-    if (p.prim) p.prim[i] = found ? h.prim : -1;
-    if (p.bary) { p.bary[2 * i] = found ? h.bary[0] : 0.f; p.bary[2 * i + 1] = found ? h.bary[1] : 0.f; }
+    gbuffer_write(p, i, found, o, h.pos, h.normal, h.prim, h.bary[0], h.bary[1]);
 }
 
 #define MR_SCATTER_MAX_C 8
@@ -201,14 +226,26 @@ extern "C" {
 
 int mirres_gbuffer_primary(const void *packed_nodes, const void *packed_tris, const float *org, const float *dir, int n,
                            const float *vnormal, const int *tri, float *occ, float *pos, float *normal, float *depth,
-                           int *prim, float *bary, void *stream)
+                           int *prim, float *bary, void *workspace, size_t workspace_bytes, void *stream)
 {
     if (!packed_nodes || !packed_tris || !org || !dir || !occ || !pos || !normal || !depth) return MIRRES_ERR_NULL;
     if (vnormal && !tri) return MIRRES_ERR_NULL;
     if (n < 0) return MIRRES_ERR_SHAPE;
     if (n == 0) return 0;
-    GbufParams p = {{(const PackedNode *)packed_nodes, (const float4 *)packed_tris}, org, dir, vnormal, tri, occ, pos, normal, depth, prim, bary};
-    return foreach_item<GbufParams, gbuffer_item, 128>(p, n, (cudaStream_t)stream);
+    GbufParams p = {{(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris}, org, dir, vnormal, tri, occ, pos, normal, depth, prim, bary};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!workspace) return foreach_item<GbufParams, gbuffer_item, 128>(p, n, st);
+    if ((uintptr_t)workspace & 255) return MIRRES_ERR_ALIGN;
+    if (workspace_bytes < workspace_carve(nullptr, n, nullptr)) return MIRRES_ERR_SCRATCH;
+    GbufWaveParams w;
+    w.g = p;
+    w.n = n;
+    workspace_carve(&w.ws, n, (char *)workspace);
+    queue_reset(w.ws, st);
+    int rc;
+    if ((rc = foreach_item<GbufWaveParams, gbuffer_gen_px, 256>(w, n, st))) return rc;
+    if ((rc = trace_queues(p.bvh, w.ws, false, true, device_sm_count(), st))) return rc;
+    return foreach_item<GbufWaveParams, gbuffer_resolve_px, 256>(w, n, st);
 }
 
 int mirres_interpolate_bwd(const float *grad, int n, int C, const int *prim, const float *bary, const int *tri, int F,

@@ -32,17 +32,38 @@
 
 namespace mr {
 
+// One 32-byte sector, fetched with a single 256-bit load (LDG.E.256, new on sm_100): a divergent warp pays one L1
+// tag lookup per lane and instruction whatever the access width, and the shadow-ray kernels are bound by exactly that
+// (ncu: l1tex throughput 87 %), so a 128-byte record costs 4 lookups instead of 7-8 with 128-bit loads.
+struct alignas(32) Rec32 {
+    float v[8];
+};
+MR_DEV Rec32 load_rec(const Rec32 *p)
+{
+#if defined(__CUDA_ARCH__)
+    Rec32 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+#else
+    return *p;
+#endif
+}
+
 // entries in reference visit order: expand(right child) then expand(left child), expand(X) = [X] if X is a leaf,
 // else [right(X), left(X)].  Unused entries hold an empty box (+inf, -inf) and can never pass the slab test.
-struct alignas(16) PackedNode {
-    float4 b[6]; // entry k: floats [6k, 6k+5] = min.xyz max.xyz
-    int4 ref;    // entry refs: >= 0 internal node index, < 0: ~leaf slot
-    float4 pad;  // 128-byte stride (never loaded)
+struct alignas(32) PackedNode {
+    Rec32 e[4]; // entry k: min.xyz, max.xyz, ref bits (>= 0 internal node index, < 0: ~leaf slot), 0
+};
+struct alignas(32) PackedTri {
+    Rec32 a; // v0.xyz, primitive index bits, e1.xyz, 0
+    Rec32 b; // e2.xyz, 0 ...
 };
 
 struct BvhView {
     const PackedNode *__restrict__ nodes; // [max(F-1,1)]
-    const float4 *__restrict__ tris;      // [3*F]: (v0, prim bits) (e1, 0) (e2, 0), leaf order
+    const PackedTri *__restrict__ tris;   // [F], leaf (sorted-Morton) order
 };
 
 // ---- building the traversal records from the reference-layout tensors ---------------------------------
@@ -53,7 +74,7 @@ struct PackParams {
     const float *__restrict__ vert; // [V,3]
     const int *__restrict__ tri;    // [F,3]
     PackedNode *__restrict__ nodes;
-    float4 *__restrict__ tris;
+    PackedTri *__restrict__ tris;
 };
 MR_DEV void pack_item(const PackParams &p, int gid)
 {
@@ -63,9 +84,12 @@ MR_DEV void pack_item(const PackParams &p, int gid)
         int i0 = MR_LDG(p.tri + 3 * (size_t)prim), i1 = MR_LDG(p.tri + 3 * (size_t)prim + 1), i2 = MR_LDG(p.tri + 3 * (size_t)prim + 2);
         float3 v0 = load3(p.vert, (size_t)i0), v1 = load3(p.vert, (size_t)i1), v2 = load3(p.vert, (size_t)i2);
         float3 e1 = v1 - v0, e2 = v2 - v0;
-        p.tris[3 * (size_t)gid] = make_float4(v0.x, v0.y, v0.z, bits_float(prim));
-        p.tris[3 * (size_t)gid + 1] = make_float4(e1.x, e1.y, e1.z, 0.f);
-        p.tris[3 * (size_t)gid + 2] = make_float4(e2.x, e2.y, e2.z, 0.f);
+        PackedTri t;
+        t.a.v[0] = v0.x; t.a.v[1] = v0.y; t.a.v[2] = v0.z; t.a.v[3] = bits_float(prim);
+        t.a.v[4] = e1.x; t.a.v[5] = e1.y; t.a.v[6] = e1.z; t.a.v[7] = 0.f;
+        t.b.v[0] = e2.x; t.b.v[1] = e2.y; t.b.v[2] = e2.z; t.b.v[3] = 0.f;
+        t.b.v[4] = 0.f; t.b.v[5] = 0.f; t.b.v[6] = 0.f; t.b.v[7] = 0.f;
+        p.tris[gid] = t;
     }
     if (gid >= F - 1 && !(F == 1 && gid == 0)) return;
     const float inf = bits_float(0x7f800000);
@@ -97,9 +121,12 @@ MR_DEV void pack_item(const PackParams &p, int gid)
     }
     PackedNode n;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) n.b[k] = make_float4(box[4 * k], box[4 * k + 1], box[4 * k + 2], box[4 * k + 3]);
-    n.ref = make_int4(ref[0], ref[1], ref[2], ref[3]);
-    n.pad = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) n.e[k].v[j] = box[6 * k + j];
+        n.e[k].v[6] = bits_float(ref[k]);
+        n.e[k].v[7] = 0.f;
+    }
     p.nodes[gid] = n;
 }
 
@@ -136,12 +163,12 @@ MR_DEV void slab(const Ray &r, float minx, float miny, float minz, float maxx, f
 }
 
 // Moeller-Trumbore on a packed triangle; returns the line parameter with no range test.
-MR_DEV bool tri_test(const Ray &r, float4 q0, float4 q1, float4 q2, float &t, float &u, float &v)
+MR_DEV bool tri_test(const Ray &r, const Rec32 &a, const Rec32 &b, float &t, float &u, float &v)
 {
     const float epsilon = 1e-15f;
-    float3 v0 = make_float3(q0.x, q0.y, q0.z);
-    float3 E1 = make_float3(q1.x, q1.y, q1.z);
-    float3 E2 = make_float3(q2.x, q2.y, q2.z);
+    float3 v0 = make_float3(a.v[0], a.v[1], a.v[2]);
+    float3 E1 = make_float3(a.v[4], a.v[5], a.v[6]);
+    float3 E2 = make_float3(b.v[0], b.v[1], b.v[2]);
     float3 P = cross(r.d, E2);
     float det = dot(E1, P);
     if (det > -epsilon && det < epsilon) return false;
@@ -163,26 +190,34 @@ struct TraceStats {
 // one wide record: entry distances of its four entries
 struct WideHit {
     float tn[4], tf[4];
-    int4 ref;
+    int ref[4];
 };
-MR_DEV void wide_slabs(const Ray &r, float4 q0, float4 q1, float4 q2, float4 q3, float4 q4, float4 q5, WideHit &w)
+MR_DEV void wide_slabs(const Ray &r, const Rec32 &e0, const Rec32 &e1, const Rec32 &e2, const Rec32 &e3, WideHit &w)
 {
-    slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, w.tn[0], w.tf[0]);
-    slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, w.tn[1], w.tf[1]);
-    slab(r, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, w.tn[2], w.tf[2]);
-    slab(r, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, w.tn[3], w.tf[3]);
+    slab(r, e0.v[0], e0.v[1], e0.v[2], e0.v[3], e0.v[4], e0.v[5], w.tn[0], w.tf[0]);
+    slab(r, e1.v[0], e1.v[1], e1.v[2], e1.v[3], e1.v[4], e1.v[5], w.tn[1], w.tf[1]);
+    slab(r, e2.v[0], e2.v[1], e2.v[2], e2.v[3], e2.v[4], e2.v[5], w.tn[2], w.tf[2]);
+    slab(r, e3.v[0], e3.v[1], e3.v[2], e3.v[3], e3.v[4], e3.v[5], w.tn[3], w.tf[3]);
+    w.ref[0] = float_bits(e0.v[6]);
+    w.ref[1] = float_bits(e1.v[6]);
+    w.ref[2] = float_bits(e2.v[6]);
+    w.ref[3] = float_bits(e3.v[6]);
 }
 MR_DEV void wide_fetch(const Ray &r, const PackedNode *pn, WideHit &w)
 {
-    const float4 q0 = MR_LDG(&pn->b[0]), q1 = MR_LDG(&pn->b[1]), q2 = MR_LDG(&pn->b[2]);
-    const float4 q3 = MR_LDG(&pn->b[3]), q4 = MR_LDG(&pn->b[4]), q5 = MR_LDG(&pn->b[5]);
-    w.ref = MR_LDG(&pn->ref);
-    wide_slabs(r, q0, q1, q2, q3, q4, q5, w);
+    const Rec32 e0 = load_rec(&pn->e[0]), e1 = load_rec(&pn->e[1]), e2 = load_rec(&pn->e[2]), e3 = load_rec(&pn->e[3]);
+    wide_slabs(r, e0, e1, e2, e3, w);
 }
 // record address of a traversal reference: wide node (>= 0) or packed triangle (< 0)
-MR_DEV const float4 *ref_address(const BvhView &bvh, int ref)
+MR_DEV const Rec32 *ref_address(const BvhView &bvh, int ref)
 {
-    return ref >= 0 ? reinterpret_cast<const float4 *>(bvh.nodes + ref) : bvh.tris + 3 * (size_t)(~ref);
+    return ref >= 0 ? reinterpret_cast<const Rec32 *>(bvh.nodes + ref) : reinterpret_cast<const Rec32 *>(bvh.tris + (size_t)(~ref));
+}
+MR_DEV bool tri_test_at(const BvhView &bvh, const Ray &r, int leaf_slot, float &t, float &u, float &v)
+{
+    const PackedTri *tp = bvh.tris + (size_t)leaf_slot;
+    const Rec32 a = load_rec(&tp->a), b = load_rec(&tp->b);
+    return tri_test(r, a, b, t, u, v);
 }
 
 // Boolean query: true iff the reference's bvh_hit(rayo, rayd, 0, 1e7) returns true.
@@ -198,14 +233,13 @@ MR_DEV bool any_hit(const BvhView &bvh, float3 origin, float3 dir, TraceStats *s
         WideHit w;
         wide_fetch(r, bvh.nodes + node, w);
         if (STATS) st->nodes += 1;
-        const int refs[4] = {w.ref.x, w.ref.y, w.ref.z, w.ref.w};
         int next = 0;
         bool have = false;
 #pragma unroll
         for (int k = 3; k >= 0; --k) {
             if (fminf(t_max, w.tf[k]) > w.tn[k]) {
                 if (have) stack[sp++] = next;
-                next = refs[k];
+                next = w.ref[k];
                 have = true;
             }
         }
@@ -216,10 +250,9 @@ MR_DEV bool any_hit(const BvhView &bvh, float3 origin, float3 dir, TraceStats *s
             }
             have = false;
             if (next >= 0) break;
-            const float4 *tp = bvh.tris + 3 * (size_t)(~next);
             float t, u, v;
             if (STATS) st->tris += 1;
-            if (tri_test(r, MR_LDG(tp), MR_LDG(tp + 1), MR_LDG(tp + 2), t, u, v)) return true;
+            if (tri_test_at(bvh, r, ~next, t, u, v)) return true;
         }
         node = next;
     }
@@ -241,16 +274,16 @@ MR_DEV void closest_finish(const BvhView &bvh, const Ray &r, int best_slot, floa
     prim = -1;
     if (bary_uv) { bary_uv[0] = 0.f; bary_uv[1] = 0.f; }
     if (best_slot >= 0) {
-        const float4 *tp = bvh.tris + 3 * (size_t)best_slot;
-        float4 q0 = MR_LDG(tp), q1 = MR_LDG(tp + 1), q2 = MR_LDG(tp + 2);
+        const PackedTri *tp = bvh.tris + (size_t)best_slot;
+        const Rec32 a = load_rec(&tp->a), b = load_rec(&tp->b);
         float t, u, v;
-        tri_test(r, q0, q1, q2, t, u, v);
-        float3 fn = normalize(cross(make_float3(q1.x, q1.y, q1.z), make_float3(q2.x, q2.y, q2.z)));
+        tri_test(r, a, b, t, u, v);
+        float3 fn = normalize(cross(make_float3(a.v[4], a.v[5], a.v[6]), make_float3(b.v[0], b.v[1], b.v[2])));
         float w = 1.0f - u - v;
         n = u * fn + v * fn + w * fn;
         if (dot(-r.d, n) < 0) n = -n;
         n = normalize(n);
-        prim = float_bits(q0.w);
+        prim = float_bits(a.v[3]);
         if (bary_uv) { bary_uv[0] = u; bary_uv[1] = v; }
     }
 }
@@ -271,7 +304,6 @@ MR_DEV bool closest_hit(const BvhView &bvh, float3 origin, float3 dir, Hit &out,
         WideHit w;
         wide_fetch(r, bvh.nodes + node, w);
         if (STATS) st->nodes += 1;
-        const int refs[4] = {w.ref.x, w.ref.y, w.ref.z, w.ref.w};
         int next = 0;
         float next_t = 0.f;
         bool have = false;
@@ -284,7 +316,7 @@ MR_DEV bool closest_hit(const BvhView &bvh, float3 origin, float3 dir, Hit &out,
                     stack_t[sp] = next_t;
                     ++sp;
                 }
-                next = refs[k];
+                next = w.ref[k];
                 next_t = w.tn[k];
                 have = true;
             }
@@ -306,10 +338,9 @@ MR_DEV bool closest_hit(const BvhView &bvh, float3 origin, float3 dir, Hit &out,
             have = false;
             if (next >= 0) break;
             const int slot = ~next;
-            const float4 *tp = bvh.tris + 3 * (size_t)slot;
             float t, u, v;
             if (STATS) st->tris += 1;
-            if (tri_test(r, MR_LDG(tp), MR_LDG(tp + 1), MR_LDG(tp + 2), t, u, v)) {
+            if (tri_test_at(bvh, r, slot, t, u, v)) {
                 // closest = min(t, closest); the normal follows the latest hit with t <= previous closest
                 if (t <= closest) best_slot = slot;
                 closest = fminf(t, closest);

@@ -43,7 +43,7 @@ struct Workspace {
     unsigned int *hit; // [N * 10] per SLOT: MR_HIT_*
     float4 *cray_o;    // [N] dense closest-hit queue: origin.xyz, w = result slot (int bits)
     float4 *cray_d;    // [N]
-    float4 *chit;      // [N * 2] per SLOT (= active pixel): (pos.xyz, -1 no ray / 0 miss / 1 hit) (normal.xyz, t)
+    float4 *chit;      // [N * 3] per SLOT: (pos.xyz, -1 no ray / 0 miss / 1 hit) (normal.xyz, t) (prim bits, u, v, 0)
     float *px;         // [N * MR_PX_SCRATCH_FLOATS] per-active-pixel state carried from gen to resolve
     float *stop_in;    // [N] stop flag of every pixel as it was on entry to a bounce kernel
     int capacity;      // N
@@ -63,7 +63,7 @@ static inline size_t workspace_carve(Workspace *w, int N, char *base)
     p = take((size_t)N * MR_MAX_RAYS_PER_PIXEL * sizeof(unsigned int)); if (w) w->hit = (unsigned int *)p;
     p = take((size_t)N * sizeof(float4)); if (w) w->cray_o = (float4 *)p;
     p = take((size_t)N * sizeof(float4)); if (w) w->cray_d = (float4 *)p;
-    p = take((size_t)N * 2 * sizeof(float4)); if (w) w->chit = (float4 *)p;
+    p = take((size_t)N * 3 * sizeof(float4)); if (w) w->chit = (float4 *)p;
     p = take((size_t)N * MR_PX_SCRATCH_FLOATS * sizeof(float)); if (w) w->px = (float *)p;
     p = take((size_t)N * sizeof(float)); if (w) w->stop_in = (float *)p;
     if (w) w->capacity = N;
@@ -104,7 +104,7 @@ MR_DEV void queue_closest_ray(const Workspace &w, size_t slot, float3 o, float3 
     w.cray_o[q] = make_float4(o.x, o.y, o.z, bits_float((int)slot));
     w.cray_d[q] = make_float4(d.x, d.y, d.z, 0.0f);
 }
-MR_DEV void queue_closest_empty(const Workspace &w, size_t slot) { w.chit[2 * slot] = make_float4(0.f, 0.f, 0.f, -1.0f); }
+MR_DEV void queue_closest_empty(const Workspace &w, size_t slot) { w.chit[3 * slot] = make_float4(0.f, 0.f, 0.f, -1.0f); }
 
 // ---- one-thread-per-entry tracers: the host-check flavour of the queue tracers ------------------------------------
 struct QueueTraceParams {
@@ -126,9 +126,12 @@ MR_DEV void queue_closest_item(const QueueTraceParams &p, int q)
     h.t = 0.f;
     h.pos = f3(0.f);
     h.normal = f3(1.f);
+    h.prim = -1;
+    h.bary[0] = h.bary[1] = 0.f;
     bool found = closest_hit<false>(p.bvh, make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), h, nullptr);
-    p.ws.chit[2 * slot] = make_float4(h.pos.x, h.pos.y, h.pos.z, found ? 1.0f : 0.0f);
-    p.ws.chit[2 * slot + 1] = make_float4(h.normal.x, h.normal.y, h.normal.z, h.t);
+    p.ws.chit[3 * slot] = make_float4(h.pos.x, h.pos.y, h.pos.z, found ? 1.0f : 0.0f);
+    p.ws.chit[3 * slot + 1] = make_float4(h.normal.x, h.normal.y, h.normal.z, h.t);
+    p.ws.chit[3 * slot + 2] = make_float4(bits_float(found ? h.prim : -1), h.bary[0], h.bary[1], 0.f);
 }
 
 // queue tracers and device query: defined once, in wave.cu.  queue_reset must be enqueued before the gen kernel of

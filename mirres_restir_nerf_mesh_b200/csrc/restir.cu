@@ -582,7 +582,7 @@ int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris,
     InitialParams p;
     int rc = ws_open(p.ws, n, workspace, workspace_bytes);
     if (rc) return rc;
-    p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
+    p.bvh = {(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris};
     p.env = {env_tex, env_w, env_h, pdf_, nullptr, mpdf_, nullptr};
     p.g = {occ, normal_depth, brdf_map, ray_dir};
     p.pos_map = pos_map;
@@ -644,7 +644,7 @@ int mirres_spatial_resampling(const void *packed_nodes, const void *packed_tris,
     SpatialParams p;
     int rc = ws_open(p.ws, n, workspace, workspace_bytes);
     if (rc) return rc;
-    p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
+    p.bvh = {(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris};
     p.env = {env_tex, env_w, env_h, nullptr, nullptr, nullptr, nullptr};
     p.g = {occ, normal_depth, brdf_map, ray_dir};
     p.pos_map = pos_map;
@@ -670,7 +670,7 @@ int mirres_final_visibility(const void *packed_nodes, const void *packed_tris, c
     VisParams p;
     int rc = ws_open(p.ws, n, workspace, workspace_bytes);
     if (rc) return rc;
-    p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
+    p.bvh = {(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris};
     p.res_ld = res_ld; p.pos_map = pos_map; p.vis = vis_map; p.n = n;
     queue_reset(p.ws, st);
     if ((rc = foreach_item<VisParams, final_visibility_gen_px, 256>(p, n, st))) return rc;

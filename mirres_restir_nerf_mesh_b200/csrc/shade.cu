@@ -254,10 +254,10 @@ MR_DEV void continue_path_gen(const BounceParams &p, int a, size_t i, const Surf
 
 MR_DEV void continue_path_resolve(const BounceParams &p, int a)
 {
-    const float4 h0 = p.ws.chit[2 * (size_t)a];
+    const float4 h0 = p.ws.chit[3 * (size_t)a];
     if (h0.w < 0.0f) return; // no continuation ray
     const size_t i = (size_t)p.ws.active[a];
-    const float4 h1 = p.ws.chit[2 * (size_t)a + 1];
+    const float4 h1 = p.ws.chit[3 * (size_t)a + 1];
     if (h0.w != 0.0f) {
         p.prd[5 * i + 4] = 0.f;
         store3(p.new_pos, i, make_float3(h0.x, h0.y, h0.z));
@@ -481,7 +481,7 @@ static int fill_bounce(BounceParams &p, const void *packed_nodes, const void *pa
     const int n = fx * fy;
     if (workspace_bytes < workspace_carve(nullptr, n, nullptr)) return MIRRES_ERR_SCRATCH;
     workspace_carve(&p.ws, n, (char *)workspace);
-    p.bvh = {(const PackedNode *)packed_nodes, (const float4 *)packed_tris};
+    p.bvh = {(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris};
     p.frame = frame_index; p.bounce_count = bounce_count; p.max_bounce = max_bounce; p.fx = fx; p.fy = fy;
     p.occ = occ; p.pos_map = pos_map; p.normal = normal; p.ray_dir = ray_dir; p.prd = prd; p.kd = diffuse_map; p.rm = rough_metal;
     p.new_pos = new_pos; p.new_ray_d = new_ray_d; p.new_occ = new_occ; p.new_normal = new_normal;

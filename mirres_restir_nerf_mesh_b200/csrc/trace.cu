@@ -60,7 +60,7 @@ int mirres_trace_closest(const void *packed_nodes, const void *packed_tris, cons
     if (!packed_nodes || !packed_tris || !org || !dir || !hit) return MIRRES_ERR_NULL;
     if (n < 0) return MIRRES_ERR_SHAPE;
     if (n == 0) return 0;
-    TraceParams p = {{(const PackedNode *)packed_nodes, (const float4 *)packed_tris}, org, dir, hit, t, pos, normal, prim, visits};
+    TraceParams p = {{(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris}, org, dir, hit, t, pos, normal, prim, visits};
     return foreach_item<TraceParams, trace_closest_item, 128>(p, n, (cudaStream_t)stream);
 }
 
@@ -70,7 +70,7 @@ int mirres_trace_any(const void *packed_nodes, const void *packed_tris, const fl
     if (!packed_nodes || !packed_tris || !org || !dir || !hit) return MIRRES_ERR_NULL;
     if (n < 0) return MIRRES_ERR_SHAPE;
     if (n == 0) return 0;
-    TraceParams p = {{(const PackedNode *)packed_nodes, (const float4 *)packed_tris}, org, dir, hit, nullptr, nullptr, nullptr, nullptr, visits};
+    TraceParams p = {{(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris}, org, dir, hit, nullptr, nullptr, nullptr, nullptr, visits};
     return foreach_item<TraceParams, trace_any_item, 128>(p, n, (cudaStream_t)stream);
 }
 
@@ -80,8 +80,8 @@ int mirres_bvh_pack(const int *info, const float *aabb, const float *vert, const
 {
     if (!info || !aabb || !vert || !tri || !packed_nodes || !packed_tris) return MIRRES_ERR_NULL;
     if (F < 1) return MIRRES_ERR_SHAPE;
-    if (((uintptr_t)packed_nodes & 15) || ((uintptr_t)packed_tris & 15)) return MIRRES_ERR_ALIGN;
-    PackParams pp = {F, info, aabb, vert, tri, (PackedNode *)packed_nodes, (float4 *)packed_tris};
+    if (((uintptr_t)packed_nodes & 31) || ((uintptr_t)packed_tris & 31)) return MIRRES_ERR_ALIGN;
+    PackParams pp = {F, info, aabb, vert, tri, (PackedNode *)packed_nodes, (PackedTri *)packed_tris};
     return foreach_item<PackParams, pack_item, 256>(pp, F, (cudaStream_t)stream);
 }
 

@@ -208,14 +208,12 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
             if (!have) break;
             // load phase common to both record kinds, so that node lanes and leaf lanes of a diverged warp wait for
             // their L2 round trip at the same time
-            const float4 *rec = ref_address(bvh, cur);
-            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+            const Rec32 *rec = ref_address(bvh, cur);
+            const Rec32 e0 = load_rec(rec), e1 = load_rec(rec + 1);
             if (cur >= 0) {
-                const float4 q3 = __ldg(rec + 3), q4 = __ldg(rec + 4), q5 = __ldg(rec + 5);
-                const int4 ref = __ldg(reinterpret_cast<const int4 *>(rec + 6));
+                const Rec32 e2 = load_rec(rec + 2), e3 = load_rec(rec + 3);
                 WideHit w;
-                wide_slabs(r, q0, q1, q2, q3, q4, q5, w);
-                const int refs[4] = {ref.x, ref.y, ref.z, ref.w};
+                wide_slabs(r, e0, e1, e2, e3, w);
                 int next = 0;
                 bool got = false;
 #pragma unroll
@@ -225,7 +223,7 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
                             if (PREFETCH) prefetch_l1(ref_address(bvh, next));
                             stack[sp++] = next;
                         }
-                        next = refs[k];
+                        next = w.ref[k];
                         got = true;
                     }
                 }
@@ -238,7 +236,7 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
                 }
             } else {
                 float t, u, v;
-                if (tri_test(r, q0, q1, q2, t, u, v)) {
+                if (tri_test(r, e0, e1, t, u, v)) {
                     ws.hit[slot] = MR_HIT_HIT;
                     have = false;
                     found = true;
@@ -311,14 +309,12 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
         for (int it = 0; it < MR_TRACE_STEPS; ++it) {
             if (!have) break;
             bool pop = false;
-            const float4 *rec = ref_address(bvh, cur);
-            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+            const Rec32 *rec = ref_address(bvh, cur);
+            const Rec32 e0 = load_rec(rec), e1 = load_rec(rec + 1);
             if (cur >= 0) {
-                const float4 q3 = __ldg(rec + 3), q4 = __ldg(rec + 4), q5 = __ldg(rec + 5);
-                const int4 ref = __ldg(reinterpret_cast<const int4 *>(rec + 6));
+                const Rec32 e2 = load_rec(rec + 2), e3 = load_rec(rec + 3);
                 WideHit w;
-                wide_slabs(r, q0, q1, q2, q3, q4, q5, w);
-                const int refs[4] = {ref.x, ref.y, ref.z, ref.w};
+                wide_slabs(r, e0, e1, e2, e3, w);
                 int next = 0;
                 float next_t = 0.f;
                 bool got = false;
@@ -331,7 +327,7 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
                             stack_t[sp] = next_t;
                             ++sp;
                         }
-                        next = refs[k];
+                        next = w.ref[k];
                         next_t = w.tn[k];
                         got = true;
                     }
@@ -341,7 +337,7 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
             } else {
                 const int leaf = ~cur;
                 float t, u, v;
-                if (tri_test(r, q0, q1, q2, t, u, v)) {
+                if (tri_test(r, e0, e1, t, u, v)) {
                     if (t <= closest) best_slot = leaf;
                     closest = fminf(t, closest);
                     any = true;
@@ -360,13 +356,15 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
                 }
                 if (!found) {
                     float3 pos = f3(0.f), n = f3(1.0f);
+                    int prim = -1;
+                    float bary[2] = {0.f, 0.f};
                     if (any) {
-                        int prim_unused;
                         pos = r.o + closest * r.d;
-                        closest_finish(bvh, r, best_slot, n, prim_unused);
+                        closest_finish(bvh, r, best_slot, n, prim, bary);
                     }
-                    ws.chit[2 * (size_t)slot] = make_float4(pos.x, pos.y, pos.z, any ? 1.0f : 0.0f);
-                    ws.chit[2 * (size_t)slot + 1] = make_float4(n.x, n.y, n.z, any ? closest : 0.f);
+                    ws.chit[3 * (size_t)slot] = make_float4(pos.x, pos.y, pos.z, any ? 1.0f : 0.0f);
+                    ws.chit[3 * (size_t)slot + 1] = make_float4(n.x, n.y, n.z, any ? closest : 0.f);
+                    ws.chit[3 * (size_t)slot + 2] = make_float4(__int_as_float(prim), bary[0], bary[1], 0.f);
                     have = false;
                 }
             }

@@ -255,16 +255,41 @@ class Kernels:
                                      self._stream())
         self._check(rc, "mirres_eaw_bwd")
 
+    def _ptr_array(self, tensors, optional=False):
+        arr = (ctypes.c_void_p * len(tensors))()
+        for i, t in enumerate(tensors):
+            p = self._f(t, optional)
+            arr[i] = None if p is None else p.value
+        return arr
+
+    def eaw_fwd_multi(self, c_phi, n_phi, p_phi, fx, fy, step_width, occ, normal, pos, colors, outs, cum_w=None):
+        rc = self.lib.mirres_eaw_fwd_multi(float(c_phi), float(n_phi), float(p_phi), fx, fy, float(step_width),
+                                           self._f(occ), self._f(normal), self._f(pos), len(colors),
+                                           self._ptr_array(colors), self._ptr_array(outs),
+                                           None if cum_w is None else self._ptr_array(cum_w, True), self._stream())
+        self._check(rc, "mirres_eaw_fwd_multi")
+
+    def eaw_bwd_multi(self, c_phi, n_phi, p_phi, fx, fy, step_width, occ, normal, pos, colors, outs, cum_w, g_outs,
+                      g_colors, g_normals, g_pos):
+        rc = self.lib.mirres_eaw_bwd_multi(float(c_phi), float(n_phi), float(p_phi), fx, fy, float(step_width),
+                                           self._f(occ), self._f(normal), self._f(pos), len(colors),
+                                           self._ptr_array(colors), self._ptr_array(outs), self._ptr_array(cum_w),
+                                           self._ptr_array(g_outs), self._ptr_array(g_colors),
+                                           self._ptr_array(g_normals), self._ptr_array(g_pos), self._stream())
+        self._check(rc, "mirres_eaw_bwd_multi")
+
     def normal_ao(self, fx, fy, occ, normal, out_ao):
         rc = self.lib.mirres_normal_ao(fx, fy, self._f(occ), self._f(normal), self._f(out_ao), self._stream())
         self._check(rc, "mirres_normal_ao")
 
     # -- G-buffer producer / gradient scatter ------------------------------------------------------------------------
-    def gbuffer_primary(self, packed, org, dirs, occ, pos, normal, depth, prim=None, bary=None, vnormal=None, tri=None):
+    def gbuffer_primary(self, packed, org, dirs, occ, pos, normal, depth, prim=None, bary=None, vnormal=None, tri=None,
+                        ws=None):
+        wsp = (None, 0) if ws is None else self._ws(ws)
         rc = self.lib.mirres_gbuffer_primary(self._p(packed[0]), self._p(packed[1]), self._f(org), self._f(dirs),
                                              org.shape[0], self._f(vnormal, True), self._i(tri, True), self._f(occ),
                                              self._f(pos), self._f(normal), self._f(depth), self._i(prim, True),
-                                             self._f(bary, True), self._stream())
+                                             self._f(bary, True), wsp[0], wsp[1], self._stream())
         self._check(rc, "mirres_gbuffer_primary")
 
     def interpolate_bwd(self, grad, prim, bary, tri, out):

@@ -297,6 +297,74 @@ class EAWDenoise_run(torch.autograd.Function):
         return (None, None, None, None, None, None, None, None, grad_color, grad_normal, grad_pos)
 
 
+class EAWDenoiseMulti(torch.autograd.Function):
+    """One a-trous level over several images that share occ / normal / pos (mirres_eaw_fwd_multi): per image the same
+    arithmetic as EAWDenoise_run, one launch for all.  Gradients are produced only for the images that need them."""
+
+    @staticmethod
+    def forward(ctx, c_phi, n_phi, p_phi, framedim_x, framedim_y, stepWidth, occ_map, normal_map, pos_map, *colors):
+        k = get_kernels()
+        n, dev = framedim_x * framedim_y, occ_map.device
+        cols = [c.contiguous() for c in colors]
+        outs = [torch.empty((n, 3), dtype=torch.float, device=dev) for _ in cols]
+        needs = [bool(c.requires_grad) for c in colors]
+        cum = [torch.empty((n,), dtype=torch.float, device=dev) if needs[i] else None for i in range(len(cols))]
+        occ, nrm, pos = occ_map.contiguous(), normal_map.contiguous(), pos_map.contiguous()
+        k.eaw_fwd_multi(c_phi, n_phi, p_phi, int(framedim_x), int(framedim_y), int(stepWidth), occ, nrm, pos, cols, outs,
+                        cum if any(c is not None for c in cum) else None)
+        ctx.nums = (c_phi, n_phi, p_phi, int(framedim_x), int(framedim_y), int(stepWidth))
+        ctx.needs = needs
+        ctx.n_img = len(cols)
+        ctx.save_for_backward(occ, nrm, pos, *cols, *outs, *[c for c in cum if c is not None])
+        ctx.has_cum = [c is not None for c in cum]
+        # outputs of images that carry no gradient stay out of the graph (they correspond to the reference's no_grad
+        # passes), so the next a-trous level sees the same differentiable / non-differentiable split
+        ctx.mark_non_differentiable(*[o for o, nd in zip(outs, needs) if not nd])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grad_outs):
+        c_phi, n_phi, p_phi, fx, fy, step = ctx.nums
+        saved = ctx.saved_tensors
+        occ, nrm, pos = saved[0:3]
+        ni = ctx.n_img
+        cols, outs = saved[3:3 + ni], saved[3 + ni:3 + 2 * ni]
+        cum_iter = iter(saved[3 + 2 * ni:])
+        cum = [next(cum_iter) if h else None for h in ctx.has_cum]
+        # only images whose colour is differentiable take part, exactly the passes the reference runs through
+        # EAWDenoise_run (the others go through the no_grad twin and never reach autograd)
+        active = [i for i in range(ni) if ctx.needs[i] and grad_outs[i] is not None]
+        g_colors = [None] * ni
+        g_normal = g_pos = None
+        if active:
+            k = get_kernels()
+            mk = lambda: torch.empty_like(cols[0], memory_format=torch.contiguous_format)
+            gc, gn, gp = [mk() for _ in active], [mk() for _ in active], [mk() for _ in active]
+            k.eaw_bwd_multi(c_phi, n_phi, p_phi, fx, fy, step, occ, nrm, pos, [cols[i] for i in active],
+                            [outs[i] for i in active], [cum[i] for i in active],
+                            [grad_outs[i].contiguous() for i in active], gc, gn, gp)
+            for j, i in enumerate(active):
+                if ctx.needs[i]:
+                    g_colors[i] = gc[j]
+            if ctx.needs_input_grad[7]:
+                g_normal = gn[0] if len(gn) == 1 else torch.stack(gn).sum(0)
+            if ctx.needs_input_grad[8]:
+                g_pos = gp[0] if len(gp) == 1 else torch.stack(gp).sum(0)
+        return (None, None, None, None, None, None, None, g_normal, g_pos, *g_colors)
+
+
+def EAWDenoise_multi_use_phi(c_phi, n_phi, p_phi, stepWidth, iter_time, framedim_x, framedim_y, occ_map, colors,
+                             normal_map, pos_map):
+    """Denoising.py:151-197 for several images at once: `iter_time` a-trous levels with step widths stepWidth,
+    stepWidth/2, ...; images that do not require grad behave like EAWDenoise_use_phi_no_di."""
+    outs = tuple(colors)
+    for _ in range(iter_time):
+        outs = EAWDenoiseMulti.apply(c_phi, n_phi, p_phi, framedim_x, framedim_y, stepWidth, occ_map, normal_map, pos_map,
+                                     *outs)
+        stepWidth /= 2
+    return outs
+
+
 def EAWDenoise_run_no_di(m, c_phi, n_phi, p_phi, framedim_x, framedim_y, stepWidth, occ_map, color, normal_map,
                          pos_map):
     out_color = torch.zeros((framedim_x * framedim_y, 3), dtype=torch.float, device=occ_map.device)
@@ -549,7 +617,7 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
                           ray_dir_map, pos_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir,
                           framedim_x, framedim_y, spp, denoise_iter, stepWidth, c_phi_scale=1.0, n_phi_scale=0.1,
                           p_phi_scale=0.1, *, random_offset=None, max_bounce=None, hooks=None, bilateral=None,
-                          overlap=None):
+                          overlap=None, batched_denoise=True):
     occ_map.masked_fill_(occ_map <= 0.5, 0)  # in place, as the reference does (:484-485), but without a host sync
     ray_dir_map = _normalize_rows(ray_dir_map)
     n, dev = framedim_x * framedim_y, pos_map.device
@@ -572,7 +640,14 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
     total_spec_light_1 = total_spec_light_1 / mFrameIndex
     combined_color_indirect = total_diff_light_1 + total_spec_light_1
 
-    if gb_depth is None:
+    if gb_depth is None and batched_denoise:
+        # the five images share occ / normal / pos: one launch per a-trous level (per-image arithmetic unchanged)
+        (denoised_diffuse, denoised_spec, denoised_indirect, denoised_indirect_diff,
+         denoised_indirect_spec) = EAWDenoise_multi_use_phi(
+            c_phi_scale, n_phi_scale, p_phi_scale, stepWidth, denoise_iter, framedim_x, framedim_y, occ_map,
+            (total_diff_light, total_spec_light, combined_color_indirect.detach(), total_diff_light_1.detach(),
+             total_spec_light_1.detach()), normal_map, pos_map)
+    elif gb_depth is None:
         args = (denoising_m, c_phi_scale, n_phi_scale, p_phi_scale, stepWidth, denoise_iter, framedim_x, framedim_y,
                 occ_map)
         denoised_diffuse = EAWDenoise_use_phi(*args, total_diff_light, normal_map, pos_map)

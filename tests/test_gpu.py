@@ -137,6 +137,15 @@ def test_gbuffer_primary_and_gradient_scatter(kernels, oracle):
     m = oh > 0
     assert (occ.cpu().numpy() == oh).all() and (prim.cpu().numpy() == opr).all()
     assert (pos.cpu().numpy()[m] == op[m]).all() and (nrm.cpu().numpy()[m] == on[m]).all()
+    # wavefront launch shape (persistent queue tracer): identical maps
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim
+    o2, d2 = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    p2, n2 = torch.zeros(n, 3, device=DEV), torch.zeros(n, 3, device=DEV)
+    pr2, b2 = torch.zeros(n, dtype=torch.int32, device=DEV), torch.zeros(n, 2, device=DEV)
+    kernels.gbuffer_primary(w.packed, tt(sc["rays_o"]), tt(sc["rays_d"]), o2, p2, n2, d2, pr2, b2,
+                            ws=slangpy_shim.workspace(torch.device(DEV), n))
+    for a_, b_ in ((occ, o2), (pos, p2), (nrm, n2), (depth, d2), (prim, pr2), (bary, b2)):
+        assert torch.equal(a_, b_)
     tri = tt(sc["tri"])
     V = len(sc["vert"])
     g = torch.Generator(device="cpu").manual_seed(0)

@@ -116,6 +116,13 @@ def test_gbuffer_primary_and_interpolate_bwd(oracle):
     assert (pos.numpy()[m] == op[m]).all() and (nrm.numpy()[m] == on[m]).all()
     assert (pos.numpy()[~m] == 0).all() and (nrm.numpy()[~m] == 0).all() and (prim.numpy()[~m] == -1).all()
     np.testing.assert_allclose(depth.numpy()[m], np.linalg.norm(op[m] - sc["rays_o"][m], axis=1), rtol=1e-6)
+    # the wavefront launch shape (persistent queue tracer) gives the same maps
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim
+    o2, p2, n2, d2 = torch.zeros(n), torch.zeros(n, 3), torch.zeros(n, 3), torch.zeros(n)
+    pr2, b2 = torch.zeros(n, dtype=torch.int32), torch.zeros(n, 2)
+    k.gbuffer_primary(w.packed, H.t(sc["rays_o"]), H.t(sc["rays_d"]), o2, p2, n2, d2, pr2, b2, ws=slangpy_shim.workspace("cpu", n))
+    for a_, b_ in ((occ, o2), (pos, p2), (nrm, n2), (depth, d2), (prim, pr2), (bary, b2)):
+        assert (a_.numpy() == b_.numpy()).all()
     # barycentrics reproduce the hit point
     tri, vert = sc["tri"], sc["vert"]
     b = bary.numpy()[m]
