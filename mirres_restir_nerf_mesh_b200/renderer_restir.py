@@ -27,15 +27,16 @@ from .slangpy_shim import get_kernels
 
 TOTAL_RIS_PASSES = 5 + 15  # frame-index stride per spp iteration (nerf/renderer_restir.py:242)
 
+MAX_INDIRECT_CHAINS = 4  # concurrent indirect-path chains (one CUDA stream + path state + ray-queue workspace each)
 _SIDE_STREAMS = {}
 
 
-def _side_stream(device):
-    """One extra CUDA stream per device for the indirect-path chain (see restir_di_with_pt)."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-    st = _SIDE_STREAMS.get(key)
+def _side_stream(device, k=0):
+    """Extra CUDA streams per device for the indirect-path chains (see restir_di_with_pt)."""
+    index = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get((index, k))
     if st is None:
-        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+        st = _SIDE_STREAMS[(index, k)] = torch.cuda.Stream(device=index)
     return st
 
 
@@ -514,54 +515,92 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     scale = (scale_x, scale_y, scale_z)
 
     # The indirect path of an spp iteration (continuation ray + `max_bounce` shaded vertices) reads only the G-buffer
-    # and its own path state, never the reservoirs, so it is independent of the direct-light chain of every iteration.
-    # With `overlap` it is enqueued on a second CUDA stream with its own ray-queue workspace: the two chains then fill
-    # each other's latency tails (a traversal launch ends with a few long rays on an otherwise idle GPU).
+    # and its own path state, never the reservoirs, so it is independent of the direct-light chain AND of the indirect
+    # paths of the other iterations.  With `overlap`, up to MAX_INDIRECT_CHAINS of them run on their own CUDA streams
+    # with their own path state and ray-queue workspace; the chains fill each other's latency tails (a traversal
+    # launch ends with a few long rays on an otherwise idle GPU).  Their per-vertex outputs are added to the running
+    # sums on the main stream in the reference's order (iteration-major, bounce-minor), so the sums stay bit-identical
+    # to the sequential schedule.
     if overlap is None:
         overlap = hooks is None and pos_map.is_cuda
-    main_stream = side_stream = None
+    main_stream = None
     keepalive = []
+    chains = []
+    normal_detached = normal_map.detach()
+
+    def make_chain(tag, stream):
+        c = dict(tag=tag, stream=stream, prd=prd, ping=ping, pong=pong, kd=new_diffuse_map, rs=new_roughness_specular)
+        if tag != "main":
+            c.update(prd=zeros(n, 5),
+                     ping=dict(pos=zeros(n, 3), ray=zeros(n, 3), occ=zeros(n, 1), nrm=zeros(n, 3)),
+                     pong=dict(pos=zeros(n, 3), ray=zeros(n, 3), occ=zeros(n, 1), nrm=zeros(n, 3)),
+                     kd=torch.zeros((n, 3), dtype=torch.float, device=dev),
+                     rs=torch.zeros((n, 2), dtype=torch.float, device=dev))
+        return c
+
     if overlap:
         main_stream = torch.cuda.current_stream()
-        side_stream = _side_stream(dev)
-        side_stream.wait_stream(main_stream)
-    state = dict(kd=new_diffuse_map, rs=new_roughness_specular)
+        for c in range(min(spp, MAX_INDIRECT_CHAINS)):
+            chains.append(make_chain("indirect%d" % c, _side_stream(dev, c)))
+        for c in chains:
+            c["stream"].wait_stream(main_stream)
+    else:
+        chains.append(make_chain("main", None))
+    pending = []  # (iteration, bounce, completion event, (color, diff, spec)) not yet added to the running sums
 
-    def indirect_chain(i, first_pass):
+    def accumulate(upto_iteration):
+        while pending and pending[0][0] <= upto_iteration:
+            _, _, done, outs3 = pending.pop(0)
+            main_stream.wait_event(done)
+            sums["color_1"] += outs3[0]
+            sums["diff_1"] += outs3[1]
+            sums["spec_1"] += outs3[2]
+
+    def indirect_chain(i, first_pass, c):
         base = random_offset + TOTAL_RIS_PASSES * i
         ris_pass = first_pass
+        ping_, pong_, prd_ = c["ping"], c["pong"], c["prd"]
         process_new_dir_for_pt(FinalShading_m, *bvh, base + ris_pass, 0, framedim_x, framedim_y, occ_map, pos_map,
-                               normal_detached, ray_dir_map, prd, kd, rs, ping["pos"], ping["ray"], ping["occ"],
-                               ping["nrm"])
+                               normal_detached, ray_dir_map, prd_, kd, rs, ping_["pos"], ping_["ray"], ping_["occ"],
+                               ping_["nrm"])
         ris_pass += 5
-        src, dst = ping, pong
+        src, dst = ping_, pong_
         for bounce in range(1, max_bounce + 1):
-            keepalive.extend((state["kd"], state["rs"]))
-            state["kd"], state["rs"] = _query_material(mlp_mat, src["occ"], src["pos"], state["kd"], state["rs"],
-                                                       use_scale, scale)
+            keepalive.extend((c["kd"], c["rs"]))
+            c["kd"], c["rs"] = _query_material(mlp_mat, src["occ"], src["pos"], c["kd"], c["rs"], use_scale, scale)
+            if c["stream"] is None:
+                outs3 = (color_1, color_diff_1, color_spec_1)
+            else:
+                outs3 = (zeros(n, 3), zeros(n, 3), zeros(n, 3))  # allocated on the chain's stream, kept until the join
+                keepalive.extend(outs3)
             indirect_one_hit_divided_no_grad(FinalShading_m, *bvh, base + ris_pass, bounce, framedim_x, framedim_y,
                                              env_map, width, height, pdf_, cdf_, mpdf_, mcdf_, src["occ"], src["pos"],
-                                             src["nrm"], src["ray"], prd, state["kd"], state["rs"],
-                                             color_1, color_diff_1, color_spec_1, dst["pos"], dst["ray"], dst["occ"],
+                                             src["nrm"], src["ray"], prd_, c["kd"], c["rs"],
+                                             outs3[0], outs3[1], outs3[2], dst["pos"], dst["ray"], dst["occ"],
                                              dst["nrm"])
-            sums["color_1"] += color_1
-            sums["diff_1"] += color_diff_1
-            sums["spec_1"] += color_spec_1
+            if c["stream"] is None:
+                sums["color_1"] += outs3[0]
+                sums["diff_1"] += outs3[1]
+                sums["spec_1"] += outs3[2]
+            else:
+                done = torch.cuda.Event()
+                done.record(c["stream"])
+                pending.append((i, bounce, done, outs3))
             if hooks is not None:
-                hooks("bounce", (i, bounce), dict(color=color_1, diff=color_diff_1, spec=color_spec_1, prd=prd,
+                hooks("bounce", (i, bounce), dict(color=outs3[0], diff=outs3[1], spec=outs3[2], prd=prd_,
                                                   occ=dst["occ"], pos=dst["pos"]))
             ris_pass += 5
             src, dst = dst, src
 
-    normal_detached = normal_map.detach()
     for i in range(spp):
         base = random_offset + TOTAL_RIS_PASSES * frame
         # frame-index schedule of the reference (nerf/renderer_restir.py:314-459): tiles +0 (+1 inside), initial +2,
         # temporal +3 (i > 0), spatial next, new_dir = spatial + 1, shaded vertices +5 each
         first_indirect_pass = 4 if i == 0 else 5
         if overlap:
-            with torch.cuda.stream(side_stream), slangpy.workspace_tag("indirect"):
-                indirect_chain(i, first_indirect_pass)
+            c = chains[i % len(chains)]
+            with torch.cuda.stream(c["stream"]), slangpy.workspace_tag(c["tag"]):
+                indirect_chain(i, first_indirect_pass, c)
         ris_pass = 0
         GenerateLightTiles(generateLightTiles_m, None, env_map, pdf_, cdf_, mpdf_, mcdf_, width, height,
                            base + ris_pass, light_data, light_uv, light_inv_pdf, light_tile_count, light_tile_size)
@@ -595,7 +634,9 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                                     light_pdf=light_inv_pdf))
         assert ris_pass == first_indirect_pass
         if not overlap:
-            indirect_chain(i, first_indirect_pass)
+            indirect_chain(i, first_indirect_pass, chains[0])
+        else:
+            accumulate(i - len(chains))  # results of a chain that has certainly finished by now: no stall
         frame += 1
         reservoirs, prev_reservoirs = prev_reservoirs, reservoirs
         prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir = occ_map, normal_depth, brdf_map, ray_dir_map
@@ -603,7 +644,9 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         sums["diff"] += color_diff
         sums["spec"] += color_spec
     if overlap:
-        main_stream.wait_stream(side_stream)
+        accumulate(spp)
+        for c in chains:
+            main_stream.wait_stream(c["stream"])
     keepalive.clear()
     return (sums["color"], sums["color_1"], sums["diff"], sums["spec"], sums["diff_1"], sums["spec_1"],
             total_indirect_light, frame)
