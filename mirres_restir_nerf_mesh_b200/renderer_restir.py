@@ -82,7 +82,12 @@ class restirbvhWorker:
 
     def InitialResampling_(self, m, pos_map, reservoirs, env_tex, env_width, env_height, framedim_x, framedim_y,
                            frameIndex, occ_map, normal_depth, brdf_map, ray_dir, pdf_, cdf_, mpdf_, mcdf_, light_data,
-                           light_uv, light_inv_pdf):
+                           light_uv, light_inv_pdf, prepare=True):
+        if not prepare:
+            with slangpy.workspace_prepared():
+                return self.InitialResampling_(m, pos_map, reservoirs, env_tex, env_width, env_height, framedim_x,
+                                               framedim_y, frameIndex, occ_map, normal_depth, brdf_map, ray_dir, pdf_,
+                                               cdf_, mpdf_, mcdf_, light_data, light_uv, light_inv_pdf)
         m.process_InitialResampling_(pos_map=pos_map, reservoirs=reservoirs, env_tex=env_tex, env_width=env_width,
                                      env_height=env_height, framedim_x=framedim_x, framedim_y=framedim_y,
                                      frameIndex=frameIndex, occ_map=occ_map, normal_depth=normal_depth,
@@ -592,57 +597,128 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             ris_pass += 5
             src, dst = dst, src
 
-    for i in range(spp):
-        base = random_offset + TOTAL_RIS_PASSES * frame
-        # frame-index schedule of the reference (nerf/renderer_restir.py:314-459): tiles +0 (+1 inside), initial +2,
-        # temporal +3 (i > 0), spatial next, new_dir = spatial + 1, shaded vertices +5 each
-        first_indirect_pass = 4 if i == 0 else 5
-        if overlap:
+    if overlap:
+        # ---- pipelined schedule -------------------------------------------------------------------------------------------
+        # Only temporal -> spatial reuse carries a dependency from one spp iteration to the next.  Light tiles + initial
+        # candidates depend on the G-buffer and the envmap alone, and final visibility / evaluation / shading only
+        # consume the finished spatial reservoirs, so the three stages run on three streams:
+        #     I: tiles(i) -> initial(i) -> X[i % 2]
+        #     M: temporal(X[i % 2], prev = S[(i-1) % 2]) -> spatial(X[i % 2] -> S[i % 2])          (the critical path)
+        #     S: B <- S[i % 2]; visibility(B); evaluate(B); shade; running sums
+        # B is ONE buffer shared by all iterations, so the autograd Functions keep saving aliases of buffers that later
+        # iterations overwrite, exactly like the reference's two-buffer ping-pong.  Arithmetic, frame
+        # indices and accumulation order are those of the sequential schedule; only the enqueue order differs.
+        st_i, st_s = _side_stream(dev, MAX_INDIRECT_CHAINS), _side_stream(dev, MAX_INDIRECT_CHAINS + 1)
+        for st in (st_i, st_s):
+            st.wait_stream(main_stream)
+        X = (_reservoir_set(n, dev), _reservoir_set(n, dev))
+        S = (_reservoir_set(n, dev), _reservoir_set(n, dev))
+        B = reservoirs
+        slangpy.prepare_workspace(occ_map)
+        with torch.cuda.stream(st_i), slangpy.workspace_tag("initial"):
+            slangpy.prepare_workspace(occ_map)
+        with torch.cuda.stream(st_s), slangpy.workspace_tag("shade"):
+            slangpy.prepare_workspace(occ_map)
+        ev = lambda stream: (lambda e: (e.record(stream), e)[1])(torch.cuda.Event())
+        init_done, spatial_done, copy_done = {}, {}, {}
+        for i in range(spp):
+            base = random_offset + TOTAL_RIS_PASSES * i
+            first_indirect_pass = 4 if i == 0 else 5
             c = chains[i % len(chains)]
             with torch.cuda.stream(c["stream"]), slangpy.workspace_tag(c["tag"]):
                 indirect_chain(i, first_indirect_pass, c)
-        ris_pass = 0
-        GenerateLightTiles(generateLightTiles_m, None, env_map, pdf_, cdf_, mpdf_, mcdf_, width, height,
-                           base + ris_pass, light_data, light_uv, light_inv_pdf, light_tile_count, light_tile_size)
-        ris_pass += 2
-        worker.InitialResampling_(InitialResampling_m, pos_map, reservoirs, env_map, width, height, framedim_x,
-                                  framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map, pdf_, cdf_,
-                                  mpdf_, mcdf_, light_data, light_uv, light_inv_pdf)
-        ris_pass += 1
-        if i > 0:
-            TemporalResampling(TemporalResampling_m, reservoirs, prev_reservoirs, env_map, width, height, framedim_x,
-                               framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map, prev_occ_map,
-                               prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
+            with torch.cuda.stream(st_i), slangpy.workspace_tag("initial"):
+                if i >= 2:
+                    st_i.wait_event(spatial_done[i - 2])  # X[i % 2] was last read by spatial(i - 2)
+                GenerateLightTiles(generateLightTiles_m, None, env_map, pdf_, cdf_, mpdf_, mcdf_, width, height, base,
+                                   light_data, light_uv, light_inv_pdf, light_tile_count, light_tile_size)
+                worker.InitialResampling_(InitialResampling_m, pos_map, X[i % 2], env_map, width, height, framedim_x,
+                                          framedim_y, base + 2, occ_map, normal_depth, brdf_map, ray_dir_map, pdf_, cdf_,
+                                          mpdf_, mcdf_, light_data, light_uv, light_inv_pdf, prepare=False)
+                init_done[i] = ev(st_i)
+            main_stream.wait_event(init_done[i])
+            ris_pass = 3
+            if i > 0:
+                TemporalResampling(TemporalResampling_m, X[i % 2], S[(i - 1) % 2], env_map, width, height, framedim_x,
+                                   framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map, prev_occ_map,
+                                   prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
+                ris_pass += 1
+            if i >= 2:
+                main_stream.wait_event(copy_done[i - 2])  # S[i % 2] was last read by the copy of iteration i - 2
+            worker.SpatialResampling_(SpatialResampling_m, pos_map, S[i % 2], X[i % 2], neighborOffsets, env_map, width,
+                                      height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map,
+                                      ray_dir_map)
             ris_pass += 1
-        reservoirs, prev_reservoirs = prev_reservoirs, reservoirs
-        worker.SpatialResampling_(SpatialResampling_m, pos_map, reservoirs, prev_reservoirs, neighborOffsets, env_map,
-                                  width, height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth,
-                                  brdf_map, ray_dir_map)
-        ris_pass += 1
-        worker.EvaluateFinalSamples_get_vis(EvaluateFinalSamples_m, pos_map, reservoirs, framedim_x, framedim_y,
-                                            eva_vis_map)
-        final_Li = EvaluateFinalSamples_di.apply(EvaluateFinalSamples_m, reservoirs[0], reservoirs[1], reservoirs[2],
-                                                 reservoirs[3], env_map_init, width, height, framedim_x, framedim_y,
-                                                 final_samples[0], final_samples[1], eva_vis_map)
-        color, color_diff, color_spec = FinalShading.apply(FinalShading_m, final_samples[0], final_samples[1], final_Li,
-                                                           env_map, width, height, framedim_x, framedim_y, occ_map,
-                                                           normal_map, ray_dir_map, diffuse_map, roughness_specular)
-        if hooks is not None:
-            hooks("direct", i, dict(reservoirs=reservoirs, prev_reservoirs=prev_reservoirs, vis=eva_vis_map,
-                                    final_samples=final_samples, final_Li=final_Li, color=color, diff=color_diff,
-                                    spec=color_spec, light_data=light_data, light_uv=light_uv,
-                                    light_pdf=light_inv_pdf))
-        assert ris_pass == first_indirect_pass
-        if not overlap:
+            assert ris_pass == first_indirect_pass
+            spatial_done[i] = ev(main_stream)
+            with torch.cuda.stream(st_s), slangpy.workspace_tag("shade"):
+                st_s.wait_event(spatial_done[i])
+                for dst_t, src_t in zip(B, S[i % 2]):
+                    dst_t.data.copy_(src_t)  # raw overwrite, invisible to autograd like the reference's kernels
+                copy_done[i] = ev(st_s)
+                worker.EvaluateFinalSamples_get_vis(EvaluateFinalSamples_m, pos_map, B, framedim_x, framedim_y,
+                                                    eva_vis_map)
+                final_Li = EvaluateFinalSamples_di.apply(EvaluateFinalSamples_m, B[0], B[1], B[2], B[3], env_map_init,
+                                                         width, height, framedim_x, framedim_y, final_samples[0],
+                                                         final_samples[1], eva_vis_map)
+                color, color_diff, color_spec = FinalShading.apply(FinalShading_m, final_samples[0], final_samples[1],
+                                                                   final_Li, env_map, width, height, framedim_x,
+                                                                   framedim_y, occ_map, normal_map, ray_dir_map,
+                                                                   diffuse_map, roughness_specular)
+                sums["color"] += color
+                sums["diff"] += color_diff
+                sums["spec"] += color_spec
+            accumulate(i - len(chains))
+            frame += 1
+            prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir = occ_map, normal_depth, brdf_map, ray_dir_map
+        main_stream.wait_stream(st_i)
+        main_stream.wait_stream(st_s)
+        keepalive.extend(X + S)
+    else:
+        for i in range(spp):
+            base = random_offset + TOTAL_RIS_PASSES * frame
+            # frame-index schedule of the reference (nerf/renderer_restir.py:314-459): tiles +0 (+1 inside), initial +2,
+            # temporal +3 (i > 0), spatial next, new_dir = spatial + 1, shaded vertices +5 each
+            first_indirect_pass = 4 if i == 0 else 5
+            ris_pass = 0
+            GenerateLightTiles(generateLightTiles_m, None, env_map, pdf_, cdf_, mpdf_, mcdf_, width, height,
+                               base + ris_pass, light_data, light_uv, light_inv_pdf, light_tile_count, light_tile_size)
+            ris_pass += 2
+            worker.InitialResampling_(InitialResampling_m, pos_map, reservoirs, env_map, width, height, framedim_x,
+                                      framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map, pdf_, cdf_,
+                                      mpdf_, mcdf_, light_data, light_uv, light_inv_pdf)
+            ris_pass += 1
+            if i > 0:
+                TemporalResampling(TemporalResampling_m, reservoirs, prev_reservoirs, env_map, width, height, framedim_x,
+                                   framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map, prev_occ_map,
+                                   prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
+                ris_pass += 1
+            reservoirs, prev_reservoirs = prev_reservoirs, reservoirs
+            worker.SpatialResampling_(SpatialResampling_m, pos_map, reservoirs, prev_reservoirs, neighborOffsets, env_map,
+                                      width, height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth,
+                                      brdf_map, ray_dir_map)
+            ris_pass += 1
+            worker.EvaluateFinalSamples_get_vis(EvaluateFinalSamples_m, pos_map, reservoirs, framedim_x, framedim_y,
+                                                eva_vis_map)
+            final_Li = EvaluateFinalSamples_di.apply(EvaluateFinalSamples_m, reservoirs[0], reservoirs[1], reservoirs[2],
+                                                     reservoirs[3], env_map_init, width, height, framedim_x, framedim_y,
+                                                     final_samples[0], final_samples[1], eva_vis_map)
+            color, color_diff, color_spec = FinalShading.apply(FinalShading_m, final_samples[0], final_samples[1], final_Li,
+                                                               env_map, width, height, framedim_x, framedim_y, occ_map,
+                                                               normal_map, ray_dir_map, diffuse_map, roughness_specular)
+            if hooks is not None:
+                hooks("direct", i, dict(reservoirs=reservoirs, prev_reservoirs=prev_reservoirs, vis=eva_vis_map,
+                                        final_samples=final_samples, final_Li=final_Li, color=color, diff=color_diff,
+                                        spec=color_spec, light_data=light_data, light_uv=light_uv,
+                                        light_pdf=light_inv_pdf))
+            assert ris_pass == first_indirect_pass
             indirect_chain(i, first_indirect_pass, chains[0])
-        else:
-            accumulate(i - len(chains))  # results of a chain that has certainly finished by now: no stall
-        frame += 1
-        reservoirs, prev_reservoirs = prev_reservoirs, reservoirs
-        prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir = occ_map, normal_depth, brdf_map, ray_dir_map
-        sums["color"] += color
-        sums["diff"] += color_diff
-        sums["spec"] += color_spec
+            frame += 1
+            reservoirs, prev_reservoirs = prev_reservoirs, reservoirs
+            prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir = occ_map, normal_depth, brdf_map, ray_dir_map
+            sums["color"] += color
+            sums["diff"] += color_diff
+            sums["spec"] += color_spec
     if overlap:
         accumulate(spp)
         for c in chains:

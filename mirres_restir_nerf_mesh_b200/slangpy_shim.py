@@ -101,6 +101,26 @@ class workspace_tag:
         _WS_TAG.pop()
 
 
+_SKIP_PREPARE = [False]
+
+
+class workspace_prepared:
+    """Inside the block process_InitialResampling_ does not rebuild the foreground-pixel list of its workspace (the
+    driver has already done it with prepare_workspace for the same occupancy map)."""
+
+    def __enter__(self):
+        _SKIP_PREPARE.append(True)
+
+    def __exit__(self, *a):
+        _SKIP_PREPARE.pop()
+
+
+def prepare_workspace(occ_map):
+    """Builds the foreground-pixel list of the current workspace (see workspace_tag) from the primary occupancy."""
+    occ = _c(occ_map)
+    get_kernels().workspace_prepare(occ, workspace(occ.device, occ.shape[0]))
+
+
 def workspace(device, n_pixels):
     """Wavefront workspace (include/mirres_b200.h) for frames of n_pixels on `device`, allocated once and reused."""
     key = (str(device), int(n_pixels), _WS_TAG[-1])
@@ -200,7 +220,8 @@ def _InitialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reser
     # first kernel of every spp iteration that sees the primary occupancy: (re)build the foreground-pixel list here
     occ = _c(occ_map)
     ws = workspace(occ.device, occ.shape[0])
-    get_kernels().workspace_prepare(occ, ws)
+    if not _SKIP_PREPARE[-1]:
+        get_kernels().workspace_prepare(occ, ws)
     get_kernels().initial_resampling(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), _c(pos_map),
                                      _reservoir(reservoirs), _c(env_tex), int(env_width), int(env_height),
                                      int(framedim_x), int(framedim_y), int(frameIndex), occ, _c(normal_depth),
