@@ -473,7 +473,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                       reservoirs, prev_reservoirs, final_samples, neighborOffsets, light_tile_count, light_tile_size,
                       env_map_init, occ_map, pos_map, normal_map, depth_map, diffuse_map, roughness_specular,
                       ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors, color,
-                      *, random_offset=None, max_bounce=None, hooks=None, overlap=None):
+                      *, random_offset=None, max_bounce=None, hooks=None, overlap=None, shard=None):
     n = framedim_x * framedim_y
     dev = pos_map.device
     if random_offset is None:
@@ -527,7 +527,9 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     # sums on the main stream in the reference's order (iteration-major, bounce-minor), so the sums stay bit-identical
     # to the sequential schedule.
     if overlap is None:
-        overlap = hooks is None and pos_map.is_cuda
+        overlap = hooks is None and pos_map.is_cuda and shard is None
+    if shard is not None and overlap:
+        raise ValueError("row-band sharding uses the sequential schedule (overlap=False)")
     main_stream = None
     keepalive = []
     chains = []
@@ -698,6 +700,10 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                                       width, height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth,
                                       brdf_map, ray_dir_map)
             ris_pass += 1
+            if shard is not None:
+                # spatial reuse of the next iteration (through its temporal pass) reads reservoirs up to 31 rows outside
+                # this rank's band: replace the locally computed halo rows by their owners' values
+                shard.exchange(reservoirs)
             worker.EvaluateFinalSamples_get_vis(EvaluateFinalSamples_m, pos_map, reservoirs, framedim_x, framedim_y,
                                                 eva_vis_map)
             final_Li = EvaluateFinalSamples_di.apply(EvaluateFinalSamples_m, reservoirs[0], reservoirs[1], reservoirs[2],
@@ -736,7 +742,18 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
                           ray_dir_map, pos_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir,
                           framedim_x, framedim_y, spp, denoise_iter, stepWidth, c_phi_scale=1.0, n_phi_scale=0.1,
                           p_phi_scale=0.1, *, random_offset=None, max_bounce=None, hooks=None, bilateral=None,
-                          overlap=None, batched_denoise=True):
+                          overlap=None, batched_denoise=True, shard=None, _shard=None):
+    if shard is not None:
+        with slangpy.active_rows(shard.active[0], shard.active[1], framedim_x):
+            return run_restir_di_with_pt(
+                use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_depth, bvh_restir_worker, make_sampleable_m,
+                generateLightTiles_m, InitialResampling_m, TemporalResampling_m, SpatialResampling_m,
+                EvaluateFinalSamples_m, FinalShading_m, denoising_m, light_data, light_uv, light_inv_pdf, reservoirs,
+                prev_reservoirs, final_samples, neighborOffsets, light_tile_count, light_tile_size, env_map, occ_map,
+                normal_map, depth_map, diffuse_map, roughness_specular, ray_dir_map, pos_map, prev_occ_map,
+                prev_normal_depth, prev_brdf_map, prev_ray_dir, framedim_x, framedim_y, spp, denoise_iter, stepWidth,
+                c_phi_scale, n_phi_scale, p_phi_scale, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks,
+                bilateral=bilateral, overlap=False, batched_denoise=batched_denoise, shard=None, _shard=shard)
     occ_map.masked_fill_(occ_map <= 0.5, 0)  # in place, as the reference does (:484-485), but without a host sync
     ray_dir_map = _normalize_rows(ray_dir_map)
     n, dev = framedim_x * framedim_y, pos_map.device
@@ -750,7 +767,7 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
         final_samples, neighborOffsets, light_tile_count, light_tile_size, env_map, occ_map, pos_map, normal_map,
         depth_map, diffuse_map, roughness_specular, ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map,
         prev_ray_dir, motionVectors, color, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks,
-        overlap=overlap)
+        overlap=overlap, shard=_shard)
     total_color = total_color / mFrameIndex
     total_diff_light = total_diff_light / mFrameIndex
     total_spec_light = total_spec_light / mFrameIndex

@@ -102,6 +102,34 @@ class workspace_tag:
 
 
 _SKIP_PREPARE = [False]
+_ACTIVE_ROWS = [None]
+
+
+class active_rows:
+    """Restricts the foreground-pixel lists built inside the block to image rows [y0, y1) of a frame `fx` pixels wide
+    (row-band sharding of a frame across GPUs, see dist.py).  The kernels still see the full-frame maps -- neighbour
+    and occupancy tests are unchanged -- but only pixels of the band are processed."""
+
+    def __init__(self, y0, y1, fx):
+        self.rows = (int(y0), int(y1), int(fx))
+
+    def __enter__(self):
+        _ACTIVE_ROWS.append(self.rows)
+
+    def __exit__(self, *a):
+        _ACTIVE_ROWS.pop()
+
+
+def _band_occ(occ):
+    rows = _ACTIVE_ROWS[-1]
+    if rows is None:
+        return occ
+    y0, y1, fx = rows
+    m = occ.clone()
+    flat = m.view(-1)
+    flat[:max(y0, 0) * fx] = 0
+    flat[max(y1, 0) * fx:] = 0
+    return m
 
 
 class workspace_prepared:
@@ -118,7 +146,7 @@ class workspace_prepared:
 def prepare_workspace(occ_map):
     """Builds the foreground-pixel list of the current workspace (see workspace_tag) from the primary occupancy."""
     occ = _c(occ_map)
-    get_kernels().workspace_prepare(occ, workspace(occ.device, occ.shape[0]))
+    get_kernels().workspace_prepare(_band_occ(occ), workspace(occ.device, occ.shape[0]))
 
 
 def workspace(device, n_pixels):
@@ -221,7 +249,7 @@ def _InitialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reser
     occ = _c(occ_map)
     ws = workspace(occ.device, occ.shape[0])
     if not _SKIP_PREPARE[-1]:
-        get_kernels().workspace_prepare(occ, ws)
+        get_kernels().workspace_prepare(_band_occ(occ), ws)
     get_kernels().initial_resampling(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), _c(pos_map),
                                      _reservoir(reservoirs), _c(env_tex), int(env_width), int(env_height),
                                      int(framedim_x), int(framedim_y), int(frameIndex), occ, _c(normal_depth),
@@ -297,7 +325,7 @@ def _new_dir(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, frameIndex, bounce_count
              new_occ_map, new_normal):
     if _WS_TAG[-1] != "main" and int(bounce_count) == 0:
         # a chain with its own workspace builds its own foreground-pixel list from the primary occupancy
-        get_kernels().workspace_prepare(_c(occ_map), workspace(prd.device, prd.shape[0]))
+        get_kernels().workspace_prepare(_band_occ(_c(occ_map)), workspace(prd.device, prd.shape[0]))
     get_kernels().bounce_first(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), int(frameIndex), int(bounce_count),
                                m.define("MAX_Bounce", 2), int(framedim_x), int(framedim_y), _c(occ_map), _c(pos_map),
                                _c(normal), _c(ray_dir), prd, _c(diffuse_map), _c(linearRoughness_specular_map),
