@@ -235,6 +235,13 @@ int mirres_eaw_bwd_multi(float c_phi, float n_phi, float p_phi, int fx, int fy, 
 int mirres_gbuffer_primary(const void *packed_nodes, const void *packed_tris, const float *org, const float *dir, int n,
                            const float *vnormal, const int *tri, float *occ, float *pos, float *normal, float *depth,
                            int *prim, float *bary, void *workspace, size_t workspace_bytes, void *stream);
+/* Derived maps of run_restir_di_with_pt in one launch (nerf/renderer_restir.py:279-287 and :484-486; ~25 elementwise torch
+ * launches in the reference, same operations in the same order): occ [n] in place (occ <= 0.5 -> 0); normal_depth [n,4]
+ * = (normal, depth), 16-byte aligned; brdf_map [n,3] = (0.2126 r + 0.7152 g + 0.0722 b of kd, the same weights summed
+ * over metallic, clamp(roughness, 0.01, 1)^2); ray_dir_normalized [n,3] = d / max(|d|, 1e-6). */
+int mirres_prepare_maps(int n, float *occ, const float *normal, const float *depth, const float *diffuse_map,
+                        const float *rough_metal, const float *ray_dir, float *normal_depth, float *brdf_map,
+                        float *ray_dir_normalized, void *stream);
 int mirres_interpolate_bwd(const float *grad, int n, int C, const int *prim, const float *bary, const int *tri, int F,
                            float *out, void *stream);
 

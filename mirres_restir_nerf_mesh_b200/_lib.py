@@ -47,6 +47,7 @@ SIGNATURES = {
     "mirres_eaw_fwd_multi": "fffiif" + "ppp" + "i" + "ppp" + "p",
     "mirres_eaw_bwd_multi": "fffiif" + "ppp" + "i" + "ppppppp" + "p",
     "mirres_gbuffer_primary": "ppppi" + "pp" + "pppppp" + "pz" + "p",
+    "mirres_prepare_maps": "ippppppppp" + "p",
     "mirres_interpolate_bwd": "piipppipp",
 }
 SIZE_FUNCS = ("mirres_bvh_scratch_bytes", "mirres_bvh_packed_node_bytes", "mirres_bvh_packed_tri_bytes",

@@ -87,6 +87,39 @@ MR_DEV void gbuffer_item(const GbufParams &p, int idx)
     gbuffer_write(p, i, found, o, h.pos, h.normal, h.prim, h.bary[0], h.bary[1]);
 }
 
+// ---- derived per-pixel maps of run_restir_di_with_pt in one pass -----------------------------------------------------
+// nerf/renderer_restir.py:279-287 (normal_depth, brdf_map) and :484-486 (occupancy threshold, ray normalisation) are
+// ~25 elementwise torch launches in the reference; same operations, same order, one kernel.
+struct PrepParams {
+    float *occ;                        // [n] in place: occ <= 0.5 -> 0
+    const float *__restrict__ normal;  // [n,3]
+    const float *__restrict__ depth;   // [n]
+    const float *__restrict__ kd;      // [n,3]
+    const float *__restrict__ rs;      // [n,2] roughness, metallic
+    const float *__restrict__ ray_in;  // [n,3]
+    float *__restrict__ normal_depth;  // [n,4]
+    float *__restrict__ brdf_map;      // [n,3] luminance(kd), metallic weight, alpha
+    float *__restrict__ ray_out;       // [n,3]
+};
+MR_DEV float clamp_nan(float x, float lo, float hi) { return x != x ? x : fminf(fmaxf(x, lo), hi); } // torch.clamp
+MR_DEV void prepare_maps_px(const PrepParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    if (p.occ[i] <= 0.5f) p.occ[i] = 0.f;
+    const float3 nrm = load3(p.normal, i);
+    reinterpret_cast<float4 *>(p.normal_depth)[i] = make_float4(nrm.x, nrm.y, nrm.z, MR_LDG(p.depth + i));
+    const float3 kd = load3(p.kd, i);
+    const float r = MR_LDG(p.rs + 2 * i), m = MR_LDG(p.rs + 2 * i + 1);
+    const float lum = kd.x * 0.2126f + kd.y * 0.7152f + kd.z * 0.0722f;
+    const float met = m * 0.2126f + m * 0.7152f + m * 0.0722f;
+    const float a = clamp_nan(r, 0.01f, 1.0f);
+    store3(p.brdf_map, i, make_float3(lum, met, a * a));
+    const float3 d = load3(p.ray_in, i);
+    const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+    const float den = len != len ? len : fmaxf(len, 1e-6f);
+    store3(p.ray_out, i, make_float3(d.x / den, d.y / den, d.z / den));
+}
+
 #define MR_SCATTER_MAX_C 8
 
 struct ScatterParams {
@@ -246,6 +279,18 @@ int mirres_gbuffer_primary(const void *packed_nodes, const void *packed_tris, co
     if ((rc = foreach_item<GbufWaveParams, gbuffer_gen_px, 256>(w, n, st))) return rc;
     if ((rc = trace_queues(p.bvh, w.ws, false, true, device_sm_count(), st))) return rc;
     return foreach_item<GbufWaveParams, gbuffer_resolve_px, 256>(w, n, st);
+}
+
+int mirres_prepare_maps(int n, float *occ, const float *normal, const float *depth, const float *diffuse_map,
+                        const float *rough_metal, const float *ray_dir, float *normal_depth, float *brdf_map,
+                        float *ray_dir_normalized, void *stream)
+{
+    if (!occ || !normal || !depth || !diffuse_map || !rough_metal || !ray_dir || !normal_depth || !brdf_map || !ray_dir_normalized)
+        return MIRRES_ERR_NULL;
+    if (n < 1) return MIRRES_ERR_SHAPE;
+    if ((uintptr_t)normal_depth & 15) return MIRRES_ERR_ALIGN;
+    PrepParams p = {occ, normal, depth, diffuse_map, rough_metal, ray_dir, normal_depth, brdf_map, ray_dir_normalized};
+    return foreach_item<PrepParams, prepare_maps_px, 256>(p, n, (cudaStream_t)stream);
 }
 
 int mirres_interpolate_bwd(const float *grad, int n, int C, const int *prim, const float *bary, const int *tri, int F,

@@ -292,6 +292,12 @@ class Kernels:
                                              self._f(bary, True), wsp[0], wsp[1], self._stream())
         self._check(rc, "mirres_gbuffer_primary")
 
+    def prepare_maps(self, occ, normal, depth, diffuse, rough_metal, ray_dir, normal_depth, brdf_map, ray_out):
+        rc = self.lib.mirres_prepare_maps(occ.shape[0], self._f(occ), self._f(normal), self._f(depth), self._f(diffuse),
+                                          self._f(rough_metal), self._f(ray_dir), self._f(normal_depth),
+                                          self._f(brdf_map), self._f(ray_out), self._stream())
+        self._check(rc, "mirres_prepare_maps")
+
     def interpolate_bwd(self, grad, prim, bary, tri, out):
         rc = self.lib.mirres_interpolate_bwd(self._f(grad), grad.shape[0], grad.shape[1], self._i(prim),
                                              self._f(bary, True), self._i(tri), tri.shape[0], self._f(out),

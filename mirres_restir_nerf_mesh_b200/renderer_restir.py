@@ -114,9 +114,10 @@ class restirbvhWorker:
 # =====================================================================================================================
 # module loading and persistent buffers
 # =====================================================================================================================
-def _reservoir_set(n, device):
-    return (torch.zeros((n, 3), dtype=torch.float, device=device), torch.zeros((n, 1), dtype=torch.float, device=device),
-            torch.zeros((n, 1), dtype=torch.int, device=device), torch.zeros((n, 1), dtype=torch.float, device=device))
+def _reservoir_set(n, device, zero=True):
+    make = torch.zeros if zero else torch.empty
+    return (make((n, 3), dtype=torch.float, device=device), make((n, 1), dtype=torch.float, device=device),
+            make((n, 1), dtype=torch.int, device=device), make((n, 1), dtype=torch.float, device=device))
 
 
 def load_m_for_restir(framedim_x, framedim_y, device='cuda', max_bounce=2):
@@ -209,7 +210,7 @@ class EvaluateFinalSamples_di(torch.autograd.Function):
     @staticmethod
     def forward(ctx, m, res_light_data, res_light_pdf, res_M, res_weight, env_tex, env_width, env_height, framedim_x,
                 framedim_y, finalSamples_dir, finalSamples_distance, eva_vis_map):
-        final_Li = torch.zeros((framedim_x * framedim_y, 3), dtype=torch.float, device=res_light_data.device)
+        final_Li = torch.empty((framedim_x * framedim_y, 3), dtype=torch.float, device=res_light_data.device)  # every row is written
         m.process_EvaluateFinalSamples_di_(
             reservoirs=(res_light_data, res_light_pdf, res_M, res_weight), env_tex=env_tex, env_width=env_width,
             env_height=env_height, framedim_x=framedim_x, framedim_y=framedim_y,
@@ -240,9 +241,9 @@ class FinalShading(torch.autograd.Function):
     def forward(ctx, m, finalSamples_dir, finalSamples_distance, finalSamples_Li, env_tex, env_width, env_height,
                 framedim_x, framedim_y, occ_map, normal, ray_dir, diffuse_map, linearRoughness_specular_map):
         n, dev = framedim_x * framedim_y, occ_map.device
-        color = torch.zeros((n, 3), dtype=torch.float, device=dev)
-        color_diff = torch.zeros((n, 3), dtype=torch.float, device=dev)
-        color_spec = torch.zeros((n, 3), dtype=torch.float, device=dev)
+        color = torch.empty((n, 3), dtype=torch.float, device=dev)  # the kernel writes every pixel of all three
+        color_diff = torch.empty((n, 3), dtype=torch.float, device=dev)
+        color_spec = torch.empty((n, 3), dtype=torch.float, device=dev)
         m.process_FinalShading(finalSample=(finalSamples_dir, finalSamples_distance, finalSamples_Li), env_tex=env_tex,
                                env_width=env_width, env_height=env_height, framedim_x=framedim_x, framedim_y=framedim_y,
                                occ_map=occ_map, normal=normal, ray_dir=ray_dir, diffuse_map=diffuse_map,
@@ -261,10 +262,10 @@ class FinalShading(torch.autograd.Function):
         env_width, env_height, framedim_x, framedim_y = ctx.nums
         m = ctx.slang_m
         cf = torch.contiguous_format
-        grad_normal = torch.zeros_like(normal, memory_format=cf)
-        grad_diffuse = torch.zeros_like(diffuse_map, memory_format=cf)
-        grad_rs = torch.zeros_like(rs_map, memory_format=cf)
-        grad_Li = torch.zeros_like(fs_Li, memory_format=cf)
+        grad_normal = torch.empty_like(normal, memory_format=cf)  # mirres_final_shading_bwd overwrites all four
+        grad_diffuse = torch.empty_like(diffuse_map, memory_format=cf)
+        grad_rs = torch.empty_like(rs_map, memory_format=cf)
+        grad_Li = torch.empty_like(fs_Li, memory_format=cf)
         m.process_FinalShading.bwd(
             finalSample=m.FinalSample(dir=fs_dir, distance=fs_dist, Li=(fs_Li, grad_Li)), env_tex=env_tex,
             env_width=env_width, env_height=env_height, framedim_x=framedim_x, framedim_y=framedim_y, occ_map=occ_map,
@@ -473,7 +474,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                       reservoirs, prev_reservoirs, final_samples, neighborOffsets, light_tile_count, light_tile_size,
                       env_map_init, occ_map, pos_map, normal_map, depth_map, diffuse_map, roughness_specular,
                       ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors, color,
-                      *, random_offset=None, max_bounce=None, hooks=None, overlap=None, shard=None):
+                      *, random_offset=None, max_bounce=None, hooks=None, overlap=None, shard=None, prepared=None):
     n = framedim_x * framedim_y
     dev = pos_map.device
     if random_offset is None:
@@ -495,13 +496,16 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     new_diffuse_map = torch.zeros((n, 3), dtype=torch.float, device=dev)
     new_roughness_specular = torch.zeros((n, 2), dtype=torch.float, device=dev)
 
-    normal_depth = torch.cat((normal_map, depth_map), dim=-1).detach()
     kd, rs = diffuse_map.detach(), roughness_specular.detach()
-    brdf_map = torch.cat((kd[:, 0:1] * 0.2126 + kd[:, 1:2] * 0.7152 + kd[:, 2:3] * 0.0722,
-                          rs[:, 1:2] * 0.2126 + rs[:, 1:2] * 0.7152 + rs[:, 1:2] * 0.0722,
-                          rs[:, 0:1]), dim=-1)
-    brdf_map[:, 2].clamp_(min=0.01, max=1)
-    brdf_map[:, 2] = brdf_map[:, 2] * brdf_map[:, 2]
+    if prepared is not None:
+        normal_depth, brdf_map = prepared  # run_restir_di_with_pt has produced both with mirres_prepare_maps
+    else:
+        normal_depth = torch.cat((normal_map, depth_map), dim=-1).detach()
+        brdf_map = torch.cat((kd[:, 0:1] * 0.2126 + kd[:, 1:2] * 0.7152 + kd[:, 2:3] * 0.0722,
+                              rs[:, 1:2] * 0.2126 + rs[:, 1:2] * 0.7152 + rs[:, 1:2] * 0.0722,
+                              rs[:, 0:1]), dim=-1)
+        brdf_map[:, 2].clamp_(min=0.01, max=1)
+        brdf_map[:, 2] = brdf_map[:, 2] * brdf_map[:, 2]
     eva_vis_map = torch.ones((n, 1), dtype=torch.float, device=dev)
 
     # the reference ignores the reservoirs/prev_* it is handed for these and starts from zeros (:291-302)
@@ -538,9 +542,12 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     def make_chain(tag, stream):
         c = dict(tag=tag, stream=stream, prd=prd, ping=ping, pong=pong, kd=new_diffuse_map, rs=new_roughness_specular)
         if tag != "main":
-            c.update(prd=zeros(n, 5),
-                     ping=dict(pos=zeros(n, 3), ray=zeros(n, 3), occ=zeros(n, 1), nrm=zeros(n, 3)),
-                     pong=dict(pos=zeros(n, 3), ray=zeros(n, 3), occ=zeros(n, 1), nrm=zeros(n, 3)),
+            # path state of a concurrent chain: the bounce kernels initialise prd / new_occ for every pixel and write
+            # pos / ray / normal wherever a later kernel reads them, so only the material maps need a defined start
+            e = lambda *shape: torch.empty(shape, dtype=torch.float, device=dev)
+            c.update(prd=e(n, 5),
+                     ping=dict(pos=e(n, 3), ray=e(n, 3), occ=e(n, 1), nrm=e(n, 3)),
+                     pong=dict(pos=e(n, 3), ray=e(n, 3), occ=e(n, 1), nrm=e(n, 3)),
                      kd=torch.zeros((n, 3), dtype=torch.float, device=dev),
                      rs=torch.zeros((n, 2), dtype=torch.float, device=dev))
         return c
@@ -578,7 +585,8 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             if c["stream"] is None:
                 outs3 = (color_1, color_diff_1, color_spec_1)
             else:
-                outs3 = (zeros(n, 3), zeros(n, 3), zeros(n, 3))  # allocated on the chain's stream, kept until the join
+                # allocated on the chain's stream, kept until the join; the kernel's prologue zero-fills all three
+                outs3 = tuple(torch.empty((n, 3), dtype=torch.float, device=dev) for _ in range(3))
                 keepalive.extend(outs3)
             indirect_one_hit_divided_no_grad(FinalShading_m, *bvh, base + ris_pass, bounce, framedim_x, framedim_y,
                                              env_map, width, height, pdf_, cdf_, mpdf_, mcdf_, src["occ"], src["pos"],
@@ -613,8 +621,8 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         st_i, st_s = _side_stream(dev, MAX_INDIRECT_CHAINS), _side_stream(dev, MAX_INDIRECT_CHAINS + 1)
         for st in (st_i, st_s):
             st.wait_stream(main_stream)
-        X = (_reservoir_set(n, dev), _reservoir_set(n, dev))
-        S = (_reservoir_set(n, dev), _reservoir_set(n, dev))
+        X = (_reservoir_set(n, dev, False), _reservoir_set(n, dev, False))  # both passes write every pixel
+        S = (_reservoir_set(n, dev, False), _reservoir_set(n, dev, False))
         B = reservoirs
         slangpy.prepare_workspace(occ_map)
         with torch.cuda.stream(st_i), slangpy.workspace_tag("initial"):
@@ -742,7 +750,7 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
                           ray_dir_map, pos_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir,
                           framedim_x, framedim_y, spp, denoise_iter, stepWidth, c_phi_scale=1.0, n_phi_scale=0.1,
                           p_phi_scale=0.1, *, random_offset=None, max_bounce=None, hooks=None, bilateral=None,
-                          overlap=None, batched_denoise=True, shard=None, _shard=None):
+                          overlap=None, batched_denoise=True, shard=None, _shard=None, fused_prepare=True):
     if shard is not None:
         with slangpy.active_rows(shard.active[0], shard.active[1], framedim_x):
             return run_restir_di_with_pt(
@@ -754,9 +762,22 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
                 prev_normal_depth, prev_brdf_map, prev_ray_dir, framedim_x, framedim_y, spp, denoise_iter, stepWidth,
                 c_phi_scale, n_phi_scale, p_phi_scale, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks,
                 bilateral=bilateral, overlap=False, batched_denoise=batched_denoise, shard=None, _shard=shard)
-    occ_map.masked_fill_(occ_map <= 0.5, 0)  # in place, as the reference does (:484-485), but without a host sync
-    ray_dir_map = _normalize_rows(ray_dir_map)
     n, dev = framedim_x * framedim_y, pos_map.device
+    prepared = None
+    if fused_prepare and occ_map.is_contiguous():
+        # occupancy threshold (in place, as the reference does, :484-485), ray normalisation, normal_depth and brdf_map
+        # (:279-287) in one launch; the operations and their order are those of the torch expressions in the else branch
+        normal_depth = torch.empty((n, 4), dtype=torch.float, device=dev)
+        brdf_map = torch.empty((n, 3), dtype=torch.float, device=dev)
+        ray_out = torch.empty((n, 3), dtype=torch.float, device=dev)
+        get_kernels().prepare_maps(occ_map, normal_map.detach().contiguous(), depth_map.contiguous(),
+                                   diffuse_map.detach().contiguous(), roughness_specular.detach().contiguous(),
+                                   ray_dir_map.contiguous(), normal_depth, brdf_map, ray_out)
+        ray_dir_map = ray_out
+        prepared = (normal_depth, brdf_map)
+    else:
+        occ_map.masked_fill_(occ_map <= 0.5, 0)  # in place, as the reference does (:484-485), but without a host sync
+        ray_dir_map = _normalize_rows(ray_dir_map)
     motionVectors = None  # the reference passes zeros (:487); NULL means the same to the kernel
     color = None
     (total_color, total_color_1, total_diff_light, total_spec_light, total_diff_light_1, total_spec_light_1,
@@ -767,7 +788,7 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
         final_samples, neighborOffsets, light_tile_count, light_tile_size, env_map, occ_map, pos_map, normal_map,
         depth_map, diffuse_map, roughness_specular, ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map,
         prev_ray_dir, motionVectors, color, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks,
-        overlap=overlap, shard=_shard)
+        overlap=overlap, shard=_shard, prepared=prepared)
     total_color = total_color / mFrameIndex
     total_diff_light = total_diff_light / mFrameIndex
     total_spec_light = total_spec_light / mFrameIndex

@@ -5,13 +5,20 @@ import re
 import sys
 
 
-def main(path, out=None):
+def main(path, out=None, step=None):
+    """step = k: only the launches of the k-th step of the run (a step starts at mr::k_elements, the first kernel of the
+    LBVH rebuild); bench.py's default run is 3 eager warm-ups, 1 capture warm-up, W graph replays, K timed replays, ..."""
     rows = list(csv.reader(open(path)))
     hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     H = rows[hdr]
     ki, vi, ui = H.index("Kernel Name"), H.index("Metric Value"), H.index("Metric Unit")
     agg = collections.OrderedDict()
-    for r in rows[hdr + 1:]:
+    body = rows[hdr + 1:]
+    if step is not None:
+        starts = [i for i, r in enumerate(body) if len(r) > ki and "k_elements" in r[ki]] + [len(body)]
+        body = body[starts[step]:starts[step + 1]]
+        path = "%s [step %d of %d]" % (path, step, len(starts) - 1)
+    for r in body:
         if len(r) <= vi:
             continue
         name = r[ki]
@@ -32,4 +39,5 @@ def main(path, out=None):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != "-" else None,
+         int(sys.argv[3]) if len(sys.argv) > 3 else None)
