@@ -92,6 +92,7 @@ int mirres_trace_any(const void *packed_nodes, const void *packed_tris, const fl
  *       light_cache (optional, [T,8] f32, 16-byte aligned): world direction and emitted radiance of every slot, i.e.
  *       what get_light_info (lightDi.slang:291-298) returns for it; mirres_initial_resampling reads it instead of
  *       re-deriving both for each of the 32 candidates of every pixel (identical values, computed once per slot).
+ *       frame_offset (optional, device): added to frame_index at run time (see "frame offset" below).
  */
 int mirres_env_build_distribution(const float *env_tex, int W, int H, float *pdf_, float *cdf_, float *mpdf_,
                                   float *mcdf_, float *row_scratch, void *stream);
@@ -100,7 +101,7 @@ int mirres_env_distribution2d(int W, int H, float *pdf_, float *cdf_, void *stre
 int mirres_neighbor_offsets(int sample_count, float *out, void *stream);
 int mirres_light_tiles(const float *env_tex, int W, int H, const float *pdf_, const float *cdf_, const float *mpdf_,
                        const float *mcdf_, unsigned int frame_index, int tile_count, int tile_size, float *light_data,
-                       int *light_uv, float *light_pdf, float *light_cache, void *stream);
+                       int *light_uv, float *light_pdf, float *light_cache, const unsigned int *frame_offset, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Wavefront workspace.  Every ray-casting entry point below runs as  gen (one thread per foreground pixel) ->
@@ -109,7 +110,12 @@ int mirres_light_tiles(const float *env_tex, int W, int H, const float *pdf_, co
  * pixels (occ >= 0.1, the test every reference kernel starts with, e.g. InitialResampling.slang:166) and must be
  * called whenever the PRIMARY occupancy map changes (once per frame); the bounce kernels, whose `occ` argument is the
  * occupancy of the previous path vertex, reuse the same list (a path vertex only exists where the primary hit does).
+ * Frame offset: the 32-bit word at byte offset MIRRES_WORKSPACE_FRAME_OFFSET_BYTES of a workspace is added to the
+ * frame_index argument of every entry point that takes that workspace.  The library never writes it; the caller
+ * zero-fills the workspace once and may update the word between launches (e.g. before replaying a CUDA graph whose
+ * frame indices are baked in).  Zero reproduces the reference's frame-index schedule exactly.
  */
+#define MIRRES_WORKSPACE_FRAME_OFFSET_BYTES 32
 size_t mirres_workspace_bytes(int n_pixels);
 int mirres_workspace_prepare(const float *occ, int n_pixels, void *workspace, size_t workspace_bytes, void *stream);
 

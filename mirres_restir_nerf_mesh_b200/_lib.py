@@ -29,7 +29,7 @@ SIGNATURES = {
     "mirres_env_weights": "piipp",
     "mirres_env_distribution2d": "iippp",
     "mirres_neighbor_offsets": "ipp",
-    "mirres_light_tiles": "piippppuiippppp",
+    "mirres_light_tiles": "piippppuiipppppp",
     "mirres_workspace_prepare": "pipzp",
     "mirres_initial_resampling": "ppp" + "pppp" + "pii" + "iiu" + "pppp" + "pp" + "ppp" + "iiiii" + "pz" + "p",
     "mirres_temporal_resampling": "pppp" + "pppp" + "pii" + "iiu" + "pppp" + "pppp" + "p" + "i" + "pz" + "p",

@@ -57,7 +57,9 @@ __global__ void __launch_bounds__(256) k_elements(const float *__restrict__ vert
         if (prim_idx) prim_idx[p] = p;
     }
     if (!extent) return;
-    // warp reduce, then one atomic per warp and component
+    // warp reduce, block reduce in shared memory, then one atomic per block and component (all blocks hit the same six
+    // words, so the number of global atomics is what this kernel's time is made of)
+    __shared__ unsigned int s_mn[3][8], s_mx[3][8];
     unsigned int omn[3], omx[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -66,9 +68,20 @@ __global__ void __launch_bounds__(256) k_elements(const float *__restrict__ vert
         omn[k] = __reduce_min_sync(0xffffffffu, omn[k]);
         omx[k] = __reduce_max_sync(0xffffffffu, omx[k]);
     }
-    if ((threadIdx.x & 31) == 0) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { atomicMin(extent + k, omn[k]); atomicMax(extent + 3 + k, omx[k]); }
+        for (int k = 0; k < 3; ++k) { s_mn[k][wid] = omn[k]; s_mx[k][wid] = omx[k]; }
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            unsigned int a = lane < 8 ? s_mn[k][lane] : 0xffffffffu, b = lane < 8 ? s_mx[k][lane] : 0u;
+            a = __reduce_min_sync(0xffffffffu, a);
+            b = __reduce_max_sync(0xffffffffu, b);
+            if (lane == 0) { atomicMin(extent + k, a); atomicMax(extent + 3 + k, b); }
+        }
     }
 }
 
@@ -134,68 +147,63 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const unsigned int *
     hist[threadIdx.x * num_blocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of hist[256][num_blocks] in place (bin-major order), one block of 32 warps: warp w owns bins
-// [8w, 8w+8); it scans each of its rows with coalesced 32-wide chunks, the 256 row totals are scanned in shared memory,
-// then every row is shifted by the total of the bins before it
-__global__ void __launch_bounds__(1024) k_sort_scan(unsigned int *hist, int num_blocks)
+// exclusive scan of hist[256][num_blocks] (bin-major order): block b (one warp) scans the row of bin b in place with
+// coalesced 32-wide chunks and publishes the row total; the last block to finish scans the 256 totals into bin_base,
+// which k_sort_scatter adds to the row offsets.  `done` must be zero on entry and is reset for the next pass.
+__global__ void __launch_bounds__(32) k_sort_scan(unsigned int *hist, int num_blocks, unsigned int *bin_base, unsigned int *done)
 {
-    __shared__ unsigned int totals[256];
     const unsigned int FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int b = 0; b < 8; ++b) {
-        const int bin = wid * 8 + b;
-        unsigned int *row = hist + (size_t)bin * num_blocks;
-        unsigned int carry = 0;
-        for (int base = 0; base < num_blocks; base += 32) {
-            const int i = base + lane;
-            const unsigned int v = i < num_blocks ? row[i] : 0u;
-            unsigned int x = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned int y = __shfl_up_sync(FULL, x, o);
-                if (lane >= o) x += y;
-            }
-            if (i < num_blocks) row[i] = carry + x - v;
-            carry += __shfl_sync(FULL, x, 31);
-        }
-        if (lane == 0) totals[bin] = carry;
-    }
-    __syncthreads();
-    if (wid == 0) {
-        // exclusive scan of the 256 totals: 8 per lane
-        unsigned int loc[8], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { loc[k] = sum; sum += totals[lane * 8 + k]; }
-        unsigned int x = sum;
+    const int lane = threadIdx.x, bin = blockIdx.x;
+    unsigned int *row = hist + (size_t)bin * num_blocks;
+    unsigned int carry = 0;
+    for (int base = 0; base < num_blocks; base += 32) {
+        const int i = base + lane;
+        const unsigned int v = i < num_blocks ? row[i] : 0u;
+        unsigned int x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned int y = __shfl_up_sync(FULL, x, o);
             if (lane >= o) x += y;
         }
-        const unsigned int before = x - sum;
+        if (i < num_blocks) row[i] = carry + x - v;
+        carry += __shfl_sync(FULL, x, 31);
+    }
+    unsigned int last = 0;
+    if (lane == 0) {
+        bin_base[256 + bin] = carry; // row totals live behind the 256 bases
+        __threadfence();
+        last = atomicAdd(done, 1u) == 255u ? 1u : 0u;
+    }
+    last = __shfl_sync(FULL, last, 0);
+    if (!last) return;
+    __threadfence();
+    // exclusive scan of the 256 totals: 8 per lane
+    unsigned int loc[8], sum = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) totals[lane * 8 + k] = before + loc[k];
+    for (int k = 0; k < 8; ++k) { loc[k] = sum; sum += __ldcg(bin_base + 256 + lane * 8 + k); }
+    unsigned int x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int y = __shfl_up_sync(FULL, x, o);
+        if (lane >= o) x += y;
     }
-    __syncthreads();
-    for (int b = 0; b < 8; ++b) {
-        const int bin = wid * 8 + b;
-        const unsigned int add = totals[bin];
-        if (add == 0u) continue;
-        unsigned int *row = hist + (size_t)bin * num_blocks;
-        for (int i = lane; i < num_blocks; i += 32) row[i] += add;
-    }
+    const unsigned int before = x - sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bin_base[lane * 8 + k] = before + loc[k];
+    if (lane == 0) *done = 0u;
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const unsigned int *__restrict__ keys_in,
                                                                const int *__restrict__ vals_in, int n, int shift,
                                                                const unsigned int *__restrict__ hist, int num_blocks,
+                                                               const unsigned int *__restrict__ bin_base,
                                                                unsigned int *__restrict__ keys_out,
                                                                int *__restrict__ vals_out)
 {
     __shared__ unsigned int running[256];                     // keys of this digit already placed by this block
     __shared__ unsigned short warp_cnt[SORT_THREADS / 32][256]; // per-round, per-warp digit counts
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    running[threadIdx.x] = hist[threadIdx.x * num_blocks + blockIdx.x];
+    running[threadIdx.x] = hist[threadIdx.x * num_blocks + blockIdx.x] + bin_base[threadIdx.x];
     int base = blockIdx.x * SORT_TILE;
     for (int j = 0; j < SORT_ITEMS; ++j) {
 #pragma unroll
@@ -329,6 +337,8 @@ struct BuildScratch {
     unsigned int *keys[2];  // F each
     int *vals[2];           // F each
     unsigned int *hist;     // 256*num_blocks
+    unsigned int *bin_base; // 512: exclusive bin bases, row totals
+    unsigned int *done;     // arrival counter of the scan
     int *parent;            // 2F-1
     int *visits;            // F
     unsigned int *extent;   // 8
@@ -345,6 +355,8 @@ static size_t carve(BuildScratch *s, int F, char *base)
     for (int k = 0; k < 2; ++k) { p = take((size_t)F * 4); if (s) s->keys[k] = (unsigned int *)p; }
     for (int k = 0; k < 2; ++k) { p = take((size_t)F * 4); if (s) s->vals[k] = (int *)p; }
     p = take((size_t)256 * nb * 4); if (s) s->hist = (unsigned int *)p;
+    p = take(512 * 4); if (s) s->bin_base = (unsigned int *)p;
+    p = take(64); if (s) s->done = (unsigned int *)p;
     p = take((size_t)(2 * F) * 4); if (s) s->parent = (int *)p;
     p = take((size_t)F * 4); if (s) s->visits = (int *)p;
     p = take(64); if (s) s->extent = (unsigned int *)p;
@@ -355,12 +367,13 @@ static size_t carve(BuildScratch *s, int F, char *base)
 static int sort_pairs(BuildScratch &s, int F, cudaStream_t st)
 {
     // 4 passes; result ends in keys[0]/vals[0]
+    cudaMemsetAsync(s.done, 0, sizeof(unsigned int), st);
     for (int pass = 0; pass < 4; ++pass) {
         int in = pass & 1, out = in ^ 1;
         k_sort_hist<<<s.num_blocks, SORT_THREADS, 0, st>>>(s.keys[in], F, 8 * pass, s.hist, s.num_blocks);
-        k_sort_scan<<<1, 1024, 0, st>>>(s.hist, s.num_blocks);
+        k_sort_scan<<<256, 32, 0, st>>>(s.hist, s.num_blocks, s.bin_base, s.done);
         k_sort_scatter<<<s.num_blocks, SORT_THREADS, 0, st>>>(s.keys[in], s.vals[in], F, 8 * pass, s.hist, s.num_blocks,
-                                                             s.keys[out], s.vals[out]);
+                                                             s.bin_base, s.keys[out], s.vals[out]);
     }
     MR_CUDA_CHECK_LAUNCH();
     return 0;

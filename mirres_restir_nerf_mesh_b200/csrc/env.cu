@@ -168,6 +168,7 @@ MR_DEV void neighbor_offsets_one(const OffsetParams &p, int)
 struct TileParams {
     EnvView e;
     unsigned int frameIndex;
+    const unsigned int *__restrict__ frame_offset; // optional device-resident offset added to frameIndex
     float *__restrict__ light_data;
     int *__restrict__ light_uv;
     float *__restrict__ light_pdf;
@@ -176,7 +177,7 @@ struct TileParams {
 MR_DEV void light_tile_px(const TileParams &p, int b)
 {
     const EnvView &e = p.e;
-    const unsigned int frameIndex = p.frameIndex;
+    const unsigned int frameIndex = p.frameIndex + (p.frame_offset ? MR_LDG(p.frame_offset) : 0u);
     float *light_data = p.light_data;
     int *light_uv = p.light_uv;
     float *light_pdf = p.light_pdf;
@@ -264,12 +265,12 @@ int mirres_neighbor_offsets(int sample_count, float *out, void *stream)
 
 int mirres_light_tiles(const float *env_tex, int W, int H, const float *pdf_, const float *cdf_, const float *mpdf_,
                        const float *mcdf_, unsigned int frame_index, int tile_count, int tile_size, float *light_data,
-                       int *light_uv, float *light_pdf, float *light_cache, void *stream)
+                       int *light_uv, float *light_pdf, float *light_cache, const unsigned int *frame_offset, void *stream)
 {
     if (!env_tex || !pdf_ || !cdf_ || !mpdf_ || !mcdf_ || !light_data || !light_uv || !light_pdf) return MIRRES_ERR_NULL;
     if (W < 1 || H < 1 || tile_count < 1 || tile_size < 1) return MIRRES_ERR_SHAPE;
     if ((uintptr_t)light_cache & 15) return MIRRES_ERR_ALIGN;
-    TileParams p = {{env_tex, W, H, pdf_, cdf_, mpdf_, mcdf_}, frame_index, light_data, light_uv, light_pdf, (float4 *)light_cache};
+    TileParams p = {{env_tex, W, H, pdf_, cdf_, mpdf_, mcdf_}, frame_index, frame_offset, light_data, light_uv, light_pdf, (float4 *)light_cache};
     return foreach_item<TileParams, light_tile_px, 256>(p, tile_count * tile_size, (cudaStream_t)stream);
 }
 

@@ -33,6 +33,10 @@ namespace mr {
 #define MR_CTR_ANY_SIZE 2
 #define MR_CTR_CLOSEST_TICKET 3
 #define MR_CTR_CLOSEST_SIZE 4
+// [8] frame offset: added to the frame_index argument of every kernel that takes a workspace.  Written by the caller
+// (never by the library), so a CUDA graph whose launches have their frame indices baked in can be replayed with fresh
+// random streams (graphed.CapturedStep.set_frame_offset).  Zero = the plain reference behaviour.
+#define MR_CTR_FRAME_OFFSET 8
 
 struct Workspace {
     int *counters;     // [64] see MR_CTR_*
@@ -69,6 +73,8 @@ static inline size_t workspace_carve(Workspace *w, int N, char *base)
     if (w) w->capacity = N;
     return off;
 }
+
+MR_DEV unsigned int frame_of(const Workspace &w, unsigned int frame_index) { return frame_index + (unsigned int)w.counters[MR_CTR_FRAME_OFFSET]; }
 
 // one ticket of a queue; lanes of a warp that arrive together share one atomic
 MR_DEV int queue_alloc(int *ctr)

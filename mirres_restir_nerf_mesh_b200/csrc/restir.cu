@@ -126,10 +126,10 @@ MR_DEV void initial_gen_px(const InitialParams &p, int a)
     const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
-    uint32_t tileSg = seed_of(px / p.screen_tile, py / p.screen_tile, p.frame);
+    uint32_t tileSg = seed_of(px / p.screen_tile, py / p.screen_tile, frame_of(p.ws, p.frame));
     uint32_t tileIndex = minu(to_uint(rnd(tileSg) * (float)p.tile_count), p.tile_count - 1u);
     const uint32_t tileOffset = tileIndex * p.tile_size;
-    uint32_t sg = seed_of(px, py, p.frame);
+    uint32_t sg = seed_of(px, py, frame_of(p.ws, p.frame));
     const uint32_t stride = (p.tile_size + p.n_light - 1u) / p.n_light;
     const uint32_t offset = minu(to_uint(rnd(sg) * (float)stride), stride - 1u);
     float4 nd = load_nd(p.g.normal_depth, i);
@@ -215,7 +215,7 @@ MR_DEV void temporal_px(const TemporalParams &p, int a)
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
     if (MR_LDG(p.g.occ + i) < 0.1f) return;
-    uint32_t sg = seed_of(px, py, p.frame);
+    uint32_t sg = seed_of(px, py, frame_of(p.ws, p.frame));
     float u0 = rnd(sg), u1 = rnd(sg);
     float mvx = p.motion ? MR_LDG(p.motion + 2 * i) : 0.f, mvy = p.motion ? MR_LDG(p.motion + 2 * i + 1) : 0.f;
     int ppx = to_int((float)px + mvx * (float)(uint32_t)p.fx + (u0 * 1.f - 0.f));
@@ -279,7 +279,7 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
     const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
-    uint32_t sg = seed_of(px, py, p.frame);
+    uint32_t sg = seed_of(px, py, frame_of(p.ws, p.frame));
     float4 nd = load_nd(p.g.normal_depth, i);
     const float3 N = make_float3(nd.x, nd.y, nd.z);
     const uint32_t startIndex = to_uint(rnd(sg) * (float)p.offset_count);
@@ -316,7 +316,7 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
     const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
-    uint32_t sg = seed_of(px, py, p.frame);
+    uint32_t sg = seed_of(px, py, frame_of(p.ws, p.frame));
     float4 nd = load_nd(p.g.normal_depth, i);
     const float3 N = make_float3(nd.x, nd.y, nd.z);
     const RisSurface cur_s = ris_surface(N, load3(p.g.ray_dir, i), load3(p.g.brdf, i));

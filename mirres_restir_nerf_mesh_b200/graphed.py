@@ -11,9 +11,9 @@ recorded once and replayed:
     out = step(vert=new_vert, env=new_env)     # copies into the static inputs, replays, returns the static outputs
 
 `fn(**inputs)` must be shape-static and free of host synchronisation (use `sample_no_di_dense` materials and pass
-`random_offset`).  Frame indices are kernel arguments, so a replay repeats the random streams of the captured step;
-`frame_offset` (a device-resident counter the kernels add to their frame index) is the hook for fresh streams per
-replay once wired through -- until then a captured step is for benchmarking and for deterministic re-rendering.
+`random_offset`).  Frame indices are kernel arguments and therefore baked into the graph; `set_frame_offset(k)` writes
+a device-resident word that every kernel adds to its frame index (include/mirres_b200.h, "frame offset"), so replay k
+of a training run draws the random streams the eager call with `random_offset + k` would draw.
 """
 import torch
 
@@ -40,6 +40,12 @@ class CapturedStep:
         """Stream-ordered copies into the static input buffers (host tensors should be pinned)."""
         for k, v in inputs.items():
             self.static_in[k].copy_(v, non_blocking=True)
+
+    def set_frame_offset(self, value):
+        """Stream-ordered: the next replay draws the random streams of `random_offset + value`."""
+        from . import slangpy_shim
+        device = next(v.device for v in self.static_in.values() if isinstance(v, torch.Tensor))
+        slangpy_shim.set_frame_offset(device, value)
 
     def replay(self):
         self.graph.replay()

@@ -135,11 +135,11 @@ class Kernels:
         self._check(self.lib.mirres_neighbor_offsets(count, self._f(out), self._stream()), "mirres_neighbor_offsets")
 
     def light_tiles(self, env_tex, W, H, dist, frame_index, tile_count, tile_size, light_data, light_uv, light_pdf,
-                    light_cache=None):
+                    light_cache=None, frame_offset=None):
         rc = self.lib.mirres_light_tiles(self._f(env_tex), W, H, self._f(dist[0]), self._f(dist[1]), self._f(dist[2]),
                                          self._f(dist[3]), self._u32(frame_index), tile_count, tile_size,
                                          self._f(light_data), self._i(light_uv), self._f(light_pdf), self._f(light_cache, True),
-                                         self._stream())
+                                         self._i(frame_offset, True), self._stream())
         self._check(rc, "mirres_light_tiles")
 
     # -- wavefront workspace -----------------------------------------------------------------------------------

@@ -159,7 +159,37 @@ def workspace(device, n_pixels):
         off = (-buf.data_ptr()) % 256  # CUDA allocations are already 512-byte aligned; host ones are not
         ws = buf[off:off + nbytes]
         _WORKSPACES[key] = ws
+        if _FRAME_OFFSET.get(str(device)) is not None:
+            _frame_word(ws).copy_(_FRAME_OFFSET[str(device)])
     return ws
+
+
+FRAME_OFFSET_BYTES = 32  # MIRRES_WORKSPACE_FRAME_OFFSET_BYTES
+_FRAME_OFFSET = {}
+
+
+def _frame_word(ws):
+    return ws[FRAME_OFFSET_BYTES:FRAME_OFFSET_BYTES + 4].view(torch.int32)
+
+
+def _frame_offset_tensor(device):
+    dev = str(torch.device(device)) if not isinstance(device, str) else device
+    cur = _FRAME_OFFSET.get(dev)
+    if cur is None:
+        cur = _FRAME_OFFSET[dev] = torch.zeros(1, dtype=torch.int32, device=device)
+    return cur
+
+
+def set_frame_offset(device, value):
+    """Adds `value` to the frame index of every subsequent launch on `device` (all workspaces), stream-ordered and
+    without touching any launch argument -- which is what lets a captured CUDA graph be replayed with fresh random
+    streams.  0 restores the reference schedule."""
+    dev = str(torch.device(device)) if not isinstance(device, str) else device
+    cur = _frame_offset_tensor(device)
+    cur.fill_(int(value) & 0x7FFFFFFF)
+    for key, ws in _WORKSPACES.items():
+        if key[0] == dev:
+            _frame_word(ws).copy_(cur)
 
 
 class _Launch:
@@ -239,7 +269,7 @@ def _GenerateLightTiles(m, env_tex, pdf_, cdf_, mpdf_, mcdf_, width, height, fra
         light_data._mirres_cache = cache
     get_kernels().light_tiles(_c(env_tex), int(width), int(height), (pdf_, cdf_, mpdf_, mcdf_), int(frameIndex),
                               m.define("LIGHT_TILE_COUNT", 128), m.define("LIGHT_TILE_SIZE", 1024), light_data, light_uv,
-                              light_inv_pdf, cache)
+                              light_inv_pdf, cache, _frame_offset_tensor(light_data.device))
 
 
 def _InitialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reservoirs, env_tex, env_width, env_height,

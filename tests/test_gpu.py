@@ -324,3 +324,42 @@ def test_full_size_properties(kernels):
     nrm = torch.cross(b_ - a, c - a, dim=1)
     nrm = nrm / nrm.norm(dim=1, keepdim=True)
     assert float(((pos[m] - a) * nrm).sum(1).abs().max()) < 1e-4
+
+
+def test_captured_step_replays_with_fresh_random_streams(kernels):
+    """graphed.CapturedStep: a whole render + backward recorded into a CUDA graph (side streams included) reproduces
+    the eager call, and the device-resident frame offset gives replay k the random streams of random_offset + k."""
+    from mirres_restir_nerf_mesh_b200.graphed import CapturedStep
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim
+    sc = P.scene("T1", 0.2)
+    W, Hh = sc["W"], sc["H"]
+    worker = make_worker(sc)
+    mods = R.load_m_for_restir(W, Hh, device=DEV)
+    mat = synth.ProceduralMaterial(sc["metallic"])
+    g = {k: tt(v) for k, v in sc["gbuffer"].items()}
+    wgt = torch.linspace(0.5, 1.5, W * Hh * 3, device=DEV).reshape(W * Hh, 3)
+
+    def step(env, random_offset=900):
+        env_l = env.detach().clone().requires_grad_(True)
+        normal = g["normal_map"].clone().requires_grad_(True)
+        outs = R.run_restir_di_with_pt(False, 1, 1, 1, mat, None, worker, *mods, env_l, g["occ_map"].clone(), normal,
+                                       g["depth_map"], g["diffuse_map"], g["roughness_specular"], g["ray_dir_map"],
+                                       g["pos_map"], None, None, None, None, W, Hh, 3, 2, 2, 2.0, 0.1, 0.001,
+                                       random_offset=random_offset)
+        (outs[0] * wgt).sum().backward()
+        return outs[0].detach(), env_l.grad, normal.grad
+
+    env = tt(sc["env"])
+    cap = CapturedStep(step, dict(env=env))
+    try:
+        for k in (0, 5):
+            want = [x.clone() for x in step(env, random_offset=900 + k)]
+            cap.set_frame_offset(k)
+            got = cap(env=env)
+            torch.cuda.synchronize()
+            assert torch.equal(got[0], want[0]), (k, (got[0] - want[0]).abs().max().item(), (got[0] != want[0]).sum().item())
+            torch.testing.assert_close(got[1], want[1], rtol=GRAD_RTOL, atol=1e-5)
+            torch.testing.assert_close(got[2], want[2], rtol=GRAD_RTOL, atol=1e-5)
+        assert not torch.equal(step(env, 900)[0], step(env, 905)[0])
+    finally:
+        slangpy_shim.set_frame_offset(torch.device(DEV, torch.cuda.current_device()), 0)

@@ -145,3 +145,21 @@ def test_gbuffer_primary_and_interpolate_bwd(oracle):
         k.interpolate_bwd(H.t(grad), prim, bary if use_bary else None, H.t(tri), out)
         want = _scatter_reference(grad, prim.numpy(), bary.numpy() if use_bary else None, tri, len(vert))
         np.testing.assert_allclose(out.numpy(), want, rtol=1e-4, atol=1e-5)
+
+
+def test_frame_offset_word_shifts_every_random_stream():
+    """The device-resident frame offset (include/mirres_b200.h) must be indistinguishable from a larger random_offset:
+    it is what lets a captured CUDA graph be replayed with fresh random streams."""
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim
+    sc = P.scene("T0")
+    ref = P.oracle_run(sc)
+    want = P.product_run(sc, _worker(sc), "cpu", ref["prepared"], random_offset=4242 + 37)
+    slangpy_shim.set_frame_offset("cpu", 37)
+    try:
+        got = P.product_run(sc, _worker(sc), "cpu", ref["prepared"], random_offset=4242)
+    finally:
+        slangpy_shim.set_frame_offset("cpu", 0)
+    for a, b in zip(want["totals"], got["totals"]):
+        assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+    base = P.product_run(sc, _worker(sc), "cpu", ref["prepared"], random_offset=4242)
+    assert not np.array_equal(np.asarray(base["totals"][0]), np.asarray(got["totals"][0]))
