@@ -458,8 +458,21 @@ MR_DEV bool eval_final_bwd_terms(const EvalParams &p, int idx, Taps &t, float va
 }
 
 #if !defined(MR_HOST_CHECK)
+// Two levels of aggregation before the global atomics.  All lit pixels of a frame pick the same few bright texels (the
+// sun lobe of the C2 envmap collects most of them), and 12 atomics per warp on the same addresses serialise in L2
+// (measured 43 us per launch).  Level 1: lanes of a warp with the same tap quad are summed with shuffles
+// (__match_any_sync).  Level 2: the warp leaders add their sums into a per-block table in shared memory (open
+// addressing on the quad key, shared-memory atomics); the table is flushed with one set of global atomics per
+// distinct quad and block.
+#define EVB_SLOTS 128
+#define EVB_EMPTY 0xffffffffu
 __global__ void __launch_bounds__(256) k_eval_final_bwd(EvalParams p, int n)
 {
+    __shared__ unsigned int s_key[EVB_SLOTS];
+    __shared__ float s_val[EVB_SLOTS][12];
+    for (int i = threadIdx.x; i < EVB_SLOTS; i += 256) s_key[i] = EVB_EMPTY;
+    for (int i = threadIdx.x; i < EVB_SLOTS * 12; i += 256) (&s_val[0][0])[i] = 0.f;
+    __syncthreads();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     Taps t;
     t.i00 = t.i10 = t.i01 = t.i11 = -1;
@@ -471,48 +484,68 @@ __global__ void __launch_bounds__(256) k_eval_final_bwd(EvalParams p, int n)
     float *grad_env = p.grad_env;
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int act_mask = __ballot_sync(0xffffffffu, active);
-    if (act_mask == 0u) return;
-    // lanes that address the same tap quad (i00 and i11 identify it) are summed first
-    unsigned int peers = __match_any_sync(0xffffffffu, active ? (long long)t.i00 * 0x100000000ll + (long long)(unsigned int)t.i11
-                                                               : -1ll - (long long)lane);
-    peers &= act_mask;
-    const bool leader = active && (__ffs(peers) - 1 == (int)lane);
-    const unsigned int leaders = __ballot_sync(0xffffffffu, leader);
-    if (__popc(leaders) > 8) {
-        // too many distinct quads in this warp: aggregation would cost more than it saves
-        if (active) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                atomicAdd(grad_env + 3 * (size_t)t.i00 + c, vals[c]);
-                atomicAdd(grad_env + 3 * (size_t)t.i10 + c, vals[3 + c]);
-                atomicAdd(grad_env + 3 * (size_t)t.i01 + c, vals[6 + c]);
-                atomicAdd(grad_env + 3 * (size_t)t.i11 + c, vals[9 + c]);
-            }
-        }
-        return;
-    }
-    unsigned int todo = leaders;
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const unsigned int grp = __shfl_sync(0xffffffffu, peers, src);
-        const bool member = active && ((grp >> lane) & 1u);
+    if (act_mask != 0u) {
+        // quad key: origin texel + which of the two clamped neighbours differ from it (x1 - x0, y1 - y0 are 0 or 1)
+        const unsigned int key = active ? ((unsigned int)t.i00 << 2) | (t.i10 != t.i00 ? 1u : 0u) | (t.i01 != t.i00 ? 2u : 0u) : 0u;
+        unsigned int peers = __match_any_sync(0xffffffffu, active ? (int)key : -1 - (int)lane);
+        peers &= act_mask;
+        const bool leader = active && (__ffs(peers) - 1 == (int)lane);
+        // level 1: every lane pulls the contributions of the other members of its group
         float acc[12];
 #pragma unroll
-        for (int q = 0; q < 12; ++q) {
-            float x = member ? vals[q] : 0.f;
+        for (int q = 0; q < 12; ++q) acc[q] = vals[q];
+        unsigned int rest = peers & ~(1u << lane);
+        const int rounds = (int)__reduce_max_sync(0xffffffffu, (unsigned int)__popc(peers)) - 1;
+        for (int r = 0; r < rounds; ++r) {
+            const int src = rest ? __ffs(rest) - 1 : (int)lane;
+            const bool take = rest != 0u;
+            rest &= rest - 1u;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            acc[q] = x;
-        }
-        if ((int)lane == src) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                atomicAdd(grad_env + 3 * (size_t)t.i00 + c, acc[c]);
-                atomicAdd(grad_env + 3 * (size_t)t.i10 + c, acc[3 + c]);
-                atomicAdd(grad_env + 3 * (size_t)t.i01 + c, acc[6 + c]);
-                atomicAdd(grad_env + 3 * (size_t)t.i11 + c, acc[9 + c]);
+            for (int q = 0; q < 12; ++q) {
+                const float x = __shfl_sync(0xffffffffu, vals[q], src);
+                if (take) acc[q] += x;
             }
+        }
+        // level 2: per-block table
+        if (leader) {
+            unsigned int slot = (key * 2654435761u) >> 25; // top 7 bits
+            bool placed = false;
+            for (int probe = 0; probe < 8 && !placed; ++probe) {
+                const unsigned int prev = atomicCAS(&s_key[slot], EVB_EMPTY, key);
+                if (prev == EVB_EMPTY || prev == key) {
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) atomicAdd(&s_val[slot][q], acc[q]);
+                    placed = true;
+                } else {
+                    slot = (slot + 1u) & (EVB_SLOTS - 1u);
+                }
+            }
+            if (!placed) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    atomicAdd(grad_env + 3 * (size_t)t.i00 + c, acc[c]);
+                    atomicAdd(grad_env + 3 * (size_t)t.i10 + c, acc[3 + c]);
+                    atomicAdd(grad_env + 3 * (size_t)t.i01 + c, acc[6 + c]);
+                    atomicAdd(grad_env + 3 * (size_t)t.i11 + c, acc[9 + c]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < EVB_SLOTS && s_key[threadIdx.x] != EVB_EMPTY) {
+        const unsigned int key = s_key[threadIdx.x];
+        const int W = p.env.W;
+        const int i00 = (int)(key >> 2);
+        const int i10 = i00 + (int)(key & 1u);
+        const int i01 = i00 + ((key & 2u) ? W : 0);
+        const int i11 = i01 + (int)(key & 1u);
+        const float *v = s_val[threadIdx.x];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            atomicAdd(grad_env + 3 * (size_t)i00 + c, v[c]);
+            atomicAdd(grad_env + 3 * (size_t)i10 + c, v[3 + c]);
+            atomicAdd(grad_env + 3 * (size_t)i01 + c, v[6 + c]);
+            atomicAdd(grad_env + 3 * (size_t)i11 + c, v[9 + c]);
         }
     }
 }
