@@ -363,3 +363,59 @@ def test_captured_step_replays_with_fresh_random_streams(kernels):
         assert not torch.equal(step(env, 900)[0], step(env, 905)[0])
     finally:
         slangpy_shim.set_frame_offset(torch.device(DEV, torch.cuda.current_device()), 0)
+
+
+def _render_t2(sc, w, mods, **kw):
+    g = {k: tt(v) for k, v in sc["gbuffer"].items()}
+    env = tt(sc["env"]).requires_grad_(True)
+    normal = g["normal_map"].clone().requires_grad_(True)
+    tex = torch.cat((g["diffuse_map"], torch.zeros_like(g["diffuse_map"])), dim=1).requires_grad_(True)
+    kd = tex[:, 0:3]  # strided view, row stride 6 floats, as render_stage1 passes it (nerf/renderer.py:1018-1020)
+    rs = g["roughness_specular"].clone().requires_grad_(True)
+    outs = R.run_restir_di_with_pt(False, 1, 1, 1, synth.ProceduralMaterial(sc["metallic"]), None, w, *mods, env,
+                                   g["occ_map"], normal, g["depth_map"], kd, rs, g["ray_dir_map"], g["pos_map"], None, None,
+                                   None, None, sc["W"], sc["H"], 3, 2, 2, 2.0, 0.1, 0.001, random_offset=99, **kw)
+    wgt = torch.linspace(0.5, 1.5, outs[0].numel(), device=DEV).reshape(outs[0].shape)
+    (outs[0] * wgt).sum().backward()
+    return [o.detach() for o in outs], [env.grad, normal.grad, tex.grad, rs.grad]
+
+
+def test_concurrent_schedule_equals_sequential_schedule(kernels):
+    """The default schedule on CUDA tensors (indirect chains, initial candidates and shading on side streams, batched
+    denoiser, fused map preparation) against the reference's sequential order: images bit-identical, gradients to the
+    stated tolerance (accumulation order of the autograd engine differs)."""
+    sc = P.scene("T2", 0.3)
+    w = R.restirbvhWorker(tt(sc["vert"]), tt(sc["tri"]))
+    w.update_mesh(tt(sc["vert"]), tt(sc["tri"]))
+    mods = R.load_m_for_restir(sc["W"], sc["H"])
+    seq, gseq = _render_t2(sc, w, mods, overlap=False, batched_denoise=False, fused_prepare=False)
+    par, gpar = _render_t2(sc, w, mods)
+    for a, b in zip(seq, par):
+        assert torch.equal(a, b)
+    for a, b in zip(gseq, gpar):
+        assert a.abs().sum() > 0
+        assert (a - b).abs().max() <= GRAD_RTOL * a.abs().max()
+
+
+def test_empty_and_single_pixel_frames(kernels):
+    """Edge cases of the wavefront machinery: no foreground pixel at all (empty ray queues), and a 1x1 frame."""
+    sc = P.scene("T0")
+    w = R.restirbvhWorker(tt(sc["vert"]), tt(sc["tri"]))
+    w.update_mesh(tt(sc["vert"]), tt(sc["tri"]))
+    for W, Hh, occ_value in ((sc["W"], sc["H"], 0.0), (1, 1, 1.0)):
+        n = W * Hh
+        mods = R.load_m_for_restir(W, Hh)
+        g = {k: tt(v)[:n].clone() for k, v in sc["gbuffer"].items()}
+        if occ_value > 0:  # one foreground pixel: take the first hit of the scene
+            i = int(np.nonzero(sc["hit"] > 0)[0][0])
+            g = {k: tt(v)[i:i + 1].clone() for k, v in sc["gbuffer"].items()}
+        g["occ_map"].fill_(occ_value)
+        env = tt(sc["env"]).requires_grad_(True)
+        outs = R.run_restir_di_with_pt(False, 1, 1, 1, synth.ProceduralMaterial(0.0), None, w, *mods, env, g["occ_map"],
+                                       g["normal_map"], g["depth_map"], g["diffuse_map"], g["roughness_specular"],
+                                       g["ray_dir_map"], g["pos_map"], None, None, None, None, W, Hh, 2, 2, 2, 2.0, 0.1, 0.001,
+                                       random_offset=3)
+        torch.cuda.synchronize()
+        assert all(o.shape == (n, 3) and torch.isfinite(o).all() for o in outs)
+        if occ_value == 0:
+            assert bool((outs[0] == 1.0).all())  # background pixels of the final image are forced to 1 (:546-547)
