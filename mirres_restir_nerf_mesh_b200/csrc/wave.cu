@@ -415,7 +415,10 @@ int trace_queues(const BvhView &bvh, const Workspace &ws, bool any, bool closest
     if (!rc && closest) rc = foreach_item<QueueTraceParams, queue_closest_item, 128>(p, ws.capacity, st);
     return rc;
 #else
-    // persistent grids: exactly the number of blocks that are resident at once
+    // persistent grids: at most what is resident at once -- and deliberately fewer blocks per SM than would fit: a
+    // grid that fills the register file keeps every other stream's kernels off the SMs for its whole duration, while a
+    // traversal warp is latency-bound and loses little from lower occupancy (measured on the C2 step: 3 / 2 blocks
+    // per SM for boolean / closest-hit queues 6.4 ms, full occupancy 5 / 4 blocks 6.7 ms)
     static int occ_any = 0, occ_closest = 0, occ_mixed = 0, prefetch = 0;
     if (!occ_any) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_any, k_trace_any_persistent<false>, MR_TRACE_BLOCK, 0);
@@ -426,6 +429,13 @@ int trace_queues(const BvhView &bvh, const Workspace &ws, bool any, bool closest
         if (occ_mixed < 2) occ_mixed = 4;
         const char *e = getenv("MIRRES_PREFETCH");
         prefetch = e ? atoi(e) : 0;
+        if (occ_any > 3) occ_any = 3;
+        if (occ_closest > 2) occ_closest = 2;
+        if (occ_mixed > 4) occ_mixed = 4;
+        const char *c = getenv("MIRRES_CLOSEST_BLOCKS"); // tuning overrides
+        if (c && atoi(c) > 0) { occ_closest = atoi(c); occ_mixed = 2 * atoi(c); }
+        const char *a = getenv("MIRRES_ANY_BLOCKS");
+        if (a && atoi(a) > 0) occ_any = atoi(a);
     }
     const int g_mixed = sm_count * (occ_mixed & ~1), g_any = sm_count * occ_any, g_closest = sm_count * occ_closest;
     if (prefetch) {
