@@ -9,8 +9,20 @@ def test_fp_contract_not_contracted(oracle):
     assert oracle.fp_contract_selftest() == 0
 
 
-@pytest.mark.parametrize("op,fn,lo,hi", [(0, np.sin, -7, 7), (1, np.cos, -7, 7), (2, np.arccos, -1, 1),
-                                         (6, np.exp, -100, 80)])
+def test_expf_is_within_stated_error(oracle):
+    """mr_expf is the one contract function evaluated in fp32 (include/mirres_fpmath.h): within 1.5 ulp, monotone on
+    the range the a-trous weights use, exact limits."""
+    x = np.linspace(-100, 80, 400001, dtype=np.float32)
+    got = oracle.fpmath(6, x)
+    want = np.exp(x.astype(np.float64))
+    ulp = np.spacing(np.abs(want.astype(np.float32))).astype(np.float64)
+    assert np.max(np.abs(got.astype(np.float64) - want) / np.maximum(ulp, 1e-45)) <= 1.5
+    assert (np.diff(got) >= 0).all()
+    sp = oracle.fpmath(6, np.array([0.0, -200.0, 100.0, -0.0], np.float32))
+    assert sp[0] == 1.0 and sp[1] == 0.0 and np.isinf(sp[2]) and sp[3] == 1.0
+
+
+@pytest.mark.parametrize("op,fn,lo,hi", [(0, np.sin, -7, 7), (1, np.cos, -7, 7), (2, np.arccos, -1, 1)])
 def test_fpmath_is_correctly_rounded(oracle, op, fn, lo, hi):
     x = np.linspace(lo, hi, 400001, dtype=np.float32)
     got = oracle.fpmath(op, x)
