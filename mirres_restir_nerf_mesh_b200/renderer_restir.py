@@ -562,10 +562,12 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         chains.append(make_chain("main", None))
     pending = []  # (iteration, bounce, completion event, (color, diff, spec)) not yet added to the running sums
 
-    def accumulate(upto_iteration):
+    def accumulate(upto_iteration, stream=None):
+        # runs on `stream` (default: the caller's stream); always in (iteration, bounce) order
+        stream = stream or main_stream
         while pending and pending[0][0] <= upto_iteration:
             _, _, done, outs3 = pending.pop(0)
-            main_stream.wait_event(done)
+            stream.wait_event(done)
             sums["color_1"] += outs3[0]
             sums["diff_1"] += outs3[1]
             sums["spec_1"] += outs3[2]
@@ -678,9 +680,13 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                 sums["color"] += color
                 sums["diff"] += color_diff
                 sums["spec"] += color_spec
-            accumulate(i - len(chains))
+                # the indirect sums ride on this stream too (it has slack): a chain enqueued two iterations ago has
+                # normally finished, so the wait does not stall the shading of the next iteration
+                accumulate(i - 2, st_s)
             frame += 1
             prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir = occ_map, normal_depth, brdf_map, ray_dir_map
+        with torch.cuda.stream(st_s):
+            accumulate(spp, st_s)
         main_stream.wait_stream(st_i)
         main_stream.wait_stream(st_s)
         keepalive.extend(X + S)
