@@ -112,7 +112,7 @@ def run_reference(args):
         return
     from mirres_restir_nerf_mesh_b200 import synth
     cfg = synth.CONFIGS[args.config]
-    crop = 400
+    crop = cfg["W"]  # the full frame of the workload
     cores = os.cpu_count() or 1
     for _ in range(args.warmup):
         oracle_sample(args.config, crop, cfg["spp"])
@@ -343,10 +343,11 @@ def run_gpu(args):
                     "peak": peak, "unit": "GB/s", "frac": step_alg / (ms_dev / args.steps * 1e-3) / 1e9 / peak},
                 "kernel_ms_per_step": {k: round(v[0] / 2, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])}}
         if world == 1 and not args.no_cpu_baseline:
-            s, dt, _ = oracle_sample(args.config, 400, spp)
-            s2, dt2, _ = oracle_sample(args.config, 400, spp)
+            crop = cfg["W"]
+            s, dt, _ = oracle_sample(args.config, crop, spp)
+            s2, dt2, _ = oracle_sample(args.config, crop, spp)
             line["cpu_baseline"] = {"value": (s + s2) / (dt + dt2), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "CPU oracle: LBVH rebuild + forward spp loop on a 400x400 frame of the same scene, 2 repetitions, no backward"}
+                                    "sample": "CPU oracle (OpenMP, all host cores): LBVH rebuild + forward spp loop of the same %dx%d frame, 2 repetitions; no G-buffer, denoiser or backward" % (crop, crop)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
