@@ -157,6 +157,8 @@ struct EawMultiParams {
     float *g_pos[MR_EAW_MAX_IMAGES];
 };
 
+// (tap loops are NOT unrolled in the batched kernels: unrolled by 5 they stalled on instruction fetch -- ncu
+// stall_no_instruction 3.8 per issue in the backward, profiles/r1r_*)
 template <int NI>
 MR_DEV void eaw_fwd_multi_px(const EawMultiParams &p, int idx)
 {
@@ -178,7 +180,7 @@ MR_DEV void eaw_fwd_multi_px(const EawMultiParams &p, int idx)
     float cum[NI];
 #pragma unroll
     for (int m = 0; m < NI; ++m) { sum[m] = f3(0.f); cum[m] = 0.f; }
-#pragma unroll 5
+#pragma unroll 1
     for (int i = 0; i < 25; ++i) {
         const int ux = px + (i % 5 - 2) * p.step, uy = py + (i / 5 - 2) * p.step;
         if (!(ux >= 0 && ux < p.fx && uy >= 0 && uy < p.fy)) continue;
@@ -219,7 +221,7 @@ MR_DEV void eaw_bwd_multi_px(const EawMultiParams &p, int idx)
         Wq[m] = p.cum_w[m][q];
         gc[m] = gn[m] = gp[m] = f3(0.f);
     }
-#pragma unroll 5
+#pragma unroll 1
     for (int i = 0; i < 25; ++i) {
         const int ux = px + (i % 5 - 2) * p.step, uy = py + (i / 5 - 2) * p.step;
         if (!(ux >= 0 && ux < p.fx && uy >= 0 && uy < p.fy)) continue;
