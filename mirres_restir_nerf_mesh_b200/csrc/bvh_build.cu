@@ -367,7 +367,7 @@ static size_t carve(BuildScratch *s, int F, char *base)
 static int sort_pairs(BuildScratch &s, int F, cudaStream_t st)
 {
     // 4 passes; result ends in keys[0]/vals[0]
-    cudaMemsetAsync(s.done, 0, sizeof(unsigned int), st);
+    zero_async(s.done, sizeof(unsigned int), st);
     for (int pass = 0; pass < 4; ++pass) {
         int in = pass & 1, out = in ^ 1;
         k_sort_hist<<<s.num_blocks, SORT_THREADS, 0, st>>>(s.keys[in], F, 8 * pass, s.hist, s.num_blocks);
@@ -403,7 +403,7 @@ int mirres_bvh_build(const float *vert, int V, const int *tri, int F, int *info,
     carve(&s, F, (char *)scratch);
     const int grid = (F + 255) / 256;
     k_init_extent<<<1, 32, 0, st>>>(s.extent);
-    cudaMemsetAsync(s.visits, 0, sizeof(int) * (size_t)F, st);
+    zero_async(s.visits, sizeof(int) * (size_t)F, st);
     k_elements<<<grid, 256, 0, st>>>(vert, tri, F, s.eaabb, nullptr, s.extent);
     k_morton<<<grid, 256, 0, st>>>(s.eaabb, F, s.extent, 0, 0, 0, 0, 0, 0, s.keys[0], s.vals[0], nullptr);
     int rc = sort_pairs(s, F, st);
@@ -470,7 +470,7 @@ int mirres_bvh_hierarchy_refit(const int *sorted_pairs, const float *ele_aabb, i
     carve(&s, F, (char *)scratch);
     const int grid = (F + 255) / 256;
     k_unzip_pairs<<<grid, 256, 0, st>>>(sorted_pairs, F, s.keys[0], s.vals[0]);
-    cudaMemsetAsync(s.visits, 0, sizeof(int) * (size_t)F, st);
+    zero_async(s.visits, sizeof(int) * (size_t)F, st);
     k_hierarchy<<<grid, 256, 0, st>>>(F, s.keys[0], s.vals[0], ele_aabb, info, aabb, s.parent);
     k_refit<<<grid, 256, 0, st>>>(F, info, aabb, s.parent, s.visits);
     MR_CUDA_CHECK_LAUNCH();

@@ -590,10 +590,8 @@ static int ws_open(Workspace &ws, int n, void *workspace, size_t workspace_bytes
 }
 static void res_zero_all(const ResView &r, int n, cudaStream_t st)
 {
-    zero_async(r.ld, sizeof(float) * 3 * (size_t)n, st);
-    zero_async(r.pdf, sizeof(float) * (size_t)n, st);
-    zero_async(r.M, sizeof(int) * (size_t)n, st);
-    zero_async(r.w, sizeof(float) * (size_t)n, st);
+    ZeroRegions z = {{r.ld, r.pdf, r.M, r.w}, {3 * (size_t)n, (size_t)n, (size_t)n, (size_t)n}};
+    zero_regions_async(z, st);
 }
 
 int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris, const float *pos_map, float *res_ld,
