@@ -27,6 +27,7 @@ from .slangpy_shim import get_kernels
 
 TOTAL_RIS_PASSES = 5 + 15  # frame-index stride per spp iteration (nerf/renderer_restir.py:242)
 
+MAX_INITIAL_STREAMS = 4   # concurrent initial-candidate stages (light tiles + initial RIS of different spp iterations)
 MAX_INDIRECT_CHAINS = 4  # concurrent indirect-path chains (one CUDA stream + path state + ray-queue workspace each)
 _SIDE_STREAMS = {}
 
@@ -620,15 +621,23 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         # B is ONE buffer shared by all iterations, so the autograd Functions keep saving aliases of buffers that later
         # iterations overwrite, exactly like the reference's two-buffer ping-pong.  Arithmetic, frame
         # indices and accumulation order are those of the sequential schedule; only the enqueue order differs.
-        st_i, st_s = _side_stream(dev, MAX_INDIRECT_CHAINS), _side_stream(dev, MAX_INDIRECT_CHAINS + 1)
-        for st in (st_i, st_s):
+        st_s = _side_stream(dev, MAX_INDIRECT_CHAINS)
+        # initial candidates of different iterations are independent of each other as well: a ring of R streams, each
+        # with its own light-tile set, reservoir buffer and workspace, lets them all start as soon as the G-buffer exists
+        R = min(spp, MAX_INITIAL_STREAMS)
+        st_init = [_side_stream(dev, MAX_INDIRECT_CHAINS + 1 + r) for r in range(R)]
+        for st in [st_s] + st_init:
             st.wait_stream(main_stream)
-        X = (_reservoir_set(n, dev, False), _reservoir_set(n, dev, False))  # both passes write every pixel
+        X = tuple(_reservoir_set(n, dev, False) for _ in range(R))  # both passes write every pixel
         S = (_reservoir_set(n, dev, False), _reservoir_set(n, dev, False))
+        tiles = [(light_data, light_uv, light_inv_pdf)] + [
+            (torch.empty_like(light_data), torch.empty_like(light_uv), torch.empty_like(light_inv_pdf))
+            for _ in range(R - 1)]
         B = reservoirs
         slangpy.prepare_workspace(occ_map)
-        with torch.cuda.stream(st_i), slangpy.workspace_tag("initial"):
-            slangpy.prepare_workspace(occ_map)
+        for r in range(R):
+            with torch.cuda.stream(st_init[r]), slangpy.workspace_tag("initial%d" % r):
+                slangpy.prepare_workspace(occ_map)
         with torch.cuda.stream(st_s), slangpy.workspace_tag("shade"):
             slangpy.prepare_workspace(occ_map)
         ev = lambda stream: (lambda e: (e.record(stream), e)[1])(torch.cuda.Event())
@@ -639,25 +648,26 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             c = chains[i % len(chains)]
             with torch.cuda.stream(c["stream"]), slangpy.workspace_tag(c["tag"]):
                 indirect_chain(i, first_indirect_pass, c)
-            with torch.cuda.stream(st_i), slangpy.workspace_tag("initial"):
-                if i >= 2:
-                    st_i.wait_event(spatial_done[i - 2])  # X[i % 2] was last read by spatial(i - 2)
+            r = i % R
+            with torch.cuda.stream(st_init[r]), slangpy.workspace_tag("initial%d" % r):
+                if i >= R:
+                    st_init[r].wait_event(spatial_done[i - R])  # X[r] was last read by spatial(i - R)
                 GenerateLightTiles(generateLightTiles_m, None, env_map, pdf_, cdf_, mpdf_, mcdf_, width, height, base,
-                                   light_data, light_uv, light_inv_pdf, light_tile_count, light_tile_size)
-                worker.InitialResampling_(InitialResampling_m, pos_map, X[i % 2], env_map, width, height, framedim_x,
+                                   *tiles[r], light_tile_count, light_tile_size)
+                worker.InitialResampling_(InitialResampling_m, pos_map, X[r], env_map, width, height, framedim_x,
                                           framedim_y, base + 2, occ_map, normal_depth, brdf_map, ray_dir_map, pdf_, cdf_,
-                                          mpdf_, mcdf_, light_data, light_uv, light_inv_pdf, prepare=False)
-                init_done[i] = ev(st_i)
+                                          mpdf_, mcdf_, *tiles[r], prepare=False)
+                init_done[i] = ev(st_init[r])
             main_stream.wait_event(init_done[i])
             ris_pass = 3
             if i > 0:
-                TemporalResampling(TemporalResampling_m, X[i % 2], S[(i - 1) % 2], env_map, width, height, framedim_x,
+                TemporalResampling(TemporalResampling_m, X[r], S[(i - 1) % 2], env_map, width, height, framedim_x,
                                    framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map, prev_occ_map,
                                    prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
                 ris_pass += 1
             if i >= 2:
                 main_stream.wait_event(copy_done[i - 2])  # S[i % 2] was last read by the copy of iteration i - 2
-            worker.SpatialResampling_(SpatialResampling_m, pos_map, S[i % 2], X[i % 2], neighborOffsets, env_map, width,
+            worker.SpatialResampling_(SpatialResampling_m, pos_map, S[i % 2], X[r], neighborOffsets, env_map, width,
                                       height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map,
                                       ray_dir_map)
             ris_pass += 1
@@ -687,9 +697,10 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir = occ_map, normal_depth, brdf_map, ray_dir_map
         with torch.cuda.stream(st_s):
             accumulate(spp, st_s)
-        main_stream.wait_stream(st_i)
-        main_stream.wait_stream(st_s)
+        for st in [st_s] + st_init:
+            main_stream.wait_stream(st)
         keepalive.extend(X + S)
+        keepalive.extend(tiles)
     else:
         for i in range(spp):
             base = random_offset + TOTAL_RIS_PASSES * frame
