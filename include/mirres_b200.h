@@ -208,6 +208,17 @@ int mirres_eaw_bwd(float c_phi, float n_phi, float p_phi, int fx, int fy, float 
                    const float *grad_out, float *grad_color, float *grad_normal, float *grad_pos, float *cum_w_scratch,
                    void *stream);
 int mirres_normal_ao(int fx, int fy, const float *occ, const float *normal, float *out_ao, void *stream);
+/* Cross-bilateral denoiser of --use_bi_de: bilateral_denoiser_fwd / _bwd_kernel,
+ * nerf/renderutils/c_src/denoising.cu:14-130, reached from nerf/renderer_restir.py:529-541 through
+ * nerf/renderutils/ops.py:173-212.  Frame fx x fy, sigma = max(2 factor, 1e-4), filter radius 2 ceil(2.5 sigma) + 1.
+ * col [N,3], nrm [N,3] (normalised by the caller, ops.py:197), zdz [N,2] = (depth, depth gradient).
+ *   fwd: out [N,4] = (sum_t w col_t, max(sum_t w, 1e-4)),  w = exp(-d^2 / 2 sigma^2) * clamp(n_t . n_c, 1e-4, 1)^128 *
+ *        exp(-|z_t - z_c| / max(dz_c d, 1e-4))
+ *   bwd: col_grad [N,3] = transposed gather of out_grad [N,4] (first three channels), depth term with the tap's dz. */
+int mirres_bilateral_fwd(int fx, int fy, float sigma, const float *col, const float *nrm, const float *zdz, float *out,
+                         void *stream);
+int mirres_bilateral_bwd(int fx, int fy, float sigma, const float *nrm, const float *zdz, const float *out_grad,
+                         float *col_grad, void *stream);
 /* Batched a-trous level: n_images (<= 8) colour images filtered over the same occ / normal / pos in one pass -- the five
  * images run_restir_di_with_pt denoises per level (nerf/renderer_restir.py:517-541).  colors / out_colors / ... are HOST
  * arrays of n_images device pointers (read at launch).  Per-image results are bit-identical to mirres_eaw_fwd / _bwd;

@@ -257,6 +257,18 @@ MR_HD float mr_pow5f(float x)
     return x4 * x;
 }
 
+/* pow(x,128) of the cross-bilateral normal weight (nerf/renderutils/c_src/denoising.cu:56), by seven squarings. */
+MR_HD float mr_pow128f(float x)
+{
+    float x2 = x * x;
+    float x4 = x2 * x2;
+    float x8 = x4 * x4;
+    float x16 = x8 * x8;
+    float x32 = x16 * x16;
+    float x64 = x32 * x32;
+    return x64 * x64;
+}
+
 MR_HD float mr_pow8f(float x)
 {
     float x2 = x * x;

@@ -44,6 +44,8 @@ SIGNATURES = {
     "mirres_eaw_fwd": "fffiif" + "ppppp" + "p",
     "mirres_eaw_bwd": "fffiif" + "ppppp" + "ppppp" + "p",
     "mirres_normal_ao": "iipppp",
+    "mirres_bilateral_fwd": "iifppppp",
+    "mirres_bilateral_bwd": "iifppppp",
     "mirres_eaw_fwd_multi": "fffiif" + "ppp" + "i" + "ppp" + "p",
     "mirres_eaw_bwd_multi": "fffiif" + "ppp" + "i" + "ppppppp" + "p",
     "mirres_gbuffer_primary": "ppppi" + "pp" + "pppppp" + "pz" + "p",

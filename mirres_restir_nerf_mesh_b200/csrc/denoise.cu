@@ -284,6 +284,58 @@ static int eaw_multi_dispatch(const EawMultiParams &p, bool backward, cudaStream
     }
 }
 
+// ---- cross-bilateral denoiser (--use_bi_de) ---------------------------------------------------------------
+// nerf/renderutils/c_src/denoising.cu:14-130 (nvdiffrec's bilateral_denoiser_fwd/bwd_kernel), called from
+// nerf/renderer_restir.py:529-541 through nerf/renderutils/ops.py:173-212.  Same tap order and arithmetic; expf and
+// powf(., 128) are the contract functions mr_expf / mr_pow128f.  Both directions are gathers, as in the reference.
+struct BilateralParams {
+    int fx, fy, rad;
+    float variance;
+    const float *__restrict__ col;      // [N,3] forward only
+    const float *__restrict__ nrm;      // [N,3]
+    const float *__restrict__ zdz;      // [N,2]
+    const float *__restrict__ out_grad; // [N,4] backward only
+    float *__restrict__ out;            // forward: [N,4]; backward: col_grad [N,3]
+};
+template <bool BACKWARD>
+MR_DEV void bilateral_px(const BilateralParams &p, int idx)
+{
+    const float FLT_EPS = 0.0001f;
+    const int px = idx % p.fx, py = idx / p.fx;
+    const float3 c_nrm = load3(p.nrm, (size_t)idx);
+    const float c_z = MR_LDG(p.zdz + 2 * (size_t)idx), c_dz = MR_LDG(p.zdz + 2 * (size_t)idx + 1);
+    float accum_w = 0.0f;
+    float3 accum = f3(0.f);
+    for (int oy = -p.rad; oy <= p.rad; ++oy) {
+        const int y = py + oy;
+        if (y < 0 || y >= p.fy) continue;
+        for (int ox = -p.rad; ox <= p.rad; ++ox) {
+            const int x = px + ox;
+            if (x < 0 || x >= p.fx) continue;
+            const size_t t = (size_t)y * p.fx + x;
+            const float dist_sqr = (float)(ox * ox + oy * oy);
+            const float dist = sqrtf(dist_sqr);
+            const float w_xy = mr_expf(-dist_sqr / (2.0f * p.variance));
+            const float w_normal = mr_pow128f(fminf(fmaxf(dot(load3(p.nrm, t), c_nrm), FLT_EPS), 1.0f));
+            const float dz = BACKWARD ? MR_LDG(p.zdz + 2 * t + 1) : c_dz; // the transposed gather uses the tap's gradient
+            const float w_depth = mr_expf(-(fabsf(MR_LDG(p.zdz + 2 * t) - c_z) / fmaxf(dz * dist, FLT_EPS)));
+            const float w = w_xy * w_normal * w_depth;
+            if (BACKWARD) {
+                accum += make_float3(MR_LDG(p.out_grad + 4 * t), MR_LDG(p.out_grad + 4 * t + 1), MR_LDG(p.out_grad + 4 * t + 2)) * w;
+            } else {
+                accum = accum + load3(p.col, t) * w;
+                accum_w += w;
+            }
+        }
+    }
+    if (BACKWARD) {
+        store3(p.out, (size_t)idx, accum);
+    } else {
+        p.out[4 * (size_t)idx] = accum.x; p.out[4 * (size_t)idx + 1] = accum.y; p.out[4 * (size_t)idx + 2] = accum.z;
+        p.out[4 * (size_t)idx + 3] = fmaxf(accum_w, 0.0001f);
+    }
+}
+
 struct AoParams {
     int fx, fy;
     const float *__restrict__ occ;
@@ -393,6 +445,24 @@ int mirres_eaw_bwd_multi(float c_phi, float n_phi, float p_phi, int fx, int fy, 
         p.g_pos[m] = grad_pos[m];
     }
     return eaw_multi_dispatch(p, true, (cudaStream_t)stream);
+}
+
+int mirres_bilateral_fwd(int fx, int fy, float sigma, const float *col, const float *nrm, const float *zdz, float *out,
+                         void *stream)
+{
+    if (!col || !nrm || !zdz || !out) return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1 || !(sigma > 0.f)) return MIRRES_ERR_SHAPE;
+    BilateralParams p = {fx, fy, 2 * (int)ceilf(sigma * 2.5f) + 1, sigma * sigma, col, nrm, zdz, nullptr, out};
+    return foreach_item<BilateralParams, bilateral_px<false>, 128>(p, fx * fy, (cudaStream_t)stream);
+}
+
+int mirres_bilateral_bwd(int fx, int fy, float sigma, const float *nrm, const float *zdz, const float *out_grad,
+                         float *col_grad, void *stream)
+{
+    if (!nrm || !zdz || !out_grad || !col_grad) return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1 || !(sigma > 0.f)) return MIRRES_ERR_SHAPE;
+    BilateralParams p = {fx, fy, 2 * (int)ceilf(sigma * 2.5f) + 1, sigma * sigma, nullptr, nrm, zdz, out_grad, col_grad};
+    return foreach_item<BilateralParams, bilateral_px<true>, 128>(p, fx * fy, (cudaStream_t)stream);
 }
 
 int mirres_normal_ao(int fx, int fy, const float *occ, const float *normal, float *out_ao, void *stream)

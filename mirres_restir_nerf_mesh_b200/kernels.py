@@ -278,6 +278,16 @@ class Kernels:
                                            self._ptr_array(g_normals), self._ptr_array(g_pos), self._stream())
         self._check(rc, "mirres_eaw_bwd_multi")
 
+    def bilateral_fwd(self, fx, fy, sigma, col, nrm, zdz, out):
+        rc = self.lib.mirres_bilateral_fwd(int(fx), int(fy), float(sigma), self._f(col), self._f(nrm), self._f(zdz),
+                                           self._f(out), self._stream())
+        self._check(rc, "mirres_bilateral_fwd")
+
+    def bilateral_bwd(self, fx, fy, sigma, nrm, zdz, out_grad, col_grad):
+        rc = self.lib.mirres_bilateral_bwd(int(fx), int(fy), float(sigma), self._f(nrm), self._f(zdz), self._f(out_grad),
+                                           self._f(col_grad), self._stream())
+        self._check(rc, "mirres_bilateral_bwd")
+
     def normal_ao(self, fx, fy, occ, normal, out_ao):
         rc = self.lib.mirres_normal_ao(fx, fy, self._f(occ), self._f(normal), self._f(out_ao), self._stream())
         self._check(rc, "mirres_normal_ao")

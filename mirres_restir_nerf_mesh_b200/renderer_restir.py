@@ -373,6 +373,46 @@ def EAWDenoise_multi_use_phi(c_phi, n_phi, p_phi, stepWidth, iter_time, framedim
     return outs
 
 
+# ---- cross-bilateral denoiser of --use_bi_de (nerf/renderutils/ops.py:173-212) ---------------------------------------------
+class _bilateral_denoiser_func(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, col, nrm, zdz, sigma):
+        _, h, w, _ = col.shape
+        col_c, nrm_c, zdz_c = col.reshape(-1, 3).contiguous(), nrm.reshape(-1, 3).contiguous(), zdz.reshape(-1, 2).contiguous()
+        out = torch.empty((h * w, 4), dtype=torch.float, device=col.device)
+        get_kernels().bilateral_fwd(w, h, sigma, col_c, nrm_c, zdz_c, out)
+        ctx.save_for_backward(nrm_c, zdz_c)
+        ctx.dims = (h, w, sigma)
+        return out.view(1, h, w, 4)
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        nrm_c, zdz_c = ctx.saved_tensors
+        h, w, sigma = ctx.dims
+        col_grad = torch.empty((h * w, 3), dtype=torch.float, device=nrm_c.device)
+        get_kernels().bilateral_bwd(w, h, sigma, nrm_c, zdz_c, out_grad.reshape(-1, 4).contiguous(), col_grad)
+        return col_grad.view(1, h, w, 3), None, None, None
+
+
+def _safe_normalize(x, eps=1e-20):
+    return x / torch.sqrt(torch.clamp(torch.sum(x * x, -1, keepdim=True), min=eps))
+
+
+def bilateral_denoiser(h, w, input, factor=1.0):
+    """nerf/renderutils/ops.py:193-201: input [N, 8] = (colour, normal, depth, depth gradient)."""
+    input = input.reshape(1, h, w, input.shape[-1])
+    sigma = max(factor * 2, 0.0001)
+    col_w = _bilateral_denoiser_func.apply(input[..., 0:3], _safe_normalize(input[..., 3:6]), input[..., 6:8], sigma)
+    out_val = col_w[..., 0:3] / col_w[..., 3:4]
+    return out_val.view(-1, out_val.shape[-1])
+
+
+@torch.no_grad()
+def bilateral_denoiser_no_di(h, w, input, factor=1.0):
+    """nerf/renderutils/ops.py:203-212."""
+    return bilateral_denoiser(h, w, input, factor)
+
+
 def EAWDenoise_run_no_di(m, c_phi, n_phi, p_phi, framedim_x, framedim_y, stepWidth, occ_map, color, normal_map,
                          pos_map):
     out_color = torch.zeros((framedim_x * framedim_y, 3), dtype=torch.float, device=occ_map.device)
@@ -830,11 +870,8 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
         denoised_indirect_diff = EAWDenoise_use_phi_no_di(*args, total_diff_light_1, normal_map, pos_map)
         denoised_indirect_spec = EAWDenoise_use_phi_no_di(*args, total_spec_light_1, normal_map, pos_map)
     else:
-        if bilateral is None:
-            raise NotImplementedError(
-                "gb_depth selects the cross-bilateral denoiser of nerf/renderutils (--use_bi_de), which is outside this "
-                "library (SURVEY.md 8f-3); pass bilateral=(bilateral_denoiser, bilateral_denoiser_no_di)")
-        bi, bi_no_di = bilateral
+        # --use_bi_de: the cross-bilateral denoiser of nerf/renderutils; `bilateral=` swaps in another pair
+        bi, bi_no_di = bilateral if bilateral is not None else (bilateral_denoiser, bilateral_denoiser_no_di)
         factor = 2.0
         cat = lambda c: torch.cat((c, normal_map, gb_depth), dim=-1)
         denoised_diffuse = bi(framedim_y, framedim_x, cat(total_diff_light), factor)

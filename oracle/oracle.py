@@ -240,3 +240,19 @@ def eval_final_taps(res_ld, W, H):
     valid = np.zeros(n, np.int32)
     assert lib().orc_eval_final_taps(_p(res_ld), int(W), int(H), int(n), _p(taps), _p(uv), _p(valid)) == 0
     return taps, uv, valid
+
+
+def bilateral_fwd(fx, fy, sigma, col, nrm, zdz):
+    """nerf/renderutils/c_src/denoising.cu:14-70 -> out [N,4]"""
+    out = np.zeros((fx * fy, 4), np.float32)
+    rc = lib().orc_bilateral_fwd(int(fx), int(fy), ctypes.c_float(sigma), _p(_f32(col)), _p(_f32(nrm)), _p(_f32(zdz)), _p(out))
+    assert rc == 0
+    return out
+
+
+def bilateral_bwd(fx, fy, sigma, nrm, zdz, out_grad):
+    """nerf/renderutils/c_src/denoising.cu:72-130 -> col_grad [N,3]"""
+    g = np.zeros((fx * fy, 3), np.float32)
+    rc = lib().orc_bilateral_bwd(int(fx), int(fy), ctypes.c_float(sigma), _p(_f32(nrm)), _p(_f32(zdz)), _p(_f32(out_grad)), _p(g))
+    assert rc == 0
+    return g

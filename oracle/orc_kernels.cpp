@@ -825,3 +825,67 @@ extern "C" int orc_eval_final_taps(const float *res_ld, int env_w, int env_h, in
     }
     return 0;
 }
+
+
+// ---- cross-bilateral denoiser (--use_bi_de), nerf/renderutils/c_src/denoising.cu:14-130 --------------------------------
+// col [N,3], nrm [N,3] (already normalised by ops.py:197), zdz [N,2] (depth, depth gradient); out [N,4] = (sum of
+// weighted colours, max(sum of weights, 1e-4)).  expf / powf(.,128) of the reference -> mr_expf / mr_pow128f.
+static inline float bilateral_weight(int ox, int oy, f3 t_nrm, f3 c_nrm, float t_z, float c_z, float dz, float variance)
+{
+    const float FLT_EPS = 0.0001f;
+    float dist_sqr = (float)(ox * ox + oy * oy);
+    float dist = sqrtf(dist_sqr);
+    float w_xy = mr_expf(-dist_sqr / (2.0f * variance));
+    float w_normal = mr_pow128f(smin(smax(dot(t_nrm, c_nrm), FLT_EPS), 1.0f));
+    float w_depth = mr_expf(-(fabsf(t_z - c_z) / smax(dz * dist, FLT_EPS)));
+    return w_xy * w_normal * w_depth;
+}
+extern "C" int orc_bilateral_fwd(int fx, int fy, float sigma, const float *col, const float *nrm, const float *zdz, float *out)
+{
+    const float variance = sigma * sigma;
+    const int rad = 2 * (int)ceilf(sigma * 2.5f) + 1;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int idx = 0; idx < fx * fy; ++idx) {
+        const int px = idx % fx, py = idx / fx;
+        f3 c_nrm = ld3(nrm, (size_t)idx);
+        float c_z = zdz[2 * (size_t)idx], c_dz = zdz[2 * (size_t)idx + 1];
+        float accum_w = 0.0f;
+        f3 accum = mk3(0.f);
+        for (int oy = -rad; oy <= rad; ++oy)
+            for (int ox = -rad; ox <= rad; ++ox) {
+                int y = py + oy, x = px + ox;
+                if (y < 0 || x < 0 || y >= fy || x >= fx) continue;
+                size_t t = (size_t)y * fx + x;
+                float w = bilateral_weight(ox, oy, ld3(nrm, t), c_nrm, zdz[2 * t], c_z, c_dz, variance);
+                accum = accum + ld3(col, t) * w;
+                accum_w += w;
+            }
+        out[4 * (size_t)idx] = accum.x; out[4 * (size_t)idx + 1] = accum.y; out[4 * (size_t)idx + 2] = accum.z;
+        out[4 * (size_t)idx + 3] = smax(accum_w, 0.0001f);
+    }
+    return 0;
+}
+// reverse mode w.r.t. col: the transposed gather of denoising.cu:72-130 (depth term with the TAP's dz)
+extern "C" int orc_bilateral_bwd(int fx, int fy, float sigma, const float *nrm, const float *zdz, const float *out_grad /*[N,4]*/,
+                                 float *col_grad /*[N,3]*/)
+{
+    const float variance = sigma * sigma;
+    const int rad = 2 * (int)ceilf(sigma * 2.5f) + 1;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int idx = 0; idx < fx * fy; ++idx) {
+        const int px = idx % fx, py = idx / fx;
+        f3 c_nrm = ld3(nrm, (size_t)idx);
+        float c_z = zdz[2 * (size_t)idx];
+        f3 accum = mk3(0.f);
+        for (int oy = -rad; oy <= rad; ++oy)
+            for (int ox = -rad; ox <= rad; ++ox) {
+                int y = py + oy, x = px + ox;
+                if (y < 0 || x < 0 || y >= fy || x >= fx) continue;
+                size_t t = (size_t)y * fx + x;
+                float w = bilateral_weight(ox, oy, ld3(nrm, t), c_nrm, zdz[2 * t], c_z, zdz[2 * t + 1], variance);
+                accum += mk3(out_grad[4 * t], out_grad[4 * t + 1], out_grad[4 * t + 2]) * w;
+            }
+        st3(col_grad, (size_t)idx, accum);
+    }
+    return 0;
+}

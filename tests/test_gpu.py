@@ -419,3 +419,19 @@ def test_empty_and_single_pixel_frames(kernels):
         assert all(o.shape == (n, 3) and torch.isfinite(o).all() for o in outs)
         if occ_value == 0:
             assert bool((outs[0] == 1.0).all())  # background pixels of the final image are forced to 1 (:546-547)
+
+
+def test_cross_bilateral_denoiser_gpu(kernels, oracle):
+    """SURVEY.md 8f-3 through the C ABI: bit-exact against the oracle (both directions are deterministic gathers)."""
+    import test_hostcheck_parity as THP
+    sc = P.scene("T1")
+    W, Hh = sc["W"], sc["H"]
+    col, nrm, zdz = THP._bilateral_inputs(sc, 3)
+    for sigma in (1.0, 4.0):  # 4.0 = the reference's factor 2 (radius 21, 1849 taps)
+        out = torch.zeros(W * Hh, 4, device=DEV)
+        kernels.bilateral_fwd(W, Hh, sigma, tt(col), tt(nrm), tt(zdz), out)
+        assert np.array_equal(out.cpu().numpy(), oracle.bilateral_fwd(W, Hh, sigma, col, nrm, zdz))
+        go = np.random.default_rng(1).standard_normal((W * Hh, 4)).astype(np.float32)
+        g = torch.zeros(W * Hh, 3, device=DEV)
+        kernels.bilateral_bwd(W, Hh, sigma, tt(nrm), tt(zdz), tt(go), g)
+        assert np.array_equal(g.cpu().numpy(), oracle.bilateral_bwd(W, Hh, sigma, nrm, zdz, go))

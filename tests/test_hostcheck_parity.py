@@ -163,3 +163,65 @@ def test_frame_offset_word_shifts_every_random_stream():
         assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
     base = P.product_run(sc, _worker(sc), "cpu", ref["prepared"], random_offset=4242)
     assert not np.array_equal(np.asarray(base["totals"][0]), np.asarray(got["totals"][0]))
+
+
+def _bilateral_inputs(sc, seed=0):
+    rng = np.random.default_rng(seed)
+    g = sc["gbuffer"]
+    n = sc["W"] * sc["H"]
+    col = (rng.random((n, 3)) * g["occ_map"]).astype(np.float32)
+    nrm = g["normal_map"] + 0.05 * rng.standard_normal((n, 3)).astype(np.float32)
+    nrm = (nrm / np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-10)).astype(np.float32)
+    z = g["depth_map"].astype(np.float32)
+    zdz = np.concatenate([z, np.abs(rng.standard_normal((n, 1))).astype(np.float32) * 0.01 + 1e-3], 1).astype(np.float32)
+    return col, nrm, zdz
+
+
+def test_cross_bilateral_denoiser(oracle):
+    """SURVEY.md 8f-3 (--use_bi_de): forward and transposed-gather backward bit-exact against the oracle's restatement of
+    nerf/renderutils/c_src/denoising.cu; the backward is the adjoint of the forward (float64 autograd); the gb_depth
+    branch of run_restir_di_with_pt runs on it."""
+    from mirres_restir_nerf_mesh_b200 import renderer_restir as R, synth
+    sc = P.scene("T0")
+    W, Hh = sc["W"], sc["H"]
+    col, nrm, zdz = _bilateral_inputs(sc)
+    k = H.kernels()
+    sigma = 1.0  # radius 7: 225 taps
+    out = torch.zeros(W * Hh, 4)
+    k.bilateral_fwd(W, Hh, sigma, H.t(col), H.t(nrm), H.t(zdz), out)
+    want = oracle.bilateral_fwd(W, Hh, sigma, col, nrm, zdz)
+    assert np.array_equal(out.numpy(), want)
+    go = np.random.default_rng(1).standard_normal((W * Hh, 4)).astype(np.float32)
+    g = torch.zeros(W * Hh, 3)
+    k.bilateral_bwd(W, Hh, sigma, H.t(nrm), H.t(zdz), H.t(go), g)
+    assert np.array_equal(g.numpy(), oracle.bilateral_bwd(W, Hh, sigma, nrm, zdz, go))
+    # adjoint check in float64: out[:, :3] is linear in col with weights w(c, t)
+    rad = 2 * int(np.ceil(sigma * 2.5)) + 1
+    c64 = torch.tensor(col, dtype=torch.float64).view(Hh, W, 3).requires_grad_(True)
+    n64, z64 = torch.tensor(nrm, dtype=torch.float64).view(Hh, W, 3), torch.tensor(zdz, dtype=torch.float64).view(Hh, W, 2)
+    acc = torch.zeros(Hh, W, 3, dtype=torch.float64)
+    ys, xs = torch.meshgrid(torch.arange(Hh), torch.arange(W), indexing="ij")
+    for oy in range(-rad, rad + 1):
+        for ox in range(-rad, rad + 1):
+            y, x = ys + oy, xs + ox
+            ok = (y >= 0) & (y < Hh) & (x >= 0) & (x < W)
+            yc, xc = y.clamp(0, Hh - 1), x.clamp(0, W - 1)
+            d2 = float(ox * ox + oy * oy)
+            w = np.exp(-d2 / (2 * sigma * sigma)) * (n64[yc, xc] * n64).sum(-1).clamp(1e-4, 1.0) ** 128 * torch.exp(
+                -(z64[yc, xc, 0] - z64[..., 0]).abs() / (z64[..., 1] * np.sqrt(d2)).clamp(min=1e-4))
+            acc = acc + (w * ok)[..., None] * c64[yc, xc]
+    (acc * torch.tensor(go[:, :3], dtype=torch.float64).view(Hh, W, 3)).sum().backward()
+    ref = c64.grad.view(-1, 3).numpy()
+    assert np.abs(g.numpy() - ref).max() <= 1e-3 * np.abs(ref).max()
+    np.testing.assert_allclose(out.numpy()[:, :3], acc.detach().view(-1, 3).numpy(), rtol=2e-4, atol=1e-6)
+    # the driver's gb_depth branch (nerf/renderer_restir.py:529-541)
+    w_ = _worker(sc)
+    mods = R.load_m_for_restir(W, Hh, device="cpu")
+    gb = {kk: H.t(v) for kk, v in sc["gbuffer"].items()}
+    kd = gb["diffuse_map"].clone().requires_grad_(True)
+    outs = R.run_restir_di_with_pt(False, 1, 1, 1, synth.ProceduralMaterial(0.0), H.t(zdz), w_, *mods, H.t(sc["env"]),
+                                   gb["occ_map"], gb["normal_map"], gb["depth_map"], kd, gb["roughness_specular"],
+                                   gb["ray_dir_map"], gb["pos_map"], None, None, None, None, W, Hh, 2, 2, 2, 2.0, 0.1, 0.001,
+                                   random_offset=5)
+    outs[0].sum().backward()
+    assert all(torch.isfinite(o).all() for o in outs) and kd.grad.abs().sum() > 0
