@@ -203,9 +203,11 @@ def run_gpu(args):
     # ---- synthetic scene; each rank renders its own training view (weak scaling over views) -------------------------
     vert_np, tri_np = synth.make_mesh(cfg)
     env_np = synth.envmap(*cfg["env"])
-    ro_np, rd_np = synth.camera_rays(W, H, view=rank * 7)
+    pose_np = synth.camera_pose(view=rank * 7)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    host = dict(vert=pin(vert_np), tri=pin(tri_np), env=pin(env_np), rays_o=pin(ro_np), rays_d=pin(rd_np))
+    # the inputs of a step: mesh, envmap, camera pose (rays are generated on the device from the pose, as the reference's
+    # get_rays does)
+    host = dict(vert=pin(vert_np), tri=pin(tri_np), env=pin(env_np), pose=pin(pose_np))
     device_in = {k: v.to(dev) for k, v in host.items()}
     worker = R.restirbvhWorker(device_in["vert"], device_in["tri"])
     mat = synth.ProceduralMaterial(0.0)
@@ -215,10 +217,12 @@ def run_gpu(args):
     flat_grad = torch.zeros(ne + V * 3 + V * 5, device=dev)  # env | vertex-normal | vertex-texture (kd, rough, metal)
     opts = dict(overlap=not args.no_overlap)
 
-    def full_step(vert, tri, env, rays_o, rays_d):
-        """One stage-1 training step of one view: LBVH rebuild (nerf/renderer.py:975), G-buffer, ReSTIR + path tracer,
-        denoise + composite, loss, backward into env / normals / kd / ks, scatter to vertices and vertex texture."""
+    def full_step(vert, tri, env, pose):
+        """One stage-1 training step of one view: LBVH rebuild (nerf/renderer.py:975), camera rays, G-buffer, ReSTIR +
+        path tracer, denoise + composite, loss, backward into env / normals / kd / ks, scatter to vertices and vertex
+        texture."""
         worker.update_mesh(vert, tri)
+        rays_o, rays_d = synth.camera_rays_torch(W, H, pose)
         occ, depth = torch.empty(n, 1, device=dev), torch.empty(n, 1, device=dev)
         pos, nrm = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
         prim, bary = torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, 2, device=dev)

@@ -91,6 +91,31 @@ def camera_rays(W, H, view=0, n_views=100, radius=3.2, elevation_deg=30.0, fov_x
     return o.reshape(-1, 3).astype(np.float32).copy(), d.reshape(-1, 3).astype(np.float32)
 
 
+def camera_pose(view=0, n_views=100, radius=3.2, elevation_deg=30.0):
+    """[4,3] f32 rows (right, up, forward, eye) of the camera `camera_rays` uses for `view`."""
+    az = 2 * np.pi * view / n_views
+    el = np.deg2rad(elevation_deg)
+    eye = radius * np.array([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)])
+    fwd = -eye / np.linalg.norm(eye)
+    right = np.cross(fwd, np.array([0.0, 0.0, 1.0]))
+    right /= np.linalg.norm(right)
+    upv = np.cross(right, fwd)
+    return np.stack([right, upv, fwd, eye]).astype(np.float32)
+
+
+def camera_rays_torch(W, H, pose, fov_x=0.6911112):
+    """Device-side twin of `camera_rays` (the reference generates rays on the GPU from the pose as well, nerf/utils.py
+    get_rays): pose [4,3] tensor -> (rays_o [N,3], rays_d [N,3] unit), pixelIndex = y*W + x."""
+    import torch
+    fl = W / (2.0 * np.tan(fov_x / 2.0))
+    dev = pose.device
+    xs = (torch.arange(W, device=dev, dtype=torch.float32) + 0.5 - W / 2.0) / fl
+    ys = -(torch.arange(H, device=dev, dtype=torch.float32) + 0.5 - H / 2.0) / fl
+    d = xs[None, :, None] * pose[0][None, None, :] + ys[:, None, None] * pose[1][None, None, :] + pose[2][None, None, :]
+    d = d / torch.sqrt((d * d).sum(-1, keepdim=True))
+    return pose[3].expand(H * W, 3).contiguous(), d.reshape(-1, 3).contiguous()
+
+
 def envmap(He=256, We=512, seed=0):
     """HDR `[He,We,3]` f32, the layout of `lgt.base` (nerf/render_helper.py)."""
     rng = np.random.default_rng(seed)
