@@ -435,3 +435,41 @@ def test_cross_bilateral_denoiser_gpu(kernels, oracle):
         g = torch.zeros(W * Hh, 3, device=DEV)
         kernels.bilateral_bwd(W, Hh, sigma, tt(nrm), tt(zdz), tt(go), g)
         assert np.array_equal(g.cpu().numpy(), oracle.bilateral_bwd(W, Hh, sigma, nrm, zdz, go))
+
+
+def test_c2_full_size_parity_against_oracle(kernels, oracle):
+    """BASELINE config C2 at FULL size (500 000 triangles, 800 x 800, spp 4, 3 path vertices): LBVH, primary G-buffer and
+    every intermediate tensor of the forward spp loop against the oracle (the oracle needs a few seconds on the host
+    cores), then the concurrent schedule against the sequential one."""
+    sc = P.scene("C2")
+    ref = P.oracle_run(sc)
+    w = make_worker(sc)
+    assert (w.sorted_codes.cpu().numpy() == sc["bvh"].sorted_codes).all()
+    assert (w.LBVHNode_info.cpu().numpy() == sc["bvh"].info).all()
+    assert (w.LBVHNode_aabb.cpu().numpy() == sc["bvh"].aabb).all()
+    n = sc["W"] * sc["H"]
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim
+    occ, depth = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    pos, nrm = torch.zeros(n, 3, device=DEV), torch.zeros(n, 3, device=DEV)
+    prim, bary = torch.zeros(n, dtype=torch.int32, device=DEV), torch.zeros(n, 2, device=DEV)
+    kernels.gbuffer_primary(w.packed, tt(sc["rays_o"]), tt(sc["rays_d"]), occ, pos, nrm, depth, prim, bary,
+                            ws=slangpy_shim.workspace(torch.device(DEV), n))
+    m = sc["hit"] > 0
+    assert (occ.cpu().numpy() == sc["hit"]).all() and (prim.cpu().numpy() == sc["prim"]).all()
+    assert (pos.cpu().numpy()[m] == sc["pos"][m]).all() and (nrm.cpu().numpy()[m] == sc["nrm"][m]).all()
+    got = P.product_run(sc, w, DEV, ref["prepared"])
+    bad = P.compare(ref, got, rtol=FWD_RTOL)
+    assert not bad, bad[:5]
+    assert not P.compare(ref, got, rtol=0.0), "forward pass is expected to be bit-exact"
+    # default (concurrent) schedule == sequential schedule at full size
+    mods = R.load_m_for_restir(sc["W"], sc["H"])
+    g = {k: tt(v) for k, v in sc["gbuffer"].items()}
+    outs = []
+    for kw in (dict(overlap=False, batched_denoise=False, fused_prepare=False), dict()):
+        with torch.no_grad():
+            outs.append(R.run_restir_di_with_pt(False, 1, 1, 1, synth.ProceduralMaterial(0.0), None, w, *mods, tt(sc["env"]),
+                                                g["occ_map"].clone(), g["normal_map"], g["depth_map"], g["diffuse_map"],
+                                                g["roughness_specular"], g["ray_dir_map"], g["pos_map"], None, None, None,
+                                                None, sc["W"], sc["H"], 4, 2, 2, 2.0, 0.1, 0.001, random_offset=4242, **kw))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
