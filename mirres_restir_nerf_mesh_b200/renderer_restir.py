@@ -27,8 +27,9 @@ from .slangpy_shim import get_kernels
 
 TOTAL_RIS_PASSES = 5 + 15  # frame-index stride per spp iteration (nerf/renderer_restir.py:242)
 
-MAX_INITIAL_STREAMS = 4   # concurrent initial-candidate stages (light tiles + initial RIS of different spp iterations)
-MAX_INDIRECT_CHAINS = 4  # concurrent indirect-path chains (one CUDA stream + path state + ray-queue workspace each)
+import os as _os
+MAX_INITIAL_STREAMS = int(_os.environ.get("MIRRES_INITIAL_STREAMS", 4))   # concurrent initial-candidate stages (light tiles + initial RIS of different spp iterations)
+MAX_INDIRECT_CHAINS = int(_os.environ.get("MIRRES_INDIRECT_CHAINS", 2))  # concurrent indirect-path chains (one CUDA stream + path state + ray-queue workspace each)
 _SIDE_STREAMS = {}
 
 
