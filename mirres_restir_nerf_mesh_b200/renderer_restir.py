@@ -529,14 +529,20 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     def zeros(*shape):
         return torch.zeros(shape, dtype=torch.float, device=dev)
 
+    if overlap is None:
+        overlap = hooks is None and pos_map.is_cuda and shard is None
+    if shard is not None and overlap:
+        raise ValueError("row-band sharding uses the sequential schedule (overlap=False)")
     sums = {k: zeros(n, 3) for k in ("color", "diff", "spec", "color_1", "diff_1", "spec_1")}
     total_indirect_light = zeros(n, 3)
-    color_1, color_diff_1, color_spec_1 = zeros(n, 3), zeros(n, 3), zeros(n, 3)
-    prd = zeros(n, 5)
-    ping = dict(pos=zeros(n, 3), ray=zeros(n, 3), occ=zeros(n, 1), nrm=zeros(n, 3))
-    pong = dict(pos=zeros(n, 3), ray=zeros(n, 3), occ=zeros(n, 1), nrm=zeros(n, 3))
-    new_diffuse_map = torch.zeros((n, 3), dtype=torch.float, device=dev)
-    new_roughness_specular = torch.zeros((n, 2), dtype=torch.float, device=dev)
+    prd = ping = pong = color_1 = color_diff_1 = color_spec_1 = new_diffuse_map = new_roughness_specular = None
+    if not overlap:  # path state of the sequential schedule (the concurrent chains own theirs)
+        color_1, color_diff_1, color_spec_1 = zeros(n, 3), zeros(n, 3), zeros(n, 3)
+        prd = zeros(n, 5)
+        ping = dict(pos=zeros(n, 3), ray=zeros(n, 3), occ=zeros(n, 1), nrm=zeros(n, 3))
+        pong = dict(pos=zeros(n, 3), ray=zeros(n, 3), occ=zeros(n, 1), nrm=zeros(n, 3))
+        new_diffuse_map = torch.zeros((n, 3), dtype=torch.float, device=dev)
+        new_roughness_specular = torch.zeros((n, 2), dtype=torch.float, device=dev)
 
     kd, rs = diffuse_map.detach(), roughness_specular.detach()
     if prepared is not None:
@@ -551,7 +557,8 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     eva_vis_map = torch.ones((n, 1), dtype=torch.float, device=dev)
 
     # the reference ignores the reservoirs/prev_* it is handed for these and starts from zeros (:291-302)
-    prev_reservoirs = _reservoir_set(n, dev)
+    if not overlap:
+        prev_reservoirs = _reservoir_set(n, dev)
     prev_occ_map = zeros(*occ_map.shape)
     prev_normal_depth = zeros(n, 4)
     prev_brdf_map = zeros(*brdf_map.shape)
@@ -572,10 +579,6 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     # launch ends with a few long rays on an otherwise idle GPU).  Their per-vertex outputs are added to the running
     # sums on the main stream in the reference's order (iteration-major, bounce-minor), so the sums stay bit-identical
     # to the sequential schedule.
-    if overlap is None:
-        overlap = hooks is None and pos_map.is_cuda and shard is None
-    if shard is not None and overlap:
-        raise ValueError("row-band sharding uses the sequential schedule (overlap=False)")
     main_stream = None
     keepalive = []
     chains = []
