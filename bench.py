@@ -227,15 +227,15 @@ def run_gpu(args):
         pos, nrm = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
         prim, bary = torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, 2, device=dev)
         pk.gbuffer_primary(worker.packed, rays_o, rays_d, occ, pos, nrm, depth, prim, bary, ws=slangpy_shim.workspace(dev, n))
-        kdks = mat.sample_no_di_dense(pos) * occ   # stand-in for the tiny-cuda-nn material MLP (out of scope)
+        kd, rs = mat.gbuffer_materials(pos, occ)   # stand-in for the tiny-cuda-nn material MLP (out of scope)
         env_l = env.detach().clone().requires_grad_(True)
         normal = nrm.requires_grad_(True)
-        kd = kdks[:, 0:3].contiguous().requires_grad_(True)
-        rs = kdks[:, 4:6].contiguous().requires_grad_(True)
+        kd.requires_grad_(True)
+        rs.requires_grad_(True)
         outs = R.run_restir_di_with_pt(False, 1, 1, 1, mat, None, worker, *mods, env_l, occ, normal, depth, kd, rs, rays_d,
                                        pos, None, None, None, None, W, H, spp, 2, 2, 2.0, 0.1, 0.001,
                                        random_offset=1234 + 17 * rank, max_bounce=mb, **opts)
-        loss = ((outs[0] - target) ** 2).mean()
+        loss = torch.nn.functional.mse_loss(outs[0], target)
         loss.backward()
         # gradients leave the path as grad_env [He,We,3] and dense per-pixel grads; the latter are scattered to vertices /
         # vertex texture here (the reference: nvdiffrast / tcnn backward), everything lands in ONE flat buffer

@@ -262,6 +262,45 @@ int mirres_prepare_maps(int n, float *occ, const float *normal, const float *dep
 int mirres_interpolate_bwd(const float *grad, int n, int C, const int *prim, const float *bary, const int *tri, int F,
                            float *out, void *stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-side chains of the spp loop as single launches.  Same operations in the same order as the
+ * torch expressions they replace, so results are bit-identical.
+ *   mirres_material_procedural   the synthetic stand-in of the `mlp_mat` query between bounces
+ *        (nerf/renderer_restir.py:398-408, 428-438): kd_c = 0.1 + 0.8 tri(1.7 pos_c), roughness = 0.08 + 0.92
+ *        tri(0.8 pos_x + 0.5 pos_y), tri(x) = |2 frac(x) - 1|, metallic constant.  mode 0: kd / rough_metal = value * occ
+ *        (occ NULL: value) -- the G-buffer materials; mode 1: the torch.where merge -- pixels with occ >= 0.5 take the new
+ *        value (kd times scale_xyz when given), the others keep theirs; with scale_xyz (HOST pointer to 3 floats, read at
+ *        launch) kd is clamped to [0,1] afterwards (:405-408).
+ *   mirres_sum_images            dst[i] = ((accumulate ? dst[i] : 0) + src_0[i] + src_1[i] + ...) [/ divisor if != 0]:
+ *        the running sums of the per-iteration outputs and `total / mFrameIndex` (:443-459, :505-515).  src: HOST
+ *        array of n_src <= 32 device pointers.
+ *   mirres_composite_fwd / _bwd  final_color = nan_to_num(where(occ <= 0.1, 1, kd (1 - metallic) dd + ds + di))
+ *        (:543-549) and its reverse mode w.r.t. kd, (roughness, metallic), dd, ds (what torch autograd derives).
+ *   mirres_final_shading_bwd_multi   mirres_final_shading_bwd for the n_passes <= 16 shading passes of an spp loop in one
+ *        launch: the passes share surface inputs and upstream gradients (grad_color may be NULL = zeros; divided by
+ *        grad_divisor first when it is != 0, the backward of `total / mFrameIndex`) and differ in their final samples;
+ *        fs_dir / fs_dist / fs_Li / grad_Li are HOST arrays of n_passes device pointers.
+ *        grad_normal / grad_diffuse / grad_rough_metal receive the sum over passes (last pass first, the autograd
+ *        engine's order; accumulate != 0 continues an earlier call).  grad_Li[k] is written per pass, or -- with
+ *        sum_grad_Li -- grad_Li[0] receives the sum (for passes that evaluated one shared reservoir buffer).
+ */
+int mirres_material_procedural(int n, const float *pos, const float *occ, int mode, float metallic, const float *scale_xyz,
+                               float *kd, float *rough_metal, void *stream);
+int mirres_sum_images(int n_floats, int n_src, const float *const *src, float divisor, int accumulate, float *dst, void *stream);
+int mirres_composite_fwd(int n, const float *occ, const float *diffuse_map, const float *rough_metal, const float *denoised_diffuse,
+                         const float *denoised_spec, const float *denoised_indirect, float *final_color, void *stream);
+int mirres_composite_bwd(int n, const float *occ, const float *diffuse_map, const float *rough_metal, const float *denoised_diffuse,
+                         const float *denoised_spec, const float *denoised_indirect, const float *grad_final_color,
+                         float *grad_diffuse_map, float *grad_rough_metal, float *grad_denoised_diffuse,
+                         float *grad_denoised_spec, void *stream);
+int mirres_final_shading_bwd_multi(int n_passes, const float *const *fs_dir, const float *const *fs_dist,
+                                   const float *const *fs_Li, int fx, int fy, const float *occ, const float *normal,
+                                   const float *ray_dir, const float *diffuse_map, const float *rough_metal,
+                                   const float *grad_color, const float *grad_diff_light, const float *grad_spec_light,
+                                   float grad_divisor, int accumulate, float *grad_normal, float *grad_diffuse, float *grad_rough_metal,
+                                   int sum_grad_Li, float *const *grad_Li, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

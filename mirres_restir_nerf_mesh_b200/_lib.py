@@ -51,6 +51,11 @@ SIGNATURES = {
     "mirres_gbuffer_primary": "ppppi" + "pp" + "pppppp" + "pz" + "p",
     "mirres_prepare_maps": "ippppppppp" + "p",
     "mirres_interpolate_bwd": "piipppipp",
+    "mirres_material_procedural": "ippifpppp",
+    "mirres_sum_images": "iipfipp",
+    "mirres_composite_fwd": "ipppppppp",
+    "mirres_composite_bwd": "ipppppp" + "p" + "pppp" + "p",
+    "mirres_final_shading_bwd_multi": "ippp" + "ii" + "ppppp" + "ppp" + "fippp" + "ip" + "p",
 }
 SIZE_FUNCS = ("mirres_bvh_scratch_bytes", "mirres_bvh_packed_node_bytes", "mirres_bvh_packed_tri_bytes",
               "mirres_workspace_bytes")

@@ -11,8 +11,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["bvh_build.cu", "trace.cu", "wave.cu", "env.cu", "restir.cu", "shade.cu", "denoise.cu", "gbuffer.cu"]
-HOSTCHECK_SOURCES = ["trace.cu", "wave.cu", "env.cu", "restir.cu", "shade.cu", "denoise.cu", "gbuffer.cu"]
+SOURCES = ["bvh_build.cu", "trace.cu", "wave.cu", "env.cu", "restir.cu", "shade.cu", "denoise.cu", "gbuffer.cu", "screen.cu"]
+HOSTCHECK_SOURCES = ["trace.cu", "wave.cu", "env.cu", "restir.cu", "shade.cu", "denoise.cu", "gbuffer.cu", "screen.cu"]
 LIB = os.path.join(HERE, "libmirres_b200.so")
 HOSTCHECK_LIB = os.path.join(HERE, "..", "tests", "_build", "libmirres_hostcheck.so")
 

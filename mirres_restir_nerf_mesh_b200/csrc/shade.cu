@@ -70,121 +70,200 @@ MR_DEV void final_shading_px(const ShadeParams &p, int idx)
 // Reverse mode of final_shading_px with respect to normal, kd, (roughness, metallic) and Li.  Branch predicates
 // (occupancy, distance, lobe probabilities, the 1e-6 / alpha == 0 gates, clamps) are frozen, as Slang's autodiff
 // does.  The lobe probabilities only gate branches, so no gradient flows through them.
+struct ShadeGrads {
+    float3 gN, gKd, gLi;
+    float gR, gM;
+};
+// gradients of one lit pixel (occ > 0.1 and sample distance > 0); gC / gD / gS: upstream on color / diff_light / spec_light
+MR_DEV ShadeGrads final_shading_grads(float3 N, float3 rd, float3 kd, float rough, float metallic, float3 L, float3 Li,
+                                      float3 gC, float3 gD, float3 gS)
+{
+    float3 gN = f3(0.f), gKd = f3(0.f), gLi = f3(0.f);
+    float gR = 0.f, gM = 0.f;
+    const float INV_PI = 0.31830988f;
+    const float PI = 3.141592653589793f;
+    const float F0 = 0.04f;
+    const Surface s = surface_of(N, rd, kd, rough, metallic);
+    const float3 V = -rd;
+    const float3 wo = s.wo;
+    const float3 wi = to_frame(s.frame, L);
+    // forward values
+    const bool gate = !(fminf(wo.z, wi.z) < 1e-6f);
+    float Dl = 0.f;
+    if (s.pD > 0.f && gate) Dl = fmaxf(INV_PI * wi.z, 0.0f);
+    const float3 diffuse_val = f3(Dl) * Li;
+    // upstream on diffuse_val / specular_val
+    const float3 gDv = gC * (kd * (1.0f - metallic)) + gD;
+    const float3 gSv = gC + gS;
+    // color = kd (1-m) diffuse_val + specular_val
+    gKd += gC * diffuse_val * (1.0f - metallic);
+    gM += -(gC.x * kd.x * diffuse_val.x + gC.y * kd.y * diffuse_val.y + gC.z * kd.z * diffuse_val.z);
+    gLi += gDv * Dl;
+    float3 gwo = f3(0.f), gwi = f3(0.f);
+    if (s.pD > 0.f && gate && INV_PI * wi.z > 0.0f) gwi.z += INV_PI * (gDv.x * Li.x + gDv.y * Li.y + gDv.z * Li.z);
+    if (s.pS > 0.f && gate && s.alpha != 0.f) {
+        const float alpha = s.alpha;
+        const float3 sum = wo + wi;
+        const float len = sqrtf(dot(sum, sum));
+        const float3 h = sum / len;
+        const float c = dot(wo, h);
+        const float a2 = alpha * alpha;
+        const float dd = ((h.z * a2 - h.z) * h.z + 1);
+        const float D = a2 / (dd * dd * PI);
+        const float lI = ggx_lambda(a2, wo.z), lO = ggx_lambda(a2, wi.z);
+        const float G = 1 / (1 + lI + lO);
+        const float om = fmaxf(1 - c, 0);
+        const float p5 = mr_pow5f(om);
+        const float3 F = make_float3(s.spec.x + (1 - s.spec.x) * p5, s.spec.y + (1 - s.spec.y) * p5, s.spec.z + (1 - s.spec.z) * p5);
+        const float sc = D * G * 0.25f / wo.z; // Fs = F * sc
+        gLi += gSv * (F * sc);
+        const float3 gFs = gSv * Li;
+        const float3 gF = gFs * sc;
+        const float gsc = gFs.x * F.x + gFs.y * F.y + gFs.z * F.z;
+        // F = spec + (1 - spec) p5
+        const float3 gspec = gF * (1 - p5);
+        const float gp5 = gF.x * (1 - s.spec.x) + gF.y * (1 - s.spec.y) + gF.z * (1 - s.spec.z);
+        float gc = 0.f;
+        if (1 - c > 0) gc = -gp5 * 5.0f * (om * om) * (om * om);
+        // sc = D G / (4 wo.z)
+        const float gD_ = gsc * G * 0.25f / wo.z;
+        const float gG = gsc * D * 0.25f / wo.z;
+        gwo.z += -gsc * sc / wo.z;
+        // D(a2, hz)
+        float ga2 = gD_ * (1 / (dd * dd * PI) - 2 * a2 * (h.z * h.z) / (dd * dd * dd * PI));
+        float ghz = gD_ * (-2 * a2 / (dd * dd * dd * PI)) * (2 * h.z * (a2 - 1));
+        // G = 1 / (1 + lI + lO)
+        const float gl = -gG * G * G;
+        {
+            const float cs[2] = {wo.z, wi.z};
+            float gcs[2] = {0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float cz = cs[k];
+                if (cz > 0) {
+                    const float c2 = cz * cz;
+                    const float num = fmaxf(1 - c2, 0);
+                    const float t = num / c2;
+                    const float root = sqrtf(1 + a2 * t);
+                    ga2 += gl * 0.25f * t / root;
+                    if (1 - c2 > 0) gcs[k] = gl * (0.25f * a2 / root) * (-2.0f / (c2 * cz));
+                }
+            }
+            gwo.z += gcs[0];
+            gwi.z += gcs[1];
+        }
+        // c = dot(wo, h), hz = h.z, h = normalize(wo + wi)
+        float3 gh = gc * wo;
+        gh.z += ghz;
+        gwo += gc * h;
+        const float3 gsum = (gh - h * dot(h, gh)) / len;
+        gwo += gsum;
+        gwi += gsum;
+        // alpha = rough^2 (frozen to 0 below the threshold, in which case this branch is not taken)
+        gR += ga2 * 2 * alpha * 2 * rough;
+        // spec = F0 (1-m) + kd m
+        gKd += gspec * metallic;
+        gM += gspec.x * (kd.x - F0) + gspec.y * (kd.y - F0) + gspec.z * (kd.z - F0);
+    }
+    // wo = frame(N)^T V, wi = frame(N)^T L
+    const float3 gfx = gwo.x * V + gwi.x * L;
+    const float3 gfy = gwo.y * V + gwi.y * L;
+    const float3 gfz = gwo.z * V + gwi.z * L;
+    gN += gfz;
+    {
+        const float sign = N.z > 0 ? 1.0f : -1.0f;
+        const float a = -1.0f / (sign + N.z);
+        const float gb = gfx.y * sign + gfy.x;
+        const float ga = gfx.x * sign * N.x * N.x + gfy.y * N.y * N.y + gb * N.x * N.y;
+        gN.x += gfx.x * sign * 2 * N.x * a + gb * N.y * a - gfx.z * sign;
+        gN.y += gfy.y * 2 * N.y * a + gb * N.x * a - gfy.z;
+        gN.z += ga * (a * a); // a = -1/(sign+nz)  =>  da/dnz = 1/(sign+nz)^2 = a^2
+    }
+    ShadeGrads r;
+    r.gN = gN; r.gKd = gKd; r.gLi = gLi; r.gR = gR; r.gM = gM;
+    return r;
+}
+
 MR_DEV void final_shading_bwd_px(const ShadeParams &p, int idx)
 {
     const size_t i = (size_t)idx;
-    float3 gN = f3(0.f), gKd = f3(0.f), gLi = f3(0.f);
-    float gR = 0.f, gM = 0.f;
-    if (MR_LDG(p.occ + i) > 0.1f && MR_LDG(p.fs_dist + i) > 0.f) {
-        const float INV_PI = 0.31830988f;
-        const float PI = 3.141592653589793f;
-        const float F0 = 0.04f;
-        const float3 N = load3(p.normal, i), rd = load3(p.ray_dir, i), kd = load3(p.kd, i);
-        const float rough = MR_LDG(p.rm + 2 * i), metallic = MR_LDG(p.rm + 2 * i + 1);
-        const float3 L = load3(p.fs_dir, i), Li = load3(p.fs_Li, i);
-        const float3 gC = load3(p.g_color, i), gD = load3(p.g_diff, i), gS = load3(p.g_spec, i);
-        const Surface s = surface_of(N, rd, kd, rough, metallic);
-        const float3 V = -rd;
-        const float3 wo = s.wo;
-        const float3 wi = to_frame(s.frame, L);
-        // forward values
-        const bool gate = !(fminf(wo.z, wi.z) < 1e-6f);
-        float Dl = 0.f;
-        if (s.pD > 0.f && gate) Dl = fmaxf(INV_PI * wi.z, 0.0f);
-        const float3 diffuse_val = f3(Dl) * Li;
-        // upstream on diffuse_val / specular_val
-        const float3 gDv = gC * (kd * (1.0f - metallic)) + gD;
-        const float3 gSv = gC + gS;
-        // color = kd (1-m) diffuse_val + specular_val
-        gKd += gC * diffuse_val * (1.0f - metallic);
-        gM += -(gC.x * kd.x * diffuse_val.x + gC.y * kd.y * diffuse_val.y + gC.z * kd.z * diffuse_val.z);
-        gLi += gDv * Dl;
-        float3 gwo = f3(0.f), gwi = f3(0.f);
-        if (s.pD > 0.f && gate && INV_PI * wi.z > 0.0f) gwi.z += INV_PI * (gDv.x * Li.x + gDv.y * Li.y + gDv.z * Li.z);
-        if (s.pS > 0.f && gate && s.alpha != 0.f) {
-            const float alpha = s.alpha;
-            const float3 sum = wo + wi;
-            const float len = sqrtf(dot(sum, sum));
-            const float3 h = sum / len;
-            const float c = dot(wo, h);
-            const float a2 = alpha * alpha;
-            const float dd = ((h.z * a2 - h.z) * h.z + 1);
-            const float D = a2 / (dd * dd * PI);
-            const float lI = ggx_lambda(a2, wo.z), lO = ggx_lambda(a2, wi.z);
-            const float G = 1 / (1 + lI + lO);
-            const float om = fmaxf(1 - c, 0);
-            const float p5 = mr_pow5f(om);
-            const float3 F = make_float3(s.spec.x + (1 - s.spec.x) * p5, s.spec.y + (1 - s.spec.y) * p5, s.spec.z + (1 - s.spec.z) * p5);
-            const float sc = D * G * 0.25f / wo.z; // Fs = F * sc
-            gLi += gSv * (F * sc);
-            const float3 gFs = gSv * Li;
-            const float3 gF = gFs * sc;
-            const float gsc = gFs.x * F.x + gFs.y * F.y + gFs.z * F.z;
-            // F = spec + (1 - spec) p5
-            const float3 gspec = gF * (1 - p5);
-            const float gp5 = gF.x * (1 - s.spec.x) + gF.y * (1 - s.spec.y) + gF.z * (1 - s.spec.z);
-            float gc = 0.f;
-            if (1 - c > 0) gc = -gp5 * 5.0f * (om * om) * (om * om);
-            // sc = D G / (4 wo.z)
-            const float gD_ = gsc * G * 0.25f / wo.z;
-            const float gG = gsc * D * 0.25f / wo.z;
-            gwo.z += -gsc * sc / wo.z;
-            // D(a2, hz)
-            float ga2 = gD_ * (1 / (dd * dd * PI) - 2 * a2 * (h.z * h.z) / (dd * dd * dd * PI));
-            float ghz = gD_ * (-2 * a2 / (dd * dd * dd * PI)) * (2 * h.z * (a2 - 1));
-            // G = 1 / (1 + lI + lO)
-            const float gl = -gG * G * G;
-            {
-                const float cs[2] = {wo.z, wi.z};
-                float gcs[2] = {0.f, 0.f};
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const float cz = cs[k];
-                    if (cz > 0) {
-                        const float c2 = cz * cz;
-                        const float num = fmaxf(1 - c2, 0);
-                        const float t = num / c2;
-                        const float root = sqrtf(1 + a2 * t);
-                        ga2 += gl * 0.25f * t / root;
-                        if (1 - c2 > 0) gcs[k] = gl * (0.25f * a2 / root) * (-2.0f / (c2 * cz));
-                    }
-                }
-                gwo.z += gcs[0];
-                gwi.z += gcs[1];
-            }
-            // c = dot(wo, h), hz = h.z, h = normalize(wo + wi)
-            float3 gh = gc * wo;
-            gh.z += ghz;
-            gwo += gc * h;
-            const float3 gsum = (gh - h * dot(h, gh)) / len;
-            gwo += gsum;
-            gwi += gsum;
-            // alpha = rough^2 (frozen to 0 below the threshold, in which case this branch is not taken)
-            gR += ga2 * 2 * alpha * 2 * rough;
-            // spec = F0 (1-m) + kd m
-            gKd += gspec * metallic;
-            gM += gspec.x * (kd.x - F0) + gspec.y * (kd.y - F0) + gspec.z * (kd.z - F0);
-        }
-        // wo = frame(N)^T V, wi = frame(N)^T L
-        const float3 gfx = gwo.x * V + gwi.x * L;
-        const float3 gfy = gwo.y * V + gwi.y * L;
-        const float3 gfz = gwo.z * V + gwi.z * L;
-        gN += gfz;
-        {
-            const float sign = N.z > 0 ? 1.0f : -1.0f;
-            const float a = -1.0f / (sign + N.z);
-            const float gb = gfx.y * sign + gfy.x;
-            const float ga = gfx.x * sign * N.x * N.x + gfy.y * N.y * N.y + gb * N.x * N.y;
-            gN.x += gfx.x * sign * 2 * N.x * a + gb * N.y * a - gfx.z * sign;
-            gN.y += gfy.y * 2 * N.y * a + gb * N.x * a - gfy.z;
-            gN.z += ga * (a * a); // a = -1/(sign+nz)  =>  da/dnz = 1/(sign+nz)^2 = a^2
-        }
+    ShadeGrads g;
+    g.gN = g.gKd = g.gLi = f3(0.f);
+    g.gR = g.gM = 0.f;
+    if (MR_LDG(p.occ + i) > 0.1f && MR_LDG(p.fs_dist + i) > 0.f)
+        g = final_shading_grads(load3(p.normal, i), load3(p.ray_dir, i), load3(p.kd, i), MR_LDG(p.rm + 2 * i), MR_LDG(p.rm + 2 * i + 1),
+                                load3(p.fs_dir, i), load3(p.fs_Li, i), load3(p.g_color, i), load3(p.g_diff, i), load3(p.g_spec, i));
+    store3(p.g_normal, i, g.gN);
+    store3(p.g_kd, i, g.gKd);
+    p.g_rm[2 * i] = g.gR;
+    p.g_rm[2 * i + 1] = g.gM;
+    store3(p.g_Li, i, g.gLi);
+}
+
+// The same gradients for the K shading passes of an spp loop in one pass: the K passes share the surface inputs and the
+// upstream gradients (the loop adds their outputs, nerf/renderer_restir.py:443-459) and differ in the final sample
+// (direction, distance, Li).  Per-pass gradients are added in the order the autograd engine would add them (last pass
+// first).  g_Li[k] receives the radiance gradient of pass k; with `sum_gli` all passes add into g_Li[0] instead (valid
+// when the K passes evaluated the SAME reservoir buffer, which is what the reference's saved aliases amount to,
+// the env-gradient scatter is linear in grad_Li).
+#define MR_SHADE_MULTI_MAX 16
+struct ShadeMultiParams {
+    const float *fs_dir[MR_SHADE_MULTI_MAX];
+    const float *fs_dist[MR_SHADE_MULTI_MAX];
+    const float *fs_Li[MR_SHADE_MULTI_MAX];
+    float *g_Li[MR_SHADE_MULTI_MAX];
+    int K, sum_gli, accumulate;
+    float g_div; // != 0: upstream gradients are divided by it first (the loop's `total / mFrameIndex`)
+    const float *__restrict__ occ;
+    const float *__restrict__ normal;
+    const float *__restrict__ ray_dir;
+    const float *__restrict__ kd;
+    const float *__restrict__ rm;
+    const float *__restrict__ g_color; // may be null (= zeros)
+    const float *__restrict__ g_diff;
+    const float *__restrict__ g_spec;
+    float *g_normal, *g_kd, *g_rm;
+};
+MR_DEV void final_shading_bwd_multi_px(const ShadeMultiParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    float3 aN = f3(0.f), aKd = f3(0.f), aLi = f3(0.f);
+    float aR = 0.f, aM = 0.f;
+    if (p.accumulate) {
+        aN = load3_rw(p.g_normal, i);
+        aKd = load3_rw(p.g_kd, i);
+        aR = p.g_rm[2 * i];
+        aM = p.g_rm[2 * i + 1];
+        if (p.sum_gli) aLi = load3_rw(p.g_Li[0], i);
     }
-    store3(p.g_normal, i, gN);
-    store3(p.g_kd, i, gKd);
-    p.g_rm[2 * i] = gR;
-    p.g_rm[2 * i + 1] = gM;
-    store3(p.g_Li, i, gLi);
+    const bool lit = MR_LDG(p.occ + i) > 0.1f;
+    float3 N = f3(0.f), rd = f3(0.f), kd = f3(0.f), gC = f3(0.f), gD = f3(0.f), gS = f3(0.f);
+    float rough = 0.f, metallic = 0.f;
+    if (lit) {
+        N = load3(p.normal, i); rd = load3(p.ray_dir, i); kd = load3(p.kd, i);
+        rough = MR_LDG(p.rm + 2 * i); metallic = MR_LDG(p.rm + 2 * i + 1);
+        if (p.g_color) gC = load3(p.g_color, i);
+        gD = load3(p.g_diff, i); gS = load3(p.g_spec, i);
+        if (p.g_div != 0.0f) { gC = gC / p.g_div; gD = gD / p.g_div; gS = gS / p.g_div; }
+    }
+    for (int k = p.K - 1; k >= 0; --k) {
+        float3 gLi = f3(0.f);
+        if (lit && MR_LDG(p.fs_dist[k] + i) > 0.f) {
+            const ShadeGrads g = final_shading_grads(N, rd, kd, rough, metallic, load3(p.fs_dir[k], i), load3(p.fs_Li[k], i), gC, gD, gS);
+            aN += g.gN;
+            aKd += g.gKd;
+            aR += g.gR;
+            aM += g.gM;
+            gLi = g.gLi;
+        }
+        if (p.sum_gli) aLi += gLi;
+        else store3(p.g_Li[k], i, gLi);
+    }
+    store3(p.g_normal, i, aN);
+    store3(p.g_kd, i, aKd);
+    p.g_rm[2 * i] = aR;
+    p.g_rm[2 * i + 1] = aM;
+    if (p.sum_gli) store3(p.g_Li[0], i, aLi);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -464,6 +543,31 @@ int mirres_final_shading_bwd(const float *fs_dir, const float *fs_dist, const fl
     p.g_color = grad_color; p.g_diff = grad_diff_light; p.g_spec = grad_spec_light;
     p.g_normal = grad_normal; p.g_kd = grad_diffuse; p.g_rm = grad_rough_metal; p.g_Li = grad_Li;
     return foreach_item<ShadeParams, final_shading_bwd_px, 256>(p, fx * fy, (cudaStream_t)stream);
+}
+
+int mirres_final_shading_bwd_multi(int n_passes, const float *const *fs_dir, const float *const *fs_dist,
+                                   const float *const *fs_Li, int fx, int fy, const float *occ, const float *normal,
+                                   const float *ray_dir, const float *diffuse_map, const float *rough_metal,
+                                   const float *grad_color, const float *grad_diff_light, const float *grad_spec_light,
+                                   float grad_divisor, int accumulate, float *grad_normal, float *grad_diffuse, float *grad_rough_metal,
+                                   int sum_grad_Li, float *const *grad_Li, void *stream)
+{
+    if (!fs_dir || !fs_dist || !fs_Li || !occ || !normal || !ray_dir || !diffuse_map || !rough_metal || !grad_diff_light ||
+        !grad_spec_light || !grad_normal || !grad_diffuse || !grad_rough_metal || !grad_Li)
+        return MIRRES_ERR_NULL;
+    if (fx < 1 || fy < 1 || n_passes < 1 || n_passes > MR_SHADE_MULTI_MAX) return MIRRES_ERR_SHAPE;
+    ShadeMultiParams p = {};
+    for (int k = 0; k < n_passes; ++k) {
+        if (!fs_dir[k] || !fs_dist[k] || !fs_Li[k] || (!sum_grad_Li && !grad_Li[k])) return MIRRES_ERR_NULL;
+        p.fs_dir[k] = fs_dir[k]; p.fs_dist[k] = fs_dist[k]; p.fs_Li[k] = fs_Li[k];
+        p.g_Li[k] = sum_grad_Li ? grad_Li[0] : grad_Li[k];
+    }
+    if (!p.g_Li[0]) return MIRRES_ERR_NULL;
+    p.K = n_passes; p.sum_gli = sum_grad_Li ? 1 : 0; p.accumulate = accumulate ? 1 : 0; p.g_div = grad_divisor;
+    p.occ = occ; p.normal = normal; p.ray_dir = ray_dir; p.kd = diffuse_map; p.rm = rough_metal;
+    p.g_color = grad_color; p.g_diff = grad_diff_light; p.g_spec = grad_spec_light;
+    p.g_normal = grad_normal; p.g_kd = grad_diffuse; p.g_rm = grad_rough_metal;
+    return foreach_item<ShadeMultiParams, final_shading_bwd_multi_px, 256>(p, fx * fy, (cudaStream_t)stream);
 }
 
 static int fill_bounce(BounceParams &p, const void *packed_nodes, const void *packed_tris, unsigned int frame_index,

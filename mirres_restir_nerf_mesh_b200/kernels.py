@@ -313,3 +313,40 @@ class Kernels:
                                              self._f(bary, True), self._i(tri), tri.shape[0], self._f(out),
                                              self._stream())
         self._check(rc, "mirres_interpolate_bwd")
+
+    # -- host-side chains of the spp loop as single launches -----------------------------------------
+    def material_procedural(self, pos, occ, mode, metallic, kd, rough_metal, scale=None):
+        sc = None if scale is None else (ctypes.c_float * 3)(*[float(x) for x in scale])
+        rc = self.lib.mirres_material_procedural(pos.shape[0], self._f(pos), self._f(occ, True), int(mode), float(metallic),
+                                                 sc, self._f(kd), self._f(rough_metal), self._stream())
+        self._check(rc, "mirres_material_procedural")
+
+    def sum_images(self, srcs, dst, divisor=0.0, accumulate=False):
+        n = dst.numel()
+        for s in srcs:
+            if s.numel() != n:
+                raise AbiError("mirres_sum_images: size mismatch")
+        rc = self.lib.mirres_sum_images(n, len(srcs), self._ptr_array(srcs) if srcs else None, float(divisor),
+                                        1 if accumulate else 0, self._f(dst), self._stream())
+        self._check(rc, "mirres_sum_images")
+
+    def composite_fwd(self, occ, kd, rough_metal, dd, ds, di, out):
+        rc = self.lib.mirres_composite_fwd(occ.shape[0], self._f(occ), self._f(kd), self._f(rough_metal), self._f(dd),
+                                           self._f(ds), self._f(di), self._f(out), self._stream())
+        self._check(rc, "mirres_composite_fwd")
+
+    def composite_bwd(self, occ, kd, rough_metal, dd, ds, di, g_out, g_kd, g_rm, g_dd, g_ds):
+        rc = self.lib.mirres_composite_bwd(occ.shape[0], self._f(occ), self._f(kd), self._f(rough_metal), self._f(dd),
+                                           self._f(ds), self._f(di), self._f(g_out), self._f(g_kd), self._f(g_rm),
+                                           self._f(g_dd), self._f(g_ds), self._stream())
+        self._check(rc, "mirres_composite_bwd")
+
+    def final_shading_bwd_multi(self, fs_dirs, fs_dists, fs_Lis, fx, fy, occ, normal, ray_dir, diffuse, rough_metal, g_color,
+                                g_diff, g_spec, g_normal, g_diffuse, g_rough_metal, g_Lis, sum_grad_Li=False,
+                                accumulate=False, grad_divisor=0.0):
+        rc = self.lib.mirres_final_shading_bwd_multi(
+            len(fs_dirs), self._ptr_array(fs_dirs), self._ptr_array(fs_dists), self._ptr_array(fs_Lis), fx, fy,
+            self._f(occ), self._f(normal), self._f(ray_dir), self._f(diffuse), self._f(rough_metal), self._f(g_color, True),
+            self._f(g_diff), self._f(g_spec), float(grad_divisor), 1 if accumulate else 0, self._f(g_normal), self._f(g_diffuse),
+            self._f(g_rough_metal), 1 if sum_grad_Li else 0, self._ptr_array(g_Lis), self._stream())
+        self._check(rc, "mirres_final_shading_bwd_multi")

@@ -19,6 +19,8 @@ material object offers `sample_no_di_dense`; backward of the denoiser is a deter
 Extensions are keyword-only with reference defaults: `random_offset` (reference: np.random.randint(2**20)),
 `max_bounce` (reference: MAX_Bounce = 2), `strict_reference_aliasing` (reference behaviour).
 """
+import contextlib
+
 import numpy as np
 import torch
 
@@ -33,8 +35,34 @@ MAX_INDIRECT_CHAINS = int(_os.environ.get("MIRRES_INDIRECT_CHAINS", 2))  # concu
 _SIDE_STREAMS = {}
 
 
+class _NullStream:
+    """Stand-in for a CUDA stream when the concurrent schedule is driven over CPU tensors (the host-check flavour of the
+    kernels in the CPU test-suite): everything runs in program order, so waits and records are no-ops."""
+
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, event):
+        pass
+
+
+class _NullEvent:
+    def record(self, stream=None):
+        pass
+
+
+def _on(stream):
+    return torch.cuda.stream(stream) if isinstance(stream, torch.cuda.Stream) else contextlib.nullcontext()
+
+
+def _host_kernels_bound():
+    return not get_kernels().require_cuda
+
+
 def _side_stream(device, k=0):
     """Extra CUDA streams per device for the indirect-path chains (see restir_di_with_pt)."""
+    if torch.device(device).type != "cuda":
+        return _NullStream()
     index = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
     st = _SIDE_STREAMS.get((index, k))
     if st is None:
@@ -278,6 +306,87 @@ class FinalShading(torch.autograd.Function):
         return (None, None, None, grad_Li, None, None, None, None, None, None, grad_normal, None, grad_diffuse, grad_rs)
 
 
+class DirectLightSum(torch.autograd.Function):
+    """All K (evaluate final samples -> final shading) passes of an spp loop as ONE autograd node (concurrent schedule).
+
+    The reference builds K x (EvaluateFinalSamples_di, FinalShading) nodes and adds their outputs (:443-459); backward then
+    runs 2 K kernels plus the engine's accumulations, one after the other.  The passes share their surface inputs and --
+    because the loop only sums them -- their upstream gradients, so here the forward kernels run outside autograd, the
+    sums and `total / mFrameIndex` are one launch each, and backward is one mirres_final_shading_bwd_multi launch plus one
+    env-gradient scatter when the passes saved aliases of one reservoir buffer (the reference's behaviour, SURVEY.md
+    7.3-3; K scatters otherwise).  Per-pass arithmetic is that of the two Functions above; gradients of the passes are
+    added in the engine's order (last pass first)."""
+
+    @staticmethod
+    def forward(ctx, env_tex, normal, diffuse_map, rs_map, pack):
+        ctx.pack = pack
+        ctx.save_for_backward(env_tex, normal, diffuse_map, rs_map)
+        ctx.set_materialize_grads(False)
+        return pack["color"], pack["diff"], pack["spec"]
+
+    @staticmethod
+    def backward(ctx, g_color, g_diff, g_spec):
+        env_tex, normal, diffuse_map, rs_map = ctx.saved_tensors
+        pack = ctx.pack
+        k = get_kernels()
+        fx, fy, W, H = pack["dims"]
+        n, dev = fx * fy, normal.device
+        passes = pack["passes"]  # (res4, fs_dir, fs_dist, fs_Li, vis) per pass
+        cf = torch.contiguous_format
+        zeros3 = lambda: torch.zeros((n, 3), dtype=torch.float, device=dev)
+        g_diff = zeros3() if g_diff is None else g_diff.contiguous()
+        g_spec = zeros3() if g_spec is None else g_spec.contiguous()
+        g_color = None if g_color is None else g_color.contiguous()
+        g_normal = torch.empty((n, 3), dtype=torch.float, device=dev)
+        g_kd = torch.empty((n, 3), dtype=torch.float, device=dev)
+        g_rs = torch.empty((n, 2), dtype=torch.float, device=dev)
+        key = lambda ps: tuple(t.data_ptr() for t in ps[0]) + (ps[1].data_ptr(), ps[2].data_ptr(), ps[4].data_ptr())
+        aliased = all(key(ps) == key(passes[0]) for ps in passes)
+        g_Li = [torch.empty((n, 3), dtype=torch.float, device=dev) for _ in range(1 if aliased else len(passes))]
+        occ, ray = pack["occ"], pack["ray"]
+        nrm_c, kd_c, rs_c = normal.contiguous(), diffuse_map.contiguous(), rs_map.contiguous()
+        CH = 16
+        first = True
+        for hi in range(len(passes), 0, -CH):  # last pass first
+            lo = max(0, hi - CH)
+            chunk = passes[lo:hi]
+            k.final_shading_bwd_multi([c[1] for c in chunk], [c[2] for c in chunk], [c[3] for c in chunk], fx, fy, occ, nrm_c,
+                                      ray, kd_c, rs_c, g_color, g_diff, g_spec, g_normal, g_kd, g_rs,
+                                      g_Li if aliased else g_Li[lo:hi], sum_grad_Li=aliased, accumulate=not first,
+                                      grad_divisor=float(pack["frame"]))
+            first = False
+        grad_env = None
+        if ctx.needs_input_grad[0]:
+            grad_env = torch.zeros_like(env_tex, memory_format=cf)
+            if aliased:
+                ps = passes[-1]
+                k.eval_final_bwd(ps[0], W, H, fx, fy, ps[4], g_Li[0], grad_env)
+            else:
+                for j in range(len(passes) - 1, -1, -1):
+                    k.eval_final_bwd(passes[j][0], W, H, fx, fy, passes[j][4], g_Li[j], grad_env)
+        return grad_env, g_normal, g_kd, g_rs, None
+
+
+class Composite(torch.autograd.Function):
+    """final_color = nan_to_num(where(occ <= 0.1, 1, kd (1 - metallic) dd + ds + di)) (nerf/renderer_restir.py:543-549) as
+    one launch per direction instead of ~10 + ~15 elementwise torch kernels; same operations in the same order."""
+
+    @staticmethod
+    def forward(ctx, occ_map, diffuse_map, rs_map, dd, ds, di):
+        args = [t.detach().contiguous() for t in (occ_map, diffuse_map, rs_map, dd, ds, di)]
+        out = torch.empty_like(args[3])
+        get_kernels().composite_fwd(*args, out)
+        ctx.save_for_backward(*args)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        occ, kd, rs, dd, ds, di = ctx.saved_tensors
+        g_kd, g_rs, g_dd, g_ds = torch.empty_like(kd), torch.empty_like(rs), torch.empty_like(dd), torch.empty_like(ds)
+        get_kernels().composite_bwd(occ, kd, rs, dd, ds, di, g_out.contiguous(), g_kd, g_rs, g_dd, g_ds)
+        return None, g_kd, g_rs, g_dd, g_ds, None
+
+
 class EAWDenoise_run(torch.autograd.Function):
     @staticmethod
     def forward(ctx, m, c_phi, n_phi, p_phi, framedim_x, framedim_y, stepWidth, occ_map, color, normal_map, pos_map):
@@ -478,8 +587,14 @@ def indirect_one_hit_divided_no_grad(m, LBVHNode_info, LBVHNode_aabb, vert, vert
 
 def _query_material(mlp_mat, occ, pos, kd_out, rs_out, use_scale, scale):
     """Material lookup at the indirect vertices (nerf/renderer_restir.py:398-408).  Objects that implement
-    `sample_no_di_dense(pos[N,3]) -> [N,6]` are evaluated on every pixel and merged with a mask (no host sync);
-    anything else gets the reference protocol: compact with torch.where, call `sample_no_di`, scatter."""
+    `sample_no_di_masked_(occ, pos, kd_out, rs_out, scale)` update the maps in place where occ >= 0.5 (one launch);
+    objects with `sample_no_di_dense(pos[N,3]) -> [N,6]` are evaluated on every pixel and merged with a mask (no host
+    sync); anything else gets the reference protocol: compact with torch.where, call `sample_no_di`, scatter."""
+    masked = getattr(mlp_mat, "sample_no_di_masked_", None)
+    if masked is not None and (pos.is_cuda or _host_kernels_bound()):
+        # the lookup and the merge under the occupancy mask in one launch, in place (stream order protects the readers)
+        masked(occ, pos, kd_out, rs_out, scale if use_scale else None)
+        return kd_out, rs_out
     hit = occ >= 0.5
     dense = getattr(mlp_mat, "sample_no_di_dense", None)
     if dense is not None:
@@ -516,7 +631,9 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                       reservoirs, prev_reservoirs, final_samples, neighborOffsets, light_tile_count, light_tile_size,
                       env_map_init, occ_map, pos_map, normal_map, depth_map, diffuse_map, roughness_specular,
                       ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors, color,
-                      *, random_offset=None, max_bounce=None, hooks=None, overlap=None, shard=None, prepared=None):
+                      *, random_offset=None, max_bounce=None, hooks=None, overlap=None, shard=None, prepared=None,
+                      normalize=False):
+    # normalize=True (run_restir_di_with_pt): the six sums come back already divided by the frame count (:505-515)
     n = framedim_x * framedim_y
     dev = pos_map.device
     if random_offset is None:
@@ -598,7 +715,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         return c
 
     if overlap:
-        main_stream = torch.cuda.current_stream()
+        main_stream = torch.cuda.current_stream() if pos_map.is_cuda else _NullStream()
         for c in range(min(spp, MAX_INDIRECT_CHAINS)):
             chains.append(make_chain("indirect%d" % c, _side_stream(dev, c)))
         for c in chains:
@@ -607,15 +724,23 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         chains.append(make_chain("main", None))
     pending = []  # (iteration, bounce, completion event, (color, diff, spec)) not yet added to the running sums
 
-    def accumulate(upto_iteration, stream=None):
-        # runs on `stream` (default: the caller's stream); always in (iteration, bounce) order
+    def accumulate(upto_iteration, stream=None, divisor=0.0):
+        # runs on `stream` (the caller has made it current); always in (iteration, bounce) order: one launch per output
+        # adds up to 32 per-vertex images to the running sum, the last call also divides by the frame count
         stream = stream or main_stream
+        batch = []
         while pending and pending[0][0] <= upto_iteration:
-            _, _, done, outs3 = pending.pop(0)
+            batch.append(pending.pop(0))
+        if not batch and divisor == 0.0:
+            return
+        for _, _, done, _ in batch:
             stream.wait_event(done)
-            sums["color_1"] += outs3[0]
-            sums["diff_1"] += outs3[1]
-            sums["spec_1"] += outs3[2]
+        k = get_kernels()
+        for lo in range(0, max(len(batch), 1), 32):
+            part = batch[lo:lo + 32]
+            last = lo + 32 >= len(batch)
+            for j, name in enumerate(("color_1", "diff_1", "spec_1")):
+                k.sum_images([b[3][j] for b in part], sums[name], divisor if last else 0.0, accumulate=True)
 
     def indirect_chain(i, first_pass, c):
         base = random_offset + TOTAL_RIS_PASSES * i
@@ -645,7 +770,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                 sums["diff_1"] += outs3[1]
                 sums["spec_1"] += outs3[2]
             else:
-                done = torch.cuda.Event()
+                done = torch.cuda.Event() if pos_map.is_cuda else _NullEvent()
                 done.record(c["stream"])
                 pending.append((i, bounce, done, outs3))
             if hooks is not None:
@@ -680,20 +805,29 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         B = reservoirs
         slangpy.prepare_workspace(occ_map)
         for r in range(R):
-            with torch.cuda.stream(st_init[r]), slangpy.workspace_tag("initial%d" % r):
+            with _on(st_init[r]), slangpy.workspace_tag("initial%d" % r):
                 slangpy.prepare_workspace(occ_map)
-        with torch.cuda.stream(st_s), slangpy.workspace_tag("shade"):
+        with _on(st_s), slangpy.workspace_tag("shade"):
             slangpy.prepare_workspace(occ_map)
-        ev = lambda stream: (lambda e: (e.record(stream), e)[1])(torch.cuda.Event())
+        ev = lambda stream: (lambda e: (e.record(stream), e)[1])(torch.cuda.Event() if pos_map.is_cuda else _NullEvent())
         init_done, spatial_done, copy_done = {}, {}, {}
+        passes, direct_outs = [], []
+
+        def flush_direct(divisor=0.0):
+            # running sums of the shading outputs in iteration order (the reference's `total += color`, :443-459)
+            k = get_kernels()
+            for j, name in enumerate(("color", "diff", "spec")):
+                k.sum_images([o[j] for o in direct_outs], sums[name], divisor, accumulate=True)
+            keepalive.extend(direct_outs)
+            direct_outs.clear()
         for i in range(spp):
             base = random_offset + TOTAL_RIS_PASSES * i
             first_indirect_pass = 4 if i == 0 else 5
             c = chains[i % len(chains)]
-            with torch.cuda.stream(c["stream"]), slangpy.workspace_tag(c["tag"]):
+            with _on(c["stream"]), slangpy.workspace_tag(c["tag"]):
                 indirect_chain(i, first_indirect_pass, c)
             r = i % R
-            with torch.cuda.stream(st_init[r]), slangpy.workspace_tag("initial%d" % r):
+            with _on(st_init[r]), slangpy.workspace_tag("initial%d" % r):
                 if i >= R:
                     st_init[r].wait_event(spatial_done[i - R])  # X[r] was last read by spatial(i - R)
                 GenerateLightTiles(generateLightTiles_m, None, env_map, pdf_, cdf_, mpdf_, mcdf_, width, height, base,
@@ -717,30 +851,49 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             ris_pass += 1
             assert ris_pass == first_indirect_pass
             spatial_done[i] = ev(main_stream)
-            with torch.cuda.stream(st_s), slangpy.workspace_tag("shade"):
+            with _on(st_s), slangpy.workspace_tag("shade"):
                 st_s.wait_event(spatial_done[i])
                 for dst_t, src_t in zip(B, S[i % 2]):
                     dst_t.data.copy_(src_t)  # raw overwrite, invisible to autograd like the reference's kernels
                 copy_done[i] = ev(st_s)
                 worker.EvaluateFinalSamples_get_vis(EvaluateFinalSamples_m, pos_map, B, framedim_x, framedim_y,
                                                     eva_vis_map)
-                final_Li = EvaluateFinalSamples_di.apply(EvaluateFinalSamples_m, B[0], B[1], B[2], B[3], env_map_init,
-                                                         width, height, framedim_x, framedim_y, final_samples[0],
-                                                         final_samples[1], eva_vis_map)
-                color, color_diff, color_spec = FinalShading.apply(FinalShading_m, final_samples[0], final_samples[1],
-                                                                   final_Li, env_map, width, height, framedim_x,
-                                                                   framedim_y, occ_map, normal_map, ray_dir_map,
-                                                                   diffuse_map, roughness_specular)
-                sums["color"] += color
-                sums["diff"] += color_diff
-                sums["spec"] += color_spec
-                # the indirect sums ride on this stream too (it has slack): a chain enqueued two iterations ago has
-                # normally finished, so the wait does not stall the shading of the next iteration
-                accumulate(i - 2, st_s)
+                # evaluation + shading outside autograd; DirectLightSum (below) is the one node that stands for all passes
+                with torch.no_grad():
+                    final_Li = torch.empty((n, 3), dtype=torch.float, device=dev)
+                    EvaluateFinalSamples_m.process_EvaluateFinalSamples_di_(
+                        reservoirs=B, env_tex=env_map, env_width=width, env_height=height, framedim_x=framedim_x,
+                        framedim_y=framedim_y, finalSample=(final_samples[0], final_samples[1], final_Li),
+                        vis_map=eva_vis_map).launchRaw()
+                    outs_d = tuple(torch.empty((n, 3), dtype=torch.float, device=dev) for _ in range(3))
+                    FinalShading_m.process_FinalShading(
+                        finalSample=(final_samples[0], final_samples[1], final_Li), env_tex=env_map, env_width=width,
+                        env_height=height, framedim_x=framedim_x, framedim_y=framedim_y, occ_map=occ_map,
+                        normal=normal_detached, ray_dir=ray_dir_map, diffuse_map=kd, linearRoughness_specular_map=rs,
+                        color=outs_d[0], diff_light=outs_d[1], spec_light=outs_d[2]).launchRaw()
+                passes.append((tuple(_keep(t) for t in B), _keep(final_samples[0]), _keep(final_samples[1]), final_Li,
+                               _keep(eva_vis_map)))
+                direct_outs.append(outs_d)
+                if len(direct_outs) >= 16:
+                    flush_direct()
+                if len(pending) >= 16:  # bounds the memory held by long loops (--spp 512); normally one flush at the end
+                    accumulate(i - 2, st_s)
             frame += 1
             prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir = occ_map, normal_depth, brdf_map, ray_dir_map
-        with torch.cuda.stream(st_s):
-            accumulate(spp, st_s)
+        div = float(frame) if normalize else 0.0
+        with _on(st_s):
+            flush_direct(div)
+            for c in chains:
+                st_s.wait_stream(c["stream"])
+            accumulate(spp, st_s, div)
+            if torch.is_grad_enabled() and any(t.requires_grad for t in (env_map_init, normal_map, diffuse_map,
+                                                                         roughness_specular)):
+                # the node lives on the shading stream, like the per-pass Functions it stands for: its backward runs there
+                pack = dict(color=sums["color"], diff=sums["diff"], spec=sums["spec"], passes=passes,
+                            dims=(framedim_x, framedim_y, width, height), occ=slangpy._c(occ_map),
+                            ray=slangpy._c(ray_dir_map), frame=div)
+                sums["color"], sums["diff"], sums["spec"] = DirectLightSum.apply(env_map_init, normal_map, diffuse_map,
+                                                                                 roughness_specular, pack)
         for st in [st_s] + st_init:
             main_stream.wait_stream(st)
         keepalive.extend(X + S)
@@ -795,9 +948,11 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             sums["diff"] += color_diff
             sums["spec"] += color_spec
     if overlap:
-        accumulate(spp)
         for c in chains:
             main_stream.wait_stream(c["stream"])
+    elif normalize:
+        for name in sums:
+            sums[name] = sums[name] / frame
     keepalive.clear()
     return (sums["color"], sums["color_1"], sums["diff"], sums["spec"], sums["diff_1"], sums["spec_1"],
             total_indirect_light, frame)
@@ -811,7 +966,7 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
                           ray_dir_map, pos_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir,
                           framedim_x, framedim_y, spp, denoise_iter, stepWidth, c_phi_scale=1.0, n_phi_scale=0.1,
                           p_phi_scale=0.1, *, random_offset=None, max_bounce=None, hooks=None, bilateral=None,
-                          overlap=None, batched_denoise=True, shard=None, _shard=None, fused_prepare=True):
+                          overlap=None, batched_denoise=True, shard=None, _shard=None, fused_prepare=True, fused_composite=True):
     if shard is not None:
         with slangpy.active_rows(shard.active[0], shard.active[1], framedim_x):
             return run_restir_di_with_pt(
@@ -822,7 +977,8 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
                 normal_map, depth_map, diffuse_map, roughness_specular, ray_dir_map, pos_map, prev_occ_map,
                 prev_normal_depth, prev_brdf_map, prev_ray_dir, framedim_x, framedim_y, spp, denoise_iter, stepWidth,
                 c_phi_scale, n_phi_scale, p_phi_scale, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks,
-                bilateral=bilateral, overlap=False, batched_denoise=batched_denoise, shard=None, _shard=shard)
+                bilateral=bilateral, overlap=False, batched_denoise=batched_denoise, shard=None, _shard=shard,
+                fused_prepare=fused_prepare, fused_composite=fused_composite)
     n, dev = framedim_x * framedim_y, pos_map.device
     prepared = None
     if fused_prepare and occ_map.is_contiguous():
@@ -849,13 +1005,8 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
         final_samples, neighborOffsets, light_tile_count, light_tile_size, env_map, occ_map, pos_map, normal_map,
         depth_map, diffuse_map, roughness_specular, ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map,
         prev_ray_dir, motionVectors, color, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks,
-        overlap=overlap, shard=_shard, prepared=prepared)
-    total_color = total_color / mFrameIndex
-    total_diff_light = total_diff_light / mFrameIndex
-    total_spec_light = total_spec_light / mFrameIndex
-    total_color_1 = total_color_1 / mFrameIndex
-    total_diff_light_1 = total_diff_light_1 / mFrameIndex
-    total_spec_light_1 = total_spec_light_1 / mFrameIndex
+        overlap=overlap, shard=_shard, prepared=prepared, normalize=True)
+    # `total / mFrameIndex` of all six sums (:505-515) has happened inside (normalize=True)
     combined_color_indirect = total_diff_light_1 + total_spec_light_1
 
     if gb_depth is None and batched_denoise:
@@ -884,9 +1035,13 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
         denoised_indirect_diff = bi_no_di(framedim_y, framedim_x, cat(total_diff_light_1), factor)
         denoised_indirect_spec = bi_no_di(framedim_y, framedim_x, cat(total_spec_light_1), factor)
 
-    diffuse = diffuse_map * (1.0 - roughness_specular[..., 1:2])
-    final_color = diffuse * denoised_diffuse + denoised_spec + denoised_indirect
-    final_color = torch.where(occ_map <= 0.1, torch.ones_like(final_color), final_color)
-    final_color = torch.nan_to_num(final_color, 0.0)
+    if fused_composite and (occ_map.is_cuda or _host_kernels_bound()):
+        final_color = Composite.apply(occ_map, diffuse_map, roughness_specular, denoised_diffuse, denoised_spec,
+                                      denoised_indirect)
+    else:
+        diffuse = diffuse_map * (1.0 - roughness_specular[..., 1:2])
+        final_color = diffuse * denoised_diffuse + denoised_spec + denoised_indirect
+        final_color = torch.where(occ_map <= 0.1, torch.ones_like(final_color), final_color)
+        final_color = torch.nan_to_num(final_color, 0.0)
     return (final_color, denoised_diffuse, denoised_spec, denoised_indirect, denoised_indirect_diff,
             denoised_indirect_spec)

@@ -181,6 +181,24 @@ class ProceduralMaterial:
     # evaluated on every pixel and merged with a mask by the driver: no host synchronisation in the spp loop
     sample_no_di_dense = sample_no_di
 
+    def sample_no_di_masked_(self, occ, pos, kd_out, rs_out, scale=None):
+        """The lookup and the driver's torch.where merge in ONE launch (mirres_material_procedural, CUDA tensors only):
+        pixels with occ >= 0.5 get the material at `pos`, the others keep theirs; same values as sample_no_di."""
+        from .slangpy_shim import get_kernels, _c
+        get_kernels().material_procedural(_c(pos), _c(occ), 1, self.metallic, kd_out, rs_out, scale)
+        return kd_out, rs_out
+
+    def gbuffer_materials(self, pos, occ):
+        """kd [n,3] and (roughness, metallic) [n,2] of the primary hits, zero where occ is zero: the columns 0:3 and 4:6 of
+        `sample_no_di_dense(pos) * occ`, one launch on CUDA tensors."""
+        import torch
+        from .slangpy_shim import get_kernels, _c
+        n = pos.shape[0]
+        kd = torch.empty((n, 3), dtype=torch.float32, device=pos.device)
+        rs = torch.empty((n, 2), dtype=torch.float32, device=pos.device)
+        get_kernels().material_procedural(_c(pos), _c(occ), 0, self.metallic, kd, rs)
+        return kd, rs
+
 
 def gbuffer_from_hits(rays_o, rays_d, hit, t, pos, normal, metallic=0.0):
     """Assemble the G-buffer maps render_stage1 hands to run_restir_di_with_pt (nerf/renderer.py:1092-1096,1121)."""

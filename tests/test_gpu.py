@@ -473,3 +473,13 @@ def test_c2_full_size_parity_against_oracle(kernels, oracle):
                                                 None, sc["W"], sc["H"], 4, 2, 2, 2.0, 0.1, 0.001, random_offset=4242, **kw))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_fused_screen_kernels_gpu(kernels):
+    """csrc/screen.cu and mirres_final_shading_bwd_multi on the GPU against the torch expressions / single-pass kernels
+    they replace (the same checks the CPU suite runs on the host-check flavour)."""
+    import fused_checks as C
+    C.material_kernel_equals_torch_and_numpy_expressions(kernels, DEV)
+    C.sum_images_is_the_sequential_torch_sum(kernels, DEV)
+    C.composite_forward_exact_backward_matches_autograd(kernels, DEV)
+    C.final_shading_bwd_multi_equals_the_single_pass_kernels(kernels, DEV)
