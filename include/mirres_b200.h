@@ -274,7 +274,8 @@ int mirres_interpolate_bwd(const float *grad, int n, int C, const int *prim, con
  *        launch) kd is clamped to [0,1] afterwards (:405-408).
  *   mirres_sum_images            dst[i] = ((accumulate ? dst[i] : 0) + src_0[i] + src_1[i] + ...) [/ divisor if != 0]:
  *        the running sums of the per-iteration outputs and `total / mFrameIndex` (:443-459, :505-515).  src: HOST
- *        array of n_src <= 32 device pointers.
+ *        array of n_src <= 32 device pointers.  The division is evaluated the way torch evaluates tensor / python
+ *        scalar on a CUDA tensor: multiplication by the fp32 reciprocal of the divisor.
  *   mirres_composite_fwd / _bwd  final_color = nan_to_num(where(occ <= 0.1, 1, kd (1 - metallic) dd + ds + di))
  *        (:543-549) and its reverse mode w.r.t. kd, (roughness, metallic), dd, ds (what torch autograd derives).
  *   mirres_final_shading_bwd_multi   mirres_final_shading_bwd for the n_passes <= 16 shading passes of an spp loop in one

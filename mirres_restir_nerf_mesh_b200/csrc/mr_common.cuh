@@ -84,6 +84,18 @@ MR_DEV uint32_t to_uint(float x)
 #endif
 }
 
+// `tensor / python_scalar` as torch evaluates it: CUDA multiplies by the fp32 reciprocal of the scalar
+// (BinaryDivTrueKernel.cu, "a * reciprocal(b)" for a CPU-scalar divisor), the CPU kernel divides.  The driver's
+// `total / mFrameIndex` (nerf/renderer_restir.py:505-515) and its autograd backward are such divisions.
+MR_DEV float div_by_scalar(float x, float d)
+{
+#if defined(__CUDA_ARCH__)
+    return x * (1.0f / d);
+#else
+    return x / d;
+#endif
+}
+
 // [n,3] fp32 rows (12-byte stride, the reference's external layout)
 MR_DEV float3 load3(const float *__restrict__ p, size_t i) { return make_float3(MR_LDG(p + 3 * i), MR_LDG(p + 3 * i + 1), MR_LDG(p + 3 * i + 2)); }
 MR_DEV float3 load3_rw(const float *p, size_t i) { return make_float3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }

@@ -78,7 +78,7 @@ MR_DEV void sum_item(const SumParams &p, int idx)
     const size_t i = (size_t)idx;
     float acc = p.accumulate ? p.dst[i] : 0.0f;
     for (int k = 0; k < p.n_src; ++k) acc += MR_LDG(p.src[k] + i);
-    if (p.divisor != 0.0f) acc = acc / p.divisor;
+    if (p.divisor != 0.0f) acc = div_by_scalar(acc, p.divisor);
     p.dst[i] = acc;
 }
 

@@ -244,7 +244,11 @@ MR_DEV void final_shading_bwd_multi_px(const ShadeMultiParams &p, int idx)
         rough = MR_LDG(p.rm + 2 * i); metallic = MR_LDG(p.rm + 2 * i + 1);
         if (p.g_color) gC = load3(p.g_color, i);
         gD = load3(p.g_diff, i); gS = load3(p.g_spec, i);
-        if (p.g_div != 0.0f) { gC = gC / p.g_div; gD = gD / p.g_div; gS = gS / p.g_div; }
+        if (p.g_div != 0.0f) {
+            gC = make_float3(div_by_scalar(gC.x, p.g_div), div_by_scalar(gC.y, p.g_div), div_by_scalar(gC.z, p.g_div));
+            gD = make_float3(div_by_scalar(gD.x, p.g_div), div_by_scalar(gD.y, p.g_div), div_by_scalar(gD.z, p.g_div));
+            gS = make_float3(div_by_scalar(gS.x, p.g_div), div_by_scalar(gS.y, p.g_div), div_by_scalar(gS.z, p.g_div));
+        }
     }
     for (int k = p.K - 1; k >= 0; --k) {
         float3 gLi = f3(0.f);

@@ -32,6 +32,7 @@ TOTAL_RIS_PASSES = 5 + 15  # frame-index stride per spp iteration (nerf/renderer
 import os as _os
 MAX_INITIAL_STREAMS = int(_os.environ.get("MIRRES_INITIAL_STREAMS", 4))   # concurrent initial-candidate stages (light tiles + initial RIS of different spp iterations)
 MAX_INDIRECT_CHAINS = int(_os.environ.get("MIRRES_INDIRECT_CHAINS", 2))  # concurrent indirect-path chains (one CUDA stream + path state + ray-queue workspace each)
+USE_PRIORITIES = int(_os.environ.get("MIRRES_PRIORITIES", 1))  # stream priorities for the critical reuse chain
 _SIDE_STREAMS = {}
 
 
@@ -59,14 +60,17 @@ def _host_kernels_bound():
     return not get_kernels().require_cuda
 
 
-def _side_stream(device, k=0):
-    """Extra CUDA streams per device for the indirect-path chains (see restir_di_with_pt)."""
+def _side_stream(device, k=0, priority=0):
+    """Extra CUDA streams per device for the concurrent schedule (see restir_di_with_pt).  `priority`: 0 = default, more
+    negative = served first by the block scheduler when several kernels have blocks pending."""
     if torch.device(device).type != "cuda":
         return _NullStream()
     index = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-    st = _SIDE_STREAMS.get((index, k))
+    if not USE_PRIORITIES:
+        priority = 0
+    st = _SIDE_STREAMS.get((index, k, priority))
     if st is None:
-        st = _SIDE_STREAMS[(index, k)] = torch.cuda.Stream(device=index)
+        st = _SIDE_STREAMS[(index, k, priority)] = torch.cuda.Stream(device=index, priority=priority)
     return st
 
 
