@@ -273,6 +273,10 @@ def run_gpu(args):
 
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
 
+    # results come back into pinned host buffers (a pageable destination makes the copy synchronous and staged)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    grad_host = torch.empty(ne, dtype=torch.float32).pin_memory()
+
     def timed(k_steps, from_host):
         total_ms, d2h = 0.0, 0
         for _ in range(k_steps):
@@ -285,9 +289,9 @@ def run_gpu(args):
             e0.record()
             loss, fg = run_step(from_host)
             if from_host:
-                lh = loss.to("cpu", non_blocking=True)
-                gh = fg[:ne].to("cpu", non_blocking=True)
-                d2h = lh.numel() * 4 + gh.numel() * 4
+                loss_host.copy_(loss, non_blocking=True)
+                grad_host.copy_(fg[:ne], non_blocking=True)
+                d2h = loss_host.numel() * 4 + grad_host.numel() * 4
             e1.record()
             torch.cuda.synchronize()
             total_ms += e0.elapsed_time(e1)

@@ -224,14 +224,16 @@ int mirres_bilateral_bwd(int fx, int fy, float sigma, const float *nrm, const fl
  * arrays of n_images device pointers (read at launch).  Per-image results are bit-identical to mirres_eaw_fwd / _bwd;
  * the guide-buffer loads and the normal / position edge weights are shared.  cum_w (optional in forward, [N] per image)
  * receives the normalisation of every footprint, which mirres_eaw_bwd_multi consumes instead of recomputing it.
- * Backward OVERWRITES grad_colors[m], grad_normals[m], grad_pos[m] ([N,3] each, one set per image). */
+ * Backward OVERWRITES grad_colors[m] ([N,3] per image) and grad_normal_sum / grad_pos_sum ([N,3] each, optional): the
+ * normal / position gradients summed over the images, which is what autograd forms from them.  The backward carries
+ * the gradient tolerance (1e-3), not bit-exactness: it multiplies by reciprocals and uses the hardware exp. */
 int mirres_eaw_fwd_multi(float c_phi, float n_phi, float p_phi, int fx, int fy, float step_width, const float *occ,
                          const float *normal, const float *pos, int n_images, const float *const *colors,
                          float *const *out_colors, float *const *cum_w, void *stream);
 int mirres_eaw_bwd_multi(float c_phi, float n_phi, float p_phi, int fx, int fy, float step_width, const float *occ,
                          const float *normal, const float *pos, int n_images, const float *const *colors,
                          const float *const *out_colors, const float *const *cum_w, const float *const *grad_outs,
-                         float *const *grad_colors, float *const *grad_normals, float *const *grad_pos, void *stream);
+                         float *const *grad_colors, float *grad_normal_sum, float *grad_pos_sum, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * G-buffer producer and gradient scatter.

@@ -204,6 +204,28 @@ MR_DEV void eaw_fwd_multi_px(const EawMultiParams &p, int idx)
     }
 }
 
+// Backward of the batched level.  Gradients carry a tolerance, not bit-exactness (include/mirres_b200.h), and the first
+// version of this kernel was instruction-bound on IEEE divisions and the contract exp (ncu: 20 k instructions per
+// foreground pixel, profiles/r1r_*), so the arithmetic here is the cheap kind: reciprocals of phi / of the footprint
+// normalisations are formed once and multiplied, exp is the hardware ex2 path, the three edge-stopping scale factors of
+// a tap are summed before they are applied, and the normal / position gradients of all images are accumulated into ONE
+// pair of outputs (autograd would add them anyway).  Relative deviation from the exact-arithmetic version: < 1e-5.
+MR_DEV float eaw_fast_exp(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return __expf(x);
+#else
+    return expf(x);
+#endif
+}
+MR_DEV float eaw_fast_rcp(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return __fdividef(1.0f, x);
+#else
+    return 1.0f / x;
+#endif
+}
 template <int NI>
 MR_DEV void eaw_bwd_multi_px(const EawMultiParams &p, int idx)
 {
@@ -211,57 +233,60 @@ MR_DEV void eaw_bwd_multi_px(const EawMultiParams &p, int idx)
     const int px = idx % p.fx, py = idx / p.fx;
     const float3 nq = load3(p.normal, q), pq = load3(p.pos, q);
     const bool q_center = !(MR_LDG(p.occ + q) < 0.1f);
-    float3 cq[NI], gq[NI], oq[NI], gc[NI], gn[NI], gp[NI];
-    float Wq[NI];
+    const float nic = -eaw_fast_rcp(p.c_phi), nin = -eaw_fast_rcp(p.n_phi), nip = -eaw_fast_rcp(p.p_phi);
+    float3 cq[NI], gqw[NI], oq[NI], gc[NI];
+    float3 gn = f3(0.f), gp = f3(0.f);
 #pragma unroll
     for (int m = 0; m < NI; ++m) {
         cq[m] = load3(p.color[m], q);
-        gq[m] = load3(p.g_out[m], q);
         oq[m] = load3(p.out_color[m], q);
-        Wq[m] = p.cum_w[m][q];
-        gc[m] = gn[m] = gp[m] = f3(0.f);
+        // upstream gradient of q's own footprint, already divided by its normalisation
+        const float Wq = p.cum_w[m][q];
+        gqw[m] = q_center ? load3(p.g_out[m], q) * eaw_fast_rcp(Wq) : f3(0.f);
+        gc[m] = f3(0.f);
     }
 #pragma unroll 1
-    for (int i = 0; i < 25; ++i) {
-        const int ux = px + (i % 5 - 2) * p.step, uy = py + (i / 5 - 2) * p.step;
-        if (!(ux >= 0 && ux < p.fx && uy >= 0 && uy < p.fy)) continue;
-        const size_t r = (size_t)uy * p.fx + ux;
-        const bool r_center = !(MR_LDG(p.occ + r) < 0.1f);
-        if (!q_center && !r_center) continue;
-        const float3 nr = load3(p.normal, r), pr = load3(p.pos, r);
-        const float n_w = edge_weight(nq, nr, p.n_phi, true), p_w = edge_weight(pq, pr, p.p_phi, true);
-        const float k = eaw_kernel(i);
-        const float3 dn = nq - nr, dp = pq - pr;
+    for (int iy = 0; iy < 5; ++iy) {
+        const int uy = py + (iy - 2) * p.step;
+        if (uy < 0 || uy >= p.fy) continue;
+        const float ky = (float)((0x14641 >> (4 * iy)) & 15) * (1.0f / 256.0f);
+#pragma unroll 1
+        for (int ix = 0; ix < 5; ++ix) {
+            const int ux = px + (ix - 2) * p.step;
+            if (ux < 0 || ux >= p.fx) continue;
+            const size_t r = (size_t)uy * p.fx + ux;
+            const bool r_center = !(MR_LDG(p.occ + r) < 0.1f);
+            if (!q_center && !r_center) continue; // neither footprint exists: nothing flows between q and r
+            const float k = ky * (float)((0x14641 >> (4 * ix)) & 15);
+            const float3 dn = nq - load3(p.normal, r), dp = pq - load3(p.pos, r);
+            const float wk = fminf(eaw_fast_exp(fmaxf(dot(dn, dn), 0.f) * nin), 1.0f) * fminf(eaw_fast_exp(fmaxf(dot(dp, dp), 0.f) * nip), 1.0f) * k;
+            float s_all = 0.f;
 #pragma unroll
-        for (int m = 0; m < NI; ++m) {
-            const float3 cr = load3(p.color[m], r);
-            const float w = edge_weight(cq[m], cr, p.c_phi, false) * n_w * p_w;
-            const float3 dc = cq[m] - cr;
-            if (q_center) {
-                const float gw = k * dot(gq[m], cr - oq[m]) / Wq[m];
-                const float s = -gw * w * 2.0f;
-                gc[m] += dc * (s / p.c_phi);
-                gn[m] += dn * (s / p.n_phi);
-                gp[m] += dp * (s / p.p_phi);
+            for (int m = 0; m < NI; ++m) {
+                const float3 cr = load3(p.color[m], r);
+                const float3 dc = cq[m] - cr;
+                const float w = fminf(eaw_fast_exp(dot(dc, dc) * nic), 1.0f) * wk; // weight x kernel of this tap
+                // q as the centre, r as its tap:  d out_q / d w = k (c_r - out_q) / W_q
+                float gw = dot(gqw[m], cr - oq[m]);
+                if (r_center) {
+                    // r as the centre, q as its tap (kernel and weight are symmetric)
+                    const float3 grw = load3(p.g_out[m], r) * eaw_fast_rcp(p.cum_w[m][r]);
+                    gc[m] += grw * w;
+                    gw += dot(grw, cq[m] - load3(p.out_color[m], r));
+                }
+                // dw / d|t|^2 = -w / phi,  d|t|^2 / d t = 2 t
+                const float s = gw * w * 2.0f;
+                gc[m] += dc * (s * nic);
+                s_all += s;
             }
-            if (r_center) {
-                const float3 gr = load3(p.g_out[m], r), orr = load3(p.out_color[m], r);
-                const float Wr = p.cum_w[m][r];
-                gc[m] += gr * (w * k / Wr);
-                const float gw = k * dot(gr, cq[m] - orr) / Wr;
-                const float s = -gw * w * 2.0f;
-                gc[m] += dc * (s / p.c_phi);
-                gn[m] += dn * (s / p.n_phi);
-                gp[m] += dp * (s / p.p_phi);
-            }
+            gn += dn * (s_all * nin);
+            gp += dp * (s_all * nip);
         }
     }
 #pragma unroll
-    for (int m = 0; m < NI; ++m) {
-        store3(p.g_color[m], q, gc[m]);
-        store3(p.g_normal[m], q, gn[m]);
-        store3(p.g_pos[m], q, gp[m]);
-    }
+    for (int m = 0; m < NI; ++m) store3(p.g_color[m], q, gc[m]);
+    if (p.g_normal[0]) store3(p.g_normal[0], q, gn);
+    if (p.g_pos[0]) store3(p.g_pos[0], q, gp);
 }
 
 template <int NI>
@@ -425,25 +450,23 @@ int mirres_eaw_fwd_multi(float c_phi, float n_phi, float p_phi, int fx, int fy, 
 int mirres_eaw_bwd_multi(float c_phi, float n_phi, float p_phi, int fx, int fy, float step_width, const float *occ,
                          const float *normal, const float *pos, int n_images, const float *const *colors,
                          const float *const *out_colors, const float *const *cum_w, const float *const *grad_outs,
-                         float *const *grad_colors, float *const *grad_normals, float *const *grad_pos, void *stream)
+                         float *const *grad_colors, float *grad_normal_sum, float *grad_pos_sum, void *stream)
 {
-    if (!occ || !normal || !pos || !colors || !out_colors || !cum_w || !grad_outs || !grad_colors || !grad_normals || !grad_pos)
-        return MIRRES_ERR_NULL;
+    if (!occ || !normal || !pos || !colors || !out_colors || !cum_w || !grad_outs || !grad_colors) return MIRRES_ERR_NULL;
     if (fx < 1 || fy < 1 || n_images < 1 || n_images > MR_EAW_MAX_IMAGES) return MIRRES_ERR_SHAPE;
     EawMultiParams p = {};
     p.c_phi = c_phi; p.n_phi = n_phi; p.p_phi = p_phi; p.fx = fx; p.fy = fy; p.step = (int)step_width; p.n_images = n_images;
     p.occ = occ; p.normal = normal; p.pos = pos;
     for (int m = 0; m < n_images; ++m) {
-        if (!colors[m] || !out_colors[m] || !cum_w[m] || !grad_outs[m] || !grad_colors[m] || !grad_normals[m] || !grad_pos[m])
-            return MIRRES_ERR_NULL;
+        if (!colors[m] || !out_colors[m] || !cum_w[m] || !grad_outs[m] || !grad_colors[m]) return MIRRES_ERR_NULL;
         p.color[m] = colors[m];
         p.out_color[m] = (float *)out_colors[m];
         p.cum_w[m] = (float *)cum_w[m];
         p.g_out[m] = grad_outs[m];
         p.g_color[m] = grad_colors[m];
-        p.g_normal[m] = grad_normals[m];
-        p.g_pos[m] = grad_pos[m];
     }
+    p.g_normal[0] = grad_normal_sum;
+    p.g_pos[0] = grad_pos_sum;
     return eaw_multi_dispatch(p, true, (cudaStream_t)stream);
 }
 

@@ -270,12 +270,12 @@ class Kernels:
         self._check(rc, "mirres_eaw_fwd_multi")
 
     def eaw_bwd_multi(self, c_phi, n_phi, p_phi, fx, fy, step_width, occ, normal, pos, colors, outs, cum_w, g_outs,
-                      g_colors, g_normals, g_pos):
+                      g_colors, g_normal_sum, g_pos_sum):
         rc = self.lib.mirres_eaw_bwd_multi(float(c_phi), float(n_phi), float(p_phi), fx, fy, float(step_width),
                                            self._f(occ), self._f(normal), self._f(pos), len(colors),
                                            self._ptr_array(colors), self._ptr_array(outs), self._ptr_array(cum_w),
                                            self._ptr_array(g_outs), self._ptr_array(g_colors),
-                                           self._ptr_array(g_normals), self._ptr_array(g_pos), self._stream())
+                                           self._f(g_normal_sum, True), self._f(g_pos_sum, True), self._stream())
         self._check(rc, "mirres_eaw_bwd_multi")
 
     def bilateral_fwd(self, fx, fy, sigma, col, nrm, zdz, out):

@@ -461,17 +461,15 @@ class EAWDenoiseMulti(torch.autograd.Function):
         if active:
             k = get_kernels()
             mk = lambda: torch.empty_like(cols[0], memory_format=torch.contiguous_format)
-            gc, gn, gp = [mk() for _ in active], [mk() for _ in active], [mk() for _ in active]
+            gc = [mk() for _ in active]
+            g_normal = mk() if ctx.needs_input_grad[7] else None
+            g_pos = mk() if ctx.needs_input_grad[8] else None
             k.eaw_bwd_multi(c_phi, n_phi, p_phi, fx, fy, step, occ, nrm, pos, [cols[i] for i in active],
                             [outs[i] for i in active], [cum[i] for i in active],
-                            [grad_outs[i].contiguous() for i in active], gc, gn, gp)
+                            [grad_outs[i].contiguous() for i in active], gc, g_normal, g_pos)
             for j, i in enumerate(active):
                 if ctx.needs[i]:
                     g_colors[i] = gc[j]
-            if ctx.needs_input_grad[7]:
-                g_normal = gn[0] if len(gn) == 1 else torch.stack(gn).sum(0)
-            if ctx.needs_input_grad[8]:
-                g_pos = gp[0] if len(gp) == 1 else torch.stack(gp).sum(0)
         return (None, None, None, None, None, None, None, g_normal, g_pos, *g_colors)
 
 
@@ -718,12 +716,16 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                      rs=torch.zeros((n, 2), dtype=torch.float, device=dev))
         return c
 
+    caller_stream = None
     if overlap:
-        main_stream = torch.cuda.current_stream() if pos_map.is_cuda else _NullStream()
+        caller_stream = torch.cuda.current_stream() if pos_map.is_cuda else _NullStream()
+        # the reuse chain (temporal -> spatial of consecutive iterations) is the critical path of the loop: it gets a stream
+        # of its own with the highest priority, so its blocks are placed before the pending blocks of everything else
+        main_stream = _side_stream(dev, "reuse", -3) if (pos_map.is_cuda and USE_PRIORITIES) else caller_stream
         for c in range(min(spp, MAX_INDIRECT_CHAINS)):
             chains.append(make_chain("indirect%d" % c, _side_stream(dev, c)))
         for c in chains:
-            c["stream"].wait_stream(main_stream)
+            c["stream"].wait_stream(caller_stream)
     else:
         chains.append(make_chain("main", None))
     pending = []  # (iteration, bounce, completion event, (color, diff, spec)) not yet added to the running sums
@@ -794,13 +796,12 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         # B is ONE buffer shared by all iterations, so the autograd Functions keep saving aliases of buffers that later
         # iterations overwrite, exactly like the reference's two-buffer ping-pong.  Arithmetic, frame
         # indices and accumulation order are those of the sequential schedule; only the enqueue order differs.
-        st_s = _side_stream(dev, MAX_INDIRECT_CHAINS)
+        st_s = _side_stream(dev, MAX_INDIRECT_CHAINS, -1)
         # initial candidates of different iterations are independent of each other as well: a ring of R streams, each
         # with its own light-tile set, reservoir buffer and workspace, lets them all start as soon as the G-buffer exists
         R = min(spp, MAX_INITIAL_STREAMS)
-        st_init = [_side_stream(dev, MAX_INDIRECT_CHAINS + 1 + r) for r in range(R)]
-        for st in [st_s] + st_init:
-            st.wait_stream(main_stream)
+        # the first iteration's candidates gate the whole reuse chain, the later ones have slack
+        st_init = [_side_stream(dev, MAX_INDIRECT_CHAINS + 1 + r, -2 if r == 0 else -1) for r in range(R)]
         X = tuple(_reservoir_set(n, dev, False) for _ in range(R))  # both passes write every pixel
         S = (_reservoir_set(n, dev, False), _reservoir_set(n, dev, False))
         tiles = [(light_data, light_uv, light_inv_pdf)] + [
@@ -808,6 +809,8 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             for _ in range(R - 1)]
         B = reservoirs
         slangpy.prepare_workspace(occ_map)
+        for st in [st_s] + st_init + ([main_stream] if main_stream is not caller_stream else []):
+            st.wait_stream(caller_stream)
         for r in range(R):
             with _on(st_init[r]), slangpy.workspace_tag("initial%d" % r):
                 slangpy.prepare_workspace(occ_map)
@@ -842,16 +845,17 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                 init_done[i] = ev(st_init[r])
             main_stream.wait_event(init_done[i])
             ris_pass = 3
-            if i > 0:
-                TemporalResampling(TemporalResampling_m, X[r], S[(i - 1) % 2], env_map, width, height, framedim_x,
-                                   framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map, prev_occ_map,
-                                   prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
-                ris_pass += 1
-            if i >= 2:
-                main_stream.wait_event(copy_done[i - 2])  # S[i % 2] was last read by the copy of iteration i - 2
-            worker.SpatialResampling_(SpatialResampling_m, pos_map, S[i % 2], X[r], neighborOffsets, env_map, width,
-                                      height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map,
-                                      ray_dir_map)
+            with _on(main_stream):
+                if i > 0:
+                    TemporalResampling(TemporalResampling_m, X[r], S[(i - 1) % 2], env_map, width, height, framedim_x,
+                                       framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map,
+                                       prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
+                    ris_pass += 1
+                if i >= 2:
+                    main_stream.wait_event(copy_done[i - 2])  # S[i % 2] was last read by the copy of iteration i - 2
+                worker.SpatialResampling_(SpatialResampling_m, pos_map, S[i % 2], X[r], neighborOffsets, env_map, width,
+                                          height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map,
+                                          ray_dir_map)
             ris_pass += 1
             assert ris_pass == first_indirect_pass
             spatial_done[i] = ev(main_stream)
@@ -898,8 +902,8 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                             ray=slangpy._c(ray_dir_map), frame=div)
                 sums["color"], sums["diff"], sums["spec"] = DirectLightSum.apply(env_map_init, normal_map, diffuse_map,
                                                                                  roughness_specular, pack)
-        for st in [st_s] + st_init:
-            main_stream.wait_stream(st)
+        for st in [st_s] + st_init + ([main_stream] if main_stream is not caller_stream else []):
+            caller_stream.wait_stream(st)
         keepalive.extend(X + S)
         keepalive.extend(tiles)
     else:
@@ -953,7 +957,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             sums["spec"] += color_spec
     if overlap:
         for c in chains:
-            main_stream.wait_stream(c["stream"])
+            caller_stream.wait_stream(c["stream"])
     elif normalize:
         for name in sums:
             sums[name] = sums[name] / frame
