@@ -634,7 +634,10 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                       env_map_init, occ_map, pos_map, normal_map, depth_map, diffuse_map, roughness_specular,
                       ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors, color,
                       *, random_offset=None, max_bounce=None, hooks=None, overlap=None, shard=None, prepared=None,
-                      normalize=False):
+                      normalize=False, indirect_done=None):
+    # indirect_done(color_1, diff_1, spec_1): called once the indirect sums are final (normalised when `normalize`), in the
+    # concurrent schedule on the stream that produced them, so the caller can post-process them while the direct-light
+    # chain is still running
     # normalize=True (run_restir_di_with_pt): the six sums come back already divided by the frame count (:505-515)
     n = framedim_x * framedim_y
     dev = pos_map.device
@@ -797,6 +800,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         # iterations overwrite, exactly like the reference's two-buffer ping-pong.  Arithmetic, frame
         # indices and accumulation order are those of the sequential schedule; only the enqueue order differs.
         st_s = _side_stream(dev, MAX_INDIRECT_CHAINS, -1)
+        st_i = _side_stream(dev, "indirect_sum")
         # initial candidates of different iterations are independent of each other as well: a ring of R streams, each
         # with its own light-tile set, reservoir buffer and workspace, lets them all start as soon as the G-buffer exists
         R = min(spp, MAX_INITIAL_STREAMS)
@@ -809,7 +813,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             for _ in range(R - 1)]
         B = reservoirs
         slangpy.prepare_workspace(occ_map)
-        for st in [st_s] + st_init + ([main_stream] if main_stream is not caller_stream else []):
+        for st in [st_s, st_i] + st_init + ([main_stream] if main_stream is not caller_stream else []):
             st.wait_stream(caller_stream)
         for r in range(R):
             with _on(st_init[r]), slangpy.workspace_tag("initial%d" % r):
@@ -884,16 +888,14 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                 direct_outs.append(outs_d)
                 if len(direct_outs) >= 16:
                     flush_direct()
-                if len(pending) >= 16:  # bounds the memory held by long loops (--spp 512); normally one flush at the end
-                    accumulate(i - 2, st_s)
+            if len(pending) >= 16:  # bounds the memory held by long loops (--spp 512); normally one flush at the end
+                with _on(st_i):
+                    accumulate(i - 2, st_i)
             frame += 1
             prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir = occ_map, normal_depth, brdf_map, ray_dir_map
         div = float(frame) if normalize else 0.0
         with _on(st_s):
             flush_direct(div)
-            for c in chains:
-                st_s.wait_stream(c["stream"])
-            accumulate(spp, st_s, div)
             if torch.is_grad_enabled() and any(t.requires_grad for t in (env_map_init, normal_map, diffuse_map,
                                                                          roughness_specular)):
                 # the node lives on the shading stream, like the per-pass Functions it stands for: its backward runs there
@@ -902,7 +904,16 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                             ray=slangpy._c(ray_dir_map), frame=div)
                 sums["color"], sums["diff"], sums["spec"] = DirectLightSum.apply(env_map_init, normal_map, diffuse_map,
                                                                                  roughness_specular, pack)
-        for st in [st_s] + st_init + ([main_stream] if main_stream is not caller_stream else []):
+        with _on(st_i):
+            # the indirect sums never meet the direct-light chain: they are finished (and handed to the caller's
+            # post-processing) on their own stream, typically while the last reuse passes are still running
+            for c in chains:
+                st_i.wait_stream(c["stream"])
+            accumulate(spp, st_i, div)
+            if indirect_done is not None:
+                indirect_done(sums["color_1"], sums["diff_1"], sums["spec_1"])
+                indirect_done = None
+        for st in [st_s, st_i] + st_init + ([main_stream] if main_stream is not caller_stream else []):
             caller_stream.wait_stream(st)
         keepalive.extend(X + S)
         keepalive.extend(tiles)
@@ -961,6 +972,8 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     elif normalize:
         for name in sums:
             sums[name] = sums[name] / frame
+    if indirect_done is not None:
+        indirect_done(sums["color_1"], sums["diff_1"], sums["spec_1"])
     keepalive.clear()
     return (sums["color"], sums["color_1"], sums["diff"], sums["spec"], sums["diff_1"], sums["spec_1"],
             total_indirect_light, frame)
@@ -1005,6 +1018,19 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
         ray_dir_map = _normalize_rows(ray_dir_map)
     motionVectors = None  # the reference passes zeros (:487); NULL means the same to the kernel
     color = None
+    early = {}
+
+    def denoise_indirect(color_1, diff_1, spec_1):
+        # the three indirect images carry no gradient and do not depend on the direct-light chain: they are denoised as soon
+        # as their sums exist (concurrent schedule: on the stream that finished them, overlapping the last reuse passes)
+        with torch.no_grad():
+            combined = diff_1 + spec_1
+            early["combined"] = combined
+            early["outs"] = EAWDenoise_multi_use_phi(c_phi_scale, n_phi_scale, p_phi_scale, stepWidth, denoise_iter,
+                                                     framedim_x, framedim_y, occ_map, (combined, diff_1, spec_1),
+                                                     normal_map.detach(), pos_map.detach())
+
+    split_denoise = gb_depth is None and batched_denoise
     (total_color, total_color_1, total_diff_light, total_spec_light, total_diff_light_1, total_spec_light_1,
      total_indirect_light, mFrameIndex) = restir_di_with_pt(
         use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_worker, spp, framedim_x, framedim_y,
@@ -1013,17 +1039,18 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
         final_samples, neighborOffsets, light_tile_count, light_tile_size, env_map, occ_map, pos_map, normal_map,
         depth_map, diffuse_map, roughness_specular, ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map,
         prev_ray_dir, motionVectors, color, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks,
-        overlap=overlap, shard=_shard, prepared=prepared, normalize=True)
+        overlap=overlap, shard=_shard, prepared=prepared, normalize=True,
+        indirect_done=denoise_indirect if split_denoise else None)
     # `total / mFrameIndex` of all six sums (:505-515) has happened inside (normalize=True)
-    combined_color_indirect = total_diff_light_1 + total_spec_light_1
+    combined_color_indirect = early["combined"] if split_denoise else total_diff_light_1 + total_spec_light_1
 
-    if gb_depth is None and batched_denoise:
-        # the five images share occ / normal / pos: one launch per a-trous level (per-image arithmetic unchanged)
-        (denoised_diffuse, denoised_spec, denoised_indirect, denoised_indirect_diff,
-         denoised_indirect_spec) = EAWDenoise_multi_use_phi(
+    if split_denoise:
+        # images that share occ / normal / pos go through one launch per a-trous level (per-image arithmetic unchanged):
+        # the two differentiable ones here, the three indirect ones in denoise_indirect above
+        denoised_diffuse, denoised_spec = EAWDenoise_multi_use_phi(
             c_phi_scale, n_phi_scale, p_phi_scale, stepWidth, denoise_iter, framedim_x, framedim_y, occ_map,
-            (total_diff_light, total_spec_light, combined_color_indirect.detach(), total_diff_light_1.detach(),
-             total_spec_light_1.detach()), normal_map, pos_map)
+            (total_diff_light, total_spec_light), normal_map, pos_map)
+        denoised_indirect, denoised_indirect_diff, denoised_indirect_spec = early["outs"]
     elif gb_depth is None:
         args = (denoising_m, c_phi_scale, n_phi_scale, p_phi_scale, stepWidth, denoise_iter, framedim_x, framedim_y,
                 occ_map)
