@@ -33,6 +33,14 @@ extern "C" {
 
 int mirres_abi_version(void);
 
+/* Launch-shape tuning, the only process-wide state of the library (SURVEY.md 8b allows a tuning context): blocks per SM of
+ * the persistent queue tracers launched by SUBSEQUENT calls from any entry point; value <= 0 restores the default (3 for
+ * boolean rays, 2 for closest-hit rays: small grids leave room for kernels of other streams).  A host that runs its
+ * critical chain on a high-priority stream raises the value around those calls.  Results do not depend on it. */
+#define MIRRES_TUNE_ANY_BLOCKS 0
+#define MIRRES_TUNE_CLOSEST_BLOCKS 1
+int mirres_set_tuning(int key, int value);
+
 /* ------------------------------------------------------------------------------------------------------------
  * LBVH construction.  Replaces restirbvhWorker.update_bvh, nerf/renderer_restir.py:25-89, and the Slang
  * kernels it launches (nerf/bvhworkers/{get_elements,lbvh_morton_codes,lbvh_single_radixsort,lbvh_hierarchy,

@@ -17,6 +17,7 @@ _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "u": ctypes.c_uint, "f": ctypes.c
 # name -> argument kinds (p pointer, i int, u unsigned, f float, z size_t); every function returns int unless noted
 SIGNATURES = {
     "mirres_abi_version": "",
+    "mirres_set_tuning": "ii",
     "mirres_bvh_build": "pipippppppzp",
     "mirres_bvh_elements": "ppippp",
     "mirres_bvh_morton": "piffffffpp",

@@ -400,6 +400,9 @@ __global__ void __launch_bounds__(MR_TRACE_BLOCK, 4) k_trace_mixed_persistent(Bv
 }
 #endif
 
+// tuning overrides of the persistent grids (blocks per SM), 0 = default; see mirres_set_tuning
+static int g_tune_any_blocks = 0, g_tune_closest_blocks = 0;
+
 void queue_reset(const Workspace &ws, cudaStream_t st)
 {
     zero_async(ws.counters + 1, 4 * sizeof(int), st);
@@ -437,7 +440,18 @@ int trace_queues(const BvhView &bvh, const Workspace &ws, bool any, bool closest
         const char *a = getenv("MIRRES_ANY_BLOCKS");
         if (a && atoi(a) > 0) occ_any = atoi(a);
     }
-    const int g_mixed = sm_count * (occ_mixed & ~1), g_any = sm_count * occ_any, g_closest = sm_count * occ_closest;
+    // per-call override (mirres_set_tuning): the host raises the grid of the launches on its critical chain, which run on
+    // a high-priority stream, and leaves the background chains at the small default
+    static int occ_any_max = 0, occ_closest_max = 0;
+    if (!occ_any_max) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_any_max, k_trace_any_persistent<false>, MR_TRACE_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_closest_max, k_trace_closest_persistent<false>, MR_TRACE_BLOCK, 0);
+        if (occ_any_max < 1) occ_any_max = 4;
+        if (occ_closest_max < 1) occ_closest_max = 4;
+    }
+    const int use_any = g_tune_any_blocks > 0 ? min(g_tune_any_blocks, occ_any_max) : occ_any;
+    const int use_closest = g_tune_closest_blocks > 0 ? min(g_tune_closest_blocks, occ_closest_max) : occ_closest;
+    const int g_mixed = sm_count * (occ_mixed & ~1), g_any = sm_count * use_any, g_closest = sm_count * use_closest;
     if (prefetch) {
         if (any && closest) k_trace_mixed_persistent<true><<<g_mixed, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
         else if (any) k_trace_any_persistent<true><<<g_any, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
@@ -474,6 +488,14 @@ int device_sm_count()
 using namespace mr;
 
 extern "C" {
+
+int mirres_set_tuning(int key, int value)
+{
+    if (key == MIRRES_TUNE_ANY_BLOCKS) g_tune_any_blocks = value > 0 ? value : 0;
+    else if (key == MIRRES_TUNE_CLOSEST_BLOCKS) g_tune_closest_blocks = value > 0 ? value : 0;
+    else return MIRRES_ERR_SHAPE;
+    return 0;
+}
 
 size_t mirres_workspace_bytes(int n_pixels) { return n_pixels < 1 ? 0 : workspace_carve(nullptr, n_pixels, nullptr); }
 

@@ -64,6 +64,12 @@ class Kernels:
     def _u32(x):
         return ctypes.c_uint(int(x) & 0xFFFFFFFF)
 
+    # -- tuning ------------------------------------------------------------------------------------------------
+    TUNE_ANY_BLOCKS, TUNE_CLOSEST_BLOCKS = 0, 1
+
+    def set_tuning(self, key, value):
+        self._check(self.lib.mirres_set_tuning(int(key), int(value)), "mirres_set_tuning")
+
     # -- BVH ---------------------------------------------------------------------------------------------------
     def bvh_sizes(self, F):
         return (self.lib.mirres_bvh_scratch_bytes(F), self.lib.mirres_bvh_packed_node_bytes(F),

@@ -32,6 +32,7 @@ TOTAL_RIS_PASSES = 5 + 15  # frame-index stride per spp iteration (nerf/renderer
 import os as _os
 MAX_INITIAL_STREAMS = int(_os.environ.get("MIRRES_INITIAL_STREAMS", 4))   # concurrent initial-candidate stages (light tiles + initial RIS of different spp iterations)
 MAX_INDIRECT_CHAINS = int(_os.environ.get("MIRRES_INDIRECT_CHAINS", 2))  # concurrent indirect-path chains (one CUDA stream + path state + ray-queue workspace each)
+CRITICAL_ANY_BLOCKS = int(_os.environ.get("MIRRES_CRITICAL_ANY_BLOCKS", 0))  # persistent grid (blocks / SM) of the reuse chain's boolean-ray launches; 0 = library default
 USE_PRIORITIES = int(_os.environ.get("MIRRES_PRIORITIES", 1))  # stream priorities for the critical reuse chain
 _SIDE_STREAMS = {}
 
@@ -857,9 +858,10 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                     ris_pass += 1
                 if i >= 2:
                     main_stream.wait_event(copy_done[i - 2])  # S[i % 2] was last read by the copy of iteration i - 2
-                worker.SpatialResampling_(SpatialResampling_m, pos_map, S[i % 2], X[r], neighborOffsets, env_map, width,
-                                          height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map,
-                                          ray_dir_map)
+                with slangpy.trace_blocks(any_blocks=CRITICAL_ANY_BLOCKS):
+                    worker.SpatialResampling_(SpatialResampling_m, pos_map, S[i % 2], X[r], neighborOffsets, env_map,
+                                              width, height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth,
+                                              brdf_map, ray_dir_map)
             ris_pass += 1
             assert ris_pass == first_indirect_pass
             spatial_done[i] = ev(main_stream)

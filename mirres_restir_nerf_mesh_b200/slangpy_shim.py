@@ -143,6 +143,25 @@ class workspace_prepared:
         _SKIP_PREPARE.pop()
 
 
+class trace_blocks:
+    """Blocks per SM of the persistent queue tracers for the ray-casting calls inside the block (mirres_set_tuning).  The
+    driver wraps the launches of its critical chain, which it issues on a high-priority stream, so that they get a full
+    grid while the background chains keep the small default."""
+
+    def __init__(self, any_blocks=0, closest_blocks=0):
+        self.values = (int(any_blocks), int(closest_blocks))
+
+    def __enter__(self):
+        k = get_kernels()
+        k.set_tuning(k.TUNE_ANY_BLOCKS, self.values[0])
+        k.set_tuning(k.TUNE_CLOSEST_BLOCKS, self.values[1])
+
+    def __exit__(self, *a):
+        k = get_kernels()
+        k.set_tuning(k.TUNE_ANY_BLOCKS, 0)
+        k.set_tuning(k.TUNE_CLOSEST_BLOCKS, 0)
+
+
 def prepare_workspace(occ_map):
     """Builds the foreground-pixel list of the current workspace (see workspace_tag) from the primary occupancy."""
     occ = _c(occ_map)
