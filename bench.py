@@ -216,25 +216,33 @@ def run_gpu(args):
     target = torch.full((n, 3), 0.5, device=dev)
     flat_grad = torch.zeros(ne + V * 3 + V * 5, device=dev)  # env | vertex-normal | vertex-texture (kd, rough, metal)
     opts = dict(overlap=not args.no_overlap)
+    bvh_stream = torch.cuda.Stream()
 
     def full_step(vert, tri, env, pose):
         """One stage-1 training step of one view: LBVH rebuild (nerf/renderer.py:975), camera rays, G-buffer, ReSTIR +
         path tracer, denoise + composite, loss, backward into env / normals / kd / ks, scatter to vertices and vertex
         texture."""
-        worker.update_mesh(vert, tri)
+        # the LBVH rebuild runs beside everything that does not need it: camera rays, the environment distribution and
+        # the light tiles of the spp loop
+        cur = torch.cuda.current_stream()
+        bvh_stream.wait_stream(cur)
+        with torch.cuda.stream(bvh_stream):
+            worker.update_mesh(vert, tri)
         rays_o, rays_d = synth.camera_rays_torch(W, H, pose)
+        env_l = env.detach().clone().requires_grad_(True)
+        lighting = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env_l, spp, 1234 + 17 * rank)
+        cur.wait_stream(bvh_stream)
         occ, depth = torch.empty(n, 1, device=dev), torch.empty(n, 1, device=dev)
         pos, nrm = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
         prim, bary = torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, 2, device=dev)
         pk.gbuffer_primary(worker.packed, rays_o, rays_d, occ, pos, nrm, depth, prim, bary, ws=slangpy_shim.workspace(dev, n))
         kd, rs = mat.gbuffer_materials(pos, occ)   # stand-in for the tiny-cuda-nn material MLP (out of scope)
-        env_l = env.detach().clone().requires_grad_(True)
         normal = nrm.requires_grad_(True)
         kd.requires_grad_(True)
         rs.requires_grad_(True)
         outs = R.run_restir_di_with_pt(False, 1, 1, 1, mat, None, worker, *mods, env_l, occ, normal, depth, kd, rs, rays_d,
                                        pos, None, None, None, None, W, H, spp, 2, 2, 2.0, 0.1, 0.001,
-                                       random_offset=1234 + 17 * rank, max_bounce=mb, **opts)
+                                       random_offset=1234 + 17 * rank, max_bounce=mb, lighting=lighting, **opts)
         loss = torch.nn.functional.mse_loss(outs[0], target)
         loss.backward()
         # gradients leave the path as grad_env [He,We,3] and dense per-pixel grads; the latter are scattered to vertices /

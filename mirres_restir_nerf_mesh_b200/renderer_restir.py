@@ -625,6 +625,25 @@ def _normalize_rows(x, eps=1e-6):
     return x / torch.clamp(n, min=eps)
 
 
+def prepare_lighting(make_sampleable_m, generateLightTiles_m, light_data, light_uv, light_inv_pdf, env_map_init, spp,
+                     random_offset, light_tile_count=128, light_tile_size=1024):
+    """Everything restir_di_with_pt derives from the environment map alone: the flipped map, its sampling distribution
+    (nerf/renderer_restir.py:305-312) and the light tiles of the first min(spp, MAX_INITIAL_STREAMS) iterations (:320-325).
+    None of it needs the G-buffer, so a caller that produces the G-buffer itself can enqueue this first (or on another
+    stream) and hand the result to run_restir_di_with_pt(lighting=...): the values are the ones the loop would compute."""
+    height, width = env_map_init.shape[0], env_map_init.shape[1]
+    env_map = torch.flip(env_map_init.detach(), dims=[0]).reshape(-1, env_map_init.shape[2])
+    dist = make_sampleable(make_sampleable_m, env_map, width, height)
+    R = min(int(spp), MAX_INITIAL_STREAMS)
+    tiles = [(light_data, light_uv, light_inv_pdf)] + [
+        (torch.empty_like(light_data), torch.empty_like(light_uv), torch.empty_like(light_inv_pdf)) for _ in range(R - 1)]
+    for i in range(R):
+        GenerateLightTiles(generateLightTiles_m, None, env_map, *dist, width, height,
+                           random_offset + TOTAL_RIS_PASSES * i, *tiles[i], light_tile_count, light_tile_size)
+    return dict(env_map=env_map, dist=dist, tiles=tiles, ready=R, random_offset=random_offset, spp=int(spp),
+                env_ptr=env_map_init.data_ptr())
+
+
 # =====================================================================================================================
 # the spp loop
 # =====================================================================================================================
@@ -635,7 +654,9 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                       env_map_init, occ_map, pos_map, normal_map, depth_map, diffuse_map, roughness_specular,
                       ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors, color,
                       *, random_offset=None, max_bounce=None, hooks=None, overlap=None, shard=None, prepared=None,
-                      normalize=False, indirect_done=None):
+                      normalize=False, indirect_done=None, lighting=None):
+    # lighting: result of prepare_lighting() for this env map / spp / random_offset (environment distribution and the light
+    # tiles of the first iterations, computed earlier by the caller, e.g. while the G-buffer is still being traced)
     # indirect_done(color_1, diff_1, spec_1): called once the indirect sums are final (normalised when `normalize`), in the
     # concurrent schedule on the stream that produced them, so the caller can post-process them while the direct-light
     # chain is still running
@@ -688,9 +709,14 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     prev_ray_dir = zeros(*ray_dir_map.shape)
 
     height, width = env_map_init.shape[0], env_map_init.shape[1]
-    env_map = torch.flip(env_map_init.detach(), dims=[0]).reshape(-1, env_map_init.shape[2])
+    if lighting is not None and not (lighting["random_offset"] == random_offset and lighting["spp"] == spp and
+                                     lighting["env_ptr"] == env_map_init.data_ptr()):
+        lighting = None  # prepared for another call
+    env_map = lighting["env_map"] if lighting is not None else \
+        torch.flip(env_map_init.detach(), dims=[0]).reshape(-1, env_map_init.shape[2])
     env_map_init = torch.flip(env_map_init, dims=[0]).reshape(-1, env_map_init.shape[2])
-    pdf_, cdf_, mpdf_, mcdf_ = make_sampleable(make_sampleable_m, env_map, width, height)
+    pdf_, cdf_, mpdf_, mcdf_ = lighting["dist"] if lighting is not None else \
+        make_sampleable(make_sampleable_m, env_map, width, height)
 
     frame = 0
     scale = (scale_x, scale_y, scale_z)
@@ -809,9 +835,10 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         st_init = [_side_stream(dev, MAX_INDIRECT_CHAINS + 1 + r, -2 if r == 0 else -1) for r in range(R)]
         X = tuple(_reservoir_set(n, dev, False) for _ in range(R))  # both passes write every pixel
         S = (_reservoir_set(n, dev, False), _reservoir_set(n, dev, False))
-        tiles = [(light_data, light_uv, light_inv_pdf)] + [
+        tiles = lighting["tiles"] if lighting is not None else [(light_data, light_uv, light_inv_pdf)] + [
             (torch.empty_like(light_data), torch.empty_like(light_uv), torch.empty_like(light_inv_pdf))
             for _ in range(R - 1)]
+        tiles_ready = lighting["ready"] if lighting is not None else 0
         B = reservoirs
         slangpy.prepare_workspace(occ_map)
         for st in [st_s, st_i] + st_init + ([main_stream] if main_stream is not caller_stream else []):
@@ -842,8 +869,9 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             with _on(st_init[r]), slangpy.workspace_tag("initial%d" % r):
                 if i >= R:
                     st_init[r].wait_event(spatial_done[i - R])  # X[r] was last read by spatial(i - R)
-                GenerateLightTiles(generateLightTiles_m, None, env_map, pdf_, cdf_, mpdf_, mcdf_, width, height, base,
-                                   *tiles[r], light_tile_count, light_tile_size)
+                if i >= tiles_ready:
+                    GenerateLightTiles(generateLightTiles_m, None, env_map, pdf_, cdf_, mpdf_, mcdf_, width, height, base,
+                                       *tiles[r], light_tile_count, light_tile_size)
                 worker.InitialResampling_(InitialResampling_m, pos_map, X[r], env_map, width, height, framedim_x,
                                           framedim_y, base + 2, occ_map, normal_depth, brdf_map, ray_dir_map, pdf_, cdf_,
                                           mpdf_, mcdf_, *tiles[r], prepare=False)
@@ -989,7 +1017,8 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
                           ray_dir_map, pos_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir,
                           framedim_x, framedim_y, spp, denoise_iter, stepWidth, c_phi_scale=1.0, n_phi_scale=0.1,
                           p_phi_scale=0.1, *, random_offset=None, max_bounce=None, hooks=None, bilateral=None,
-                          overlap=None, batched_denoise=True, shard=None, _shard=None, fused_prepare=True, fused_composite=True):
+                          overlap=None, batched_denoise=True, shard=None, _shard=None, fused_prepare=True, fused_composite=True,
+                          lighting=None):
     if shard is not None:
         with slangpy.active_rows(shard.active[0], shard.active[1], framedim_x):
             return run_restir_di_with_pt(
@@ -1042,7 +1071,7 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
         depth_map, diffuse_map, roughness_specular, ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map,
         prev_ray_dir, motionVectors, color, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks,
         overlap=overlap, shard=_shard, prepared=prepared, normalize=True,
-        indirect_done=denoise_indirect if split_denoise else None)
+        indirect_done=denoise_indirect if split_denoise else None, lighting=lighting)
     # `total / mFrameIndex` of all six sums (:505-515) has happened inside (normalize=True)
     combined_color_indirect = early["combined"] if split_denoise else total_diff_light_1 + total_spec_light_1
 

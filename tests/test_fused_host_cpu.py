@@ -36,10 +36,12 @@ def test_final_shading_bwd_multi_equals_the_single_pass_kernels():
     C.final_shading_bwd_multi_equals_the_single_pass_kernels(H.kernels(), "cpu")
 
 
-def _render(sc, w, **kw):
+def _render(sc, w, prepared_lighting=False, **kw):
     mods = R.load_m_for_restir(sc["W"], sc["H"], device="cpu")
     g = {k: H.t(v) for k, v in sc["gbuffer"].items()}
     env = H.t(sc["env"]).requires_grad_(True)
+    if prepared_lighting:
+        kw["lighting"] = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env, 3, 99)
     normal = g["normal_map"].clone().requires_grad_(True)
     tex = torch.cat((g["diffuse_map"], torch.zeros_like(g["diffuse_map"])), dim=1).requires_grad_(True)
     kd = tex[:, 0:3]  # strided view, as render_stage1 passes it
@@ -72,3 +74,14 @@ def test_concurrent_schedule_host_logic_equals_sequential_schedule(strict):
     for a, b in zip(gseq, gpar):
         assert a.abs().sum() > 0
         assert (a - b).abs().max() <= 1e-5 * a.abs().max()
+
+
+def test_prepared_lighting_changes_nothing():
+    """prepare_lighting() + run_restir_di_with_pt(lighting=...) == the loop computing the same things itself."""
+    sc = P.scene("T0", 0.0)
+    w = H.OracleBvhWorker(H.t(sc["vert"]), H.t(sc["tri"]))
+    w.update_mesh(H.t(sc["vert"]), H.t(sc["tri"]))
+    a, ga = _render(sc, w, overlap=True)
+    b, gb = _render(sc, w, prepared_lighting=True, overlap=True)
+    for x, y in zip(a + ga, b + gb):
+        assert torch.equal(x, y)
