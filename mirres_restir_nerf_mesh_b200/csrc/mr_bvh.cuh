@@ -53,6 +53,10 @@ MR_DEV Rec32 load_rec(const Rec32 *p)
 
 // entries in reference visit order: expand(right child) then expand(left child), expand(X) = [X] if X is a leaf,
 // else [right(X), left(X)].  Unused entries hold an empty box (+inf, -inf) and can never pass the slab test.
+//
+// A reference to an internal node carries, in bits 28-29, how many of the node's trailing entries are unused (0-2): near
+// the leaves most records hold two or three boxes, and the traversal kernels are bound by L1 wavefronts (one per lane
+// and 32-byte sector), so a walker that knows the count BEFORE the fetch skips the sectors that hold nothing.
 struct alignas(32) PackedNode {
     Rec32 e[4]; // entry k: min.xyz, max.xyz, ref bits (>= 0 internal node index, < 0: ~leaf slot), 0
 };
@@ -60,6 +64,10 @@ struct alignas(32) PackedTri {
     Rec32 a; // v0.xyz, primitive index bits, e1.xyz, 0
     Rec32 b; // e2.xyz, 0 ...
 };
+
+#define MR_REF_NODE_MASK 0x0fffffff
+MR_DEV int ref_node(int ref) { return ref & MR_REF_NODE_MASK; }       // ref >= 0 only
+MR_DEV int ref_missing(int ref) { return (ref >> 28) & 3; }           // unused trailing entries of the referenced record
 
 struct BvhView {
     const PackedNode *__restrict__ nodes; // [max(F-1,1)]
@@ -105,7 +113,14 @@ MR_DEV void pack_item(const PackParams &p, int gid)
         const float *b = p.aabb + 6 * (size_t)node;
 #pragma unroll
         for (int k = 0; k < 6; ++k) box[6 * cnt + k] = MR_LDG(b + k);
-        ref[cnt] = node < LEAF ? node : ~(node - LEAF);
+        if (node < LEAF) {
+            // entries of the referenced record: one per leaf child, two per internal child
+            const int l = MR_LDG(p.info + 3 * (size_t)node), rr = MR_LDG(p.info + 3 * (size_t)node + 1);
+            const int missing = (l >= LEAF ? 1 : 0) + (rr >= LEAF ? 1 : 0);
+            ref[cnt] = node | (missing << 28);
+        } else {
+            ref[cnt] = ~(node - LEAF);
+        }
         ++cnt;
     };
     auto expand = [&](int node) {
@@ -203,15 +218,32 @@ MR_DEV void wide_slabs(const Ray &r, const Rec32 &e0, const Rec32 &e1, const Rec
     w.ref[2] = float_bits(e2.v[6]);
     w.ref[3] = float_bits(e3.v[6]);
 }
-MR_DEV void wide_fetch(const Ray &r, const PackedNode *pn, WideHit &w)
+MR_DEV Rec32 empty_rec()
 {
-    const Rec32 e0 = load_rec(&pn->e[0]), e1 = load_rec(&pn->e[1]), e2 = load_rec(&pn->e[2]), e3 = load_rec(&pn->e[3]);
+    Rec32 e;
+    const float inf = bits_float(0x7f800000);
+    e.v[0] = e.v[1] = e.v[2] = inf;
+    e.v[3] = e.v[4] = e.v[5] = -inf;
+    e.v[6] = e.v[7] = 0.f;
+    return e;
+}
+// entries 2 and 3 of a record are fetched only when the reference says they are in use
+MR_DEV void load_tail(const Rec32 *rec, int missing, Rec32 &e2, Rec32 &e3)
+{
+    e2 = e3 = empty_rec();
+    if (missing < 2) e2 = load_rec(rec + 2);
+    if (missing < 1) e3 = load_rec(rec + 3);
+}
+MR_DEV void wide_fetch(const Ray &r, const PackedNode *nodes, int ref, WideHit &w)
+{
+    const Rec32 *rec = reinterpret_cast<const Rec32 *>(nodes + ref_node(ref));
+    const Rec32 e0 = load_rec(rec), e1 = load_rec(rec + 1), e2 = load_rec(rec + 2), e3 = load_rec(rec + 3);
     wide_slabs(r, e0, e1, e2, e3, w);
 }
 // record address of a traversal reference: wide node (>= 0) or packed triangle (< 0)
 MR_DEV const Rec32 *ref_address(const BvhView &bvh, int ref)
 {
-    return ref >= 0 ? reinterpret_cast<const Rec32 *>(bvh.nodes + ref) : reinterpret_cast<const Rec32 *>(bvh.tris + (size_t)(~ref));
+    return ref >= 0 ? reinterpret_cast<const Rec32 *>(bvh.nodes + ref_node(ref)) : reinterpret_cast<const Rec32 *>(bvh.tris + (size_t)(~ref));
 }
 MR_DEV bool tri_test_at(const BvhView &bvh, const Ray &r, int leaf_slot, float &t, float &u, float &v)
 {
@@ -231,7 +263,7 @@ MR_DEV bool any_hit(const BvhView &bvh, float3 origin, float3 dir, TraceStats *s
     int node = 0;
     for (;;) {
         WideHit w;
-        wide_fetch(r, bvh.nodes + node, w);
+        wide_fetch(r, bvh.nodes, node, w);
         if (STATS) st->nodes += 1;
         int next = 0;
         bool have = false;
@@ -302,7 +334,7 @@ MR_DEV bool closest_hit(const BvhView &bvh, float3 origin, float3 dir, Hit &out,
     int node = 0;
     for (;;) {
         WideHit w;
-        wide_fetch(r, bvh.nodes + node, w);
+        wide_fetch(r, bvh.nodes, node, w);
         if (STATS) st->nodes += 1;
         int next = 0;
         float next_t = 0.f;

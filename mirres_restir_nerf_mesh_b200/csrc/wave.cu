@@ -211,7 +211,8 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
             const Rec32 *rec = ref_address(bvh, cur);
             const Rec32 e0 = load_rec(rec), e1 = load_rec(rec + 1);
             if (cur >= 0) {
-                const Rec32 e2 = load_rec(rec + 2), e3 = load_rec(rec + 3);
+                Rec32 e2, e3;
+                load_tail(rec, ref_missing(cur), e2, e3); // trailing sectors only when the reference says they are in use
                 WideHit w;
                 wide_slabs(r, e0, e1, e2, e3, w);
                 int next = 0;
@@ -312,6 +313,8 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
             const Rec32 *rec = ref_address(bvh, cur);
             const Rec32 e0 = load_rec(rec), e1 = load_rec(rec + 1);
             if (cur >= 0) {
+                // all four sectors, unconditionally: this walk is bound by the latency of one ray's dependent fetches, and
+                // making two of them conditional on the reference's entry count lengthened every step (+10 % measured)
                 const Rec32 e2 = load_rec(rec + 2), e3 = load_rec(rec + 3);
                 WideHit w;
                 wide_slabs(r, e0, e1, e2, e3, w);

@@ -30,8 +30,8 @@ from .slangpy_shim import get_kernels
 TOTAL_RIS_PASSES = 5 + 15  # frame-index stride per spp iteration (nerf/renderer_restir.py:242)
 
 import os as _os
-MAX_INITIAL_STREAMS = int(_os.environ.get("MIRRES_INITIAL_STREAMS", 4))   # concurrent initial-candidate stages (light tiles + initial RIS of different spp iterations)
-MAX_INDIRECT_CHAINS = int(_os.environ.get("MIRRES_INDIRECT_CHAINS", 2))  # concurrent indirect-path chains (one CUDA stream + path state + ray-queue workspace each)
+MAX_INITIAL_STREAMS = int(_os.environ.get("MIRRES_INITIAL_STREAMS", 3))   # concurrent initial-candidate stages (light tiles + initial RIS of different spp iterations)
+MAX_INDIRECT_CHAINS = int(_os.environ.get("MIRRES_INDIRECT_CHAINS", 4))  # concurrent indirect-path chains (one CUDA stream + path state + ray-queue workspace each)
 CRITICAL_ANY_BLOCKS = int(_os.environ.get("MIRRES_CRITICAL_ANY_BLOCKS", 0))  # persistent grid (blocks / SM) of the reuse chain's boolean-ray launches; 0 = library default
 USE_PRIORITIES = int(_os.environ.get("MIRRES_PRIORITIES", 1))  # stream priorities for the critical reuse chain
 _SIDE_STREAMS = {}
