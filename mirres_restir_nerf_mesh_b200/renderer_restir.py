@@ -777,6 +777,13 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             last = lo + 32 >= len(batch)
             for j, name in enumerate(("color_1", "diff_1", "spec_1")):
                 k.sum_images([b[3][j] for b in part], sums[name], divisor if last else 0.0, accumulate=True)
+        if batch and pos_map.is_cuda:
+            # the summed images were allocated on the chains' streams: those streams wait for this read before the blocks
+            # can be handed out again, so the images can be released now instead of living until the end of the loop
+            consumed = torch.cuda.Event()
+            consumed.record(stream)
+            for c in chains:
+                c["stream"].wait_event(consumed)
 
     def indirect_chain(i, first_pass, c):
         base = random_offset + TOTAL_RIS_PASSES * i
@@ -795,7 +802,6 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             else:
                 # allocated on the chain's stream, kept until the join; the kernel's prologue zero-fills all three
                 outs3 = tuple(torch.empty((n, 3), dtype=torch.float, device=dev) for _ in range(3))
-                keepalive.extend(outs3)
             indirect_one_hit_divided_no_grad(FinalShading_m, *bvh, base + ris_pass, bounce, framedim_x, framedim_y,
                                              env_map, width, height, pdf_, cdf_, mpdf_, mcdf_, src["occ"], src["pos"],
                                              src["nrm"], src["ray"], prd_, c["kd"], c["rs"],
@@ -851,14 +857,15 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         ev = lambda stream: (lambda e: (e.record(stream), e)[1])(torch.cuda.Event() if pos_map.is_cuda else _NullEvent())
         init_done, spatial_done, copy_done = {}, {}, {}
         passes, direct_outs = [], []
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (env_map_init, normal_map, diffuse_map,
+                                                                               roughness_specular))
 
         def flush_direct(divisor=0.0):
             # running sums of the shading outputs in iteration order (the reference's `total += color`, :443-459)
             k = get_kernels()
             for j, name in enumerate(("color", "diff", "spec")):
                 k.sum_images([o[j] for o in direct_outs], sums[name], divisor, accumulate=True)
-            keepalive.extend(direct_outs)
-            direct_outs.clear()
+            direct_outs.clear()  # allocated and read on the shading stream: stream order protects the blocks
         for i in range(spp):
             base = random_offset + TOTAL_RIS_PASSES * i
             first_indirect_pass = 4 if i == 0 else 5
@@ -913,8 +920,9 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                         env_height=height, framedim_x=framedim_x, framedim_y=framedim_y, occ_map=occ_map,
                         normal=normal_detached, ray_dir=ray_dir_map, diffuse_map=kd, linearRoughness_specular_map=rs,
                         color=outs_d[0], diff_light=outs_d[1], spec_light=outs_d[2]).launchRaw()
-                passes.append((tuple(_keep(t) for t in B), _keep(final_samples[0]), _keep(final_samples[1]), final_Li,
-                               _keep(eva_vis_map)))
+                if needs_grad:
+                    passes.append((tuple(_keep(t) for t in B), _keep(final_samples[0]), _keep(final_samples[1]), final_Li,
+                                   _keep(eva_vis_map)))
                 direct_outs.append(outs_d)
                 if len(direct_outs) >= 16:
                     flush_direct()
@@ -926,8 +934,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         div = float(frame) if normalize else 0.0
         with _on(st_s):
             flush_direct(div)
-            if torch.is_grad_enabled() and any(t.requires_grad for t in (env_map_init, normal_map, diffuse_map,
-                                                                         roughness_specular)):
+            if needs_grad:
                 # the node lives on the shading stream, like the per-pass Functions it stands for: its backward runs there
                 pack = dict(color=sums["color"], diff=sums["diff"], spec=sums["spec"], passes=passes,
                             dims=(framedim_x, framedim_y, width, height), occ=slangpy._c(occ_map),
