@@ -36,19 +36,19 @@ def test_final_shading_bwd_multi_equals_the_single_pass_kernels():
     C.final_shading_bwd_multi_equals_the_single_pass_kernels(H.kernels(), "cpu")
 
 
-def _render(sc, w, prepared_lighting=False, **kw):
+def _render(sc, w, prepared_lighting=False, spp=3, **kw):
     mods = R.load_m_for_restir(sc["W"], sc["H"], device="cpu")
     g = {k: H.t(v) for k, v in sc["gbuffer"].items()}
     env = H.t(sc["env"]).requires_grad_(True)
     if prepared_lighting:
-        kw["lighting"] = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env, 3, 99)
+        kw["lighting"] = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env, spp, 99)
     normal = g["normal_map"].clone().requires_grad_(True)
     tex = torch.cat((g["diffuse_map"], torch.zeros_like(g["diffuse_map"])), dim=1).requires_grad_(True)
     kd = tex[:, 0:3]  # strided view, as render_stage1 passes it
     rs = g["roughness_specular"].clone().requires_grad_(True)
     outs = R.run_restir_di_with_pt(False, 1, 1, 1, synth.ProceduralMaterial(sc["metallic"]), None, w, *mods, env,
                                    g["occ_map"].clone(), normal, g["depth_map"], kd, rs, g["ray_dir_map"], g["pos_map"], None,
-                                   None, None, None, sc["W"], sc["H"], 3, 2, 2, 2.0, 0.1, 0.001, random_offset=99, **kw)
+                                   None, None, None, sc["W"], sc["H"], spp, 2, 2, 2.0, 0.1, 0.001, random_offset=99, **kw)
     wgt = torch.linspace(0.5, 1.5, outs[0].numel()).reshape(outs[0].shape)
     (outs[0] * wgt).sum().backward()
     return [o.detach() for o in outs], [env.grad, normal.grad, tex.grad, rs.grad]
@@ -85,3 +85,18 @@ def test_prepared_lighting_changes_nothing():
     b, gb = _render(sc, w, prepared_lighting=True, overlap=True)
     for x, y in zip(a + ga, b + gb):
         assert torch.equal(x, y)
+
+
+def test_long_loop_flushes_and_chunked_backward():
+    """spp = 19: the concurrent schedule flushes its running sums every 16 images and the one-node backward runs in two
+    chunks of passes (16 + 3); results must still equal the sequential schedule."""
+    sc = P.scene("T0", 0.0)
+    w = H.OracleBvhWorker(H.t(sc["vert"]), H.t(sc["tri"]))
+    w.update_mesh(H.t(sc["vert"]), H.t(sc["tri"]))
+    seq, gseq = _render(sc, w, spp=19, overlap=False, batched_denoise=False, fused_prepare=False, fused_composite=False)
+    par, gpar = _render(sc, w, spp=19, overlap=True)
+    for a, b in zip(seq, par):
+        assert torch.equal(a, b)
+    for a, b in zip(gseq, gpar):
+        assert a.abs().sum() > 0
+        assert (a - b).abs().max() <= 1e-5 * a.abs().max()
