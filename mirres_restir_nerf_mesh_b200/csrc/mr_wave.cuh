@@ -50,6 +50,7 @@ struct Workspace {
     float4 *chit;      // [N * 3] per SLOT: (pos.xyz, -1 no ray / 0 miss / 1 hit) (normal.xyz, t) (prim bits, u, v, 0)
     float *px;         // [N * MR_PX_SCRATCH_FLOATS] per-active-pixel state carried from gen to resolve
     float *stop_in;    // [N] stop flag of every pixel as it was on entry to a bounce kernel
+    float4 *lcache;    // [N * 2] per PIXEL: (emitted radiance, 0) (direction, 0) of the pixel's reservoir sample (spatial pass)
     int capacity;      // N
 };
 
@@ -70,6 +71,7 @@ static inline size_t workspace_carve(Workspace *w, int N, char *base)
     p = take((size_t)N * 3 * sizeof(float4)); if (w) w->chit = (float4 *)p;
     p = take((size_t)N * MR_PX_SCRATCH_FLOATS * sizeof(float)); if (w) w->px = (float *)p;
     p = take((size_t)N * sizeof(float)); if (w) w->stop_in = (float *)p;
+    p = take((size_t)N * 2 * sizeof(float4)); if (w) w->lcache = (float4 *)p;
     if (w) w->capacity = N;
     return off;
 }

@@ -284,7 +284,12 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
     const float3 N = make_float3(nd.x, nd.y, nd.z);
     const uint32_t startIndex = to_uint(rnd(sg) * (float)p.offset_count);
     const float3 cur_ld = load3(p.prev.ld, i);
-    const float3 cL = oct_decode(cur_ld.y, cur_ld.z);
+    // radiance and direction of this pixel's sample, evaluated ONCE per pixel here: the resolve pass needs them for the
+    // pixel itself and for each of its neighbours (six env lookups with their trigonometry per pixel otherwise)
+    float3 cLe, cL;
+    light_of(p.env, cur_ld.y, cur_ld.z, cLe, cL);
+    p.ws.lcache[2 * i] = make_float4(cLe.x, cLe.y, cLe.z, 0.f);
+    p.ws.lcache[2 * i + 1] = make_float4(cL.x, cL.y, cL.z, 0.f);
     const float3 cur_pos = load3(p.pos_map, i);
     const size_t base = (size_t)a * MR_MAX_RAYS_PER_PIXEL;
     for (uint32_t k = 0; k < p.neighbor_count; ++k) {
@@ -323,8 +328,8 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
     Ris st = ris_empty();
     const uint32_t startIndex = to_uint(rnd(sg) * (float)p.offset_count);
     const Reservoir cur = res_load(p.prev, i);
-    float3 cLe, cL;
-    light_of(p.env, cur.ld.y, cur.ld.z, cLe, cL);
+    const float4 c0 = p.ws.lcache[2 * i], c1 = p.ws.lcache[2 * i + 1]; // light_of(cur.ld), written by the gen pass
+    const float3 cLe = make_float3(c0.x, c0.y, c0.z), cL = make_float3(c1.x, c1.y, c1.z);
     const float currentTargetPdf = target_pdf(cur_s, cLe, cL);
     st.canonical = 1.f;
     uint32_t validNeighbors = 1;
@@ -338,8 +343,8 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
         const Reservoir nr = res_load(p.prev, n);
         const RisSurface nb_s = ris_surface(nN, load3(p.g.ray_dir, n), load3(p.g.brdf, n));
         ++validNeighbors;
-        float3 nLe, nL;
-        light_of(p.env, nr.ld.y, nr.ld.z, nLe, nL);
+        const float4 n0 = p.ws.lcache[2 * n], n1 = p.ws.lcache[2 * n + 1]; // light_of(nr.ld): n is a foreground pixel
+        const float3 nLe = make_float3(n0.x, n0.y, n0.z), nL = make_float3(n1.x, n1.y, n1.z);
         const bool canonical_hit = p.ws.hit[base + 2 * k] == MR_HIT_HIT;
         const bool candidate_hit = p.ws.hit[base + 2 * k + 1] == MR_HIT_HIT;
         float candidateVisibility = candidate_hit ? 0.f : 1.0f;
