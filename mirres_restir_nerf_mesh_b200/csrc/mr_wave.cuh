@@ -50,7 +50,7 @@ struct Workspace {
     float4 *chit;      // [N * 3] per SLOT: (pos.xyz, -1 no ray / 0 miss / 1 hit) (normal.xyz, t) (prim bits, u, v, 0)
     float *px;         // [N * MR_PX_SCRATCH_FLOATS] per-active-pixel state carried from gen to resolve
     float *stop_in;    // [N] stop flag of every pixel as it was on entry to a bounce kernel
-    float4 *lcache;    // [N * 2] per PIXEL: (emitted radiance, 0) (direction, 0) of the pixel's reservoir sample (spatial pass)
+    float4 *lcache;    // [N * 2] per PIXEL: (emitted radiance, own target density) (direction, 0) of the pixel's reservoir sample (spatial pass)
     int capacity;      // N
 };
 

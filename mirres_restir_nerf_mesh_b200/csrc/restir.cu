@@ -288,7 +288,10 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
     // pixel itself and for each of its neighbours (six env lookups with their trigonometry per pixel otherwise)
     float3 cLe, cL;
     light_of(p.env, cur_ld.y, cur_ld.z, cLe, cL);
-    p.ws.lcache[2 * i] = make_float4(cLe.x, cLe.y, cLe.z, 0.f);
+    // ... and so is the target density of that sample at its own surface, which every pixel that picks this one as a
+    // neighbour needs as well (candAtOwn of the pairwise MIS)
+    const float own_target = target_pdf(ris_surface(N, load3(p.g.ray_dir, i), load3(p.g.brdf, i)), cLe, cL);
+    p.ws.lcache[2 * i] = make_float4(cLe.x, cLe.y, cLe.z, own_target);
     p.ws.lcache[2 * i + 1] = make_float4(cL.x, cL.y, cL.z, 0.f);
     const float3 cur_pos = load3(p.pos_map, i);
     const size_t base = (size_t)a * MR_MAX_RAYS_PER_PIXEL;
@@ -330,7 +333,7 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
     const Reservoir cur = res_load(p.prev, i);
     const float4 c0 = p.ws.lcache[2 * i], c1 = p.ws.lcache[2 * i + 1]; // light_of(cur.ld), written by the gen pass
     const float3 cLe = make_float3(c0.x, c0.y, c0.z), cL = make_float3(c1.x, c1.y, c1.z);
-    const float currentTargetPdf = target_pdf(cur_s, cLe, cL);
+    const float currentTargetPdf = c0.w; // target_pdf(cur_s, cLe, cL), from the gen pass
     st.canonical = 1.f;
     uint32_t validNeighbors = 1;
     const size_t base = (size_t)a * MR_MAX_RAYS_PER_PIXEL;
@@ -349,7 +352,7 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
         const bool candidate_hit = p.ws.hit[base + 2 * k + 1] == MR_HIT_HIT;
         float candidateVisibility = candidate_hit ? 0.f : 1.0f;
         float canonicalVisibility = canonical_hit ? 0.f : 1.0f;
-        float candAtOwn = target_pdf(nb_s, nLe, nL);
+        float candAtOwn = n0.w; // target_pdf(nb_s, nLe, nL): the neighbour's own target density, from the gen pass
         float candAtCur = target_pdf(cur_s, nLe, nL);
         float canonAtNb = target_pdf(nb_s, cLe, cL);
         candAtCur *= canonicalVisibility;
