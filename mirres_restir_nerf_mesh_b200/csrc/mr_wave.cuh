@@ -105,6 +105,13 @@ MR_DEV void queue_ray(const Workspace &w, size_t slot, float3 o, float3 d)
     w.ray_d[q] = make_float4(d.x, d.y, d.z, 0.0f);
 }
 MR_DEV void queue_empty(const Workspace &w, size_t slot) { w.hit[slot] = MR_HIT_NONE; }
+// entry q of the boolean-ray queue, for callers that reserve a block of tickets themselves
+MR_DEV void queue_ray_at(const Workspace &w, int q, size_t slot, float3 o, float3 d)
+{
+    w.hit[slot] = MR_HIT_MISS;
+    w.ray_o[q] = make_float4(o.x, o.y, o.z, bits_float((int)slot));
+    w.ray_d[q] = make_float4(d.x, d.y, d.z, 0.0f);
+}
 
 MR_DEV void queue_closest_ray(const Workspace &w, size_t slot, float3 o, float3 d)
 {

@@ -273,9 +273,13 @@ MR_DEV bool spatial_neighbor(const SpatialParams &p, uint32_t px, uint32_t py, u
 
 // gen: picks the neighbours, applies the reuse heuristics and queues the two visibility rays of every accepted one
 // (SpatialResampling.slang:229-277): slot 2k = own surface -> neighbour's light, slot 2k+1 = neighbour surface -> own light
+#define MR_MAX_NEIGHBORS (MR_MAX_RAYS_PER_PIXEL / 2)
 MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
 {
     if (a >= p.ws.counters[0]) return;
+#if defined(__CUDA_ARCH__)
+    const unsigned int act = __activemask(); // the lanes of this warp that have a pixel
+#endif
     const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
@@ -284,6 +288,36 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
     const float3 N = make_float3(nd.x, nd.y, nd.z);
     const uint32_t startIndex = to_uint(rnd(sg) * (float)p.offset_count);
     const float3 cur_ld = load3(p.prev.ld, i);
+    // The kernel was bound by latency (ncu: issue active 20 %, 26 warps stalled on the long scoreboard per issue): per
+    // neighbour a chain of gathers and then two queue tickets, i.e. ten atomic round trips to L2 per warp one after the
+    // other.  Here every field of every in-frame neighbour is requested at once, the tests run on registers in the
+    // reference's order, and the warp draws ALL its tickets with one atomic; inside the reserved block the rays keep the
+    // order the ticket-per-ray version produced (neighbour-major, lanes ascending), so the tracer sees the same queue.
+    size_t nb[MR_MAX_NEIGHBORS];
+    bool ok[MR_MAX_NEIGHBORS];
+    float4 nnd[MR_MAX_NEIGHBORS];
+    int nM[MR_MAX_NEIGHBORS];
+    float nocc[MR_MAX_NEIGHBORS];
+    float3 nld[MR_MAX_NEIGHBORS], npos[MR_MAX_NEIGHBORS];
+#pragma unroll
+    for (uint32_t k = 0; k < MR_MAX_NEIGHBORS; ++k) {
+        nb[k] = 0;
+        ok[k] = k < p.neighbor_count && spatial_neighbor(p, px, py, startIndex, k, nb[k]);
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < MR_MAX_NEIGHBORS; ++k) {
+        nnd[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        nM[k] = 0;
+        nocc[k] = 0.f;
+        nld[k] = npos[k] = f3(0.f);
+        if (ok[k]) {
+            nnd[k] = load_nd(p.g.normal_depth, nb[k]);
+            nM[k] = MR_LDG(p.prev.M + nb[k]);
+            nocc[k] = MR_LDG(p.g.occ + nb[k]);
+            nld[k] = load3(p.prev.ld, nb[k]);
+            npos[k] = load3(p.pos_map, nb[k]);
+        }
+    }
     // radiance and direction of this pixel's sample, evaluated ONCE per pixel here: the resolve pass needs them for the
     // pixel itself and for each of its neighbours (six env lookups with their trigonometry per pixel otherwise)
     float3 cLe, cL;
@@ -295,26 +329,54 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
     p.ws.lcache[2 * i + 1] = make_float4(cL.x, cL.y, cL.z, 0.f);
     const float3 cur_pos = load3(p.pos_map, i);
     const size_t base = (size_t)a * MR_MAX_RAYS_PER_PIXEL;
-    for (uint32_t k = 0; k < p.neighbor_count; ++k) {
-        size_t n;
-        bool ok = spatial_neighbor(p, px, py, startIndex, k, n);
-        float3 nld = f3(0.f);
-        if (ok) {
-            float4 nnd = load_nd(p.g.normal_depth, n);
-            ok = neighbor_ok(N, nd.w, make_float3(nnd.x, nnd.y, nnd.z), nnd.w);
+#pragma unroll
+    for (uint32_t k = 0; k < MR_MAX_NEIGHBORS; ++k) {
+        if (ok[k]) ok[k] = neighbor_ok(N, nd.w, make_float3(nnd[k].x, nnd[k].y, nnd[k].z), nnd[k].w);
+        if (ok[k]) ok[k] = nM[k] != 0;
+        if (ok[k]) ok[k] = !(nocc[k] < 0.1f);
+    }
+#if defined(__CUDA_ARCH__)
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    unsigned int okm[MR_MAX_NEIGHBORS];
+    int total = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < MR_MAX_NEIGHBORS; ++k) {
+        okm[k] = __ballot_sync(act, ok[k]);
+        total += 2 * __popc(okm[k]);
+    }
+    int q0 = 0;
+    const int leader = __ffs(act) - 1;
+    if ((int)lane == leader && total > 0) q0 = atomicAdd(p.ws.counters + MR_CTR_ANY_SIZE, total);
+    q0 = __shfl_sync(act, q0, leader);
+#pragma unroll
+    for (uint32_t k = 0; k < MR_MAX_NEIGHBORS; ++k) {
+        if (k < p.neighbor_count) {
+            const int cnt = __popc(okm[k]);
+            if (ok[k]) {
+                const int rank = __popc(okm[k] & lt_mask);
+                const float3 nL = oct_decode(nld[k].y, nld[k].z);
+                queue_ray_at(p.ws, q0 + rank, base + 2 * k, cur_pos + VIS_NEAR * nL, nL);
+                queue_ray_at(p.ws, q0 + cnt + rank, base + 2 * k + 1, npos[k] + VIS_NEAR * cL, cL);
+            } else {
+                queue_empty(p.ws, base + 2 * k);
+                queue_empty(p.ws, base + 2 * k + 1);
+            }
+            q0 += 2 * cnt;
         }
-        if (ok) ok = MR_LDG(p.prev.M + n) != 0;
-        if (ok) ok = !(MR_LDG(p.g.occ + n) < 0.1f);
-        if (ok) {
-            nld = load3(p.prev.ld, n);
-            const float3 nL = oct_decode(nld.y, nld.z);
+    }
+#else
+    for (uint32_t k = 0; k < p.neighbor_count; ++k) {
+        if (ok[k]) {
+            const float3 nL = oct_decode(nld[k].y, nld[k].z);
             queue_ray(p.ws, base + 2 * k, cur_pos + VIS_NEAR * nL, nL);
-            queue_ray(p.ws, base + 2 * k + 1, load3(p.pos_map, n) + VIS_NEAR * cL, cL);
+            queue_ray(p.ws, base + 2 * k + 1, npos[k] + VIS_NEAR * cL, cL);
         } else {
             queue_empty(p.ws, base + 2 * k);
             queue_empty(p.ws, base + 2 * k + 1);
         }
     }
+#endif
 }
 
 // resolve: the pairwise-MIS streaming pass with the traced visibilities (res.slang:173-232)
