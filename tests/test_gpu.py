@@ -483,3 +483,39 @@ def test_fused_screen_kernels_gpu(kernels):
     C.sum_images_is_the_sequential_torch_sum(kernels, DEV)
     C.composite_forward_exact_backward_matches_autograd(kernels, DEV)
     C.final_shading_bwd_multi_equals_the_single_pass_kernels(kernels, DEV)
+
+
+def test_long_loop_and_prepared_lighting_gpu(kernels):
+    """spp = 19 on the GPU: the concurrent schedule flushes its running sums every 16 images, releases the per-iteration
+    images early and runs the one-node backward in two chunks; with and without prepare_lighting() the images equal the
+    sequential schedule's bit for bit, the gradients to the stated tolerance."""
+    sc = P.scene("T0", 0.3)
+    w = R.restirbvhWorker(tt(sc["vert"]), tt(sc["tri"]))
+    w.update_mesh(tt(sc["vert"]), tt(sc["tri"]))
+    W, Hh, spp = sc["W"], sc["H"], 19
+
+    def render(prepared, **kw):
+        mods = R.load_m_for_restir(W, Hh)
+        g = {k: tt(v) for k, v in sc["gbuffer"].items()}
+        env = tt(sc["env"]).requires_grad_(True)
+        normal = g["normal_map"].clone().requires_grad_(True)
+        kd = g["diffuse_map"].clone().requires_grad_(True)
+        rs = g["roughness_specular"].clone().requires_grad_(True)
+        if prepared:
+            kw["lighting"] = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env, spp, 321)
+        outs = R.run_restir_di_with_pt(False, 1, 1, 1, synth.ProceduralMaterial(sc["metallic"]), None, w, *mods, env,
+                                       g["occ_map"].clone(), normal, g["depth_map"], kd, rs, g["ray_dir_map"], g["pos_map"],
+                                       None, None, None, None, W, Hh, spp, 2, 2, 2.0, 0.1, 0.001, random_offset=321, **kw)
+        wgt = torch.linspace(0.5, 1.5, outs[0].numel(), device=DEV).reshape(outs[0].shape)
+        (outs[0] * wgt).sum().backward()
+        torch.cuda.synchronize()
+        return [o.detach() for o in outs], [env.grad, normal.grad, kd.grad, rs.grad]
+
+    seq, gseq = render(False, overlap=False, batched_denoise=False, fused_prepare=False, fused_composite=False)
+    for prepared in (False, True):
+        par, gpar = render(prepared)
+        for a, b in zip(seq, par):
+            assert torch.equal(a, b)
+        for a, b in zip(gseq, gpar):
+            assert a.abs().sum() > 0
+            assert (a - b).abs().max() <= GRAD_RTOL * a.abs().max()
