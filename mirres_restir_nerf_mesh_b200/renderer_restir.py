@@ -674,9 +674,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         return torch.zeros(shape, dtype=torch.float, device=dev)
 
     if overlap is None:
-        overlap = hooks is None and pos_map.is_cuda and shard is None
-    if shard is not None and overlap:
-        raise ValueError("row-band sharding uses the sequential schedule (overlap=False)")
+        overlap = hooks is None and pos_map.is_cuda
     sums = {k: zeros(n, 3) for k in ("color", "diff", "spec", "color_1", "diff_1", "spec_1")}
     total_indirect_light = zeros(n, 3)
     prd = ping = pong = color_1 = color_diff_1 = color_spec_1 = new_diffuse_map = new_roughness_specular = None
@@ -897,6 +895,10 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                     worker.SpatialResampling_(SpatialResampling_m, pos_map, S[i % 2], X[r], neighborOffsets, env_map,
                                               width, height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth,
                                               brdf_map, ray_dir_map)
+                if shard is not None:
+                    # row bands: the halo rows this rank reads in the next iteration (through its temporal pass) take their
+                    # owners' values; the collective is ordered on the reuse chain's stream
+                    shard.exchange(S[i % 2])
             ris_pass += 1
             assert ris_pass == first_indirect_pass
             spatial_done[i] = ev(main_stream)
@@ -1036,7 +1038,7 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
                 normal_map, depth_map, diffuse_map, roughness_specular, ray_dir_map, pos_map, prev_occ_map,
                 prev_normal_depth, prev_brdf_map, prev_ray_dir, framedim_x, framedim_y, spp, denoise_iter, stepWidth,
                 c_phi_scale, n_phi_scale, p_phi_scale, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks,
-                bilateral=bilateral, overlap=False, batched_denoise=batched_denoise, shard=None, _shard=shard,
+                bilateral=bilateral, overlap=overlap, batched_denoise=batched_denoise, shard=None, _shard=shard,
                 fused_prepare=fused_prepare, fused_composite=fused_composite)
     n, dev = framedim_x * framedim_y, pos_map.device
     prepared = None

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SPP, DENOISE_ITER, STEP, PHI = 3, 2, 2, (2.0, 0.1, 0.001)
 
 
-def _render(sc, shard):
+def _render(sc, shard, overlap=None):
     import hostcheck as H
     from mirres_restir_nerf_mesh_b200 import renderer_restir as R, synth
     W, Hh = sc["W"], sc["H"]
@@ -27,10 +27,10 @@ def _render(sc, shard):
         return R.run_restir_di_with_pt(False, 1, 1, 1, synth.ProceduralMaterial(sc["metallic"]), None, w, *mods,
                                        H.t(sc["env"]), g["occ_map"], g["normal_map"], g["depth_map"], g["diffuse_map"],
                                        g["roughness_specular"], g["ray_dir_map"], g["pos_map"], None, None, None, None,
-                                       W, Hh, SPP, DENOISE_ITER, STEP, *PHI, random_offset=777, shard=shard)
+                                       W, Hh, SPP, DENOISE_ITER, STEP, *PHI, random_offset=777, shard=shard, overlap=overlap)
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, overlap=None):
     for p in (os.path.dirname(HERE), HERE):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -43,7 +43,7 @@ def _worker(rank, world, port, out_dir):
     H.activate()
     sc = P.scene("T2", 0.4)
     shard = D.RowBandShard(sc["W"], sc["H"])
-    outs = _render(sc, shard)
+    outs = _render(sc, shard, overlap)
     full = [shard.gather_image(o) for o in outs]
     flat = torch.full((5,), float(rank + 1))
     D.allreduce_gradients(flat)
@@ -53,13 +53,14 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_row_band_sharding_is_bit_identical(tmp_path, world):
+@pytest.mark.parametrize("world,overlap", [(2, None), (4, None), (2, True)])
+def test_row_band_sharding_is_bit_identical(tmp_path, world, overlap):
+    """overlap=True drives the concurrent schedule's host logic (exchange on the reuse chain) over CPU tensors."""
     import hostcheck as H
     import parity as P
     from mirres_restir_nerf_mesh_b200 import slangpy_shim
-    port = 29500 + (os.getpid() + 7 * world) % 2000
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    port = 29500 + (os.getpid() + 7 * world + (3 if overlap else 0)) % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path), overlap), nprocs=world, join=True)
     got = np.load(os.path.join(str(tmp_path), "sharded.npz"))
     H.activate()
     try:

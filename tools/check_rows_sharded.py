@@ -2,7 +2,7 @@
 cut into row bands over the ranks (dist.RowBandShard: 31-row halo, reservoir exchange after every spatial pass, NCCL).
 Rank 0 also renders the whole frame alone and compares: the assembled image must be bit-identical.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/check_rows_sharded.py [spp]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/check_rows_sharded.py [spp] [C3|C5]
 """
 import os
 import sys
@@ -15,12 +15,12 @@ sys.path.insert(0, ROOT)
 from mirres_restir_nerf_mesh_b200 import synth, renderer_restir as R, slangpy_shim, dist as D  # noqa: E402
 
 
-def main(spp):
+def main(spp, cfg_name="C3"):
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    cfg = synth.CONFIGS["C3"]
+    cfg = synth.CONFIGS[cfg_name]
     W, H, mb = cfg["W"], cfg["H"], cfg["max_bounce"]
     n = W * H
     v, f = synth.make_mesh(cfg)
@@ -41,7 +41,7 @@ def main(spp):
         kd, rs = mat.gbuffer_materials(pos, occ)
         return R.run_restir_di_with_pt(False, 1, 1, 1, mat, None, worker, *mods, env, occ, nrm, depth, kd, rs, rd, pos, None,
                                        None, None, None, W, H, spp, 2, 2, 2.0, 0.1, 0.001, random_offset=5, max_bounce=mb,
-                                       shard=shard, overlap=None if shard is None else False)
+                                       shard=shard)
 
     with torch.no_grad():
         shard = D.RowBandShard(W, H)
@@ -63,8 +63,8 @@ def main(spp):
             e1.record()
             torch.cuda.synchronize()
             same = bool(torch.equal(full, want))
-            print("row bands over %d GPUs: %dx%d spp %d forward: %.1f ms (max over ranks, sequential schedule + exchange), "
-                  "%.3e samples/s; one GPU alone (concurrent schedule): %.1f ms; assembled image bit-identical: %s"
+            print(cfg_name + " row bands over %d GPUs: %dx%d spp %d forward: %.1f ms (max over ranks, incl. reservoir exchange), "
+                  "%.3e samples/s; one GPU alone: %.1f ms; assembled image bit-identical: %s"
                   % (world, W, H, spp, float(ms), n * spp / (float(ms) * 1e-3), e0.elapsed_time(e1), same))
             assert same
     dist.barrier()
@@ -72,4 +72,4 @@ def main(spp):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 16)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 16, sys.argv[2] if len(sys.argv) > 2 else "C3")
