@@ -225,6 +225,7 @@ def run_gpu(args):
         # the LBVH rebuild runs beside everything that does not need it: camera rays, the environment distribution and
         # the light tiles of the spp loop
         cur = torch.cuda.current_stream()
+        flat_grad.zero_()  # early: the fill has left the serial tail of the step by the time the scatters need it
         bvh_stream.wait_stream(cur)
         with torch.cuda.stream(bvh_stream):
             worker.update_mesh(vert, tri)
@@ -247,7 +248,6 @@ def run_gpu(args):
         loss.backward()
         # gradients leave the path as grad_env [He,We,3] and dense per-pixel grads; the latter are scattered to vertices /
         # vertex texture here (the reference: nvdiffrast / tcnn backward), everything lands in ONE flat buffer
-        flat_grad.zero_()
         flat_grad[:ne].copy_(env_l.grad.reshape(-1))
         pk.interpolate_bwd(normal.grad, prim, bary, tri, flat_grad[ne:ne + 3 * V].view(V, 3))
         pk.interpolate_bwd(torch.cat((kd.grad, rs.grad), dim=1), prim, bary, tri, flat_grad[ne + 3 * V:].view(V, 5))

@@ -294,7 +294,9 @@ int mirres_interpolate_bwd(const float *grad, int n, int C, const int *prim, con
  *        fs_dir / fs_dist / fs_Li / grad_Li are HOST arrays of n_passes device pointers.
  *        grad_normal / grad_diffuse / grad_rough_metal receive the sum over passes (last pass first, the autograd
  *        engine's order; accumulate != 0 continues an earlier call).  grad_Li[k] is written per pass, or -- with
- *        sum_grad_Li -- grad_Li[0] receives the sum (for passes that evaluated one shared reservoir buffer).
+ *        sum_grad_Li -- grad_Li[0] receives the sum (for passes that evaluated one shared reservoir buffer).  When in
+ *        addition every pass names the SAME fs_dir / fs_dist buffers, the passes are evaluated once on the summed fs_Li
+ *        (all gradients but grad_Li are linear in Li); the result differs from per-pass evaluation by rounding only.
  */
 int mirres_material_procedural(int n, const float *pos, const float *occ, int mode, float metallic, const float *scale_xyz,
                                float *kd, float *rough_metal, void *stream);

@@ -213,6 +213,7 @@ struct ShadeMultiParams {
     const float *fs_Li[MR_SHADE_MULTI_MAX];
     float *g_Li[MR_SHADE_MULTI_MAX];
     int K, sum_gli, accumulate;
+    int same_sample; // every pass has the same (fs_dir, fs_dist): the gradients are linear in Li, one evaluation on the summed Li
     float g_div; // != 0: upstream gradients are divided by it first (the loop's `total / mFrameIndex`)
     const float *__restrict__ occ;
     const float *__restrict__ normal;
@@ -249,6 +250,27 @@ MR_DEV void final_shading_bwd_multi_px(const ShadeMultiParams &p, int idx)
             gD = make_float3(div_by_scalar(gD.x, p.g_div), div_by_scalar(gD.y, p.g_div), div_by_scalar(gD.z, p.g_div));
             gS = make_float3(div_by_scalar(gS.x, p.g_div), div_by_scalar(gS.y, p.g_div), div_by_scalar(gS.z, p.g_div));
         }
+    }
+    if (p.same_sample && p.sum_gli) {
+        // The passes saved aliases of ONE final-sample buffer (the reference's behaviour): same direction, same distance,
+        // different radiance.  Every gradient but grad_Li is linear in Li and grad_Li does not depend on it, so the K passes
+        // collapse into one evaluation on the summed radiance (rounding differs from K separate evaluations by ~1e-7).
+        if (lit && MR_LDG(p.fs_dist[0] + i) > 0.f) {
+            float3 Li = f3(0.f);
+            for (int k = p.K - 1; k >= 0; --k) Li += load3(p.fs_Li[k], i);
+            const ShadeGrads g = final_shading_grads(N, rd, kd, rough, metallic, load3(p.fs_dir[0], i), Li, gC, gD, gS);
+            aN += g.gN;
+            aKd += g.gKd;
+            aR += g.gR;
+            aM += g.gM;
+            aLi += g.gLi * (float)p.K;
+        }
+        store3(p.g_normal, i, aN);
+        store3(p.g_kd, i, aKd);
+        p.g_rm[2 * i] = aR;
+        p.g_rm[2 * i + 1] = aM;
+        store3(p.g_Li[0], i, aLi);
+        return;
     }
     for (int k = p.K - 1; k >= 0; --k) {
         float3 gLi = f3(0.f);
@@ -568,6 +590,9 @@ int mirres_final_shading_bwd_multi(int n_passes, const float *const *fs_dir, con
     }
     if (!p.g_Li[0]) return MIRRES_ERR_NULL;
     p.K = n_passes; p.sum_gli = sum_grad_Li ? 1 : 0; p.accumulate = accumulate ? 1 : 0; p.g_div = grad_divisor;
+    p.same_sample = 1;
+    for (int k = 1; k < n_passes; ++k)
+        if (fs_dir[k] != fs_dir[0] || fs_dist[k] != fs_dist[0]) p.same_sample = 0;
     p.occ = occ; p.normal = normal; p.ray_dir = ray_dir; p.kd = diffuse_map; p.rm = rough_metal;
     p.g_color = grad_color; p.g_diff = grad_diff_light; p.g_spec = grad_spec_light;
     p.g_normal = grad_normal; p.g_kd = grad_diffuse; p.g_rm = grad_rough_metal;

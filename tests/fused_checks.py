@@ -143,3 +143,19 @@ def final_shading_bwd_multi_equals_the_single_pass_kernels(k, dev):
     for c in range(3):
         assert torch.equal(out2[c], want[c])
     assert torch.equal(gsum[0], want[3])
+    # passes that share direction and distance (the reference's saved aliases): one evaluation on the summed radiance
+    singles1 = []
+    for j in range(K):
+        o = (e(3), e(3), e(2), e(3))
+        k.final_shading_bwd(dirs[0], dists[0], Lis[j], fx, fy, occ, nrm, ray, kd, rs, gC, gD, gS, *o)
+        singles1.append(o)
+    want1 = [singles1[K - 1][c].clone() for c in range(4)]
+    for j in range(K - 2, -1, -1):
+        for c in range(4):
+            want1[c] += singles1[j][c]
+    out3, gsum3 = (e(3), e(3), e(2)), [e(3)]
+    k.final_shading_bwd_multi([dirs[0]] * K, [dists[0]] * K, Lis, fx, fy, occ, nrm, ray, kd, rs, gC, gD, gS, *out3, gsum3,
+                              sum_grad_Li=True)
+    for got, want_ in zip(list(out3) + gsum3, want1):
+        assert want_.abs().sum() > 0
+        assert (got - want_).abs().max() <= 2e-6 * want_.abs().max()
