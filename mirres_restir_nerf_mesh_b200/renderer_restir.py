@@ -675,8 +675,18 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
 
     if overlap is None:
         overlap = hooks is None and pos_map.is_cuda
-    sums = {k: zeros(n, 3) for k in ("color", "diff", "spec", "color_1", "diff_1", "spec_1")}
-    total_indirect_light = zeros(n, 3)
+    # the six running sums and total_indirect_light (:291-297) as slices of ONE zero-filled block: one fill on the serial
+    # front of the step instead of seven
+    # (concurrent schedule only: there the sums are written by raw launches; the sequential schedule accumulates through
+    # autograd, in place, which wants tensors of their own)
+    names = ("color", "diff", "spec", "color_1", "diff_1", "spec_1")
+    if overlap:
+        block = zeros(7, n, 3)
+        sums = {k: block[j] for j, k in enumerate(names)}
+        total_indirect_light = block[6]
+    else:
+        sums = {k: zeros(n, 3) for k in names}
+        total_indirect_light = zeros(n, 3)
     prd = ping = pong = color_1 = color_diff_1 = color_spec_1 = new_diffuse_map = new_roughness_specular = None
     if not overlap:  # path state of the sequential schedule (the concurrent chains own theirs)
         color_1, color_diff_1, color_spec_1 = zeros(n, 3), zeros(n, 3), zeros(n, 3)
@@ -696,15 +706,14 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                               rs[:, 0:1]), dim=-1)
         brdf_map[:, 2].clamp_(min=0.01, max=1)
         brdf_map[:, 2] = brdf_map[:, 2] * brdf_map[:, 2]
-    eva_vis_map = torch.ones((n, 1), dtype=torch.float, device=dev)
+    eva_vis_map = torch.empty((n, 1), dtype=torch.float, device=dev)  # get_vis sets every pixel (to 1 first, :103)
 
     # the reference ignores the reservoirs/prev_* it is handed for these and starts from zeros (:291-302)
     if not overlap:
         prev_reservoirs = _reservoir_set(n, dev)
-    prev_occ_map = zeros(*occ_map.shape)
-    prev_normal_depth = zeros(n, 4)
-    prev_brdf_map = zeros(*brdf_map.shape)
-    prev_ray_dir = zeros(*ray_dir_map.shape)
+    # the zero-filled prev_* maps of the reference (:299-302) are never read: temporal reuse starts at the second
+    # iteration, by which time they have been replaced by the current maps (:455-458)
+    prev_occ_map = prev_normal_depth = prev_brdf_map = prev_ray_dir = None
 
     height, width = env_map_init.shape[0], env_map_init.shape[1]
     if lighting is not None and not (lighting["random_offset"] == random_offset and lighting["spp"] == spp and
