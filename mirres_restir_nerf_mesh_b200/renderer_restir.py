@@ -749,8 +749,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             c.update(prd=e(n, 5),
                      ping=dict(pos=e(n, 3), ray=e(n, 3), occ=e(n, 1), nrm=e(n, 3)),
                      pong=dict(pos=e(n, 3), ray=e(n, 3), occ=e(n, 1), nrm=e(n, 3)),
-                     kd=torch.zeros((n, 3), dtype=torch.float, device=dev),
-                     rs=torch.zeros((n, 2), dtype=torch.float, device=dev))
+                     kd=chain_kd[len(chains)], rs=chain_rs[len(chains)])
         return c
 
     caller_stream = None
@@ -759,7 +758,11 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         # the reuse chain (temporal -> spatial of consecutive iterations) is the critical path of the loop: it gets a stream
         # of its own with the highest priority, so its blocks are placed before the pending blocks of everything else
         main_stream = _side_stream(dev, "reuse", -3) if (pos_map.is_cuda and USE_PRIORITIES) else caller_stream
-        for c in range(min(spp, MAX_INDIRECT_CHAINS)):
+        n_chains = min(spp, MAX_INDIRECT_CHAINS)
+        # material maps of all chains: two fills on the serial front instead of two per chain
+        chain_kd = torch.zeros((n_chains, n, 3), dtype=torch.float, device=dev)
+        chain_rs = torch.zeros((n_chains, n, 2), dtype=torch.float, device=dev)
+        for c in range(n_chains):
             chains.append(make_chain("indirect%d" % c, _side_stream(dev, c)))
         for c in chains:
             c["stream"].wait_stream(caller_stream)
@@ -853,9 +856,11 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             for _ in range(R - 1)]
         tiles_ready = lighting["ready"] if lighting is not None else 0
         B = reservoirs
-        slangpy.prepare_workspace(occ_map)
+        # fork first: the chains' own foreground lists are then built beside the reuse chain's, not after it
         for st in [st_s, st_i] + st_init + ([main_stream] if main_stream is not caller_stream else []):
             st.wait_stream(caller_stream)
+        with _on(main_stream):
+            slangpy.prepare_workspace(occ_map)
         for r in range(R):
             with _on(st_init[r]), slangpy.workspace_tag("initial%d" % r):
                 slangpy.prepare_workspace(occ_map)
