@@ -202,17 +202,18 @@ static inline int foreach_item(const P &p, int n, cudaStream_t st)
 // Zero-fill that is stream-ordered on the device and immediate in the host-check flavour.  A KERNEL, not
 // cudaMemsetAsync: inside a captured CUDA graph a memset node runs on a copy engine, and the hand-over between that
 // engine and the SMs cost 45-90 us per memset on the serial front of the step (B200 timeline, profiles/README.md);
-// a kernel node costs ~2 us.  Up to four regions per launch (a reservoir is four arrays).
+// a kernel node costs ~2 us.  Up to five regions per launch (a reservoir is four arrays, plus the queue counters).
+#define MR_ZERO_REGIONS 5
 struct ZeroRegions {
-    void *ptr[4];
-    size_t words[4]; // 32-bit words
+    void *ptr[MR_ZERO_REGIONS];
+    size_t words[MR_ZERO_REGIONS]; // 32-bit words
 };
 #if !defined(MR_HOST_CHECK)
 static __global__ void __launch_bounds__(256) k_zero_regions(ZeroRegions z)
 {
     const size_t stride = (size_t)gridDim.x * 256;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < MR_ZERO_REGIONS; ++k) {
         uint32_t *p = static_cast<uint32_t *>(z.ptr[k]);
         for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < z.words[k]; i += stride) p[i] = 0u;
     }
@@ -222,11 +223,11 @@ static inline void zero_regions_async(const ZeroRegions &z, cudaStream_t st)
 {
 #if defined(MR_HOST_CHECK)
     (void)st;
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < MR_ZERO_REGIONS; ++k)
         if (z.words[k]) memset(z.ptr[k], 0, z.words[k] * 4);
 #else
     size_t most = 0;
-    for (int k = 0; k < 4; ++k) most = z.words[k] > most ? z.words[k] : most;
+    for (int k = 0; k < MR_ZERO_REGIONS; ++k) most = z.words[k] > most ? z.words[k] : most;
     if (!most) return;
     size_t blocks = (most + 1023) / 1024; // four words per thread
     if (blocks > 148 * 8) blocks = 148 * 8;
@@ -235,7 +236,7 @@ static inline void zero_regions_async(const ZeroRegions &z, cudaStream_t st)
 }
 static inline void zero_async(void *ptr, size_t bytes, cudaStream_t st)
 {
-    ZeroRegions z = {{ptr, nullptr, nullptr, nullptr}, {bytes / 4, 0, 0, 0}};
+    ZeroRegions z = {{ptr, nullptr, nullptr, nullptr, nullptr}, {bytes / 4, 0, 0, 0, 0}};
     zero_regions_async(z, st);
 }
 

@@ -658,9 +658,10 @@ static int ws_open(Workspace &ws, int n, void *workspace, size_t workspace_bytes
     workspace_carve(&ws, n, (char *)workspace);
     return 0;
 }
-static void res_zero_all(const ResView &r, int n, cudaStream_t st)
+// zero reservoirs for the background pixels and (one launch) the queue counters of the stage that follows
+static void res_zero_all(const ResView &r, int n, const Workspace &ws, cudaStream_t st)
 {
-    ZeroRegions z = {{r.ld, r.pdf, r.M, r.w}, {3 * (size_t)n, (size_t)n, (size_t)n, (size_t)n}};
+    ZeroRegions z = {{r.ld, r.pdf, r.M, r.w, ws.counters + 1}, {3 * (size_t)n, (size_t)n, (size_t)n, (size_t)n, 4}};
     zero_regions_async(z, st);
 }
 
@@ -693,8 +694,7 @@ int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris,
     p.light_cache = (const float4 *)light_cache;
     p.fx = fx; p.fy = fy; p.frame = frame_index;
     p.tile_count = tile_count; p.tile_size = tile_size; p.screen_tile = screen_tile; p.n_light = n_light; p.n_brdf = n_brdf;
-    res_zero_all(p.res, n, st); // background pixels (InitialResampling.slang:166-176)
-    queue_reset(p.ws, st);
+    res_zero_all(p.res, n, p.ws, st); // background pixels (InitialResampling.slang:166-176) + queue_reset
     if ((rc = foreach_item<InitialParams, initial_gen_px, 128>(p, n, st))) return rc;
     if ((rc = trace_queues(p.bvh, p.ws, true, false, device_sm_count(), st))) return rc;
     return foreach_item<InitialParams, initial_resolve_px, 256>(p, n, st);
@@ -754,8 +754,7 @@ int mirres_spatial_resampling(const void *packed_nodes, const void *packed_tris,
     p.offsets = neighbor_offsets;
     p.fx = fx; p.fy = fy; p.frame = frame_index;
     p.offset_count = offset_count; p.neighbor_count = neighbor_count; p.radius = gather_radius;
-    res_zero_all(p.res, n, st); // background pixels (SpatialResampling.slang:192-201)
-    queue_reset(p.ws, st);
+    res_zero_all(p.res, n, p.ws, st); // background pixels (SpatialResampling.slang:192-201) + queue_reset
     if ((rc = foreach_item<SpatialParams, spatial_gen_px, 128>(p, n, st))) return rc;
     if ((rc = trace_queues(p.bvh, p.ws, true, false, device_sm_count(), st))) return rc;
     return foreach_item<SpatialParams, spatial_resolve_px, 128>(p, n, st);
