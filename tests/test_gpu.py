@@ -437,6 +437,45 @@ def test_cross_bilateral_denoiser_gpu(kernels, oracle):
         assert np.array_equal(g.cpu().numpy(), oracle.bilateral_bwd(W, Hh, sigma, nrm, zdz, go))
 
 
+def test_cross_bilateral_against_reference_kernel(kernels, oracle):
+    """The REFERENCE's own kernels (nerf/renderutils/c_src/denoising.cu:14-130, compiled unmodified from the reference
+    tree into oracle/_ref/libref_renderutils.so and launched as torch_bindings.cpp:201-246 launches them) against the
+    product (mirres_bilateral_fwd/_bwd) and against the oracle's restatement.  The reference build contracts to FMA and
+    calls libdevice expf / powf, the product evaluates the same expression tree without contraction, so the bar is the
+    north-star tolerance (1e-4 forward, 1e-3 gradients), not bit-exactness.  Frames with ragged 8 x 8 block edges."""
+    from oracle import ref as REF
+    if not REF.available():
+        pytest.skip("oracle/_ref/libref_renderutils.so not built (needs the reference tree at build time)")
+    import test_hostcheck_parity as THP
+    sc = P.scene("T1")
+    W, Hh = sc["W"], sc["H"]
+    col, nrm, zdz = THP._bilateral_inputs(sc, 3)
+
+    def close(got, want, rtol):
+        # signed sums (backward) cancel: scale the absolute term by the magnitude of the data
+        return np.allclose(got, want, rtol=rtol, atol=rtol * 1e-2 * float(np.abs(want).max()))
+
+    for fx, fy in ((W, Hh), (W - 3, Hh - 5), (5, 3), (1, 1)):
+        n = fx * fy
+        c, nn, z = col[:n].copy(), nrm[:n].copy(), zdz[:n].copy()
+        for sigma in (1.0, 4.0, 1e-4):  # 4.0 = the reference's factor 2 (radius 21); 1e-4 = its lower clamp (ops.py:195)
+            want = REF.bilateral_fwd(fx, fy, sigma, tt(c), tt(nn), tt(z)).cpu().numpy()
+            out = torch.zeros(n, 4, device=DEV)
+            kernels.bilateral_fwd(fx, fy, sigma, tt(c), tt(nn), tt(z), out)
+            assert close(out.cpu().numpy(), want, FWD_RTOL), (fx, fy, sigma)
+            assert close(oracle.bilateral_fwd(fx, fy, sigma, c, nn, z), want, FWD_RTOL), (fx, fy, sigma)
+            go = np.random.default_rng(1).standard_normal((n, 4)).astype(np.float32)
+            wantg = REF.bilateral_bwd(fx, fy, sigma, tt(c), tt(nn), tt(z), tt(go)).cpu().numpy()
+            g = torch.zeros(n, 3, device=DEV)
+            kernels.bilateral_bwd(fx, fy, sigma, tt(nn), tt(z), tt(go), g)
+            assert close(g.cpu().numpy(), wantg, GRAD_RTOL), (fx, fy, sigma)
+            assert close(oracle.bilateral_bwd(fx, fy, sigma, nn, z, go), wantg, GRAD_RTOL), (fx, fy, sigma)
+            # the composed op of ops.py:192-200 (normalised colour), on lit pixels
+            lit = want[:, 3] > 1e-3
+            assert np.allclose(out.cpu().numpy()[lit, :3] / out.cpu().numpy()[lit, 3:4], want[lit, :3] / want[lit, 3:4],
+                               rtol=FWD_RTOL, atol=1e-6)
+
+
 def test_c2_full_size_parity_against_oracle(kernels, oracle):
     """BASELINE config C2 at FULL size (500 000 triangles, 800 x 800, spp 4, 3 path vertices): LBVH, primary G-buffer and
     every intermediate tensor of the forward spp loop against the oracle (the oracle needs a few seconds on the host
