@@ -271,6 +271,24 @@ int mirres_prepare_maps(int n, float *occ, const float *normal, const float *dep
                         float *ray_dir_normalized, void *stream);
 int mirres_interpolate_bwd(const float *grad, int n, int C, const int *prim, const float *bary, const int *tri, int F,
                            float *out, void *stream);
+/* Shading-normal set-up of the G-buffer stage: prepare_shading_normal (nerf/renderutils/ops.py:129-163) =
+ * PrepareShadingNormalFwdKernel / BwdKernel (nerf/renderutils/c_src/normal.cu:95-178), called at nerf/renderer.py:1013
+ * on the rasterised maps before run_restir_di_with_pt.  Tangent-frame perturbation, two-sided flip, bending of
+ * back-facing normals towards the eye (threshold 0.1).  Six inputs of 3 floats per pixel, each with a row stride in
+ * floats: 3 = dense [n,3], 0 = one row broadcast (the reference passes view_pos and perturbed_nrm as [1,1,1,3]), any
+ * other non-negative stride for a view into a wider tensor.  out [n,3].  The backward writes (not accumulates) full
+ * [n,3] gradients for the inputs whose pointer is non-NULL -- like the reference it leaves the reduction over a
+ * broadcast input to the caller. */
+int mirres_shading_normal_fwd(int n, const float *pos, int pos_rs, const float *view_pos, int view_rs,
+                              const float *perturbed_nrm, int perturbed_rs, const float *smooth_nrm, int smooth_nrm_rs,
+                              const float *smooth_tng, int smooth_tng_rs, const float *geom_nrm, int geom_rs, int two_sided,
+                              int opengl, float *out, void *stream);
+int mirres_shading_normal_bwd(int n, const float *pos, int pos_rs, const float *view_pos, int view_rs,
+                              const float *perturbed_nrm, int perturbed_rs, const float *smooth_nrm, int smooth_nrm_rs,
+                              const float *smooth_tng, int smooth_tng_rs, const float *geom_nrm, int geom_rs, int two_sided,
+                              int opengl, const float *grad_out, float *grad_pos, float *grad_view_pos,
+                              float *grad_perturbed_nrm, float *grad_smooth_nrm, float *grad_smooth_tng, float *grad_geom_nrm,
+                              void *stream);
 
 
 /* ------------------------------------------------------------------------------------------------------------

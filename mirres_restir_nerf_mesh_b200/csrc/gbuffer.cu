@@ -120,6 +120,118 @@ MR_DEV void prepare_maps_px(const PrepParams &p, int idx)
     store3(p.ray_out, i, make_float3(d.x / den, d.y / den, d.z / den));
 }
 
+// ---- shading-normal set-up (the prepare_shading_normal step of the G-buffer stage) ----------------------------------
+// Reference: PrepareShadingNormalFwdKernel / BwdKernel, nerf/renderutils/c_src/normal.cu:95-178, called at
+// nerf/renderer.py:1013 between rasterisation and run_restir_di_with_pt.  Per pixel:
+//   N  = nrm(smooth_nrm), T = nrm(smooth_tng), V = nrm(view_pos - pos), B = nrm(T x N)          nrm(0) = 0
+//   S  = nrm(T p.x + s B p.y + N max(p.z, 0))      p = perturbed_nrm, s = -1 (OpenGL) / +1
+//   two-sided: dot(V, G) < 0 flips S and G
+//   out = G (1 - t) + S t,  t = clamp(dot(V, S) / 0.1, 0, 1)
+// The backward below is a hand-derived reverse sweep of exactly that expression (branch predicates frozen).
+struct ShadingNormalParams {
+    const float *in[6];  // pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm
+    int rs[6];           // row strides in floats (0 = one row broadcast to every pixel)
+    int two_sided, opengl;
+    float *out;          // fwd: [n,3]
+    const float *gout;   // bwd: [n,3]
+    float *gin[6];       // bwd: [n,3] each, optional
+};
+MR_DEV float3 sn_load(const ShadingNormalParams &p, int k, size_t i)
+{
+    const float *q = p.in[k] + i * (size_t)p.rs[k];
+    return make_float3(MR_LDG(q), MR_LDG(q + 1), MR_LDG(q + 2));
+}
+MR_DEV float3 nrm0(float3 v)
+{
+    const float l = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+    return l > 0.0f ? v / l : f3(0.f);
+}
+// reverse of y = v / |v|:  dv = (dy - y (y . dy)) / |v|   (0 where |v| = 0, as the forward is constant there)
+MR_DEV float3 nrm0_bwd(float3 v, float3 dy)
+{
+    const float l = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+    if (!(l > 0.0f)) return f3(0.f);
+    const float3 y = v / l;
+    return (dy - y * dot(y, dy)) / l;
+}
+struct ShadingNormalFrame {
+    float3 N, T, V, Bu, B, Su, S, G;  // Bu / Su: before normalisation
+    float sgn, dp, t;
+    bool flip;
+};
+MR_DEV ShadingNormalFrame shading_normal_frame(const ShadingNormalParams &p, size_t i, float3 &pert, float3 &view_raw,
+                                               float3 &n_raw, float3 &t_raw)
+{
+    ShadingNormalFrame f;
+    const float3 pos = sn_load(p, 0, i), vp = sn_load(p, 1, i);
+    pert = sn_load(p, 2, i);
+    n_raw = sn_load(p, 3, i);
+    t_raw = sn_load(p, 4, i);
+    const float3 g = sn_load(p, 5, i);
+    view_raw = vp - pos;
+    f.N = nrm0(n_raw);
+    f.T = nrm0(t_raw);
+    f.V = nrm0(view_raw);
+    f.Bu = cross(f.T, f.N);
+    f.B = nrm0(f.Bu);
+    f.sgn = p.opengl ? -1.0f : 1.0f;
+    f.Su = f.T * pert.x + (f.sgn * f.B) * pert.y + f.N * fmaxf(pert.z, 0.0f);
+    const float3 s = nrm0(f.Su);
+    f.flip = p.two_sided && dot(f.V, g) < 0.0f;
+    f.S = f.flip ? -s : s;
+    f.G = f.flip ? -g : g;
+    f.dp = dot(f.V, f.S);
+    f.t = clampf(f.dp / 0.1f, 0.0f, 1.0f);
+    return f;
+}
+MR_DEV void shading_normal_fwd_px(const ShadingNormalParams &p, int idx)
+{
+    float3 pert, vr, nr, tr;
+    const ShadingNormalFrame f = shading_normal_frame(p, (size_t)idx, pert, vr, nr, tr);
+    store3(p.out, (size_t)idx, f.G * (1.0f - f.t) + f.S * f.t);
+}
+MR_DEV void shading_normal_bwd_px(const ShadingNormalParams &p, int idx)
+{
+    const size_t i = (size_t)idx;
+    float3 pert, vr, nr, tr;
+    const ShadingNormalFrame f = shading_normal_frame(p, i, pert, vr, nr, tr);
+    const float3 go = load3(p.gout, i);
+    // bend
+    float3 dS, dG = f3(0.f), dV = f3(0.f);
+    if (f.dp > 0.1f) {
+        dS = go;
+    } else {
+        dG = go * (1.0f - f.t);
+        dS = go * f.t;
+        const float dt = dot(go, f.S - f.G);
+        const float ddp = (f.dp < 0.0f || f.dp > 0.1f) ? 0.0f : dt / 0.1f;
+        dV = f.S * ddp;
+        dS += f.V * ddp;
+    }
+    if (f.flip) { dS = -dS; dG = -dG; }
+    // perturb
+    const float3 dSu = nrm0_bwd(f.Su, dS);
+    float3 dN = f3(0.f), dT, dpert = f3(0.f);
+    if (pert.z > 0.0f) {
+        dN = dSu * pert.z;
+        dpert.z = dot(dSu, f.N);
+    }
+    const float3 dB = (f.sgn * dSu) * pert.y;
+    dpert.y = f.sgn * dot(dSu, f.B);
+    dT = dSu * pert.x;
+    dpert.x = dot(dSu, f.T);
+    const float3 dBu = nrm0_bwd(f.Bu, dB);
+    dT += cross(f.N, dBu);   // Bu = T x N
+    dN += cross(dBu, f.T);
+    const float3 dview = nrm0_bwd(vr, dV);
+    if (p.gin[0]) store3(p.gin[0], i, -dview);
+    if (p.gin[1]) store3(p.gin[1], i, dview);
+    if (p.gin[2]) store3(p.gin[2], i, dpert);
+    if (p.gin[3]) store3(p.gin[3], i, nrm0_bwd(nr, dN));
+    if (p.gin[4]) store3(p.gin[4], i, nrm0_bwd(tr, dT));
+    if (p.gin[5]) store3(p.gin[5], i, dG);
+}
+
 #define MR_SCATTER_MAX_C 8
 
 struct ScatterParams {
@@ -291,6 +403,57 @@ int mirres_prepare_maps(int n, float *occ, const float *normal, const float *dep
     if ((uintptr_t)normal_depth & 15) return MIRRES_ERR_ALIGN;
     PrepParams p = {occ, normal, depth, diffuse_map, rough_metal, ray_dir, normal_depth, brdf_map, ray_dir_normalized};
     return foreach_item<PrepParams, prepare_maps_px, 256>(p, n, (cudaStream_t)stream);
+}
+
+static int shading_normal_params(mr::ShadingNormalParams &p, int n, const float *const in[6], const int rs[6], int two_sided, int opengl)
+{
+    if (n < 1) return MIRRES_ERR_SHAPE;
+    for (int k = 0; k < 6; ++k) {
+        if (!in[k]) return MIRRES_ERR_NULL;
+        if (rs[k] < 0) return MIRRES_ERR_SHAPE;
+        p.in[k] = in[k];
+        p.rs[k] = rs[k];
+        p.gin[k] = nullptr;
+    }
+    p.two_sided = two_sided != 0;
+    p.opengl = opengl != 0;
+    p.out = nullptr;
+    p.gout = nullptr;
+    return 0;
+}
+
+int mirres_shading_normal_fwd(int n, const float *pos, int pos_rs, const float *view_pos, int view_rs,
+                              const float *perturbed_nrm, int perturbed_rs, const float *smooth_nrm, int smooth_nrm_rs,
+                              const float *smooth_tng, int smooth_tng_rs, const float *geom_nrm, int geom_rs, int two_sided,
+                              int opengl, float *out, void *stream)
+{
+    if (n == 0) return 0;
+    if (!out) return MIRRES_ERR_NULL;
+    const float *in[6] = {pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm};
+    const int rs[6] = {pos_rs, view_rs, perturbed_rs, smooth_nrm_rs, smooth_tng_rs, geom_rs};
+    ShadingNormalParams p;
+    if (int rc = shading_normal_params(p, n, in, rs, two_sided, opengl)) return rc;
+    p.out = out;
+    return foreach_item<ShadingNormalParams, shading_normal_fwd_px, 256>(p, n, (cudaStream_t)stream);
+}
+
+int mirres_shading_normal_bwd(int n, const float *pos, int pos_rs, const float *view_pos, int view_rs,
+                              const float *perturbed_nrm, int perturbed_rs, const float *smooth_nrm, int smooth_nrm_rs,
+                              const float *smooth_tng, int smooth_tng_rs, const float *geom_nrm, int geom_rs, int two_sided,
+                              int opengl, const float *grad_out, float *grad_pos, float *grad_view_pos,
+                              float *grad_perturbed_nrm, float *grad_smooth_nrm, float *grad_smooth_tng, float *grad_geom_nrm,
+                              void *stream)
+{
+    if (n == 0) return 0;
+    if (!grad_out) return MIRRES_ERR_NULL;
+    const float *in[6] = {pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm};
+    const int rs[6] = {pos_rs, view_rs, perturbed_rs, smooth_nrm_rs, smooth_tng_rs, geom_rs};
+    ShadingNormalParams p;
+    if (int rc = shading_normal_params(p, n, in, rs, two_sided, opengl)) return rc;
+    p.gout = grad_out;
+    float *g[6] = {grad_pos, grad_view_pos, grad_perturbed_nrm, grad_smooth_nrm, grad_smooth_tng, grad_geom_nrm};
+    for (int k = 0; k < 6; ++k) p.gin[k] = g[k];
+    return foreach_item<ShadingNormalParams, shading_normal_bwd_px, 256>(p, n, (cudaStream_t)stream);
 }
 
 int mirres_interpolate_bwd(const float *grad, int n, int C, const int *prim, const float *bary, const int *tri, int F,

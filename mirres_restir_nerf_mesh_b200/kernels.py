@@ -314,6 +314,40 @@ class Kernels:
                                           self._f(brdf_map), self._f(ray_out), self._stream())
         self._check(rc, "mirres_prepare_maps")
 
+    def _rows3(self, t, n):
+        """[n,3] (any row stride) or [1,3] fp32 rows -> (pointer, row stride in floats, tensor kept alive)."""
+        if not isinstance(t, torch.Tensor) or t.dtype != torch.float32 or t.dim() != 2 or t.shape[1] != 3:
+            raise AbiError("expected a float32 [rows, 3] tensor")
+        if self.require_cuda and not t.is_cuda:
+            raise AbiError("mirres-b200 kernels need CUDA tensors (no CPU fallback)")
+        if t.shape[0] not in (1, n):
+            raise AbiError("expected %d rows (or 1 broadcast row), got %d" % (n, t.shape[0]))
+        if t.stride(1) != 1 or t.stride(0) < 0:
+            t = t.contiguous()
+        return ctypes.c_void_p(t.data_ptr()), (0 if t.shape[0] == 1 and n != 1 else int(t.stride(0))), t
+
+    def shading_normal_fwd(self, n, inputs, two_sided, opengl, out):
+        """inputs = (pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm), each n rows or one broadcast row"""
+        args, keep = [], []
+        for t in inputs:
+            ptr, rs, t2 = self._rows3(t, n)
+            args += [ptr, rs]
+            keep.append(t2)
+        rc = self.lib.mirres_shading_normal_fwd(int(n), *args, int(bool(two_sided)), int(bool(opengl)), self._f(out),
+                                                self._stream())
+        self._check(rc, "mirres_shading_normal_fwd")
+
+    def shading_normal_bwd(self, n, inputs, two_sided, opengl, grad_out, grads):
+        """grads: six [n,3] tensors or None (skipped)"""
+        args, keep = [], []
+        for t in inputs:
+            ptr, rs, t2 = self._rows3(t, n)
+            args += [ptr, rs]
+            keep.append(t2)
+        rc = self.lib.mirres_shading_normal_bwd(int(n), *args, int(bool(two_sided)), int(bool(opengl)),
+                                                self._f(grad_out), *[self._f(g, True) for g in grads], self._stream())
+        self._check(rc, "mirres_shading_normal_bwd")
+
     def interpolate_bwd(self, grad, prim, bary, tri, out):
         rc = self.lib.mirres_interpolate_bwd(self._f(grad), grad.shape[0], grad.shape[1], self._i(prim),
                                              self._f(bary, True), self._i(tri), tri.shape[0], self._f(out),
