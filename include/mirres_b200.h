@@ -271,6 +271,16 @@ int mirres_prepare_maps(int n, float *occ, const float *normal, const float *dep
                         float *ray_dir_normalized, void *stream);
 int mirres_interpolate_bwd(const float *grad, int n, int C, const int *prim, const float *bary, const int *tri, int F,
                            float *out, void *stream);
+/* Vertex normals of the (offset) mesh: auto_normals (meshutils.py:14-39), which nerf/renderer.py:979-1030 evaluates on
+ * the optimised vertices before interpolating them into the G-buffer normal.  Area-weighted face normals summed per
+ * vertex (float atomics, like the reference's scatter_add_), normalised; a vertex whose sum has squared length <= 1e-20
+ * (unreferenced / degenerate) gets (0, 0, 1).  vsum [V,3] (the un-normalised sums) is written by the forward and read
+ * by the backward; the forward zero-fills it.  Triangles with an index outside [0, V) are ignored.
+ * Backward: grad_vert [V,3] += d vnrm / d vert (ACCUMULATED into, like mirres_interpolate_bwd) -- with
+ * mirres_interpolate_bwd and mirres_shading_normal_bwd this carries the path's grad_normal back to the mesh vertices. */
+int mirres_vertex_normals_fwd(const float *vert, int V, const int *tri, int F, float *vsum, float *vnrm, void *stream);
+int mirres_vertex_normals_bwd(const float *vert, int V, const int *tri, int F, const float *vsum, const float *grad_vnrm,
+                              float *grad_vert, void *stream);
 /* Shading-normal set-up of the G-buffer stage: prepare_shading_normal (nerf/renderutils/ops.py:129-163) =
  * PrepareShadingNormalFwdKernel / BwdKernel (nerf/renderutils/c_src/normal.cu:95-178), called at nerf/renderer.py:1013
  * on the rasterised maps before run_restir_di_with_pt.  Tangent-frame perturbation, two-sided flip, bending of

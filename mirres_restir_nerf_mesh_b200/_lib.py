@@ -52,6 +52,8 @@ SIGNATURES = {
     "mirres_gbuffer_primary": "ppppi" + "pp" + "pppppp" + "pz" + "p",
     "mirres_prepare_maps": "ippppppppp" + "p",
     "mirres_interpolate_bwd": "piipppipp",
+    "mirres_vertex_normals_fwd": "pipippp",
+    "mirres_vertex_normals_bwd": "pipipppp",
     "mirres_shading_normal_fwd": "i" + "pi" * 6 + "ii" + "p" + "p",
     "mirres_shading_normal_bwd": "i" + "pi" * 6 + "ii" + "p" + "pppppp" + "p",
     "mirres_material_procedural": "ippifpppp",

@@ -332,6 +332,88 @@ __global__ void __launch_bounds__(256) k_interpolate_bwd(ScatterParams p)
 }
 #endif
 
+// ---- vertex normals (auto_normals, meshutils.py:14-39; called at nerf/renderer.py:979-1030 on the offset vertices) ----
+//   face normal  n_f = (v1 - v0) x (v2 - v0)           (area-weighted, not normalised)
+//   vertex sum   s_v = sum of n_f over incident faces   (scatter_add_ in the reference: float atomics, any order)
+//   vertex normal     = s_v / |s_v|  if  s_v . s_v > 1e-20,  else (0, 0, 1)
+// Backward: through the normalisation (no gradient where the fallback was taken), gathered per face, through the cross
+// product, scattered to the three corner positions.
+struct VertexNormalParams {
+    const float *__restrict__ vert; // [V,3]
+    const int *__restrict__ tri;    // [F,3]
+    float *vsum;                    // [V,3] un-normalised sums (written by fwd, read by bwd)
+    float *vnrm;                    // [V,3]
+    const float *__restrict__ gnrm; // [V,3] upstream gradient (bwd)
+    float *gvert;                   // [V,3] accumulated into (bwd)
+    int V, F;
+};
+MR_DEV bool vn_face(const VertexNormalParams &p, int f, int i[3], float3 &a, float3 &b)
+{
+    i[0] = MR_LDG(p.tri + 3 * (size_t)f), i[1] = MR_LDG(p.tri + 3 * (size_t)f + 1), i[2] = MR_LDG(p.tri + 3 * (size_t)f + 2);
+    if ((unsigned)i[0] >= (unsigned)p.V || (unsigned)i[1] >= (unsigned)p.V || (unsigned)i[2] >= (unsigned)p.V) return false;
+    const float3 v0 = load3(p.vert, (size_t)i[0]);
+    a = load3(p.vert, (size_t)i[1]) - v0;
+    b = load3(p.vert, (size_t)i[2]) - v0;
+    return true;
+}
+MR_DEV void vn_add3(float *dst, size_t row, float3 v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAdd(dst + 3 * row, v.x), atomicAdd(dst + 3 * row + 1, v.y), atomicAdd(dst + 3 * row + 2, v.z);
+#else
+    dst[3 * row] += v.x, dst[3 * row + 1] += v.y, dst[3 * row + 2] += v.z;
+#endif
+}
+MR_DEV void vertex_normal_face(const VertexNormalParams &p, int f)
+{
+    int i[3];
+    float3 a, b;
+    if (!vn_face(p, f, i, a, b)) return;
+    const float3 n = cross(a, b);
+    for (int k = 0; k < 3; ++k) vn_add3(p.vsum, (size_t)i[k], n);
+}
+MR_DEV void vertex_normal_finish(const VertexNormalParams &p, int v)
+{
+    float3 s = load3_rw(p.vsum, (size_t)v);
+    float d = dot(s, s);
+    if (!(d > 1e-20f)) { s = f3(0.f, 0.f, 1.f); d = 1.0f; }
+    store3(p.vnrm, (size_t)v, s / sqrtf(fmaxf(d, 1e-20f)));
+}
+MR_DEV void vertex_normal_bwd_face(const VertexNormalParams &p, int f)
+{
+    int i[3];
+    float3 a, b;
+    if (!vn_face(p, f, i, a, b)) return;
+    float3 dn = f3(0.f);
+    for (int k = 0; k < 3; ++k) {
+        const float3 s = load3(p.vsum, (size_t)i[k]);
+        const float d = dot(s, s);
+        if (!(d > 1e-20f)) continue;
+        const float l = sqrtf(d);
+        const float3 y = s / l, g = load3(p.gnrm, (size_t)i[k]);
+        dn += (g - y * dot(y, g)) / l;
+    }
+    if (is_black(dn)) return;
+    const float3 da = cross(b, dn), db = cross(dn, a);  // n = a x b
+    vn_add3(p.gvert, (size_t)i[1], da);
+    vn_add3(p.gvert, (size_t)i[2], db);
+    vn_add3(p.gvert, (size_t)i[0], -(da + db));
+}
+#if defined(MR_HOST_CHECK)
+template <void (*BODY)(const VertexNormalParams &, int)>
+static int vn_foreach(const VertexNormalParams &p, int n, cudaStream_t)
+{
+    for (int i = 0; i < n; ++i) BODY(p, i);  // sequential: the bodies accumulate without atomics on the host
+    return 0;
+}
+#else
+template <void (*BODY)(const VertexNormalParams &, int)>
+static int vn_foreach(const VertexNormalParams &p, int n, cudaStream_t st)
+{
+    return foreach_item<VertexNormalParams, BODY, 256>(p, n, st);
+}
+#endif
+
 static int interpolate_bwd_launch(const ScatterParams &p, cudaStream_t st)
 {
 #if defined(MR_HOST_CHECK)
@@ -403,6 +485,28 @@ int mirres_prepare_maps(int n, float *occ, const float *normal, const float *dep
     if ((uintptr_t)normal_depth & 15) return MIRRES_ERR_ALIGN;
     PrepParams p = {occ, normal, depth, diffuse_map, rough_metal, ray_dir, normal_depth, brdf_map, ray_dir_normalized};
     return foreach_item<PrepParams, prepare_maps_px, 256>(p, n, (cudaStream_t)stream);
+}
+
+int mirres_vertex_normals_fwd(const float *vert, int V, const int *tri, int F, float *vsum, float *vnrm, void *stream)
+{
+    if (!vert || !tri || !vsum || !vnrm) return MIRRES_ERR_NULL;
+    if (V < 0 || F < 0) return MIRRES_ERR_SHAPE;
+    if (V == 0) return 0;
+    VertexNormalParams p = {vert, tri, vsum, vnrm, nullptr, nullptr, V, F};
+    zero_async(vsum, (size_t)V * 12, (cudaStream_t)stream);
+    if (F > 0)
+        if (int rc = vn_foreach<vertex_normal_face>(p, F, (cudaStream_t)stream)) return rc;
+    return vn_foreach<vertex_normal_finish>(p, V, (cudaStream_t)stream);
+}
+
+int mirres_vertex_normals_bwd(const float *vert, int V, const int *tri, int F, const float *vsum, const float *grad_vnrm,
+                              float *grad_vert, void *stream)
+{
+    if (!vert || !tri || !vsum || !grad_vnrm || !grad_vert) return MIRRES_ERR_NULL;
+    if (V < 0 || F < 0) return MIRRES_ERR_SHAPE;
+    if (V == 0 || F == 0) return 0;
+    VertexNormalParams p = {vert, tri, const_cast<float *>(vsum), nullptr, grad_vnrm, grad_vert, V, F};
+    return vn_foreach<vertex_normal_bwd_face>(p, F, (cudaStream_t)stream);
 }
 
 static int shading_normal_params(mr::ShadingNormalParams &p, int n, const float *const in[6], const int rs[6], int two_sided, int opengl)

@@ -314,6 +314,16 @@ class Kernels:
                                           self._f(brdf_map), self._f(ray_out), self._stream())
         self._check(rc, "mirres_prepare_maps")
 
+    def vertex_normals_fwd(self, vert, tri, vsum, vnrm):
+        rc = self.lib.mirres_vertex_normals_fwd(self._f(vert), vert.shape[0], self._i(tri), tri.shape[0], self._f(vsum),
+                                                self._f(vnrm), self._stream())
+        self._check(rc, "mirres_vertex_normals_fwd")
+
+    def vertex_normals_bwd(self, vert, tri, vsum, grad_vnrm, grad_vert):
+        rc = self.lib.mirres_vertex_normals_bwd(self._f(vert), vert.shape[0], self._i(tri), tri.shape[0], self._f(vsum),
+                                                self._f(grad_vnrm), self._f(grad_vert), self._stream())
+        self._check(rc, "mirres_vertex_normals_bwd")
+
     def _rows3(self, t, n):
         """[n,3] (any row stride) or [1,3] fp32 rows -> (pointer, row stride in floats, tensor kept alive)."""
         if not isinstance(t, torch.Tensor) or t.dtype != torch.float32 or t.dim() != 2 or t.shape[1] != 3:

@@ -129,3 +129,122 @@ def test_gpu_against_reference_vectors_and_reference_kernel():
                 k.shading_normal_bwd(N, operands, two_sided, opengl, go, grads)
                 for n, g, w in zip(NAMES, grads, wantg):
                     assert close(g.cpu().numpy(), w.cpu().numpy(), GRAD_RTOL), (n, two_sided, opengl)
+
+
+# ---- auto_normals (meshutils.py:14-39) ---------------------------------------------------------------------------------
+AN = np.load(os.path.join(HERE, "golden", "auto_normals_ref.npz"))
+
+
+def run_auto_normals(k, dev):
+    vert, tri = torch.from_numpy(AN["vert"]).to(dev), torch.from_numpy(AN["tri"]).to(dev)
+    vsum, vnrm = torch.full_like(vert, 9.0), torch.zeros_like(vert)  # the forward zero-fills vsum itself
+    k.vertex_normals_fwd(vert, tri, vsum, vnrm)
+    assert close(vnrm.cpu().numpy(), AN["vnrm"], FWD_RTOL)
+    assert (vnrm[-1].cpu().numpy() == np.array([0, 0, 1], np.float32)).all()  # unreferenced vertex: the fallback
+    gv = torch.zeros_like(vert)
+    k.vertex_normals_bwd(vert, tri, vsum, torch.from_numpy(AN["grad_vnrm"]).to(dev), gv)
+    assert close(gv.cpu().numpy(), AN["grad_vert"], GRAD_RTOL), np.abs(gv.cpu().numpy() - AN["grad_vert"]).max()
+    assert bool((gv[-1] == 0).all())
+    # accumulation contract and out-of-range indices
+    k.vertex_normals_bwd(vert, tri, vsum, torch.from_numpy(AN["grad_vnrm"]).to(dev), gv)
+    assert close(gv.cpu().numpy(), 2 * AN["grad_vert"], GRAD_RTOL)
+    bad = torch.cat([tri, torch.tensor([[0, 1, 10 ** 6], [-1, 2, 3]], dtype=torch.int32, device=dev)])
+    vn2 = torch.zeros_like(vert)
+    k.vertex_normals_fwd(vert, bad, vsum, vn2)
+    assert close(vn2.cpu().numpy(), AN["vnrm"], FWD_RTOL)
+
+
+def run_auto_normals_operator(dev):
+    from mirres_restir_nerf_mesh_b200 import meshutils as MU
+    v = torch.from_numpy(AN["vert"]).to(dev).requires_grad_(True)
+    tri = torch.from_numpy(AN["tri"]).to(dev)
+    vn, t2 = MU.auto_normals(v, tri.long())  # the reference passes whatever integer dtype the mesh has
+    assert t2.dtype == torch.int64 and close(vn.detach().cpu().numpy(), AN["vnrm"], FWD_RTOL)
+    vn.backward(torch.from_numpy(AN["grad_vnrm"]).to(dev))
+    assert close(v.grad.cpu().numpy(), AN["grad_vert"], GRAD_RTOL)
+
+
+def test_auto_normals_host_flavour_against_reference_function():
+    import hostcheck as H
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim
+    run_auto_normals(H.kernels(), "cpu")
+    H.activate()
+    try:
+        run_auto_normals_operator("cpu")
+    finally:
+        slangpy_shim.set_kernels(None)
+
+
+@pytest.mark.gpu
+def test_auto_normals_gpu_against_reference_function():
+    from mirres_restir_nerf_mesh_b200.slangpy_shim import get_kernels, set_kernels
+    set_kernels(None)
+    run_auto_normals(get_kernels(), "cuda")
+    run_auto_normals_operator("cuda")
+
+
+@pytest.mark.gpu
+def test_vertex_gradient_chain_gpu():
+    """grad_normal of the path back to the mesh vertices: shading_normal_bwd -> interpolate_bwd -> vertex_normals_bwd
+    against torch.autograd over the same chain written in torch (C2-sized mesh, one pixel per triangle)."""
+    from mirres_restir_nerf_mesh_b200 import synth, meshutils as MU, renderutils_ops as OPS
+    from mirres_restir_nerf_mesh_b200.slangpy_shim import get_kernels, set_kernels
+    set_kernels(None)
+    k = get_kernels()
+    vert_np, tri_np = synth.torus_knot(200, 50) if hasattr(synth, "torus_knot") else (AN["vert"], AN["tri"])
+    vert = torch.from_numpy(np.ascontiguousarray(vert_np, dtype=np.float32)).cuda().requires_grad_(True)
+    tri = torch.from_numpy(np.ascontiguousarray(tri_np, dtype=np.int32)).cuda()
+    F = tri.shape[0]
+    rng = np.random.default_rng(5)
+    prim = torch.from_numpy(rng.integers(0, F, F).astype(np.int32)).cuda()
+    bary = torch.from_numpy(rng.dirichlet([1, 1, 1], F)[:, 1:].astype(np.float32)).cuda()
+    eye = torch.tensor([[0.3, 2.9, 1.1]], device="cuda")
+    go = torch.from_numpy(rng.standard_normal((F, 3)).astype(np.float32)).cuda()
+
+    def chain(auto_normals, shading_normal, interpolate):
+        v = vert.detach().clone().requires_grad_(True)
+        vn, _ = auto_normals(v, tri)
+        w = torch.cat([1 - bary.sum(1, keepdim=True), bary], 1)
+        corners = tri.long()[prim.long()]
+        smooth = interpolate(vn, corners, w)
+        pos = (v.detach()[corners] * w[..., None]).sum(1)
+        e1, e2 = v.detach()[corners[:, 1]] - v.detach()[corners[:, 0]], v.detach()[corners[:, 2]] - v.detach()[corners[:, 0]]
+        geom = torch.nn.functional.normalize(torch.linalg.cross(e1, e2), dim=-1)
+        out = shading_normal(pos.view(1, 1, F, 3), eye.view(1, 1, 1, 3), None, smooth.view(1, 1, F, 3),
+                             torch.zeros(1, 1, F, 3, device="cuda"), geom.view(1, 1, F, 3))
+        out.backward(go.view(1, 1, F, 3))
+        return out.detach(), v.grad
+
+    class _Interp(torch.autograd.Function):  # product: barycentric gather forward, mirres_interpolate_bwd backward
+        @staticmethod
+        def forward(ctx, vn, corners, w):
+            ctx.V = vn.shape[0]
+            return (vn[corners] * w[..., None]).sum(1)
+
+        @staticmethod
+        def backward(ctx, g):
+            out = torch.zeros(ctx.V, 3, device=g.device)
+            k.interpolate_bwd(g.contiguous(), prim, bary, tri, out)
+            return out, None, None
+
+    def ref_auto_normals(v, t):  # the torch expression of meshutils.py:14-39
+        i = t.long()
+        fn = torch.linalg.cross(v[i[:, 1]] - v[i[:, 0]], v[i[:, 2]] - v[i[:, 0]])
+        s = torch.zeros_like(v).index_add_(0, i[:, 0], fn).index_add_(0, i[:, 1], fn).index_add_(0, i[:, 2], fn)
+        d = (s * s).sum(-1, keepdim=True)
+        s = torch.where(d > 1e-20, s, torch.tensor([0.0, 0.0, 1.0], device=v.device))
+        return s / torch.sqrt(torch.clamp((s * s).sum(-1, keepdim=True), min=1e-20)), t
+
+    def ref_shading_normal(pos, view_pos, pert, smooth, tng, geom):  # ops.py:82-112 with pert = (0,0,1), tng = 0
+        nrm = torch.nn.functional.normalize
+        s = nrm(nrm(smooth, dim=-1), dim=-1)
+        vv = nrm(view_pos - pos, dim=-1)
+        front = (geom * vv).sum(-1, keepdim=True) > 0
+        s, g = torch.where(front, s, -s), torch.where(front, geom, -geom)
+        t = torch.clamp((vv * s).sum(-1, keepdim=True) / 0.1, min=0, max=1)
+        return torch.lerp(g, s, t)
+
+    out_p, gv_p = chain(MU.auto_normals, OPS.prepare_shading_normal, _Interp.apply)
+    out_r, gv_r = chain(ref_auto_normals, ref_shading_normal, lambda vn, c, w: (vn[c] * w[..., None]).sum(1))
+    assert close(out_p.cpu().numpy(), out_r.cpu().numpy(), FWD_RTOL)
+    assert close(gv_p.cpu().numpy(), gv_r.cpu().numpy(), GRAD_RTOL), float((gv_p - gv_r).abs().max())
