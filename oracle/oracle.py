@@ -1,6 +1,8 @@
 """ctypes front-end of the CPU oracle (oracle/libmirres_oracle.so) -- TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED (see oracle/orc_common.h).  All arrays are C-contiguous numpy arrays; outputs are
+PARITY UNPINNED for the Slang kernels (see oracle/orc_common.h); the bilateral denoiser restatement (bilateral_fwd /
+bilateral_bwd) IS pinned: tests/test_gpu.py checks it against the reference's own denoising.cu compiled into
+oracle/_ref (oracle/ref.py).  All arrays are C-contiguous numpy arrays; outputs are
 allocated here.  Function names follow the reference kernels they restate:
   bvh_build          nerf/renderer_restir.py:25-89 (+ nerf/bvhworkers/*.slang)
   trace              nerf/ScreenSpaceReSTIR/utils/helperDi.slang:313-395
