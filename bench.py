@@ -231,7 +231,8 @@ def run_gpu(args):
             worker.update_mesh(vert, tri)
         rays_o, rays_d = synth.camera_rays_torch(W, H, pose)
         env_l = env.detach().clone().requires_grad_(True)
-        lighting = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env_l, spp, 1234 + 17 * rank)
+        lighting = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env_l, spp, 1234 + 17 * rank,
+                                      frame_pixels=n)
         cur.wait_stream(bvh_stream)
         occ, depth = torch.empty(n, 1, device=dev), torch.empty(n, 1, device=dev)
         pos, nrm = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)

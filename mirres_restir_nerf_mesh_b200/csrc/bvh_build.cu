@@ -295,28 +295,43 @@ __global__ void __launch_bounds__(256) k_hierarchy(int F, const unsigned int *__
 }
 
 // ---- bottom-up refit: the second thread to arrive at a node unions its children -----------------------------
+// A level costs dependent L2 round trips, so the walk keeps them to two: the node's static data (children, parent) is
+// fetched BEFORE the arrival atomic, the walker carries the box it has just produced in registers and, once the atomic
+// has told it that it is the second arrival, fetches only its sibling's box.  Operand order of the union is (left,
+// right) as before.
 __global__ void __launch_bounds__(256) k_refit(int F, const int *__restrict__ info, float *aabb,
                                                const int *__restrict__ parent, int *visits)
 {
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= F || F < 2) return;
-    const int LEAF = F - 1;
-    int node = __ldg(parent + LEAF + gid);
+    int me = F - 1 + gid;
+    float box[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) box[k] = __ldcg(aabb + 6 * (size_t)me + k);
+    int node = __ldg(parent + me);
     for (;;) {
+        const int l = __ldg(info + 3 * (size_t)node), r = __ldg(info + 3 * (size_t)node + 1);
+        const int up = node ? __ldg(parent + node) : 0;
         __threadfence();
         int old = atomicAdd(visits + node, 1);
         if (old == 0) return;
-        int l = __ldg(info + 3 * (size_t)node), r = __ldg(info + 3 * (size_t)node + 1);
+        const bool left = l == me;
+        const int sib = left ? r : l;
         float o[6];
 #pragma unroll
+        for (int k = 0; k < 6; ++k) o[k] = __ldcg(aabb + 6 * (size_t)sib + k);
+#pragma unroll
         for (int k = 0; k < 3; ++k) {
-            o[k] = fminf(__ldcg(aabb + 6 * (size_t)l + k), __ldcg(aabb + 6 * (size_t)r + k));
-            o[3 + k] = fmaxf(__ldcg(aabb + 6 * (size_t)l + 3 + k), __ldcg(aabb + 6 * (size_t)r + 3 + k));
+            const float lmn = left ? box[k] : o[k], rmn = left ? o[k] : box[k];
+            const float lmx = left ? box[3 + k] : o[3 + k], rmx = left ? o[3 + k] : box[3 + k];
+            box[k] = fminf(lmn, rmn);
+            box[3 + k] = fmaxf(lmx, rmx);
         }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) __stcg(aabb + 6 * (size_t)node + k, o[k]);
+        for (int k = 0; k < 6; ++k) __stcg(aabb + 6 * (size_t)node + k, box[k]);
         if (node == 0) return;
-        node = __ldg(parent + node);
+        me = node;
+        node = up;
     }
 }
 

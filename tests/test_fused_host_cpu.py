@@ -36,12 +36,13 @@ def test_final_shading_bwd_multi_equals_the_single_pass_kernels():
     C.final_shading_bwd_multi_equals_the_single_pass_kernels(H.kernels(), "cpu")
 
 
-def _render(sc, w, prepared_lighting=False, spp=3, **kw):
+def _render(sc, w, prepared_lighting=False, spp=3, early_blocks=False, **kw):
     mods = R.load_m_for_restir(sc["W"], sc["H"], device="cpu")
     g = {k: H.t(v) for k, v in sc["gbuffer"].items()}
     env = H.t(sc["env"]).requires_grad_(True)
     if prepared_lighting:
-        kw["lighting"] = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env, spp, 99)
+        kw["lighting"] = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env, spp, 99,
+                                            frame_pixels=sc["W"] * sc["H"] if early_blocks else None)
     normal = g["normal_map"].clone().requires_grad_(True)
     tex = torch.cat((g["diffuse_map"], torch.zeros_like(g["diffuse_map"])), dim=1).requires_grad_(True)
     kd = tex[:, 0:3]  # strided view, as render_stage1 passes it
@@ -83,8 +84,9 @@ def test_prepared_lighting_changes_nothing():
     w.update_mesh(H.t(sc["vert"]), H.t(sc["tri"]))
     a, ga = _render(sc, w, overlap=True)
     b, gb = _render(sc, w, prepared_lighting=True, overlap=True)
-    for x, y in zip(a + ga, b + gb):
-        assert torch.equal(x, y)
+    c, gc = _render(sc, w, prepared_lighting=True, early_blocks=True, overlap=True)  # + zero-filled blocks, flipped map
+    for x, y, z in zip(a + ga, b + gb, c + gc):
+        assert torch.equal(x, y) and torch.equal(x, z)
 
 
 def test_long_loop_flushes_and_chunked_backward():

@@ -541,7 +541,8 @@ def test_long_loop_and_prepared_lighting_gpu(kernels):
         kd = g["diffuse_map"].clone().requires_grad_(True)
         rs = g["roughness_specular"].clone().requires_grad_(True)
         if prepared:
-            kw["lighting"] = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env, spp, 321)
+            kw["lighting"] = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env, spp, 321,
+                                                frame_pixels=sc["W"] * sc["H"])
         outs = R.run_restir_di_with_pt(False, 1, 1, 1, synth.ProceduralMaterial(sc["metallic"]), None, w, *mods, env,
                                        g["occ_map"].clone(), normal, g["depth_map"], kd, rs, g["ray_dir_map"], g["pos_map"],
                                        None, None, None, None, W, Hh, spp, 2, 2, 2.0, 0.1, 0.001, random_offset=321, **kw)
