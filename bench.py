@@ -185,6 +185,23 @@ def run_gpu(args):
     import torch.distributed as dist
     from mirres_restir_nerf_mesh_b200 import synth, renderer_restir as R, slangpy_shim, kernels as K
     from mirres_restir_nerf_mesh_b200.graphed import CapturedStep
+    from mirres_restir_nerf_mesh_b200 import meshutils as MU, renderutils_ops as OPS
+
+    class _Interpolated(torch.autograd.Function):
+        """the interpolated vertex normal mirres_gbuffer_primary has written, made differentiable w.r.t. the vertex
+        normals: the backward is the barycentric scatter mirres_interpolate_bwd"""
+        @staticmethod
+        def forward(ctx, vnrm, smooth, prim, bary, tri, k):
+            ctx.save_for_backward(prim, bary, tri)
+            ctx.k, ctx.V = k, vnrm.shape[0]
+            return smooth.view_as(smooth)
+
+        @staticmethod
+        def backward(ctx, g):
+            prim, bary, tri = ctx.saved_tensors
+            out = torch.zeros(ctx.V, 3, device=g.device)
+            ctx.k.interpolate_bwd(g.contiguous(), prim, bary, tri, out)
+            return out, None, None, None, None, None
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -230,6 +247,9 @@ def run_gpu(args):
         with torch.cuda.stream(bvh_stream):
             worker.update_mesh(vert, tri)
         rays_o, rays_d = synth.camera_rays_torch(W, H, pose)
+        if args.mesh_normals:
+            vert_l = vert.detach().clone().requires_grad_(True)
+            vnrm, _ = MU.auto_normals(vert_l, tri)  # beside the LBVH build
         env_l = env.detach().clone().requires_grad_(True)
         lighting = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env_l, spp, 1234 + 17 * rank,
                                       frame_pixels=n)
@@ -237,9 +257,21 @@ def run_gpu(args):
         occ, depth = torch.empty(n, 1, device=dev), torch.empty(n, 1, device=dev)
         pos, nrm = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
         prim, bary = torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, 2, device=dev)
-        pk.gbuffer_primary(worker.packed, rays_o, rays_d, occ, pos, nrm, depth, prim, bary, ws=slangpy_shim.workspace(dev, n))
+        if args.mesh_normals:
+            # the reference's normal chain (nerf/renderer.py:979-1030): vertex normals of the mesh -> interpolated ->
+            # prepare_shading_normal, differentiable back to the vertex POSITIONS
+            geom = torch.empty(n, 3, device=dev)
+            pk.gbuffer_primary(worker.packed, rays_o, rays_d, occ, pos, nrm, depth, prim, bary, vnormal=vnrm.detach(),
+                               tri=tri, ws=slangpy_shim.workspace(dev, n), geom_normal=geom)
+            smooth = _Interpolated.apply(vnrm, nrm, prim, bary, tri, pk)
+            normal = OPS.prepare_shading_normal(pos.view(1, H, W, 3), pose[3].reshape(1, 1, 1, 3), None,
+                                                smooth.view(1, H, W, 3), torch.zeros(1, 1, 1, 3, device=dev),
+                                                geom.view(1, H, W, 3)).view(n, 3)
+        else:
+            pk.gbuffer_primary(worker.packed, rays_o, rays_d, occ, pos, nrm, depth, prim, bary,
+                               ws=slangpy_shim.workspace(dev, n))
+            normal = nrm.requires_grad_(True)
         kd, rs = mat.gbuffer_materials(pos, occ)   # stand-in for the tiny-cuda-nn material MLP (out of scope)
-        normal = nrm.requires_grad_(True)
         kd.requires_grad_(True)
         rs.requires_grad_(True)
         outs = R.run_restir_di_with_pt(False, 1, 1, 1, mat, None, worker, *mods, env_l, occ, normal, depth, kd, rs, rays_d,
@@ -250,7 +282,10 @@ def run_gpu(args):
         # gradients leave the path as grad_env [He,We,3] and dense per-pixel grads; the latter are scattered to vertices /
         # vertex texture here (the reference: nvdiffrast / tcnn backward), everything lands in ONE flat buffer
         flat_grad[:ne].copy_(env_l.grad.reshape(-1))
-        pk.interpolate_bwd(normal.grad, prim, bary, tri, flat_grad[ne:ne + 3 * V].view(V, 3))
+        if args.mesh_normals:
+            flat_grad[ne:ne + 3 * V].copy_(vert_l.grad.reshape(-1))  # d loss / d vertex positions through the normals
+        else:
+            pk.interpolate_bwd(normal.grad, prim, bary, tri, flat_grad[ne:ne + 3 * V].view(V, 3))
         pk.interpolate_bwd(torch.cat((kd.grad, rs.grad), dim=1), prim, bary, tri, flat_grad[ne + 3 * V:].view(V, 5))
         return loss.detach(), flat_grad
 
@@ -348,7 +383,9 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": _workload_name(args.config, cfg), "l2": "256 MiB flush between timed steps",
+                "config": {"workload": _workload_name(args.config, cfg) + (
+                    "; G-buffer normals = auto_normals -> interpolation -> prepare_shading_normal, gradient to vertex "
+                    "positions" if args.mesh_normals else ""), "l2": "256 MiB flush between timed steps",
                            "parallelism": "one view per rank, 1 NCCL allreduce of env+vertex+texture grads per step",
                            "execution": ("CUDA graph replay of the whole step" if captured is not None else "eager") +
                                         (", direct and indirect chains on two streams" if not args.no_overlap else "")},
@@ -440,6 +477,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-overlap", action="store_true", help="direct and indirect chains on one stream")
+    ap.add_argument("--mesh-normals", action="store_true",
+                    help="G-buffer normals through the reference's chain (auto_normals -> interpolation -> "
+                         "prepare_shading_normal); the vertex segment of the gradient buffer then holds d loss / d vertex "
+                         "positions instead of normal gradients accumulated at the vertices")
     ap.add_argument("--timeline", default=None, help="diagnostics: write a per-kernel device timeline of one warm step")
     args = ap.parse_args()
     if args.impl == "reference":

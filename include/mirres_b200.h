@@ -251,7 +251,8 @@ int mirres_eaw_bwd_multi(float c_phi, float n_phi, float p_phi, int fx, int fy, 
  *        pos [n,3], normal [n,3] (face normal flipped towards the ray, or -- when vnormal [V,3] and tri [F,3] are
  *        given -- the barycentric interpolation of the vertex normals, the role of dr.interpolate over
  *        auto_normals, nerf/meshutils.py:14-39), depth [n] = |pos - org|, prim [n] i32 (-1 miss), bary [n,2] = (u, v)
- *        weights of the triangle's 2nd / 3rd vertex.  prim and bary are optional.  workspace (optional, sized by
+ *        weights of the triangle's 2nd / 3rd vertex.  prim and bary are optional; so is geom_normal [n,3], which keeps
+ *        the face normal when `normal` receives the interpolated one (prepare_shading_normal wants both).  workspace (optional, sized by
  *        mirres_workspace_bytes(n)): the rays go through the persistent queue tracer instead of one thread per ray.
  *   mirres_interpolate_bwd   reverse of that interpolation, i.e. the scatter nvdiffrast / the texture backward do
  *        for the per-pixel gradients the path emits (Resampling.py:193-214):
@@ -261,7 +262,8 @@ int mirres_eaw_bwd_multi(float c_phi, float n_phi, float p_phi, int fx, int fy, 
  */
 int mirres_gbuffer_primary(const void *packed_nodes, const void *packed_tris, const float *org, const float *dir, int n,
                            const float *vnormal, const int *tri, float *occ, float *pos, float *normal, float *depth,
-                           int *prim, float *bary, void *workspace, size_t workspace_bytes, void *stream);
+                           int *prim, float *bary, float *geom_normal, void *workspace, size_t workspace_bytes,
+                           void *stream);
 /* Derived maps of run_restir_di_with_pt in one launch (nerf/renderer_restir.py:279-287 and :484-486; ~25 elementwise torch
  * launches in the reference, same operations in the same order): occ [n] in place (occ <= 0.5 -> 0); normal_depth [n,4]
  * = (normal, depth), 16-byte aligned; brdf_map [n,3] = (0.2126 r + 0.7152 g + 0.0722 b of kd, the same weights summed

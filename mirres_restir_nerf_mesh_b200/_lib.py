@@ -49,7 +49,7 @@ SIGNATURES = {
     "mirres_bilateral_bwd": "iifppppp",
     "mirres_eaw_fwd_multi": "fffiif" + "ppp" + "i" + "ppp" + "p",
     "mirres_eaw_bwd_multi": "fffiif" + "ppp" + "i" + "ppppppp" + "p",
-    "mirres_gbuffer_primary": "ppppi" + "pp" + "pppppp" + "pz" + "p",
+    "mirres_gbuffer_primary": "ppppi" + "pp" + "pppppp" + "p" + "pz" + "p",
     "mirres_prepare_maps": "ippppppppp" + "p",
     "mirres_interpolate_bwd": "piipppipp",
     "mirres_vertex_normals_fwd": "pipippp",

@@ -28,12 +28,14 @@ struct GbufParams {
     float *__restrict__ depth;         // [n]
     int *__restrict__ prim;            // [n]
     float *__restrict__ bary;          // [n,2]
+    float *__restrict__ gnormal;       // [n,3] or null: the face normal, kept when `normal` receives the interpolated one
 };
 
 // shared tail of both launch shapes
 MR_DEV void gbuffer_write(const GbufParams &p, size_t i, bool found, float3 o, float3 x, float3 n, int prim, float u, float v)
 {
     float d = 0.f;
+    if (p.gnormal) store3(p.gnormal, i, found ? n : f3(0.f));
     if (found) {
         const float3 dv = x - o;
         d = sqrtf(dot(dv, dv));
@@ -453,13 +455,13 @@ extern "C" {
 
 int mirres_gbuffer_primary(const void *packed_nodes, const void *packed_tris, const float *org, const float *dir, int n,
                            const float *vnormal, const int *tri, float *occ, float *pos, float *normal, float *depth,
-                           int *prim, float *bary, void *workspace, size_t workspace_bytes, void *stream)
+                           int *prim, float *bary, float *geom_normal, void *workspace, size_t workspace_bytes, void *stream)
 {
     if (!packed_nodes || !packed_tris || !org || !dir || !occ || !pos || !normal || !depth) return MIRRES_ERR_NULL;
     if (vnormal && !tri) return MIRRES_ERR_NULL;
     if (n < 0) return MIRRES_ERR_SHAPE;
     if (n == 0) return 0;
-    GbufParams p = {{(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris}, org, dir, vnormal, tri, occ, pos, normal, depth, prim, bary};
+    GbufParams p = {{(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris}, org, dir, vnormal, tri, occ, pos, normal, depth, prim, bary, geom_normal};
     cudaStream_t st = (cudaStream_t)stream;
     if (!workspace) return foreach_item<GbufParams, gbuffer_item, 128>(p, n, st);
     if ((uintptr_t)workspace & 255) return MIRRES_ERR_ALIGN;

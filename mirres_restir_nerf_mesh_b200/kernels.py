@@ -300,12 +300,13 @@ class Kernels:
 
     # -- G-buffer producer / gradient scatter ------------------------------------------------------------------------
     def gbuffer_primary(self, packed, org, dirs, occ, pos, normal, depth, prim=None, bary=None, vnormal=None, tri=None,
-                        ws=None):
+                        ws=None, geom_normal=None):
         wsp = (None, 0) if ws is None else self._ws(ws)
         rc = self.lib.mirres_gbuffer_primary(self._p(packed[0]), self._p(packed[1]), self._f(org), self._f(dirs),
                                              org.shape[0], self._f(vnormal, True), self._i(tri, True), self._f(occ),
                                              self._f(pos), self._f(normal), self._f(depth), self._i(prim, True),
-                                             self._f(bary, True), wsp[0], wsp[1], self._stream())
+                                             self._f(bary, True), self._f(geom_normal, True), wsp[0], wsp[1],
+                                             self._stream())
         self._check(rc, "mirres_gbuffer_primary")
 
     def prepare_maps(self, occ, normal, depth, diffuse, rough_metal, ray_dir, normal_depth, brdf_map, ray_out):

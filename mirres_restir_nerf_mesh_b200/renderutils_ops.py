@@ -76,7 +76,9 @@ def prepare_shading_normal(pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng,
     """nerf/renderutils/ops.py:129-163 (final shading normal: tangent space, two-sided flip, normal-map perturbation,
     back-facing normals bent towards the camera)."""
     if perturbed_nrm is None:
-        perturbed_nrm = torch.tensor([0, 0, 1], dtype=torch.float32, device=pos.device)[None, None, None, ...]
+        # (0, 0, 1) built with device-side fills: a host->device copy could not be captured into a CUDA graph
+        perturbed_nrm = torch.zeros(1, 1, 1, 3, dtype=torch.float32, device=pos.device)
+        perturbed_nrm[..., 2] = 1.0
     out = _prepare_shading_normal_func.apply(pos, view_pos, perturbed_nrm, smooth_nrm, smooth_tng, geom_nrm,
                                              two_sided_shading, opengl)
     if torch.is_anomaly_enabled():

@@ -132,7 +132,10 @@ def test_gbuffer_primary_and_interpolate_bwd(oracle):
     # interpolated vertex normals
     vn = vert / np.linalg.norm(vert, axis=1, keepdims=True)
     nrm2 = torch.zeros(n, 3)
-    k.gbuffer_primary(w.packed, H.t(sc["rays_o"]), H.t(sc["rays_d"]), occ, pos, nrm2, depth, prim, bary, H.t(vn.astype(np.float32)), H.t(tri))
+    face = torch.full((n, 3), 7.0)
+    k.gbuffer_primary(w.packed, H.t(sc["rays_o"]), H.t(sc["rays_d"]), occ, pos, nrm2, depth, prim, bary, H.t(vn.astype(np.float32)), H.t(tri),
+                      geom_normal=face)
+    assert torch.equal(face, nrm)  # the face normal (zero on misses) survives beside the interpolated one
     vv = vn.astype(np.float32)[tri[opr[m]]]
     want = (1 - b[:, 0:1] - b[:, 1:2]) * vv[:, 0] + b[:, 0:1] * vv[:, 1] + b[:, 1:2] * vv[:, 2]
     np.testing.assert_allclose(nrm2.numpy()[m], want, atol=1e-6)
