@@ -148,6 +148,17 @@ def test_gbuffer_primary_and_gradient_scatter(kernels, oracle):
         assert torch.equal(a_, b_)
     tri = tt(sc["tri"])
     V = len(sc["vert"])
+    # interpolated vertex normals with the face normal kept beside them (both launch shapes)
+    vn = torch.nn.functional.normalize(tt(sc["vert"]), dim=-1)
+    for ws in (None, slangpy_shim.workspace(torch.device(DEV), n)):
+        sm, face = torch.zeros(n, 3, device=DEV), torch.full((n, 3), 7.0, device=DEV)
+        kernels.gbuffer_primary(w.packed, tt(sc["rays_o"]), tt(sc["rays_d"]), o2, p2, sm, d2, pr2, b2, vnormal=vn, tri=tri,
+                                ws=ws, geom_normal=face)
+        assert torch.equal(face, nrm)
+        fg = prim >= 0
+        c = vn[tri.long()[prim[fg].long()]]
+        want = (1 - bary[fg, 0:1] - bary[fg, 1:2]) * c[:, 0] + bary[fg, 0:1] * c[:, 1] + bary[fg, 1:2] * c[:, 2]
+        assert torch.allclose(sm[fg], want, atol=1e-6) and bool((sm[~fg] == 0).all())
     g = torch.Generator(device="cpu").manual_seed(0)
     for C, use_bary, contended in ((3, True, False), (8, True, False), (5, False, False), (8, True, True)):
         grad = torch.randn(n, C, generator=g).to(DEV)
