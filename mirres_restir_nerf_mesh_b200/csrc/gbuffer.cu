@@ -63,9 +63,20 @@ struct GbufWaveParams {
     Workspace ws;
     int n;
 };
+// Most primary rays of a view miss the mesh altogether.  The gen pass takes the walk's own first step for them -- the
+// four boxes of the root record against closest = 1e7, the test closest_hit starts with -- and hands only the rays that
+// pass one of them to the tracer; the others are the misses the tracer would have reported after the same test.
 MR_DEV void gbuffer_gen_px(const GbufWaveParams &p, int idx)
 {
-    queue_closest_ray(p.ws, (size_t)idx, load3(p.g.org, (size_t)idx), load3(p.g.dir, (size_t)idx));
+    const float3 o = load3(p.g.org, (size_t)idx), d = load3(p.g.dir, (size_t)idx);
+    const Ray r = make_ray(o, d);
+    WideHit w;
+    wide_fetch(r, p.g.bvh.nodes, 0, w);
+    bool pass = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pass = pass || fminf(1e7f, w.tf[k]) > w.tn[k];
+    if (pass) queue_closest_ray(p.ws, (size_t)idx, o, d);
+    else queue_closest_empty(p.ws, (size_t)idx);
 }
 MR_DEV void gbuffer_resolve_px(const GbufWaveParams &p, int idx)
 {
