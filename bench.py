@@ -388,7 +388,8 @@ def run_gpu(args):
                     "positions" if args.mesh_normals else ""), "l2": "256 MiB flush between timed steps",
                            "parallelism": "one view per rank, 1 NCCL allreduce of env+vertex+texture grads per step",
                            "execution": ("CUDA graph replay of the whole step" if captured is not None else "eager") +
-                                        (", direct and indirect chains on two streams" if not args.no_overlap else "")},
+                                        (", concurrent schedule (reuse chain, initial candidates, shading and the indirect chains "
+                                         "on their own streams)" if not args.no_overlap else "")},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches * args.steps, "clocks": clocks.summary(), "roofline": roof,
