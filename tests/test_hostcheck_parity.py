@@ -22,7 +22,8 @@ def _worker(sc):
     return w
 
 
-@pytest.mark.parametrize("name,metallic", [("T0", 0.0), ("T1", 0.0), ("T2", 0.4)])
+# C1 is BASELINE.json configs[0], the "CPU plumbing workload": icosphere level 5 (20 480 triangles), 256 x 256, 1 spp
+@pytest.mark.parametrize("name,metallic", [("T0", 0.0), ("T1", 0.0), ("T2", 0.4), ("C1", 0.0)])
 def test_pipeline_bit_exact(name, metallic):
     sc = P.scene(name, metallic)
     ref = P.oracle_run(sc)
