@@ -31,6 +31,15 @@ def test_pipeline_bit_exact(name, metallic):
     assert P.compare(ref, got) == []
 
 
+def test_c2_full_size_bit_exact():
+    """BASELINE.json configs[1] at FULL size (500 000 triangles, 800 x 800, spp 4, 3 path vertices): every intermediate
+    tensor of the forward spp loop, product kernel source (host flavour) against the oracle; ~10 s on 8 cores."""
+    sc = P.scene("C2", 0.0)
+    ref = P.oracle_run(sc)
+    got = P.product_run(sc, _worker(sc), "cpu", ref["prepared"])
+    assert P.compare(ref, got) == []
+
+
 def test_three_and_one_indirect_bounces():
     sc = P.scene("T0")
     for mb in (1, 3):
