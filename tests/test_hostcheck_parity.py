@@ -40,6 +40,15 @@ def test_c2_full_size_bit_exact():
     assert P.compare(ref, got) == []
 
 
+def test_c5_sizes_one_iteration_bit_exact():
+    """BASELINE.json configs[4] sizes (2 000 000 triangles, 2048 x 2048, 2k x 1k envmap, 4 path vertices), ONE spp
+    iteration: the largest shapes of the contract through the product kernel source against the oracle; ~20 s."""
+    sc = P.scene("C5", 0.0)
+    ref = P.oracle_run(sc, spp=1)
+    got = P.product_run(sc, _worker(sc), "cpu", ref["prepared"], spp=1)
+    assert P.compare(ref, got) == []
+
+
 def test_three_and_one_indirect_bounces():
     sc = P.scene("T0")
     for mb in (1, 3):
