@@ -31,6 +31,15 @@ def test_pipeline_bit_exact(name, metallic):
     assert P.compare(ref, got) == []
 
 
+@pytest.mark.parametrize("name,metallic,view", [("T2", 0.4, 13), ("T2", 0.0, 37), ("T1", 0.4, 71), ("C1", 0.4, 50)])
+def test_pipeline_bit_exact_other_views(name, metallic, view):
+    """other cameras of the 100-view ring and the metallic material variant (SURVEY.md 8d synthetic inputs)"""
+    sc = P.scene(name, metallic, view)
+    ref = P.oracle_run(sc, random_offset=977 + view)
+    got = P.product_run(sc, _worker(sc), "cpu", ref["prepared"], random_offset=977 + view)
+    assert P.compare(ref, got) == []
+
+
 def test_c2_full_size_bit_exact():
     """BASELINE.json configs[1] at FULL size (500 000 triangles, 800 x 800, spp 4, 3 path vertices): every intermediate
     tensor of the forward spp loop, product kernel source (host flavour) against the oracle; ~10 s on 8 cores."""
