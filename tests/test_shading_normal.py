@@ -248,3 +248,27 @@ def test_vertex_gradient_chain_gpu():
     out_r, gv_r = chain(ref_auto_normals, ref_shading_normal, lambda vn, c, w: (vn[c] * w[..., None]).sum(1))
     assert close(out_p.cpu().numpy(), out_r.cpu().numpy(), FWD_RTOL)
     assert close(gv_p.cpu().numpy(), gv_r.cpu().numpy(), GRAD_RTOL), float((gv_p - gv_r).abs().max())
+
+
+def test_auto_normals_c2_mesh_against_torch_expression():
+    """config C2's mesh (250 000 vertices, 500 000 triangles): vertex normals and their gradient from the product kernels
+    (host flavour) against the torch expression of meshutils.py:14-39 differentiated by autograd"""
+    import hostcheck as H
+    from mirres_restir_nerf_mesh_b200 import synth
+    v_np, t_np = synth.make_mesh(synth.CONFIGS["C2"])
+    vert, tri = torch.from_numpy(v_np), torch.from_numpy(t_np)
+    k = H.kernels()
+    vsum, vnrm = torch.empty_like(vert), torch.empty_like(vert)
+    k.vertex_normals_fwd(vert, tri, vsum, vnrm)
+    v = vert.clone().requires_grad_(True)
+    i = tri.long()
+    fn = torch.linalg.cross(v[i[:, 1]] - v[i[:, 0]], v[i[:, 2]] - v[i[:, 0]])
+    s = torch.zeros_like(v).index_add_(0, i[:, 0], fn).index_add_(0, i[:, 1], fn).index_add_(0, i[:, 2], fn)
+    want = s / torch.sqrt(torch.clamp((s * s).sum(-1, keepdim=True), min=1e-20))
+    assert close(vnrm.numpy(), want.detach().numpy(), FWD_RTOL)
+    g = torch.from_numpy(np.random.default_rng(2).standard_normal(v_np.shape).astype(np.float32))
+    want.backward(g)
+    gv = torch.zeros_like(vert)
+    k.vertex_normals_bwd(vert, tri, vsum, g, gv)
+    # the gradient of a unit normal scales with 1 / |sum of face normals| (tiny faces: ~1e5 here), compare relative to its scale
+    assert close(gv.numpy(), v.grad.numpy(), GRAD_RTOL), float((gv - v.grad).abs().max() / v.grad.abs().max())
