@@ -78,11 +78,21 @@ class Clocks:
 # ----------------------------------------------------------------------------------------------------------------------
 # reference arm: the CPU oracle (the reference itself has no CPU implementation and cannot be built here)
 # ----------------------------------------------------------------------------------------------------------------------
+def host_threads():
+    """Host threads this process may use: its CPU affinity set, not OMP_NUM_THREADS (torch.distributed.run exports
+    OMP_NUM_THREADS=1 into every rank, which would turn the reference arm into a single-threaded run)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def oracle_sample(cfg_name, crop, spp, threads=None):
     """One bounded sample of the workload on the host cores: LBVH build + forward spp loop on a crop x crop frame.
-    Returns (samples, seconds, counters)."""
+    Returns (samples, seconds, counters).  The OpenMP thread count is set explicitly (all host threads by default)."""
     from oracle import oracle as O, driver as D
     from mirres_restir_nerf_mesh_b200 import synth
+    O.set_threads(threads or host_threads())
     cfg = synth.CONFIGS[cfg_name]
     st = _ORACLE_STATE
     if "mesh" not in st:
@@ -111,9 +121,11 @@ def run_reference(args):
     if rank != 0:
         return
     from mirres_restir_nerf_mesh_b200 import synth
+    from oracle import oracle as O
     cfg = synth.CONFIGS[args.config]
     crop = cfg["W"]  # the full frame of the workload
-    cores = os.cpu_count() or 1
+    O.set_threads(host_threads())
+    cores = O.threads_in_use()  # measured inside an OpenMP region of the oracle, not read from the environment
     for _ in range(args.warmup):
         oracle_sample(args.config, crop, cfg["spp"])
     tot_s, tot_t = 0, 0.0
@@ -128,8 +140,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": _workload_name(args.config, cfg), "sample": "%dx%d" % (crop, crop)},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": _config(args, cfg),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -138,6 +151,16 @@ def _workload_name(name, cfg):
     return ("%s: stage-1 training step, %s mesh, %dx%d rays, spp=%d, %d bounces (direct + %d indirect), ReSTIR initial + "
             "temporal + spatial, LBVH rebuild, fwd+bwd" % (name, "x".join(str(x) for x in cfg["mesh"][1].values()), cfg["W"],
                                                           cfg["H"], cfg["spp"], cfg["max_bounce"] + 1, cfg["max_bounce"]))
+
+
+def _config(args, cfg):
+    """The workload both arms run -- the same dict in both JSON lines (how an arm executes it is said elsewhere:
+    `execution` in the GPU line, `cpu_baseline.sample` in the reference line)."""
+    return {"workload": _workload_name(args.config, cfg) + (
+                "; G-buffer normals = auto_normals -> interpolation -> prepare_shading_normal, gradient to vertex "
+                "positions" if getattr(args, "mesh_normals", False) else ""),
+            "l2": "256 MiB flush between timed steps",
+            "parallelism": "one view per rank, 1 NCCL allreduce of env+vertex+texture grads per step"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -368,7 +391,13 @@ def run_gpu(args):
         per_kernel, launches = pk.per_kernel_ms(), pk.launches // k_steps
 
     tms = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    per_rank = None
     if world > 1:
+        # every rank's own time beside the maximum: the ranks render different views, so imbalance between views and the
+        # cost of the collective can be told apart
+        allt = [torch.empty_like(tms) for _ in range(world)]
+        dist.all_gather(allt, tms)
+        per_rank = [[round(float(t[0]) / args.steps, 4), round(float(t[1]) / args.steps, 4)] for t in allt]
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = float(tms[0]), float(tms[1])
     samples = n * spp * world * args.steps
@@ -378,30 +407,42 @@ def run_gpu(args):
     if rank == 0:
         peaks = _peaks()
         peak = peaks["hbm_gbs"] if peaks else 6650.0
-        roof = roofline(args.config, cfg, per_kernel, 2, peak, "measured" if peaks else "fallback")
-        step_alg = step_algorithmic_bytes(args.config, cfg, spp)
+        # foreground pixels of this rank's view, counted on the device outside the timed region: background pixels leave
+        # every kernel after the compaction, so the per-pixel streams of SURVEY.md 8d are charged to the foreground only
+        occ_c, depth_c = torch.empty(n, 1, device=dev), torch.empty(n, 1, device=dev)
+        pos_c, nrm_c = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
+        ro_c, rd_c = synth.camera_rays_torch(W, H, device_in["pose"])
+        pk.gbuffer_primary(worker.packed, ro_c, rd_c, occ_c, pos_c, nrm_c, depth_c, ws=slangpy_shim.workspace(dev, n))
+        n_fg = int((occ_c >= 0.1).sum().item())
+        roof = roofline(args.config, cfg, per_kernel, 2, peak, "measured" if peaks else "fallback", n_fg)
+        step_alg_all, step_alg = step_algorithmic_bytes(args.config, cfg, spp, n_fg)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": _workload_name(args.config, cfg) + (
-                    "; G-buffer normals = auto_normals -> interpolation -> prepare_shading_normal, gradient to vertex "
-                    "positions" if args.mesh_normals else ""), "l2": "256 MiB flush between timed steps",
-                           "parallelism": "one view per rank, 1 NCCL allreduce of env+vertex+texture grads per step",
-                           "execution": ("CUDA graph replay of the whole step" if captured is not None else "eager") +
-                                        (", concurrent schedule (reuse chain, initial candidates, shading and the indirect chains "
-                                         "on their own streams)" if not args.no_overlap else "")},
+                "config": _config(args, cfg),
+                "execution": ("CUDA graph replay of the whole step" if captured is not None else "eager") +
+                             (", concurrent schedule (reuse chain, initial candidates, shading and the indirect chains "
+                              "on their own streams)" if not args.no_overlap else ""),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches * args.steps, "clocks": clocks.summary(), "roofline": roof,
+                # S_screen charged on foreground pixels (+ 4 B of occupancy per background pixel and stage-entry); the figure
+                # with S_screen charged on every pixel of the frame (round 1's) is kept beside it as *_all_pixels
                 "step_roofline": None if step_alg is None else {
                     "alg_bytes_per_step": step_alg, "achieved": step_alg / (ms_dev / args.steps * 1e-3) / 1e9,
-                    "peak": peak, "unit": "GB/s", "frac": step_alg / (ms_dev / args.steps * 1e-3) / 1e9 / peak},
+                    "peak": peak, "unit": "GB/s", "frac": step_alg / (ms_dev / args.steps * 1e-3) / 1e9 / peak,
+                    "foreground_pixels": n_fg, "frame_pixels": n,
+                    "alg_bytes_per_step_all_pixels": step_alg_all,
+                    "frac_all_pixels": step_alg_all / (ms_dev / args.steps * 1e-3) / 1e9 / peak},
                 "kernel_ms_per_step": {k: round(v[0] / 2, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])}}
+        if per_rank is not None:
+            line["per_rank_ms_per_step"] = {"device": [t[0] for t in per_rank], "e2e": [t[1] for t in per_rank]}
         if world == 1 and not args.no_cpu_baseline:
             crop = cfg["W"]
             s, dt, _ = oracle_sample(args.config, crop, spp)
             s2, dt2, _ = oracle_sample(args.config, crop, spp)
-            line["cpu_baseline"] = {"value": (s + s2) / (dt + dt2), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            from oracle import oracle as O
+            line["cpu_baseline"] = {"value": (s + s2) / (dt + dt2), "unit": UNIT, "cores": O.threads_in_use(), "kind": "port",
                                     "sample": "CPU oracle (OpenMP, all host cores): LBVH rebuild + forward spp loop of the same %dx%d frame, 2 repetitions; no G-buffer, denoiser or backward" % (crop, crop)}
         print(json.dumps(line))
     if world > 1:
@@ -409,17 +450,26 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def step_algorithmic_bytes(cfg_name, cfg, spp):
+def step_algorithmic_bytes(cfg_name, cfg, spp, n_foreground=None):
     """Algorithmic bytes of one whole step: sum over samples of S_screen + 36 V_n + 48 V_t, forward
-    (872 B first spp iteration, 1040 B after) + backward (280 B), plus 424 B per rebuilt triangle."""
+    (872 B first spp iteration, 1040 B after) + backward (280 B), plus 424 B per rebuilt triangle.
+    Returns (all_pixels, foreground): the first charges S_screen to every pixel of the frame, the second to the
+    foreground pixels only plus the 4-byte occupancy read with which a background pixel leaves each of the table's
+    11 forward + 2 backward stage entries per spp iteration (every reference kernel early-outs on occ < 0.1).  The
+    traversal term is the oracle's exact node / triangle count and is the same in both."""
     path = os.path.join(ROOT, "profiles", "oracle_counters_%s.json" % cfg_name)
     if not os.path.exists(path):
-        return None
+        return None, None
     c = json.load(open(path))
     n = cfg["W"] * cfg["H"]
     trav = c["per_sample"]["B_alg_traversal_bytes"] * n * spp
-    screen = n * (872 + 1040 * (spp - 1) + 280 * spp)
-    return trav + screen + 424 * c["triangles"]
+    per_px = 872 + 1040 * (spp - 1) + 280 * spp
+    build = 424 * c["triangles"]
+    if n_foreground is None:
+        n_foreground = int(round(c.get("hit_fraction", 1.0) * n))
+    stages = (9 + 2) * spp + (spp - 1)  # 9 forward stage entries (+ temporal for i > 0) + 2 backward per iteration
+    fg = n_foreground * per_px + (n - n_foreground) * 4 * stages
+    return trav + n * per_px + build, trav + fg + build
 
 
 def _timeline(torch, step, path):
@@ -446,7 +496,7 @@ def _timeline(torch, step, path):
             f.write("%10.1f %9.1f %8.1f  %s\n" % (s, d, gap, name[:110]))
 
 
-def roofline(cfg_name, cfg, per_kernel, steps, peak, peak_kind):
+def roofline(cfg_name, cfg, per_kernel, steps, peak, peak_kind, n_foreground=None):
     """Dominant kernel vs the HBM roofline.  Algorithmic bytes per launch = S_screen(stage) * N + 36 * V_n + 48 * V_t
      with V_n / V_t the oracle's node-pop / triangle-test counts per launch under the contract schedule
     (profiles/oracle_counters_<cfg>.json, produced by tools/oracle_counters.py)."""
@@ -459,7 +509,11 @@ def roofline(cfg_name, cfg, per_kernel, steps, peak, peak_kind):
     screen = {"spatial_resampling": 104, "initial_resampling": 80, "bounce_shade": 176, "bounce_first": 140,
               "final_visibility": 28, "temporal_resampling": 168}.get(name, 0)
     c = counters.get(name, {})
-    alg = screen * n + 36 * c.get("nodes_per_launch", 0) + 48 * c.get("tris_per_launch", 0)
+    if n_foreground is not None:  # per-pixel streams on foreground pixels, the occupancy word on the others
+        alg = screen * n_foreground + 4 * (n - n_foreground)
+    else:
+        alg = screen * n
+    alg += 36 * c.get("nodes_per_launch", 0) + 48 * c.get("tris_per_launch", 0)
     dur = ms / count * 1e-3
     achieved = alg / dur / 1e9 if alg else None
     return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",

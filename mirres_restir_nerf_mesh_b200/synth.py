@@ -219,6 +219,8 @@ CONFIGS = {
     "C1": dict(mesh=("icosphere", dict(level=5)), W=256, H=256, env=(256, 512), spp=1, max_bounce=1),
     "C2": dict(mesh=("torus_knot", dict(nu=1000, nv=250)), W=800, H=800, env=(256, 512), spp=4, max_bounce=2),
     "C3": dict(mesh=("torus_knot", dict(nu=1000, nv=250)), W=800, H=800, env=(256, 512), spp=512, max_bounce=2),
+    # the frame stage 1 really renders for 800 x 800 data: ssaa = 2 (reference main.py:140, nerf/utils.py:770-777)
+    "C2S": dict(mesh=("torus_knot", dict(nu=1000, nv=250)), W=1600, H=1600, env=(256, 512), spp=2, max_bounce=2),
     "C5": dict(mesh=("torus_knot", dict(nu=2000, nv=500)), W=2048, H=2048, env=(1024, 2048), spp=128, max_bounce=3),
     # small cases for parity tests
     "T0": dict(mesh=("icosphere", dict(level=2)), W=48, H=40, env=(16, 32), spp=2, max_bounce=2),

@@ -52,6 +52,16 @@ def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+def set_threads(n):
+    """OpenMP threads of every oracle entry point from now on (overrides an inherited OMP_NUM_THREADS)."""
+    lib().orc_set_threads(int(n))
+
+
+def threads_in_use():
+    """Threads an OpenMP region of the oracle runs with right now (measured inside a parallel region)."""
+    return int(lib().orc_threads_in_use())
+
+
 def new_counters():
     return np.zeros(9, dtype=np.int64)
 

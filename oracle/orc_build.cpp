@@ -348,3 +348,22 @@ extern "C" int orc_fpmath_eval(int op, const float *x, const float *y, float *ou
     }
     return 0;
 }
+
+// Host threads of the OpenMP regions.  Launchers such as torch.distributed.run export OMP_NUM_THREADS=1 into every rank;
+// a caller that times the oracle as the CPU baseline (bench.py --impl reference) sets the count it means explicitly and
+// reports the count that actually ran.
+#include <omp.h>
+extern "C" void orc_set_threads(int n)
+{
+    if (n > 0) omp_set_num_threads(n);
+}
+extern "C" int orc_threads_in_use(void)
+{
+    int n = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        n = omp_get_num_threads();
+    }
+    return n;
+}

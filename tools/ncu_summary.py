@@ -1,4 +1,4 @@
-"""Summarise an .ncu-rep (read here, no GPU needed): key metrics of the first kernel in the report.
+"""Summarise an .ncu-rep (read here, no GPU needed): key metrics of every kernel in the report.
 
     python tools/ncu_summary.py gpurun_out/prof_spatial_px.ncu-rep [out.txt]
 """
@@ -34,13 +34,14 @@ KEYS = [
 def main(path, out=None):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    lines = ["# %s" % path, "kernel: %s" % vals[hdr.index("Kernel Name")][:120]]
-    for k in KEYS:
-        if k in hdr:
-            i = hdr.index(k)
-            lines.append("%-80s %s %s" % (k, vals[i], units[i]))
-    # anything with 'stalled' and a notable value
+    hdr, units = rows[0], rows[1]
+    lines = ["# %s" % path]
+    for n, vals in enumerate(r for r in rows[2:] if len(r) == len(hdr)):
+        lines.append("kernel %d: %s" % (n, vals[hdr.index("Kernel Name")][:120]))
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                lines.append("%-80s %s %s" % (k, vals[i], units[i]))
     text = "\n".join(lines)
     print(text)
     if out:
