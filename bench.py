@@ -178,7 +178,7 @@ class ProfiledKernels:
 
     def __getattr__(self, name):
         fn = getattr(self._inner, name)
-        if not callable(fn) or name.startswith("_") or name in ("bvh_sizes",):
+        if not callable(fn) or name.startswith("_") or name in ("bvh_sizes", "set_tuning", "get_tuning"):
             return fn
 
         def wrapped(*a, **kw):
@@ -239,6 +239,9 @@ def run_gpu(args):
 
     pk = ProfiledKernels(K.Kernels(), torch)
     slangpy_shim.set_kernels(pk)
+    for item in args.tune or []:  # launch-shape experiments (results do not depend on them), e.g. --tune closest_split=2
+        name, value = item.split("=")
+        pk.set_tuning(getattr(K.Kernels, "TUNE_" + name.upper()), int(value))
 
     # ---- synthetic scene; each rank renders its own training view (weak scaling over views) -------------------------
     vert_np, tri_np = synth.make_mesh(cfg)
@@ -536,6 +539,7 @@ def main():
                     help="G-buffer normals through the reference's chain (auto_normals -> interpolation -> "
                          "prepare_shading_normal); the vertex segment of the gradient buffer then holds d loss / d vertex "
                          "positions instead of normal gradients accumulated at the vertices")
+    ap.add_argument("--tune", action="append", help="library tuning NAME=VALUE (mirres_set_tuning), repeatable")
     ap.add_argument("--timeline", default=None, help="diagnostics: write a per-kernel device timeline of one warm step")
     args = ap.parse_args()
     if args.impl == "reference":

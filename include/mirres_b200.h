@@ -33,13 +33,22 @@ extern "C" {
 
 int mirres_abi_version(void);
 
-/* Launch-shape tuning, the only process-wide state of the library (SURVEY.md 8b allows a tuning context): blocks per SM of
- * the persistent queue tracers launched by SUBSEQUENT calls from any entry point; value <= 0 restores the default (3 for
- * boolean rays, 2 for closest-hit rays: small grids leave room for kernels of other streams).  A host that runs its
- * critical chain on a high-priority stream raises the value around those calls.  Results do not depend on it. */
+/* Launch-shape tuning (SURVEY.md 8b allows a tuning context).  The values belong to the CALLING HOST THREAD (thread-local
+ * storage): they shape the persistent queue tracers launched by subsequent calls of that thread, so two threads that drive
+ * different streams never see each other's settings; value <= 0 restores the default.  Results do not depend on them.
+ * The library keeps no other mutable state: device properties (SM count, occupancy) are cached per device, and no
+ * environment variable is read.
+ *   ANY_BLOCKS / CLOSEST_BLOCKS / MIXED_BLOCKS   blocks per SM of the boolean-ray / closest-hit / combined tracer grids
+ *                                                (defaults 3 / 2 / 4: small grids leave room for kernels of other streams)
+ *   CLOSEST_SPLIT                                1 (default): idle lanes walk deferred subtrees of closest-hit rays and
+ *                                                the result is rebuilt exactly from their hit logs; 2: one lane per ray */
 #define MIRRES_TUNE_ANY_BLOCKS 0
 #define MIRRES_TUNE_CLOSEST_BLOCKS 1
+#define MIRRES_TUNE_MIXED_BLOCKS 2
+#define MIRRES_TUNE_CLOSEST_SPLIT 3
+#define MIRRES_TUNE_COUNT_ 8
 int mirres_set_tuning(int key, int value);
+int mirres_get_tuning(int key); /* current value of `key` for the calling thread (0 = default), or MIRRES_ERR_SHAPE */
 
 /* ------------------------------------------------------------------------------------------------------------
  * LBVH construction.  Replaces restirbvhWorker.update_bvh, nerf/renderer_restir.py:25-89, and the Slang

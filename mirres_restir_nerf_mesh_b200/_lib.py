@@ -18,6 +18,7 @@ _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "u": ctypes.c_uint, "f": ctypes.c
 SIGNATURES = {
     "mirres_abi_version": "",
     "mirres_set_tuning": "ii",
+    "mirres_get_tuning": "i",
     "mirres_bvh_build": "pipippppppzp",
     "mirres_bvh_elements": "ppippp",
     "mirres_bvh_morton": "piffffffpp",

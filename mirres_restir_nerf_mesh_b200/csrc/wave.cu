@@ -5,7 +5,10 @@
 // once per frame here and shared by all wavefront stages (mr_wave.cuh); ascending pixel order keeps neighbouring
 // lanes on neighbouring surface points.
 #include <stdlib.h>
+#include <atomic>
+#include <mutex>
 #include "mr_wave.cuh"
+#include "mr_split.cuh"
 #include "../../include/mirres_b200.h"
 
 namespace mr {
@@ -117,12 +120,6 @@ __global__ void __launch_bounds__(CP_BLOCK) k_compact_write(const float *__restr
 // is reached) the idle lanes take over the OLDEST deferred subtree of busy lanes.  bvh_hit's boolean result is the OR over
 // all leaf tests (mr_bvh.cuh), so walking the subtrees of one ray on several lanes returns the same flag while the
 // longest ray of a launch stops being a serial chain of ~10^3 dependent L2 loads.
-__device__ __forceinline__ void prefetch_l1(const void *p)
-{
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
-
-template <bool PREFETCH>
 __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Workspace &ws, int grab)
 {
     const unsigned int FULL = 0xffffffffu;
@@ -221,7 +218,6 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
                 for (int k = 3; k >= 0; --k) {
                     if (fminf(1e7f, w.tf[k]) > w.tn[k]) {
                         if (got) {
-                            if (PREFETCH) prefetch_l1(ref_address(bvh, next));
                             stack[sp++] = next;
                         }
                         next = w.ref[k];
@@ -261,155 +257,265 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
     }
 }
 
-// Closest-hit: same refill scheme, reference visit order (see closest_hit in mr_bvh.cuh), one lane per ray.
-template <bool PREFETCH>
-__device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const Workspace &ws)
+// Closest-hit: same refill scheme and the reference's visit order (closest_hit in mr_bvh.cuh); lanes that the queue
+// cannot feed take over the oldest deferred subtree of a busy lane and the result is rebuilt exactly from their hit logs
+// (mr_split.cuh).
+__device__ __forceinline__ void closest_write_result(const BvhView &bvh, const Workspace &ws, const CTask &T, float closest,
+                                                     int best, bool any)
+{
+    float3 pos = f3(0.f), n = f3(1.0f);
+    int prim = -1;
+    float bary[2] = {0.f, 0.f};
+    if (any) {
+        pos = T.r.o + closest * T.r.d;
+        closest_finish(bvh, T.r, best, n, prim, bary);
+    }
+    ws.chit[3 * (size_t)T.slot] = make_float4(pos.x, pos.y, pos.z, any ? 1.0f : 0.0f);
+    ws.chit[3 * (size_t)T.slot + 1] = make_float4(n.x, n.y, n.z, any ? closest : 0.f);
+    ws.chit[3 * (size_t)T.slot + 2] = make_float4(__int_as_float(prim), bary[0], bary[1], 0.f);
+}
+
+template <bool SPLIT, class REC>
+__device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const Workspace &ws, REC &rec, int grab)
 {
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int lt_mask = (1u << lane) - 1u;
     const int total = ws.counters[MR_CTR_CLOSEST_SIZE];
     int *ticket = ws.counters + MR_CTR_CLOSEST_TICKET;
-    int stack_ref[MR_STACK];
-    float stack_t[MR_STACK];
-    int sp = 0, cur = 0, slot = -1, best_slot = -1;
-    float closest = 1e7f;
-    bool any = false, have = false, exhausted = false;
-    Ray r;
-    r.o = r.d = r.inv = f3(0.f);
+    CTask T;
+    T.r.o = T.r.d = T.r.inv = f3(0.f);
+    T.slot = -1;
+    T.home = (int)lane;
+    T.first = true;
+    T.nosplit = false;
+    T.lo = T.hi = 0u;
+    T.sp = T.bot = 0;
+    T.cur = 0;
+    T.cur_t = 0.f;
+    T.closest = 1e7f;
+    T.best = -1;
+    T.any = false;
+    bool have = false, exhausted = false;
+    rec.pending[lane] = 0;
+    rec.nlog[lane] = 0;
+    rec.bound[lane] = 1e7f;
+    __syncwarp();
     for (;;) {
-        const unsigned int need = __ballot_sync(FULL, !have);
+        // ---- refill from the queue: a lane whose previous ray still has tasks in flight keeps its record
+        const unsigned int need = __ballot_sync(FULL, !have && rec.pending[lane] == 0);
         if (need != 0u && !exhausted) {
-            const int n_need = __popc(need);
+            const int n_take = min(__popc(need), grab);
             const int leader = __ffs(need) - 1;
             int base = 0;
-            if ((int)lane == leader) base = atomicAdd(ticket, n_need);
+            if ((int)lane == leader) base = atomicAdd(ticket, n_take);
             base = __shfl_sync(FULL, base, leader);
-            if (!have) {
-                const int s = base + __popc(need & lt_mask);
+            const int rank = __popc(need & lt_mask);
+            if (!have && rec.pending[lane] == 0 && rank < n_take) {
+                const int s = base + rank;
                 if (s < total) {
                     const float4 o = __ldg(ws.cray_o + s);
                     const float4 d = __ldg(ws.cray_d + s);
-                    r = make_ray(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z));
-                    slot = __float_as_int(o.w);
-                    sp = 0;
-                    cur = 0;
-                    closest = 1e7f;
-                    any = false;
-                    best_slot = -1;
+                    task_start_ray(T, make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), __float_as_int(o.w), (int)lane, false);
+                    rec.pending[lane] = 1;
+                    rec.nlog[lane] = 0;
+                    rec.bound[lane] = 1e7f;
                     have = true;
                 }
             }
-            if (base + n_need >= total) exhausted = true;
+            if (base + n_take >= total) exhausted = true;
         }
-        if (!__any_sync(FULL, have)) {
+        const unsigned int busy = __ballot_sync(FULL, have);
+        if (busy == 0u) {
             if (exhausted) break;
             continue;
         }
+        if (SPLIT && busy != FULL) {
+            // ---- steal: the k-th idle lane takes the bottom (last in visit order) entry of the k-th lane that can give one
+            const unsigned int donors = __ballot_sync(FULL, have && task_can_donate(T));
+            if (donors != 0u) {
+                const unsigned int idle = ~busy;
+                const int n_pairs = min(__popc(donors), __popc(idle));
+                const bool robbed = have && task_can_donate(T) && __popc(donors & lt_mask) < n_pairs;
+                int give_ref = 0;
+                float give_t = 0.f;
+                unsigned int mid = 0u, old_hi = 0u;
+                if (robbed) {
+                    give_ref = T.stack_ref[T.bot];
+                    give_t = T.stack_t[T.bot];
+                    ++T.bot;
+                    mid = T.lo + ((T.hi - T.lo) >> 1);
+                    old_hi = T.hi;
+                    T.hi = mid;
+                }
+                const int my_rank = __popc(idle & lt_mask);
+                const bool thief = !have && my_rank < n_pairs;
+                int src = (int)lane;
+                if (thief) {
+                    unsigned int m = donors;
+                    for (int j = 0; j < my_rank; ++j) m &= m - 1u;
+                    src = __ffs(m) - 1;
+                }
+                const int g_ref = __shfl_sync(FULL, give_ref, src);
+                const float g_t = __shfl_sync(FULL, give_t, src);
+                const unsigned int g_mid = __shfl_sync(FULL, mid, src), g_hi = __shfl_sync(FULL, old_hi, src);
+                const int g_slot = __shfl_sync(FULL, T.slot, src), g_home = __shfl_sync(FULL, T.home, src);
+                const float g_bound = __shfl_sync(FULL, T.closest, src);
+                const float ox = __shfl_sync(FULL, T.r.o.x, src), oy = __shfl_sync(FULL, T.r.o.y, src), oz = __shfl_sync(FULL, T.r.o.z, src);
+                const float dx = __shfl_sync(FULL, T.r.d.x, src), dy = __shfl_sync(FULL, T.r.d.y, src), dz = __shfl_sync(FULL, T.r.d.z, src);
+                const float ix = __shfl_sync(FULL, T.r.inv.x, src), iy = __shfl_sync(FULL, T.r.inv.y, src), iz = __shfl_sync(FULL, T.r.inv.z, src);
+                if (thief) {
+                    T.r.o = make_float3(ox, oy, oz);
+                    T.r.d = make_float3(dx, dy, dz);
+                    T.r.inv = make_float3(ix, iy, iz);
+                    T.slot = g_slot;
+                    T.home = g_home;
+                    T.first = false;
+                    T.nosplit = false;
+                    T.lo = g_mid;
+                    T.hi = g_hi;
+                    T.sp = T.bot = 0;
+                    T.cur = g_ref;
+                    T.cur_t = g_t;
+                    T.closest = g_bound; // stale by construction: >= every value the ray's closest distance takes later
+                    T.best = -1;
+                    T.any = false;
+                    atomicAdd(&rec.pending[g_home], 1);
+                    have = true;
+                }
+            }
+            __syncwarp();
+        }
+        bool retired = false;
 #pragma unroll 1
         for (int it = 0; it < MR_TRACE_STEPS; ++it) {
-            if (!have) break;
-            bool pop = false;
-            const Rec32 *rec = ref_address(bvh, cur);
-            const Rec32 e0 = load_rec(rec), e1 = load_rec(rec + 1);
-            if (cur >= 0) {
-                // all four sectors, unconditionally: this walk is bound by the latency of one ray's dependent fetches, and
-                // making two of them conditional on the reference's entry count lengthened every step (+10 % measured)
-                const Rec32 e2 = load_rec(rec + 2), e3 = load_rec(rec + 3);
-                WideHit w;
-                wide_slabs(r, e0, e1, e2, e3, w);
-                int next = 0;
-                float next_t = 0.f;
-                bool got = false;
-#pragma unroll
-                for (int k = 3; k >= 0; --k) {
-                    if (fminf(closest, w.tf[k]) > w.tn[k]) {
-                        if (got) {
-                            if (PREFETCH) prefetch_l1(ref_address(bvh, next));
-                            stack_ref[sp] = next;
-                            stack_t[sp] = next_t;
-                            ++sp;
-                        }
-                        next = w.ref[k];
-                        next_t = w.tn[k];
-                        got = true;
-                    }
-                }
-                if (got) cur = next;
-                else pop = true;
-            } else {
-                const int leaf = ~cur;
-                float t, u, v;
-                if (tri_test(r, e0, e1, t, u, v)) {
-                    if (t <= closest) best_slot = leaf;
-                    closest = fminf(t, closest);
-                    any = true;
-                }
-                pop = true;
-            }
-            if (pop) {
-                bool found = false;
-                while (sp > 0) {
-                    --sp;
-                    if (closest > stack_t[sp]) {
-                        cur = stack_ref[sp];
-                        found = true;
-                        break;
-                    }
-                }
-                if (!found) {
-                    float3 pos = f3(0.f), n = f3(1.0f);
-                    int prim = -1;
-                    float bary[2] = {0.f, 0.f};
-                    if (any) {
-                        pos = r.o + closest * r.d;
-                        closest_finish(bvh, r, best_slot, n, prim, bary);
-                    }
-                    ws.chit[3 * (size_t)slot] = make_float4(pos.x, pos.y, pos.z, any ? 1.0f : 0.0f);
-                    ws.chit[3 * (size_t)slot + 1] = make_float4(n.x, n.y, n.z, any ? closest : 0.f);
-                    ws.chit[3 * (size_t)slot + 2] = make_float4(__int_as_float(prim), bary[0], bary[1], 0.f);
-                    have = false;
-                }
-            }
+            if (!have || retired) break;
+            retired = task_step(bvh, T, rec);
         }
         __syncwarp();
+        // ---- retirement: the last task of a ray rebuilds the result from the first task's state and the thieves' logs
+        if (__any_sync(FULL, retired)) {
+            if (retired && T.first) {
+                rec.fin_closest[T.home] = T.closest;
+                rec.fin_best[T.home] = T.best;
+                rec.fin_any[T.home] = T.any ? 1 : 0;
+            }
+            __syncwarp();
+            bool last = false;
+            if (retired) {
+                last = atomicSub(&rec.pending[T.home], 1) == 1;
+                have = false;
+            }
+            __syncwarp();
+            if (last) {
+                float closest;
+                int best;
+                bool any;
+                if (task_replay(rec, T.home, closest, best, any)) {
+                    closest_write_result(bvh, ws, T, closest, best, any);
+                } else {
+                    // the log lost entries: the ray starts over on this lane alone (the record stays the ray's)
+                    const int home = T.home, slot = T.slot;
+                    const float3 o = T.r.o, d = T.r.d;
+                    task_start_ray(T, o, d, slot, home, true);
+                    rec.pending[home] = 1;
+                    rec.nlog[home] = 0;
+                    rec.bound[home] = 1e7f;
+                    have = true;
+                }
+            }
+            __syncwarp();
+        }
     }
 }
 
 // small queues: give every warp a few rays and let stealing spread each of them over the lanes
-__device__ __forceinline__ int any_grab_limit(const Workspace &ws, int warps)
+__device__ __forceinline__ int grab_limit(int total, int warps)
 {
-    const int total = ws.counters[MR_CTR_ANY_SIZE];
     return max(2, min(32, (total + warps - 1) / warps));
 }
 
-template <bool PREFETCH>
+#define MR_TRACE_WARPS (MR_TRACE_BLOCK / 32)
+
 __global__ void __launch_bounds__(MR_TRACE_BLOCK) k_trace_any_persistent(BvhView bvh, Workspace ws)
 {
-    trace_any_worker<PREFETCH>(bvh, ws, any_grab_limit(ws, gridDim.x * (MR_TRACE_BLOCK / 32)));
+    trace_any_worker(bvh, ws, grab_limit(ws.counters[MR_CTR_ANY_SIZE], gridDim.x * MR_TRACE_WARPS));
 }
-template <bool PREFETCH>
+// SPLIT: idle lanes walk deferred subtrees of their warp's closest-hit rays (mr_split.cuh); the hit logs live in shared
+// memory, 4.9 KB per warp.  The walker without splitting needs 0.9 KB per warp.
+template <bool SPLIT>
 __global__ void __launch_bounds__(MR_TRACE_BLOCK, 4) k_trace_closest_persistent(BvhView bvh, Workspace ws)
 {
-    trace_closest_worker<PREFETCH>(bvh, ws);
+    typedef SplitRecT<SPLIT ? MR_SPLIT_LOG : 1> Rec;
+    __shared__ Rec recs[MR_TRACE_WARPS];
+    const int grab = SPLIT ? grab_limit(ws.counters[MR_CTR_CLOSEST_SIZE], gridDim.x * MR_TRACE_WARPS) : 32;
+    trace_closest_worker<SPLIT>(bvh, ws, recs[threadIdx.x >> 5], grab);
 }
-// both queues in one launch: even blocks walk the boolean rays, odd blocks the closest-hit rays (the two queues of
-// process_path_tracing_divided_no_grad are independent, FinalShading.slang:745-977)
-template <bool PREFETCH>
+// both queues in one launch (the two queues of process_path_tracing_divided_no_grad are independent,
+// FinalShading.slang:745-977): the lower half of every block's warps walks the boolean rays, the upper half the
+// closest-hit rays, so a block carries hit logs for half of its warps only
+template <bool SPLIT>
 __global__ void __launch_bounds__(MR_TRACE_BLOCK, 4) k_trace_mixed_persistent(BvhView bvh, Workspace ws)
 {
-    if ((blockIdx.x & 1u) == 0u) trace_any_worker<PREFETCH>(bvh, ws, any_grab_limit(ws, (gridDim.x / 2) * (MR_TRACE_BLOCK / 32)));
-    else trace_closest_worker<PREFETCH>(bvh, ws);
+    typedef SplitRecT<SPLIT ? MR_SPLIT_LOG : 1> Rec;
+    __shared__ Rec recs[MR_TRACE_WARPS / 2];
+    const int w = threadIdx.x >> 5;
+    const int warps = gridDim.x * (MR_TRACE_WARPS / 2);
+    if (w < MR_TRACE_WARPS / 2) {
+        trace_any_worker(bvh, ws, grab_limit(ws.counters[MR_CTR_ANY_SIZE], warps));
+    } else {
+        const int grab = SPLIT ? grab_limit(ws.counters[MR_CTR_CLOSEST_SIZE], warps) : 32;
+        trace_closest_worker<SPLIT>(bvh, ws, recs[w - MR_TRACE_WARPS / 2], grab);
+    }
 }
 #endif
 
-// tuning overrides of the persistent grids (blocks per SM), 0 = default; see mirres_set_tuning
-static int g_tune_any_blocks = 0, g_tune_closest_blocks = 0;
+// Launch-shape tuning (mirres_set_tuning): values are per HOST THREAD, so two threads that drive different streams do
+// not see each other's settings; 0 = library default.  Results never depend on them.
+static thread_local int t_tune[MIRRES_TUNE_COUNT_] = {0};
 
 void queue_reset(const Workspace &ws, cudaStream_t st)
 {
     zero_async(ws.counters + 1, 4 * sizeof(int), st);
 }
+
+#if !defined(MR_HOST_CHECK)
+// what the tracers need to know about a device, looked up once per device (not per process)
+struct DeviceInfo {
+    std::atomic<int> ready;
+    int sm_count, occ_any, occ_closest, occ_closest_split, occ_mixed, occ_mixed_split;
+};
+#define MR_MAX_DEVICES 64
+static DeviceInfo g_devices[MR_MAX_DEVICES];
+static std::mutex g_devices_mutex;
+
+static const DeviceInfo &device_info()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= MR_MAX_DEVICES) dev = 0;
+    DeviceInfo &d = g_devices[dev];
+    if (!d.ready.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lock(g_devices_mutex);
+        if (!d.ready.load(std::memory_order_relaxed)) {
+            cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+            if (d.sm_count <= 0) d.sm_count = 148;
+            auto occ = [](auto kernel) {
+                int o = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, MR_TRACE_BLOCK, 0);
+                return o < 1 ? 1 : o;
+            };
+            d.occ_any = occ(k_trace_any_persistent);
+            d.occ_closest = occ(k_trace_closest_persistent<false>);
+            d.occ_closest_split = occ(k_trace_closest_persistent<true>);
+            d.occ_mixed = occ(k_trace_mixed_persistent<false>);
+            d.occ_mixed_split = occ(k_trace_mixed_persistent<true>);
+            d.ready.store(1, std::memory_order_release);
+        }
+    }
+    return d;
+}
+#endif
 
 int trace_queues(const BvhView &bvh, const Workspace &ws, bool any, bool closest, int sm_count, cudaStream_t st)
 {
@@ -425,44 +531,23 @@ int trace_queues(const BvhView &bvh, const Workspace &ws, bool any, bool closest
     // grid that fills the register file keeps every other stream's kernels off the SMs for its whole duration, while a
     // traversal warp is latency-bound and loses little from lower occupancy (measured on the C2 step: 3 / 2 blocks
     // per SM for boolean / closest-hit queues 6.4 ms, full occupancy 5 / 4 blocks 6.7 ms)
-    static int occ_any = 0, occ_closest = 0, occ_mixed = 0, prefetch = 0;
-    if (!occ_any) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_any, k_trace_any_persistent<false>, MR_TRACE_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_closest, k_trace_closest_persistent<false>, MR_TRACE_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mixed, k_trace_mixed_persistent<false>, MR_TRACE_BLOCK, 0);
-        if (occ_any < 1) occ_any = 4;
-        if (occ_closest < 1) occ_closest = 4;
-        if (occ_mixed < 2) occ_mixed = 4;
-        const char *e = getenv("MIRRES_PREFETCH");
-        prefetch = e ? atoi(e) : 0;
-        if (occ_any > 3) occ_any = 3;
-        if (occ_closest > 2) occ_closest = 2;
-        if (occ_mixed > 4) occ_mixed = 4;
-        const char *c = getenv("MIRRES_CLOSEST_BLOCKS"); // tuning overrides
-        if (c && atoi(c) > 0) { occ_closest = atoi(c); occ_mixed = 2 * atoi(c); }
-        const char *a = getenv("MIRRES_ANY_BLOCKS");
-        if (a && atoi(a) > 0) occ_any = atoi(a);
-    }
-    // per-call override (mirres_set_tuning): the host raises the grid of the launches on its critical chain, which run on
-    // a high-priority stream, and leaves the background chains at the small default
-    static int occ_any_max = 0, occ_closest_max = 0;
-    if (!occ_any_max) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_any_max, k_trace_any_persistent<false>, MR_TRACE_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_closest_max, k_trace_closest_persistent<false>, MR_TRACE_BLOCK, 0);
-        if (occ_any_max < 1) occ_any_max = 4;
-        if (occ_closest_max < 1) occ_closest_max = 4;
-    }
-    const int use_any = g_tune_any_blocks > 0 ? min(g_tune_any_blocks, occ_any_max) : occ_any;
-    const int use_closest = g_tune_closest_blocks > 0 ? min(g_tune_closest_blocks, occ_closest_max) : occ_closest;
-    const int g_mixed = sm_count * (occ_mixed & ~1), g_any = sm_count * use_any, g_closest = sm_count * use_closest;
-    if (prefetch) {
-        if (any && closest) k_trace_mixed_persistent<true><<<g_mixed, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
-        else if (any) k_trace_any_persistent<true><<<g_any, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
-        else if (closest) k_trace_closest_persistent<true><<<g_closest, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
-    } else {
-        if (any && closest) k_trace_mixed_persistent<false><<<g_mixed, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
-        else if (any) k_trace_any_persistent<false><<<g_any, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
-        else if (closest) k_trace_closest_persistent<false><<<g_closest, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+    (void)sm_count;
+    const DeviceInfo &d = device_info();
+    const bool split = t_tune[MIRRES_TUNE_CLOSEST_SPLIT] != 2; // 0 = default (on), 1 = on, 2 = off
+    const int any_blocks = min(t_tune[MIRRES_TUNE_ANY_BLOCKS] > 0 ? t_tune[MIRRES_TUNE_ANY_BLOCKS] : 3, d.occ_any);
+    const int closest_blocks = min(t_tune[MIRRES_TUNE_CLOSEST_BLOCKS] > 0 ? t_tune[MIRRES_TUNE_CLOSEST_BLOCKS] : 2,
+                                   split ? d.occ_closest_split : d.occ_closest);
+    const int mixed_blocks = min(t_tune[MIRRES_TUNE_MIXED_BLOCKS] > 0 ? t_tune[MIRRES_TUNE_MIXED_BLOCKS] : 4,
+                                 split ? d.occ_mixed_split : d.occ_mixed);
+    const int g_mixed = d.sm_count * mixed_blocks, g_any = d.sm_count * any_blocks, g_closest = d.sm_count * closest_blocks;
+    if (any && closest) {
+        if (split) k_trace_mixed_persistent<true><<<g_mixed, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+        else k_trace_mixed_persistent<false><<<g_mixed, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+    } else if (any) {
+        k_trace_any_persistent<<<g_any, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+    } else if (closest) {
+        if (split) k_trace_closest_persistent<true><<<g_closest, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+        else k_trace_closest_persistent<false><<<g_closest, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
     }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -100 - (int)e;
@@ -474,14 +559,7 @@ int device_sm_count()
 #if defined(MR_HOST_CHECK)
     return 1;
 #else
-    static int cached = 0;
-    if (!cached) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-        if (cached <= 0) cached = 148;
-    }
-    return cached;
+    return device_info().sm_count;
 #endif
 }
 
@@ -494,10 +572,15 @@ extern "C" {
 
 int mirres_set_tuning(int key, int value)
 {
-    if (key == MIRRES_TUNE_ANY_BLOCKS) g_tune_any_blocks = value > 0 ? value : 0;
-    else if (key == MIRRES_TUNE_CLOSEST_BLOCKS) g_tune_closest_blocks = value > 0 ? value : 0;
-    else return MIRRES_ERR_SHAPE;
+    if (key < 0 || key >= MIRRES_TUNE_COUNT_) return MIRRES_ERR_SHAPE;
+    t_tune[key] = value > 0 ? value : 0;
     return 0;
+}
+
+int mirres_get_tuning(int key)
+{
+    if (key < 0 || key >= MIRRES_TUNE_COUNT_) return MIRRES_ERR_SHAPE;
+    return t_tune[key];
 }
 
 size_t mirres_workspace_bytes(int n_pixels) { return n_pixels < 1 ? 0 : workspace_carve(nullptr, n_pixels, nullptr); }
@@ -528,6 +611,113 @@ int mirres_workspace_prepare(const float *occ, int n_pixels, void *workspace, si
     return 0;
 #endif
 }
+
+#if defined(MR_HOST_CHECK)
+} // extern "C"
+// Test-only (host-check flavour, never in the shipped library): the split closest-hit walk of mr_split.cuh -- the same
+// task_step / task_replay code the CUDA worker runs -- under a RANDOMISED scheduler: `lanes` virtual lanes share one
+// record set; every round each busy lane advances a random number of visits, idle lanes rob the bottom stack entry of
+// lanes that can give one (same pairing as the CUDA worker), rays retire in whatever order the schedule produces.  `cap`
+// picks the log capacity (1 forces overflows and restarts).  Outputs in the layout of mirres_trace_closest.
+template <int CAP>
+static void closest_split_simulate(const BvhView &bvh, const float *org, const float *dir, int n, int lanes, unsigned int seed,
+                                   int *hit, float *t, float *pos, float *normal, int *prim, int *stats)
+{
+    SplitRecT<CAP> rec;
+    CTask T[MR_SPLIT_LANES];
+    bool have[MR_SPLIT_LANES];
+    unsigned int rng = seed * 2654435761u + 12345u;
+    auto rnd = [&]() { rng = 1664525u * rng + 1013904223u; return rng >> 8; };
+    for (int l = 0; l < lanes; ++l) { have[l] = false; rec.pending[l] = 0; rec.nlog[l] = 0; rec.bound[l] = 1e7f; }
+    int next_ray = 0;
+    long steals = 0, restarts = 0, logged = 0;
+    for (;;) {
+        for (int l = 0; l < lanes; ++l) {
+            if (!have[l] && rec.pending[l] == 0 && next_ray < n && (rnd() & 3u) != 0u) {
+                const int s = next_ray++;
+                task_start_ray(T[l], load3(org, (size_t)s), load3(dir, (size_t)s), s, l, false);
+                rec.pending[l] = 1; rec.nlog[l] = 0; rec.bound[l] = 1e7f;
+                have[l] = true;
+            }
+        }
+        bool busy = false;
+        for (int l = 0; l < lanes; ++l) busy = busy || have[l];
+        if (!busy) { if (next_ray >= n) break; continue; }
+        // steal: k-th idle lane <- k-th donor
+        int donors[MR_SPLIT_LANES], nd = 0, idle[MR_SPLIT_LANES], ni = 0;
+        for (int l = 0; l < lanes; ++l) {
+            if (have[l] && task_can_donate(T[l])) donors[nd++] = l;
+            if (!have[l]) idle[ni++] = l;
+        }
+        const int pairs = nd < ni ? nd : ni;
+        for (int k = 0; k < pairs; ++k) {
+            if ((rnd() & 1u) == 0u) continue; // not every opportunity is taken
+            CTask &D = T[donors[k]], &N = T[idle[k]];
+            const unsigned int mid = D.lo + ((D.hi - D.lo) >> 1), old_hi = D.hi;
+            N.r = D.r; N.slot = D.slot; N.home = D.home; N.first = false; N.nosplit = false;
+            N.lo = mid; N.hi = old_hi; N.sp = N.bot = 0;
+            N.cur = D.stack_ref[D.bot]; N.cur_t = D.stack_t[D.bot]; ++D.bot;
+            D.hi = mid;
+            N.closest = D.closest; N.best = -1; N.any = false;
+            rec.pending[N.home] += 1;
+            have[idle[k]] = true;
+            ++steals;
+        }
+        bool retired[MR_SPLIT_LANES];
+        for (int l = 0; l < lanes; ++l) {
+            retired[l] = false;
+            if (!have[l]) continue;
+            const int steps = (int)(rnd() % 7u);
+            const int before = rec.nlog[T[l].home];
+            for (int it = 0; it < steps && !retired[l]; ++it) retired[l] = task_step(bvh, T[l], rec);
+            logged += rec.nlog[T[l].home] - before;
+        }
+        for (int l = 0; l < lanes; ++l) {
+            if (retired[l] && T[l].first) {
+                rec.fin_closest[T[l].home] = T[l].closest; rec.fin_best[T[l].home] = T[l].best; rec.fin_any[T[l].home] = T[l].any ? 1 : 0;
+            }
+        }
+        for (int l = 0; l < lanes; ++l) {
+            if (!retired[l]) continue;
+            have[l] = false;
+            if (--rec.pending[T[l].home] != 0) continue;
+            float closest; int best; bool any;
+            if (task_replay(rec, T[l].home, closest, best, any)) {
+                const size_t i = (size_t)T[l].slot;
+                float3 p = f3(0.f), nn = f3(1.0f);
+                int pr = -1;
+                if (any) { p = T[l].r.o + closest * T[l].r.d; closest_finish(bvh, T[l].r, best, nn, pr, nullptr); }
+                hit[i] = any ? 1 : 0;
+                if (t) t[i] = any ? closest : 0.f;
+                if (pos) store3(pos, i, p);
+                if (normal) store3(normal, i, nn);
+                if (prim) prim[i] = pr;
+            } else {
+                const int home = T[l].home, slot = T[l].slot;
+                task_start_ray(T[l], load3(org, (size_t)slot), load3(dir, (size_t)slot), slot, home, true);
+                rec.pending[home] = 1; rec.nlog[home] = 0; rec.bound[home] = 1e7f;
+                have[l] = true;
+                ++restarts;
+            }
+        }
+    }
+    if (stats) { stats[0] = (int)steals; stats[1] = (int)restarts; stats[2] = (int)logged; }
+}
+
+extern "C" int mirres_test_closest_split(const void *packed_nodes, const void *packed_tris, const float *org, const float *dir,
+                                         int n, int lanes, int cap, unsigned int seed, int *hit, float *t, float *pos,
+                                         float *normal, int *prim, int *stats)
+{
+    if (!packed_nodes || !packed_tris || !org || !dir || !hit) return MIRRES_ERR_NULL;
+    if (n < 0 || lanes < 1 || lanes > MR_SPLIT_LANES) return MIRRES_ERR_SHAPE;
+    BvhView bvh = {(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris};
+    if (cap == 1) closest_split_simulate<1>(bvh, org, dir, n, lanes, seed, hit, t, pos, normal, prim, stats);
+    else if (cap == 2) closest_split_simulate<2>(bvh, org, dir, n, lanes, seed, hit, t, pos, normal, prim, stats);
+    else closest_split_simulate<MR_SPLIT_LOG>(bvh, org, dir, n, lanes, seed, hit, t, pos, normal, prim, stats);
+    return 0;
+}
+extern "C" {
+#endif
 
 // test / diagnostics helper: copies out the active list header is not needed -- the list lives in the workspace at a
 // fixed offset: counters (64 ints, 256 B) then active[n_pixels].

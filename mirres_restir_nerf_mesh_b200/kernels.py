@@ -65,7 +65,12 @@ class Kernels:
         return ctypes.c_uint(int(x) & 0xFFFFFFFF)
 
     # -- tuning ------------------------------------------------------------------------------------------------
-    TUNE_ANY_BLOCKS, TUNE_CLOSEST_BLOCKS = 0, 1
+    TUNE_ANY_BLOCKS, TUNE_CLOSEST_BLOCKS, TUNE_MIXED_BLOCKS, TUNE_CLOSEST_SPLIT = 0, 1, 2, 3
+
+    def get_tuning(self, key):
+        v = self.lib.mirres_get_tuning(int(key))
+        self._check(min(v, 0), "mirres_get_tuning")
+        return v
 
     def set_tuning(self, key, value):
         self._check(self.lib.mirres_set_tuning(int(key), int(value)), "mirres_set_tuning")

@@ -150,16 +150,21 @@ class trace_blocks:
 
     def __init__(self, any_blocks=0, closest_blocks=0):
         self.values = (int(any_blocks), int(closest_blocks))
+        self.saved = None
 
     def __enter__(self):
         k = get_kernels()
-        k.set_tuning(k.TUNE_ANY_BLOCKS, self.values[0])
-        k.set_tuning(k.TUNE_CLOSEST_BLOCKS, self.values[1])
+        # 0 = "no opinion": the caller's own tuning (set through the public set_tuning) stays in force
+        self.saved = (k.get_tuning(k.TUNE_ANY_BLOCKS), k.get_tuning(k.TUNE_CLOSEST_BLOCKS))
+        if self.values[0] > 0:
+            k.set_tuning(k.TUNE_ANY_BLOCKS, self.values[0])
+        if self.values[1] > 0:
+            k.set_tuning(k.TUNE_CLOSEST_BLOCKS, self.values[1])
 
     def __exit__(self, *a):
         k = get_kernels()
-        k.set_tuning(k.TUNE_ANY_BLOCKS, 0)
-        k.set_tuning(k.TUNE_CLOSEST_BLOCKS, 0)
+        k.set_tuning(k.TUNE_ANY_BLOCKS, self.saved[0])
+        k.set_tuning(k.TUNE_CLOSEST_BLOCKS, self.saved[1])
 
 
 def prepare_workspace(occ_map):

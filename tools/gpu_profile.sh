@@ -14,7 +14,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-fi
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_launches.log 2>&1
 for spec in "$@"; do
     IFS=: read -r regex skip count name <<< "$spec"
-    ncu --set full --clock-control none --import-source on -k "regex:$regex" --launch-skip "$skip" --launch-count "$count" \
+    ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$regex" --launch-skip "$skip" --launch-count "$count" \
         -o $OUT/${TAG}_ncu_${name} -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph \
         > $OUT/${TAG}_ncu_${name}.log 2>&1
 done
