@@ -87,7 +87,7 @@ struct PackParams {
 MR_DEV void pack_item(const PackParams &p, int gid)
 {
     const int F = p.F, LEAF = F - 1;
-    {
+    if (p.tris) { // null: the caller has written the triangle records itself (mirres_bvh_build does, with the leaf records)
         int prim = MR_LDG(p.info + 3 * (size_t)(LEAF + gid) + 2);
         int i0 = MR_LDG(p.tri + 3 * (size_t)prim), i1 = MR_LDG(p.tri + 3 * (size_t)prim + 1), i2 = MR_LDG(p.tri + 3 * (size_t)prim + 2);
         float3 v0 = load3(p.vert, (size_t)i0), v1 = load3(p.vert, (size_t)i1), v2 = load3(p.vert, (size_t)i2);

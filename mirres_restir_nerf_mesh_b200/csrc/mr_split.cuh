@@ -64,9 +64,8 @@ struct CTask {
     bool first;          // holds the true state (first task in visit order)
     bool nosplit;        // restarted after a log overflow: may not be robbed
     unsigned int lo, hi; // order interval
-    int stack_ref[MR_STACK];
-    float stack_t[MR_STACK];
-    int sp, bot;         // live entries [bot, sp)
+    int sp, bot;         // live entries [bot, sp) of the task's stack (the arrays live beside the task: a struct that holds
+                         // dynamically indexed arrays is placed in local memory as a whole, scalars included)
     int cur;             // reference being processed
     float cur_t;         // its entry distance
     float closest;       // first task: the ray's closest distance; others: the bound they prune with
@@ -101,7 +100,7 @@ MR_DEV void task_start_ray(CTask &T, float3 o, float3 d, int slot, int home, boo
 
 // One visit (wide record or leaf) of a task.  Returns true when the task has no work left.
 template <class REC>
-MR_DEV bool task_step(const BvhView &bvh, CTask &T, REC &rec)
+MR_DEV bool task_step(const BvhView &bvh, CTask &T, int *__restrict__ stack_ref, float *__restrict__ stack_t, REC &rec)
 {
     const Rec32 *rp = ref_address(bvh, T.cur);
     const Rec32 e0 = load_rec(rp), e1 = load_rec(rp + 1);
@@ -119,8 +118,8 @@ MR_DEV bool task_step(const BvhView &bvh, CTask &T, REC &rec)
         for (int k = 3; k >= 0; --k) {
             if (fminf(bound, w.tf[k]) > w.tn[k]) {
                 if (got) {
-                    T.stack_ref[T.sp] = next;
-                    T.stack_t[T.sp] = next_t;
+                    stack_ref[T.sp] = next;
+                    stack_t[T.sp] = next_t;
                     ++T.sp;
                 }
                 next = w.ref[k];
@@ -165,9 +164,9 @@ MR_DEV bool task_step(const BvhView &bvh, CTask &T, REC &rec)
     if (pop) {
         while (T.sp > T.bot) {
             --T.sp;
-            if (bound > T.stack_t[T.sp]) {
-                T.cur = T.stack_ref[T.sp];
-                T.cur_t = T.stack_t[T.sp];
+            if (bound > stack_t[T.sp]) {
+                T.cur = stack_ref[T.sp];
+                T.cur_t = stack_t[T.sp];
                 return false;
             }
         }

@@ -37,6 +37,12 @@ namespace mr {
 // (never by the library), so a CUDA graph whose launches have their frame indices baked in can be replayed with fresh
 // random streams (graphed.CapturedStep.set_frame_offset).  Zero = the plain reference behaviour.
 #define MR_CTR_FRAME_OFFSET 8
+// [16], [17] sizes of the two lists of paths that are still alive (the path kernels ping-pong between them), [18], [19]
+// the signatures of the calls those lists were written for (see bounce_item in shade.cu; a kernel reads one word and
+// writes the other); cleared by mirres_workspace_prepare
+#define MR_CTR_ALIVE_SIZE 16
+#define MR_CTR_ALIVE_SIG 18
+#define MR_CTR_ALIVE_LAST 19
 
 struct Workspace {
     int *counters;     // [64] see MR_CTR_*
@@ -51,6 +57,7 @@ struct Workspace {
     float *px;         // [N * MR_PX_SCRATCH_FLOATS] per-active-pixel state carried from gen to resolve
     float *stop_in;    // [N] stop flag of every pixel as it was on entry to a bounce kernel
     float4 *lcache;    // [N * 2] per PIXEL: (emitted radiance, own target density) (direction, 0) of the pixel's reservoir sample (spatial pass)
+    int *alive[2];     // [N] each: active-list positions of the paths that continue past a path vertex (unordered)
     int capacity;      // N
 };
 
@@ -72,6 +79,8 @@ static inline size_t workspace_carve(Workspace *w, int N, char *base)
     p = take((size_t)N * MR_PX_SCRATCH_FLOATS * sizeof(float)); if (w) w->px = (float *)p;
     p = take((size_t)N * sizeof(float)); if (w) w->stop_in = (float *)p;
     p = take((size_t)N * 2 * sizeof(float4)); if (w) w->lcache = (float4 *)p;
+    p = take((size_t)N * sizeof(int)); if (w) w->alive[0] = (int *)p;
+    p = take((size_t)N * sizeof(int)); if (w) w->alive[1] = (int *)p;
     if (w) w->capacity = N;
     return off;
 }

@@ -314,13 +314,41 @@ struct BounceParams {
     float *__restrict__ new_occ;
     float *__restrict__ new_normal;
     Workspace ws;   // shadow-ray slots (2 per active pixel), continuation-ray slot (1 per active pixel), per-pixel scratch
+    int sig_in, sig_out; // signatures of this call and of the call that follows it on the same path state (bounce_item)
 };
+
+// Which foreground pixel does item j of a path-kernel launch work on?  At the first vertex every foreground pixel carries a
+// path; at vertex b >= 1 only the paths whose continuation ray found something (or left the scene on a specular bounce) are
+// alive -- 13 % and 3 % of the foreground at the second and third vertex of config C2 -- and a launch over all foreground
+// pixels ran 4.5 of 32 lanes (ncu, profiles/r3z_ncu_bounce_shade_gen_px.txt).  The resolve pass of vertex b - 1 therefore
+// appends every path it keeps alive to a list, and the kernels of vertex b walk that list.  The list is only trusted if
+// the workspace says it was written for THIS call (same path-state buffer, this vertex number): any other calling
+// sequence -- a vertex evaluated on its own, a repeated call -- finds a foreign signature and falls back to all foreground
+// pixels, for which the stop flag decides as in the reference (FinalShading.slang:657-690).  Dead paths have nothing to
+// write: the prologue has zeroed their outputs and raised their stop flag.
+MR_DEV int bounce_item(const BounceParams &p, int j)
+{
+    if (p.bounce_count > 0u && p.ws.counters[MR_CTR_ALIVE_SIG + (int)(p.bounce_count & 1u)] == p.sig_in) {
+        const int k = (int)((p.bounce_count - 1u) & 1u);
+        return j < p.ws.counters[MR_CTR_ALIVE_SIZE + k] ? p.ws.alive[k][j] : -1;
+    }
+    return j < p.ws.counters[MR_CTR_ACTIVE] ? j : -1;
+}
+// the resolve pass of vertex b signs the list for vertex b + 1 in the OTHER signature word: its own threads are still
+// comparing the word of vertex b
+MR_DEV void bounce_sign(const BounceParams &p) { p.ws.counters[MR_CTR_ALIVE_SIG + (int)((p.bounce_count + 1u) & 1u)] = p.sig_out; }
+MR_DEV void bounce_keep_alive(const BounceParams &p, int a)
+{
+    const int k = (int)(p.bounce_count & 1u);
+    p.ws.alive[k][queue_alloc(p.ws.counters + MR_CTR_ALIVE_SIZE + k)] = a;
+}
 
 // Entry sequence of both bounce kernels for EVERY pixel of the frame (FinalShading.slang:132-148, 657-690): remember
 // the incoming stop flag, clear new_occ, raise the stop flag, reset the path state at bounce 0, zero the outputs.
 MR_DEV void bounce_prologue_px(const BounceParams &p, int idx)
 {
     const size_t i = (size_t)idx;
+    if (idx == 0) p.ws.counters[MR_CTR_ALIVE_SIZE + (int)(p.bounce_count & 1u)] = 0; // the list this vertex's resolve pass fills
     p.ws.stop_in[i] = p.bounce_count == 0 ? 0.f : p.prd[5 * i + 4];
     p.new_occ[i] = 0.f;
     p.prd[5 * i + 4] = 1.f;
@@ -368,14 +396,17 @@ MR_DEV void continue_path_resolve(const BounceParams &p, int a)
         store3(p.new_pos, i, make_float3(h0.x, h0.y, h0.z));
         store3(p.new_normal, i, make_float3(h1.x, h1.y, h1.z));
         p.new_occ[i] = 1.f;
+        bounce_keep_alive(p, a);
     } else if (p.prd[5 * i + 3] > 0.f) {
         p.prd[5 * i + 4] = 0.f; // a specular bounce that leaves the scene picks up the envmap in the next kernel
+        bounce_keep_alive(p, a);
     }
 }
 
-MR_DEV void bounce_first_gen_px(const BounceParams &p, int a)
+MR_DEV void bounce_first_gen_px(const BounceParams &p, int j)
 {
-    if (a >= p.ws.counters[0]) return;
+    const int a = bounce_item(p, j);
+    if (a < 0) return;
     const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
@@ -388,9 +419,11 @@ MR_DEV void bounce_first_gen_px(const BounceParams &p, int a)
     continue_path_gen(p, a, i, s, load3(p.pos_map, i), sg, thr);
 }
 
-MR_DEV void bounce_first_resolve_px(const BounceParams &p, int a)
+MR_DEV void bounce_first_resolve_px(const BounceParams &p, int j)
 {
-    if (a >= p.ws.counters[0]) return;
+    if (j == 0) bounce_sign(p);
+    const int a = bounce_item(p, j);
+    if (a < 0) return;
     continue_path_resolve(p, a);
 }
 
@@ -401,9 +434,10 @@ MR_DEV void put9(float *q, float3 a, float3 b, float3 c)
     q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = b.x; q[4] = b.y; q[5] = b.z; q[6] = c.x; q[7] = c.y; q[8] = c.z;
 }
 
-MR_DEV void bounce_shade_gen_px(const BounceParams &p, int a)
+MR_DEV void bounce_shade_gen_px(const BounceParams &p, int j)
 {
-    if (a >= p.ws.counters[0]) return;
+    const int a = bounce_item(p, j);
+    if (a < 0) return;
     const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
@@ -508,9 +542,11 @@ MR_DEV void bounce_shade_gen_px(const BounceParams &p, int a)
     continue_path_gen(p, a, i, s, P, sg, thr);
 }
 
-MR_DEV void bounce_shade_resolve_px(const BounceParams &p, int a)
+MR_DEV void bounce_shade_resolve_px(const BounceParams &p, int j)
 {
-    if (a >= p.ws.counters[0]) return;
+    if (j == 0) bounce_sign(p);
+    const int a = bounce_item(p, j);
+    if (a < 0) return;
     const size_t i = (size_t)p.ws.active[a];
     const float *q = p.ws.px + (size_t)a * MR_PX_SCRATCH_FLOATS;
     float3 c = make_float3(q[0], q[1], q[2]), d = make_float3(q[3], q[4], q[5]), sp = make_float3(q[6], q[7], q[8]);
@@ -618,6 +654,10 @@ static int fill_bounce(BounceParams &p, const void *packed_nodes, const void *pa
     p.frame = frame_index; p.bounce_count = bounce_count; p.max_bounce = max_bounce; p.fx = fx; p.fy = fy;
     p.occ = occ; p.pos_map = pos_map; p.normal = normal; p.ray_dir = ray_dir; p.prd = prd; p.kd = diffuse_map; p.rm = rough_metal;
     p.new_pos = new_pos; p.new_ray_d = new_ray_d; p.new_occ = new_occ; p.new_normal = new_normal;
+    // never 0 (a cleared workspace matches nothing); the path state buffer and the vertex number identify the sequence
+    const unsigned int h = (unsigned int)((uintptr_t)prd >> 4) * 2654435761u;
+    p.sig_in = (int)((h ^ (bounce_count * 0x9e3779b9u)) | 1u);
+    p.sig_out = (int)((h ^ ((bounce_count + 1u) * 0x9e3779b9u)) | 1u);
     return 0;
 }
 

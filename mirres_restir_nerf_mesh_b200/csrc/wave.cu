@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(1024) k_compact_scan(int *block_counts, int nb
         counters[0] = carry;
         counters[1] = 0;
     }
+    if (threadIdx.x >= MR_CTR_ALIVE_SIZE && threadIdx.x <= MR_CTR_ALIVE_LAST) counters[threadIdx.x] = 0; // the lists refer to the old pixel list
 }
 
 __global__ void __launch_bounds__(CP_BLOCK) k_compact_write(const float *__restrict__ occ, int n, const int *__restrict__ block_offsets,
@@ -115,6 +116,8 @@ __global__ void __launch_bounds__(CP_BLOCK) k_compact_write(const float *__restr
 #define MR_TRACE_BLOCK 256
 #define MR_TRACE_STEPS 6
 #define MR_TRACE_STEPS_SHARED 4
+#define MR_SPLIT_ROUNDS 4
+#define MR_TRACE_STEPS_SPLIT 3
 
 // Any-hit.  When a warp cannot refill all of its idle lanes (queue dry, or -- for small queues -- the per-warp grab limit
 // is reached) the idle lanes take over the OLDEST deferred subtree of busy lanes.  bvh_hit's boolean result is the OR over
@@ -284,6 +287,8 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
     const int total = ws.counters[MR_CTR_CLOSEST_SIZE];
     int *ticket = ws.counters + MR_CTR_CLOSEST_TICKET;
     CTask T;
+    int stack_ref[MR_STACK];
+    float stack_t[MR_STACK];
     T.r.o = T.r.d = T.r.inv = f3(0.f);
     T.slot = -1;
     T.home = (int)lane;
@@ -331,18 +336,23 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
             continue;
         }
         if (SPLIT && busy != FULL) {
-            // ---- steal: the k-th idle lane takes the bottom (last in visit order) entry of the k-th lane that can give one
-            const unsigned int donors = __ballot_sync(FULL, have && task_can_donate(T));
-            if (donors != 0u) {
-                const unsigned int idle = ~busy;
+            // ---- steal: the k-th idle lane takes the bottom (last in visit order) entry of the k-th lane that can give one;
+            // repeated while idle lanes and donors remain, so one long ray spreads over the warp in a single visit of this
+            // block instead of one entry per round
+            unsigned int busy_now = busy;
+#pragma unroll 1
+            for (int round = 0; round < MR_SPLIT_ROUNDS; ++round) {
+                const unsigned int donors = __ballot_sync(FULL, have && task_can_donate(T));
+                if (donors == 0u || busy_now == FULL) break;
+                const unsigned int idle = ~busy_now;
                 const int n_pairs = min(__popc(donors), __popc(idle));
                 const bool robbed = have && task_can_donate(T) && __popc(donors & lt_mask) < n_pairs;
                 int give_ref = 0;
                 float give_t = 0.f;
                 unsigned int mid = 0u, old_hi = 0u;
                 if (robbed) {
-                    give_ref = T.stack_ref[T.bot];
-                    give_t = T.stack_t[T.bot];
+                    give_ref = stack_ref[T.bot];
+                    give_t = stack_t[T.bot];
                     ++T.bot;
                     mid = T.lo + ((T.hi - T.lo) >> 1);
                     old_hi = T.hi;
@@ -383,14 +393,17 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
                     atomicAdd(&rec.pending[g_home], 1);
                     have = true;
                 }
+                busy_now = __ballot_sync(FULL, have);
             }
             __syncwarp();
         }
         bool retired = false;
+        // shorter rounds while lanes are idle: a thief with a small subtree waits for the round to end before it can rob again
+        const int steps = (SPLIT && busy != FULL) ? MR_TRACE_STEPS_SPLIT : MR_TRACE_STEPS;
 #pragma unroll 1
-        for (int it = 0; it < MR_TRACE_STEPS; ++it) {
+        for (int it = 0; it < steps; ++it) {
             if (!have || retired) break;
-            retired = task_step(bvh, T, rec);
+            retired = task_step(bvh, T, stack_ref, stack_t, rec);
         }
         __syncwarp();
         // ---- retirement: the last task of a ray rebuilds the result from the first task's state and the thieves' logs
@@ -600,6 +613,7 @@ int mirres_workspace_prepare(const float *occ, int n_pixels, void *workspace, si
         if (!(occ[i] < 0.1f)) ws.active[c++] = i;
     ws.counters[0] = c;
     for (int k = 1; k < 8; ++k) ws.counters[k] = 0;
+    for (int k = MR_CTR_ALIVE_SIZE; k <= MR_CTR_ALIVE_LAST; ++k) ws.counters[k] = 0;
     return 0;
 #else
     cudaStream_t st = (cudaStream_t)stream;
@@ -625,6 +639,8 @@ static void closest_split_simulate(const BvhView &bvh, const float *org, const f
 {
     SplitRecT<CAP> rec;
     CTask T[MR_SPLIT_LANES];
+    static thread_local int stack_ref[MR_SPLIT_LANES][MR_STACK];
+    static thread_local float stack_t[MR_SPLIT_LANES][MR_STACK];
     bool have[MR_SPLIT_LANES];
     unsigned int rng = seed * 2654435761u + 12345u;
     auto rnd = [&]() { rng = 1664525u * rng + 1013904223u; return rng >> 8; };
@@ -653,10 +669,11 @@ static void closest_split_simulate(const BvhView &bvh, const float *org, const f
         for (int k = 0; k < pairs; ++k) {
             if ((rnd() & 1u) == 0u) continue; // not every opportunity is taken
             CTask &D = T[donors[k]], &N = T[idle[k]];
+            const int dl = donors[k];
             const unsigned int mid = D.lo + ((D.hi - D.lo) >> 1), old_hi = D.hi;
             N.r = D.r; N.slot = D.slot; N.home = D.home; N.first = false; N.nosplit = false;
             N.lo = mid; N.hi = old_hi; N.sp = N.bot = 0;
-            N.cur = D.stack_ref[D.bot]; N.cur_t = D.stack_t[D.bot]; ++D.bot;
+            N.cur = stack_ref[dl][D.bot]; N.cur_t = stack_t[dl][D.bot]; ++D.bot;
             D.hi = mid;
             N.closest = D.closest; N.best = -1; N.any = false;
             rec.pending[N.home] += 1;
@@ -669,7 +686,7 @@ static void closest_split_simulate(const BvhView &bvh, const float *org, const f
             if (!have[l]) continue;
             const int steps = (int)(rnd() % 7u);
             const int before = rec.nlog[T[l].home];
-            for (int it = 0; it < steps && !retired[l]; ++it) retired[l] = task_step(bvh, T[l], rec);
+            for (int it = 0; it < steps && !retired[l]; ++it) retired[l] = task_step(bvh, T[l], stack_ref[l], stack_t[l], rec);
             logged += rec.nlog[T[l].home] - before;
         }
         for (int l = 0; l < lanes; ++l) {
