@@ -126,17 +126,18 @@ def run_reference(args):
     crop = cfg["W"]  # the full frame of the workload
     O.set_threads(host_threads())
     cores = O.threads_in_use()  # measured inside an OpenMP region of the oracle, not read from the environment
+    spp_sample = _oracle_spp(args, cfg)
     for _ in range(args.warmup):
-        oracle_sample(args.config, crop, cfg["spp"])
+        oracle_sample(args.config, crop, spp_sample)
     tot_s, tot_t = 0, 0.0
     for _ in range(args.steps):
-        s, dt, _ = oracle_sample(args.config, crop, cfg["spp"])
+        s, dt, _ = oracle_sample(args.config, crop, spp_sample)
         tot_s += s
         tot_t += dt
     value = tot_s / tot_t
     sample = ("CPU oracle (oracle/, C++/OpenMP restatement of the Slang kernels; the reference has no CPU path): LBVH "
-              "rebuild of the %s mesh + forward spp loop (spp=%d, %d bounces) on a %dx%d frame, no backward" %
-              (args.config, cfg["spp"], cfg["max_bounce"] + 1, crop, crop))
+              "rebuild of the %s mesh + forward spp loop (%d of the workload's %d spp iterations, %d bounces) on a %dx%d frame, "
+              "no backward" % (args.config, spp_sample, cfg["spp"], cfg["max_bounce"] + 1, crop, crop))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -147,15 +148,33 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def _workload_name(name, cfg):
+def _workload_name(name, cfg, mode="train"):
+    if mode == "render":
+        return ("%s: novel-view render (forward only), %s mesh, %dx%d rays, spp=%d, %d bounces (direct + %d indirect), ReSTIR "
+                "initial + temporal + spatial, LBVH build + G-buffer + spp loop + denoise + composite per frame" %
+                (name, "x".join(str(x) for x in cfg["mesh"][1].values()), cfg["W"], cfg["H"], cfg["spp"], cfg["max_bounce"] + 1,
+                 cfg["max_bounce"]))
     return ("%s: stage-1 training step, %s mesh, %dx%d rays, spp=%d, %d bounces (direct + %d indirect), ReSTIR initial + "
             "temporal + spatial, LBVH rebuild, fwd+bwd" % (name, "x".join(str(x) for x in cfg["mesh"][1].values()), cfg["W"],
                                                           cfg["H"], cfg["spp"], cfg["max_bounce"] + 1, cfg["max_bounce"]))
 
 
+def _oracle_spp(args, cfg):
+    """spp iterations of the bounded CPU sample: the whole loop of the training step, a few iterations of a render (the
+    oracle needs ~0.2 s per iteration at 800 x 800 and ~15 s at 2048 x 2048 with 2 M triangles on 16 cores)."""
+    if args.mode != "render":
+        return cfg["spp"]
+    return min(cfg["spp"], 8 if cfg["W"] * cfg["H"] <= 800 * 800 else 1)
+
+
 def _config(args, cfg):
     """The workload both arms run -- the same dict in both JSON lines (how an arm executes it is said elsewhere:
     `execution` in the GPU line, `cpu_baseline.sample` in the reference line)."""
+    if args.mode == "render":
+        return {"workload": _workload_name(args.config, cfg, "render"), "l2": "256 MiB flush between timed frames",
+                "parallelism": "one frame cut into row bands of equal foreground-pixel count, one band per rank; 31 halo rows "
+                               "of the reservoirs received point to point per spp iteration; accumulated images all-gathered "
+                               "before the denoiser"}
     return {"workload": _workload_name(args.config, cfg) + (
                 "; G-buffer normals = auto_normals -> interpolation -> prepare_shading_normal, gradient to vertex "
                 "positions" if getattr(args, "mesh_normals", False) else ""),
@@ -294,8 +313,10 @@ def run_gpu(args):
                                                 smooth.view(1, H, W, 3), torch.zeros(1, 1, 1, 3, device=dev),
                                                 geom.view(1, H, W, 3)).view(n, 3)
         else:
-            pk.gbuffer_primary(worker.packed, rays_o, rays_d, occ, pos, nrm, depth, prim, bary,
-                               ws=slangpy_shim.workspace(dev, n))
+            # the primary-ray trace runs alone on the GPU (everything after it needs the G-buffer): it takes a full grid
+            with slangpy_shim.trace_blocks(closest_blocks=args.primary_blocks):
+                pk.gbuffer_primary(worker.packed, rays_o, rays_d, occ, pos, nrm, depth, prim, bary,
+                                   ws=slangpy_shim.workspace(dev, n))
             normal = nrm.requires_grad_(True)
         kd, rs = mat.gbuffer_materials(pos, occ)   # stand-in for the tiny-cuda-nn material MLP (out of scope)
         kd.requires_grad_(True)
@@ -453,6 +474,183 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_render(args):
+    """BASELINE configs[2] / configs[4]: one frame, forward only, cut into row bands over the ranks (dist.RowBandShard).
+    A step = one whole frame: LBVH build, full-frame primary G-buffer (every rank: the denoiser needs it and it is one
+    trace against spp iterations), spp loop on the band, gather, denoise, composite.  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from mirres_restir_nerf_mesh_b200 import synth, renderer_restir as R, slangpy_shim, kernels as K, dist as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(synth.CONFIGS[args.config])
+    if args.spp:
+        cfg["spp"] = args.spp
+    W, H, spp, mb = cfg["W"], cfg["H"], cfg["spp"], cfg["max_bounce"]
+    n = W * H
+    pk = ProfiledKernels(K.Kernels(), torch)
+    slangpy_shim.set_kernels(pk)
+    for item in args.tune or []:
+        name, value = item.split("=")
+        pk.set_tuning(getattr(K.Kernels, "TUNE_" + name.upper()), int(value))
+
+    vert_np, tri_np = synth.make_mesh(cfg)
+    env_np = synth.envmap(*cfg["env"])
+    pose_np = synth.camera_pose(view=0)  # the view tools/oracle_counters.py counts node pops and triangle tests for
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    host = dict(vert=pin(vert_np), tri=pin(tri_np), env=pin(env_np), pose=pin(pose_np))
+    device_in = {k: v.to(dev) for k, v in host.items()}
+    worker = R.restirbvhWorker(device_in["vert"], device_in["tri"])
+    mat = synth.ProceduralMaterial(0.0)
+    mods = R.load_m_for_restir(W, H, device=dev, max_bounce=mb)
+
+    def gbuffer(vert, tri, pose):
+        worker.update_mesh(vert, tri)
+        rays_o, rays_d = synth.camera_rays_torch(W, H, pose)
+        occ, depth = torch.empty(n, 1, device=dev), torch.empty(n, 1, device=dev)
+        pos, nrm = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
+        with slangpy_shim.trace_blocks(closest_blocks=args.primary_blocks):
+            pk.gbuffer_primary(worker.packed, rays_o, rays_d, occ, pos, nrm, depth, ws=slangpy_shim.workspace(dev, n))
+        return rays_d, occ, depth, pos, nrm
+
+    # the band boundaries follow the foreground of the view (one host synchronisation per view, outside the timed frames:
+    # the bench renders the same view again and again)
+    with torch.no_grad():
+        occ0 = gbuffer(device_in["vert"], device_in["tri"], device_in["pose"])[1]
+        bounds = D.balanced_bounds(occ0, W, H, world, min_rows=1) if not args.uniform_bands else D.uniform_bounds(H, world)
+        n_fg = int((occ0 >= 0.1).sum().item())
+    shard = D.RowBandShard(W, H, rank=rank, world=world, bounds=bounds)
+
+    def frame(vert, tri, env, pose):
+        with torch.no_grad():
+            rays_d, occ, depth, pos, nrm = gbuffer(vert, tri, pose)
+            kd, rs = mat.gbuffer_materials(pos, occ)
+            outs = R.run_restir_di_with_pt(False, 1, 1, 1, mat, None, worker, *mods, env, occ, nrm, depth, kd, rs, rays_d, pos,
+                                           None, None, None, None, W, H, spp, 2, 2, 2.0, 0.1, 0.001, random_offset=1234,
+                                           max_bounce=mb, shard=shard, overlap=not args.no_overlap)
+        return outs[0]
+
+    for _ in range(2):
+        frame(**device_in)
+    torch.cuda.synchronize()
+    captured, why_eager = None, None
+    if not args.no_graph:
+        from mirres_restir_nerf_mesh_b200.graphed import CapturedStep
+        try:
+            captured = CapturedStep(frame, device_in, warmup=1)
+        except Exception as e:  # e.g. a collective that cannot be captured: the frame then runs eagerly, and the line says so
+            why_eager = "%s: %s" % (type(e).__name__, str(e)[:200])
+            captured = None
+            torch.cuda.synchronize()
+
+    def run_step(from_host):
+        if captured is not None:
+            if from_host:
+                captured.load(**host)
+            return captured.replay()
+        src = {k: v.to(dev, non_blocking=True) for k, v in host.items()} if from_host else device_in
+        return frame(**src)
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    image_host = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+
+    def timed(k_steps, from_host):
+        total_ms, d2h = 0.0, 0
+        for _ in range(k_steps):
+            flush.fill_(1.0)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            img = run_step(from_host)
+            if from_host:
+                if rank == 0:
+                    image_host.copy_(img, non_blocking=True)  # the frame leaves through rank 0
+                d2h = image_host.numel() * 4
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        return total_ms, d2h
+
+    for _ in range(max(args.warmup, 1)):
+        run_step(False)
+    torch.cuda.synchronize()
+    with Clocks(local) as clocks:
+        ms_dev, _ = timed(args.steps, False)
+    run_step(True)
+    torch.cuda.synchronize()
+    ms_e2e, d2h_bytes = timed(args.steps, True)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    # per-kernel device times and the launch count: one eager frame with a few spp iterations, chains serialised
+    per_kernel, launches_per_iter, launches_fixed = {}, 0, 0
+    if rank == 0 or world > 1:
+        spp_full = spp
+        counts = []
+        for spp_probe in (2, 4):
+            spp = spp_probe
+            pk.launches, pk.events, pk.record = 0, [], (spp_probe == 4 and rank == 0)
+            saved = args.no_overlap
+            args.no_overlap = True
+            flush.fill_(1.0)
+            frame(**device_in)
+            torch.cuda.synchronize()
+            args.no_overlap = saved
+            counts.append(pk.launches)
+        pk.record = False
+        spp = spp_full
+        per_kernel = pk.per_kernel_ms()
+        launches_per_iter = (counts[1] - counts[0]) // 2
+        launches_fixed = counts[0] - 2 * launches_per_iter
+
+    tms = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    per_rank = None
+    if world > 1:
+        allt = [torch.empty_like(tms) for _ in range(world)]
+        dist.all_gather(allt, tms)
+        per_rank = [[round(float(t[0]) / args.steps, 3), round(float(t[1]) / args.steps, 3)] for t in allt]
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(tms[0]), float(tms[1])
+    samples = n * spp * args.steps  # the frame is ONE job whatever the number of ranks (strong scaling)
+    if rank == 0:
+        peaks = _peaks()
+        peak = peaks["hbm_gbs"] if peaks else 6650.0
+        roof = roofline(args.config, cfg, per_kernel, 1, peak, "measured" if peaks else "fallback", n_fg, probe_spp=4)
+        line = {"metric": METRIC, "value": samples / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(args, cfg),
+                "execution": ("CUDA graph replay of the whole frame (halo exchange and gather captured with it)"
+                              if captured is not None else "eager launches" + (" (graph capture failed: %s)" % why_eager if why_eager else "")) +
+                             (", concurrent schedule" if not args.no_overlap else ""),
+                "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": (launches_fixed + launches_per_iter * spp) * args.steps,
+                "clocks": clocks.summary(), "roofline": roof,
+                "bands": {"bounds": shard.bounds, "halo_bytes_per_iteration_rank0": shard.halo_bytes(),
+                          "foreground_pixels": n_fg, "frame_pixels": n},
+                "kernel_ms_per_frame_spp4_probe": {k: round(v[0], 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])[:12]}}
+        if per_rank is not None:
+            line["per_rank_ms_per_step"] = {"device": [t[0] for t in per_rank], "e2e": [t[1] for t in per_rank]}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            s_, dt, _ = oracle_sample(args.config, cfg["W"], _oracle_spp(args, cfg))
+            line["cpu_baseline"] = {"value": s_ / dt, "unit": UNIT, "cores": O.threads_in_use(), "kind": "port",
+                                    "sample": "CPU oracle (OpenMP, all host cores): LBVH build + %d spp iterations of the same %dx%d frame, "
+                                              "forward, no G-buffer or denoiser" % (_oracle_spp(args, cfg), cfg["W"], cfg["H"])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def step_algorithmic_bytes(cfg_name, cfg, spp, n_foreground=None):
     """Algorithmic bytes of one whole step: sum over samples of S_screen + 36 V_n + 48 V_t, forward
     (872 B first spp iteration, 1040 B after) + backward (280 B), plus 424 B per rebuilt triangle.
@@ -499,7 +697,7 @@ def _timeline(torch, step, path):
             f.write("%10.1f %9.1f %8.1f  %s\n" % (s, d, gap, name[:110]))
 
 
-def roofline(cfg_name, cfg, per_kernel, steps, peak, peak_kind, n_foreground=None):
+def roofline(cfg_name, cfg, per_kernel, steps, peak, peak_kind, n_foreground=None, probe_spp=None):
     """Dominant kernel vs the HBM roofline.  Algorithmic bytes per launch = S_screen(stage) * N + 36 * V_n + 48 * V_t
      with V_n / V_t the oracle's node-pop / triangle-test counts per launch under the contract schedule
     (profiles/oracle_counters_<cfg>.json, produced by tools/oracle_counters.py)."""
@@ -531,19 +729,31 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mirres_b200")
-    ap.add_argument("--config", default="C2")
+    ap.add_argument("--config", default=None, help="C2 (training step, the default), C3 / C5 (renders)")
+    ap.add_argument("--mode", default=None, choices=["train", "render"],
+                    help="train: stage-1 step, one view per rank (weak scaling); render: one frame cut into row bands over "
+                         "the ranks (strong scaling).  Default: train for C2, render for C3 / C5")
+    ap.add_argument("--spp", type=int, default=None, help="render mode: override the configuration's spp")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--uniform-bands", action="store_true", help="render mode: bands of equal height instead of equal foreground")
     ap.add_argument("--no-overlap", action="store_true", help="direct and indirect chains on one stream")
     ap.add_argument("--mesh-normals", action="store_true",
                     help="G-buffer normals through the reference's chain (auto_normals -> interpolation -> "
                          "prepare_shading_normal); the vertex segment of the gradient buffer then holds d loss / d vertex "
                          "positions instead of normal gradients accumulated at the vertices")
+    ap.add_argument("--primary-blocks", type=int, default=4, help="blocks per SM of the primary-ray tracer (0 = library default)")
     ap.add_argument("--tune", action="append", help="library tuning NAME=VALUE (mirres_set_tuning), repeatable")
     ap.add_argument("--timeline", default=None, help="diagnostics: write a per-kernel device timeline of one warm step")
     args = ap.parse_args()
+    if args.mode is None:
+        args.mode = "render" if args.config in ("C3", "C5") else "train"
+    if args.config is None:
+        args.config = "C3" if args.mode == "render" else "C2"
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "render":
+        run_render(args)
     else:
         run_gpu(args)
 

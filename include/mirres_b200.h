@@ -131,8 +131,14 @@ int mirres_light_tiles(const float *env_tex, int W, int H, const float *pdf_, co
  * frame_index argument of every entry point that takes that workspace.  The library never writes it; the caller
  * zero-fills the workspace once and may update the word between launches (e.g. before replaying a CUDA graph whose
  * frame indices are baked in).  Zero reproduces the reference's frame-index schedule exactly.
+ * Row offset: the word at MIRRES_WORKSPACE_ROW_OFFSET_BYTES is added to a pixel's ROW when its random stream is seeded
+ * (Seed_Generator(pixel, frame), nerf/ScreenSpaceReSTIR/utils/random.slang:2-39) -- and to nothing else.  The [N, k]
+ * maps are row-major, so a band of rows is a contiguous slice of every tensor: a rank that renders rows [y0, y1) of a
+ * larger frame passes the slices with framedim_y = y1 - y0 and sets this word to y0, and every pixel
+ * draws the random numbers of its position in the full frame.  Same ownership rules as the frame offset; zero = plain.
  */
 #define MIRRES_WORKSPACE_FRAME_OFFSET_BYTES 32
+#define MIRRES_WORKSPACE_ROW_OFFSET_BYTES 36
 size_t mirres_workspace_bytes(int n_pixels);
 int mirres_workspace_prepare(const float *occ, int n_pixels, void *workspace, size_t workspace_bytes, void *stream);
 

@@ -37,6 +37,11 @@ namespace mr {
 // (never by the library), so a CUDA graph whose launches have their frame indices baked in can be replayed with fresh
 // random streams (graphed.CapturedStep.set_frame_offset).  Zero = the plain reference behaviour.
 #define MR_CTR_FRAME_OFFSET 8
+// [9] row offset: added to a pixel's row when its random stream is seeded (Seed_Generator(pixel, frame), random.slang:2-39).
+// Written by the caller like the frame offset.  A rank that renders a band of a larger frame passes the band's rows as
+// a frame of its own (the [N, k] maps are row-major, so a band is a contiguous slice of every tensor) and sets this word
+// to the band's first row: every pixel then draws the random numbers it draws in the full frame.  Zero = plain behaviour.
+#define MR_CTR_ROW_OFFSET 9
 // [16], [17] sizes of the two lists of paths that are still alive (the path kernels ping-pong between them), [18], [19]
 // the signatures of the calls those lists were written for (see bounce_item in shade.cu; a kernel reads one word and
 // writes the other); cleared by mirres_workspace_prepare
@@ -85,6 +90,7 @@ static inline size_t workspace_carve(Workspace *w, int N, char *base)
     return off;
 }
 
+MR_DEV unsigned int row_of(const Workspace &w, unsigned int py) { return py + (unsigned int)w.counters[MR_CTR_ROW_OFFSET]; }
 MR_DEV unsigned int frame_of(const Workspace &w, unsigned int frame_index) { return frame_index + (unsigned int)w.counters[MR_CTR_FRAME_OFFSET]; }
 
 // one ticket of a queue; lanes of a warp that arrive together share one atomic

@@ -126,10 +126,10 @@ MR_DEV void initial_gen_px(const InitialParams &p, int a)
     const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
-    uint32_t tileSg = seed_of(px / p.screen_tile, py / p.screen_tile, frame_of(p.ws, p.frame));
+    uint32_t tileSg = seed_of(px / p.screen_tile, row_of(p.ws, py) / p.screen_tile, frame_of(p.ws, p.frame));
     uint32_t tileIndex = minu(to_uint(rnd(tileSg) * (float)p.tile_count), p.tile_count - 1u);
     const uint32_t tileOffset = tileIndex * p.tile_size;
-    uint32_t sg = seed_of(px, py, frame_of(p.ws, p.frame));
+    uint32_t sg = seed_of(px, row_of(p.ws, py), frame_of(p.ws, p.frame));
     const uint32_t stride = (p.tile_size + p.n_light - 1u) / p.n_light;
     const uint32_t offset = minu(to_uint(rnd(sg) * (float)stride), stride - 1u);
     float4 nd = load_nd(p.g.normal_depth, i);
@@ -215,7 +215,7 @@ MR_DEV void temporal_px(const TemporalParams &p, int a)
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
     if (MR_LDG(p.g.occ + i) < 0.1f) return;
-    uint32_t sg = seed_of(px, py, frame_of(p.ws, p.frame));
+    uint32_t sg = seed_of(px, row_of(p.ws, py), frame_of(p.ws, p.frame));
     float u0 = rnd(sg), u1 = rnd(sg);
     float mvx = p.motion ? MR_LDG(p.motion + 2 * i) : 0.f, mvy = p.motion ? MR_LDG(p.motion + 2 * i + 1) : 0.f;
     int ppx = to_int((float)px + mvx * (float)(uint32_t)p.fx + (u0 * 1.f - 0.f));
@@ -261,6 +261,10 @@ struct SpatialParams {
     Workspace ws;
 };
 
+// marks the per-pixel cache entries the gen pass of THIS launch has written (entries of pixels that are not on the launch's
+// pixel list keep an older mark and are evaluated by the resolve pass itself)
+MR_DEV int spatial_cache_tag(const SpatialParams &p) { return (int)(frame_of(p.ws, p.frame) | 0x80000000u); }
+
 MR_DEV bool spatial_neighbor(const SpatialParams &p, uint32_t px, uint32_t py, uint32_t startIndex, uint32_t k, size_t &n)
 {
     const uint32_t ni = (startIndex + k) & (p.offset_count - 1u);
@@ -283,7 +287,7 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
     const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
-    uint32_t sg = seed_of(px, py, frame_of(p.ws, p.frame));
+    uint32_t sg = seed_of(px, row_of(p.ws, py), frame_of(p.ws, p.frame));
     float4 nd = load_nd(p.g.normal_depth, i);
     const float3 N = make_float3(nd.x, nd.y, nd.z);
     const uint32_t startIndex = to_uint(rnd(sg) * (float)p.offset_count);
@@ -326,7 +330,7 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
     // neighbour needs as well (candAtOwn of the pairwise MIS)
     const float own_target = target_pdf(ris_surface(N, load3(p.g.ray_dir, i), load3(p.g.brdf, i)), cLe, cL);
     p.ws.lcache[2 * i] = make_float4(cLe.x, cLe.y, cLe.z, own_target);
-    p.ws.lcache[2 * i + 1] = make_float4(cL.x, cL.y, cL.z, 0.f);
+    p.ws.lcache[2 * i + 1] = make_float4(cL.x, cL.y, cL.z, bits_float(spatial_cache_tag(p)));
     const float3 cur_pos = load3(p.pos_map, i);
     const size_t base = (size_t)a * MR_MAX_RAYS_PER_PIXEL;
 #pragma unroll
@@ -386,7 +390,7 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
     const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
-    uint32_t sg = seed_of(px, py, frame_of(p.ws, p.frame));
+    uint32_t sg = seed_of(px, row_of(p.ws, py), frame_of(p.ws, p.frame));
     float4 nd = load_nd(p.g.normal_depth, i);
     const float3 N = make_float3(nd.x, nd.y, nd.z);
     const RisSurface cur_s = ris_surface(N, load3(p.g.ray_dir, i), load3(p.g.brdf, i));
@@ -408,7 +412,14 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
         const Reservoir nr = res_load(p.prev, n);
         const RisSurface nb_s = ris_surface(nN, load3(p.g.ray_dir, n), load3(p.g.brdf, n));
         ++validNeighbors;
-        const float4 n0 = p.ws.lcache[2 * n], n1 = p.ws.lcache[2 * n + 1]; // light_of(nr.ld): n is a foreground pixel
+        float4 n0 = p.ws.lcache[2 * n], n1 = p.ws.lcache[2 * n + 1]; // light_of(nr.ld): n is a foreground pixel
+        if (float_bits(n1.w) != spatial_cache_tag(p)) {
+            // the neighbour is not on this launch's pixel list (a halo row of a band, dist.py): evaluate its entry here
+            float3 le, l;
+            light_of(p.env, nr.ld.y, nr.ld.z, le, l);
+            n0 = make_float4(le.x, le.y, le.z, target_pdf(nb_s, le, l));
+            n1 = make_float4(l.x, l.y, l.z, 0.f);
+        }
         const float3 nLe = make_float3(n0.x, n0.y, n0.z), nL = make_float3(n1.x, n1.y, n1.z);
         const bool canonical_hit = p.ws.hit[base + 2 * k] == MR_HIT_HIT;
         const bool candidate_hit = p.ws.hit[base + 2 * k + 1] == MR_HIT_HIT;

@@ -414,7 +414,7 @@ MR_DEV void bounce_first_gen_px(const BounceParams &p, int j)
     if (p.ws.stop_in[i] > 0.f) return;
     if (!(MR_LDG(p.occ + i) > 0.1f)) return;
     const float3 thr = make_float3(p.prd[5 * i], p.prd[5 * i + 1], p.prd[5 * i + 2]);
-    uint32_t sg = seed_of(px, py, frame_of(p.ws, p.frame));
+    uint32_t sg = seed_of(px, row_of(p.ws, py), frame_of(p.ws, p.frame));
     const Surface s = surface_of(load3(p.normal, i), load3(p.ray_dir, i), load3(p.kd, i), MR_LDG(p.rm + 2 * i), MR_LDG(p.rm + 2 * i + 1));
     continue_path_gen(p, a, i, s, load3(p.pos_map, i), sg, thr);
 }
@@ -461,7 +461,7 @@ MR_DEV void bounce_shade_gen_px(const BounceParams &p, int j)
         p.prd[5 * i + 4] = 1.f;
         return;
     }
-    uint32_t sg = seed_of(px, py, frame_of(p.ws, p.frame));
+    uint32_t sg = seed_of(px, row_of(p.ws, py), frame_of(p.ws, p.frame));
     const float3 N = load3(p.normal, i);
     const float3 P = load3(p.pos_map, i);
     const Surface s = surface_of(N, rd, load3(p.kd, i), MR_LDG(p.rm + 2 * i), MR_LDG(p.rm + 2 * i + 1));

@@ -3,70 +3,180 @@
 Training (BASELINE config 4): data parallel over views -- every rank renders its own view and the per-step gradients
 (envmap, vertex normals, vertex texture) are summed with ONE all-reduce of a flat buffer (`allreduce_gradients`).
 
-Rendering (configs 3 and 5): the frame is cut into contiguous ROW BANDS.  Pixels are independent except that spatial
-reuse reads neighbours within 30 px and temporal reuse within 1 px (GATHER_RADIUS, nerf/renderer_restir.py:176), and the
-a-trous filter reaches 6 px.  A rank therefore processes its band plus a 31-row halo, and after every spatial pass the
-ranks exchange their own rows of the reservoirs, so that the halo rows a rank reads in the next iteration hold their
-owners' values (recomputing the halo locally is not enough: temporal reuse makes the dependency cone grow by 30 px
-per spp iteration).  RNG streams are keyed on global pixel coordinates (the maps stay full-frame; only the list of
-processed pixels is restricted), so the assembled image is bit-identical to the single-GPU one.  The BVH, the envmap
-distribution and the light tiles are rebuilt identically on every rank.
+Rendering (configs 3 and 5): the frame is cut into contiguous ROW BANDS, one per rank.  Pixels are independent except
+that spatial reuse reads the post-temporal reservoirs of neighbours within 30 px (GATHER_RADIUS,
+nerf/renderer_restir.py:176) and temporal reuse reads the previous iteration's reservoir within 1 px.  Per spp iteration
+a rank therefore runs
+    initial candidates + temporal reuse      on its band + 30 rows on either side   (`wide` rows)
+    spatial reuse, visibility, shading,
+    the indirect paths                       on its band only                       (`rows`)
+and after every spatial pass it receives the 31 rows above and below its band from the ranks that own them -- 24 bytes
+per pixel, 0.6 MB per boundary at 800 px width -- point to point, nothing else travels inside the loop.
+(Recomputing the halo locally is not enough: temporal reuse makes the dependency cone grow by 30 px per iteration.)
+RNG streams are keyed on global pixel coordinates and the maps stay full-frame (only the lists of processed pixels are
+restricted), so every reservoir a rank computes or receives is bit-identical to the single-GPU one.  After the loop the
+six accumulated images of the bands are all-gathered and denoised / composited at full frame on every rank, exactly as
+on one GPU.  The BVH, the envmap distribution and the light tiles are rebuilt identically on every rank.
+
+Band boundaries need not be uniform: `balanced_bounds` cuts the frame so that every band holds the same number of
+FOREGROUND pixels (background pixels leave every kernel after the compaction, so rows of sky cost nothing).
 """
 import torch
 import torch.distributed as dist
 
-HALO_ROWS = 31  # 30 px gather radius + 1 px temporal jitter
+REUSE_ROWS = 30                 # GATHER_RADIUS: rows of post-temporal reservoirs spatial reuse reads beyond the band
+HALO_ROWS = REUSE_ROWS + 1      # + 1 px jitter of temporal reuse: rows of finished reservoirs a rank needs from its neighbours
+
+
+def uniform_bounds(framedim_y, world):
+    """world + 1 row indices, bands of (almost) equal height."""
+    return [(framedim_y * r) // world for r in range(world + 1)]
+
+
+def balanced_bounds(occ_map, framedim_x, framedim_y, world, min_rows=1):
+    """world + 1 row indices such that every band holds about the same number of foreground pixels (occ > 0.5).  One host
+    synchronisation; every rank derives the same boundaries from the same full-frame occupancy."""
+    per_row = (occ_map.reshape(framedim_y, framedim_x) > 0.5).sum(dim=1).to(torch.float64).cpu()
+    total = float(per_row.sum())
+    if total <= 0:
+        return uniform_bounds(framedim_y, world)
+    cum = torch.cumsum(per_row, 0)
+    bounds = [0]
+    for r in range(1, world):
+        y = int(torch.searchsorted(cum, torch.tensor(total * r / world, dtype=torch.float64)).item()) + 1
+        y = max(y, bounds[-1] + min_rows)
+        y = min(y, framedim_y - (world - r) * min_rows)
+        bounds.append(y)
+    bounds.append(framedim_y)
+    return bounds
 
 
 class RowBandShard:
-    def __init__(self, framedim_x, framedim_y, rank=None, world=None, group=None, halo=HALO_ROWS):
+    def __init__(self, framedim_x, framedim_y, rank=None, world=None, group=None, halo=HALO_ROWS, bounds=None):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
-        if framedim_y % self.world:
-            raise ValueError("frame height %d is not divisible by %d ranks" % (framedim_y, self.world))
         self.fx, self.fy = int(framedim_x), int(framedim_y)
-        band = self.fy // self.world
-        self.rows = (self.rank * band, (self.rank + 1) * band)          # rows this rank owns
-        self.active = (max(self.rows[0] - halo, 0), min(self.rows[1] + halo, self.fy))  # rows it processes
+        self.bounds = [int(b) for b in (bounds if bounds is not None else uniform_bounds(self.fy, self.world))]
+        if len(self.bounds) != self.world + 1 or self.bounds[0] != 0 or self.bounds[-1] != self.fy or \
+                any(b1 < b0 for b0, b1 in zip(self.bounds, self.bounds[1:])):
+            raise ValueError("band boundaries %r do not partition %d rows over %d ranks" % (self.bounds, self.fy, self.world))
+        self.halo = int(halo)
+        self.rows = self.band(self.rank)                                                   # rows this rank owns
+        self.wide = (max(self.rows[0] - (halo - 1), 0), min(self.rows[1] + (halo - 1), self.fy))  # initial + temporal
+        self.active = (max(self.rows[0] - halo, 0), min(self.rows[1] + halo, self.fy))     # rows whose reservoirs it reads
+        # point-to-point plan: (peer, rows) -- what this rank needs from a peer = the peer's band cut with its halo
+        self.recv_plan = [(q, self._cut(self.band(q), self.active)) for q in range(self.world) if q != self.rank]
+        self.recv_plan = [(q, c) for q, c in self.recv_plan if c is not None]
+        self.send_plan = [(q, self._cut(self.rows, self._active_of(q))) for q in range(self.world) if q != self.rank]
+        self.send_plan = [(q, c) for q, c in self.send_plan if c is not None]
+        # the collective is chosen once, from the backend (gloo has no flat all-gather), never by catching a failed call
+        self._flat_gather = self.world > 1 and dist.is_initialized() and dist.get_backend(group) != "gloo"
 
-    def _own(self, t):
-        return t.view(self.fy, -1)[self.rows[0]:self.rows[1]].contiguous()
+    def band(self, r):
+        return (self.bounds[r], self.bounds[r + 1])
 
-    def exchange(self, tensors):
-        """In place: every [N, k] tensor ends up with each row band holding its owner's values.  All tensors travel in ONE
-        collective: their own rows are packed side by side as 32-bit words (fp32 and int32 alike) and unpacked after the
-        all-gather -- per spp iteration that is one NCCL call and five small copies instead of four collectives with
-        their staging."""
+    def _active_of(self, r):
+        y0, y1 = self.band(r)
+        return (max(y0 - self.halo, 0), min(y1 + self.halo, self.fy))
+
+    @staticmethod
+    def _cut(a, b):
+        y0, y1 = max(a[0], b[0]), min(a[1], b[1])
+        return (y0, y1) if y1 > y0 else None
+
+    def halo_bytes(self, row_bytes=24):
+        """Bytes this rank receives per exchange (row_bytes per pixel: the four reservoir tensors)."""
+        return sum((c[1] - c[0]) for _, c in self.recv_plan) * self.fx * row_bytes
+
+    def _peer(self, q):
+        return q if self.group is None else dist.get_global_rank(self.group, q)
+
+    def _row_views(self, tensors, row0):
+        # [rows, fx * k] views of [rows * fx, k] tensors that start at frame row `row0`, as 32-bit words
+        views = [t.view(t.shape[0] // self.fx, -1) for t in tensors]
+        return [v if v.dtype == torch.float32 else v.view(torch.float32) for v in views]
+
+    def exchange(self, tensors, row0=0):
+        """In place: the halo rows of every [rows * fx, k] tensor (rows of the frame from `row0` on; the whole frame by
+        default) take their owners' values.  Per peer ONE message carries the rows of all tensors (32-bit words, fp32 and
+        int32 alike); a rank talks to the ranks whose bands touch its halo only."""
         tensors = list(tensors)
-        band = self.rows[1] - self.rows[0]
-        own = [t.view(self.fy, -1)[self.rows[0]:self.rows[1]] for t in tensors]
-        packed = torch.cat([o.view(torch.float32) for o in own], dim=1).contiguous()
-        width = packed.shape[1]
-        out = torch.empty((self.world, band, width), dtype=torch.float32, device=packed.device)
-        try:
-            dist.all_gather_into_tensor(out.view(-1), packed.view(-1), group=self.group)
-        except (RuntimeError, NotImplementedError, AttributeError):
-            parts = [torch.empty_like(packed) for _ in range(self.world)]
-            dist.all_gather(parts, packed, group=self.group)
+        if self.world == 1 or not (self.recv_plan or self.send_plan):
+            return
+        views = self._row_views(tensors, row0)
+        ops, recvs = [], []
+        for q, (y0, y1) in self.send_plan:
+            buf = torch.cat([v[y0 - row0:y1 - row0] for v in views], dim=1).contiguous()
+            ops.append(dist.P2POp(dist.isend, buf, self._peer(q), self.group))
+        for q, (y0, y1) in self.recv_plan:
+            buf = torch.empty((y1 - y0, sum(v.shape[1] for v in views)), dtype=torch.float32, device=views[0].device)
+            ops.append(dist.P2POp(dist.irecv, buf, self._peer(q), self.group))
+            recvs.append((y0 - row0, y1 - row0, buf))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for y0, y1, buf in recvs:
+            c0 = 0
+            for v in views:
+                c1 = c0 + v.shape[1]
+                v[y0:y1].copy_(buf[:, c0:c1])
+                c0 = c1
+
+    def gather_bands(self, images, row0=0):
+        """Full-frame copies of fp32 images of which every rank holds its own band (tensors [rows * fx, k] that start at
+        frame row `row0`): one all-gather for all of them, bands padded to the tallest."""
+        images = list(images)
+        views = self._row_views(images, row0)
+        y0, y1 = self.rows
+        if self.world == 1:
+            return [v[y0 - row0:y1 - row0].reshape(-1, im.shape[1]).clone() for v, im in zip(views, images)]
+        width = sum(v.shape[1] for v in views)
+        tall = max(b1 - b0 for b0, b1 in zip(self.bounds, self.bounds[1:]))
+        mine = torch.zeros((tall, width), dtype=torch.float32, device=views[0].device)
+        mine[:y1 - y0] = torch.cat([v[y0 - row0:y1 - row0] for v in views], dim=1)
+        out = torch.empty((self.world, tall, width), dtype=torch.float32, device=mine.device)
+        if self._flat_gather:
+            dist.all_gather_into_tensor(out.view(-1), mine.view(-1), group=self.group)
+        else:
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine, group=self.group)
             out = torch.stack(parts)
-        c0 = 0
-        for t, o in zip(tensors, own):
-            c1 = c0 + o.shape[1]
-            t.view(self.world, band, o.shape[1]).view(torch.float32).copy_(out[:, :, c0:c1])
-            c0 = c1
+        full = [torch.empty((self.fy, v.shape[1]), dtype=torch.float32, device=mine.device) for v in views]
+        for r in range(self.world):
+            b0, b1 = self.band(r)
+            c0 = 0
+            for f in full:
+                c1 = c0 + f.shape[1]
+                f[b0:b1] = out[r, :b1 - b0, c0:c1]
+                c0 = c1
+        return [f.view(-1, im.shape[1]) for f, im in zip(full, images)]
 
     def gather_image(self, img):
         """Full-frame [N, k] image assembled from the bands every rank owns."""
-        out = img.clone()
-        self.exchange([out])
-        return out
+        return self.gather_bands([img])[0]
+
+    def view(self):
+        """The shard as the spp loop sees it when it is handed the rows `active` of every map as a frame of their own."""
+        return RowBandView(self)
+
+
+class RowBandView:
+    """Row numbers relative to the first row of the slice [active[0], active[1]) of the frame."""
+
+    def __init__(self, shard):
+        self.shard, self.row0 = shard, shard.active[0]
+        rel = lambda r: (r[0] - self.row0, r[1] - self.row0)
+        self.rows, self.wide, self.active = rel(shard.rows), rel(shard.wide), rel(shard.active)
+
+    def exchange(self, tensors):
+        self.shard.exchange(tensors, self.row0)
 
 
 def render_rows_sharded(run, shard, *args, **kw):
-    """`run` = renderer_restir.run_restir_di_with_pt; returns its outputs assembled over all ranks."""
+    """`run` = renderer_restir.run_restir_di_with_pt; its outputs are full-frame on every rank (the bands' accumulated
+    images are gathered before the denoiser)."""
     outs = run(*args, shard=shard, **kw)
-    return tuple(shard.gather_image(o.detach()) for o in outs)
+    return tuple(o.detach() for o in outs)
 
 
 def allreduce_gradients(flat, group=None):

@@ -34,6 +34,10 @@ MAX_INITIAL_STREAMS = int(_os.environ.get("MIRRES_INITIAL_STREAMS", 3))   # conc
 MAX_INDIRECT_CHAINS = int(_os.environ.get("MIRRES_INDIRECT_CHAINS", 4))  # concurrent indirect-path chains (one CUDA stream + path state + ray-queue workspace each)
 CRITICAL_ANY_BLOCKS = int(_os.environ.get("MIRRES_CRITICAL_ANY_BLOCKS", 0))  # persistent grid (blocks / SM) of the reuse chain's boolean-ray launches; 0 = library default
 USE_PRIORITIES = int(_os.environ.get("MIRRES_PRIORITIES", 1))  # stream priorities for the critical reuse chain
+# persistent grids (blocks / SM) of the indirect chains' tracers.  Since their closest-hit rays are split over the lanes of
+# a warp the chains have slack, and a small grid leaves the SMs to the reuse chain (C2 step 4.35 -> 4.26 ms)
+BACKGROUND_CLOSEST_BLOCKS = int(_os.environ.get("MIRRES_BACKGROUND_CLOSEST_BLOCKS", 1))
+BACKGROUND_MIXED_BLOCKS = int(_os.environ.get("MIRRES_BACKGROUND_MIXED_BLOCKS", 2))
 _SIDE_STREAMS = {}
 
 
@@ -680,6 +684,13 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     worker = bvh_restir_worker
     bvh = (worker.LBVHNode_info, worker.LBVHNode_aabb, worker.vrt, worker.v_ind)
 
+    # `shard` (dist.RowBandView): the frame handed in is a band of a larger frame plus its halo rows.  Light tiles and
+    # temporal reuse cover `shard.wide` (the band + 30 rows on either side: what spatial reuse reads), everything else
+    # -- spatial reuse, visibility, shading, the indirect paths -- the band's own rows, which is what run_restir_di_with_pt
+    # has made the ambient row restriction of the pixel lists.
+    def rows_wide():
+        return slangpy.active_rows(shard.wide[0], shard.wide[1], framedim_x) if shard is not None else contextlib.nullcontext()
+
     def zeros(*shape):
         return torch.zeros(shape, dtype=torch.float, device=dev)
 
@@ -879,8 +890,11 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             st.wait_stream(caller_stream)
         with _on(main_stream):
             slangpy.prepare_workspace(occ_map)
+            if shard is not None:
+                with slangpy.workspace_tag("temporal"), rows_wide():
+                    slangpy.prepare_workspace(occ_map)
         for r in range(R):
-            with _on(st_init[r]), slangpy.workspace_tag("initial%d" % r):
+            with _on(st_init[r]), slangpy.workspace_tag("initial%d" % r), rows_wide():
                 slangpy.prepare_workspace(occ_map)
         with _on(st_s), slangpy.workspace_tag("shade"):
             slangpy.prepare_workspace(occ_map)
@@ -900,7 +914,8 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             base = random_offset + TOTAL_RIS_PASSES * i
             first_indirect_pass = 4 if i == 0 else 5
             c = chains[i % len(chains)]
-            with _on(c["stream"]), slangpy.workspace_tag(c["tag"]):
+            with _on(c["stream"]), slangpy.workspace_tag(c["tag"]), slangpy.trace_blocks(
+                    closest_blocks=BACKGROUND_CLOSEST_BLOCKS, mixed_blocks=BACKGROUND_MIXED_BLOCKS):
                 indirect_chain(i, first_indirect_pass, c)
             r = i % R
             with _on(st_init[r]), slangpy.workspace_tag("initial%d" % r):
@@ -917,9 +932,10 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             ris_pass = 3
             with _on(main_stream):
                 if i > 0:
-                    TemporalResampling(TemporalResampling_m, X[r], S[(i - 1) % 2], env_map, width, height, framedim_x,
-                                       framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map,
-                                       prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
+                    with slangpy.workspace_tag("temporal") if shard is not None else contextlib.nullcontext():
+                        TemporalResampling(TemporalResampling_m, X[r], S[(i - 1) % 2], env_map, width, height, framedim_x,
+                                           framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map,
+                                           prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
                     ris_pass += 1
                 if i >= 2:
                     main_stream.wait_event(copy_done[i - 2])  # S[i % 2] was last read by the copy of iteration i - 2
@@ -998,9 +1014,10 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             GenerateLightTiles(generateLightTiles_m, None, env_map, pdf_, cdf_, mpdf_, mcdf_, width, height,
                                base + ris_pass, light_data, light_uv, light_inv_pdf, light_tile_count, light_tile_size)
             ris_pass += 2
-            worker.InitialResampling_(InitialResampling_m, pos_map, reservoirs, env_map, width, height, framedim_x,
-                                      framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map, pdf_, cdf_,
-                                      mpdf_, mcdf_, light_data, light_uv, light_inv_pdf)
+            with rows_wide():  # (rebuilds the pixel list of the one workspace this schedule uses)
+                worker.InitialResampling_(InitialResampling_m, pos_map, reservoirs, env_map, width, height, framedim_x,
+                                          framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map, pdf_,
+                                          cdf_, mpdf_, mcdf_, light_data, light_uv, light_inv_pdf)
             ris_pass += 1
             if i > 0:
                 TemporalResampling(TemporalResampling_m, reservoirs, prev_reservoirs, env_map, width, height, framedim_x,
@@ -1008,13 +1025,15 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                                    prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
                 ris_pass += 1
             reservoirs, prev_reservoirs = prev_reservoirs, reservoirs
+            if shard is not None:
+                slangpy.prepare_workspace(occ_map)  # from here on the band's own rows only
             worker.SpatialResampling_(SpatialResampling_m, pos_map, reservoirs, prev_reservoirs, neighborOffsets, env_map,
                                       width, height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth,
                                       brdf_map, ray_dir_map)
             ris_pass += 1
             if shard is not None:
-                # spatial reuse of the next iteration (through its temporal pass) reads reservoirs up to 31 rows outside
-                # this rank's band: replace the locally computed halo rows by their owners' values
+                # the temporal pass of the next iteration reads finished reservoirs up to 31 rows outside this rank's
+                # band: those rows take their owners' values
                 shard.exchange(reservoirs)
             worker.EvaluateFinalSamples_get_vis(EvaluateFinalSamples_m, pos_map, reservoirs, framedim_x, framedim_y,
                                                 eva_vis_map)
@@ -1058,20 +1077,8 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
                           ray_dir_map, pos_map, prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir,
                           framedim_x, framedim_y, spp, denoise_iter, stepWidth, c_phi_scale=1.0, n_phi_scale=0.1,
                           p_phi_scale=0.1, *, random_offset=None, max_bounce=None, hooks=None, bilateral=None,
-                          overlap=None, batched_denoise=True, shard=None, _shard=None, fused_prepare=True, fused_composite=True,
+                          overlap=None, batched_denoise=True, shard=None, fused_prepare=True, fused_composite=True,
                           lighting=None):
-    if shard is not None:
-        with slangpy.active_rows(shard.active[0], shard.active[1], framedim_x):
-            return run_restir_di_with_pt(
-                use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_depth, bvh_restir_worker, make_sampleable_m,
-                generateLightTiles_m, InitialResampling_m, TemporalResampling_m, SpatialResampling_m,
-                EvaluateFinalSamples_m, FinalShading_m, denoising_m, light_data, light_uv, light_inv_pdf, reservoirs,
-                prev_reservoirs, final_samples, neighborOffsets, light_tile_count, light_tile_size, env_map, occ_map,
-                normal_map, depth_map, diffuse_map, roughness_specular, ray_dir_map, pos_map, prev_occ_map,
-                prev_normal_depth, prev_brdf_map, prev_ray_dir, framedim_x, framedim_y, spp, denoise_iter, stepWidth,
-                c_phi_scale, n_phi_scale, p_phi_scale, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks,
-                bilateral=bilateral, overlap=overlap, batched_denoise=batched_denoise, shard=None, _shard=shard,
-                fused_prepare=fused_prepare, fused_composite=fused_composite)
     n, dev = framedim_x * framedim_y, pos_map.device
     prepared = None
     if fused_prepare and occ_map.is_contiguous():
@@ -1102,17 +1109,40 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
                                                      framedim_x, framedim_y, occ_map, (combined, diff_1, spec_1),
                                                      normal_map.detach(), pos_map.detach())
 
-    split_denoise = gb_depth is None and batched_denoise
-    (total_color, total_color_1, total_diff_light, total_spec_light, total_diff_light_1, total_spec_light_1,
-     total_indirect_light, mFrameIndex) = restir_di_with_pt(
-        use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_worker, spp, framedim_x, framedim_y,
-        make_sampleable_m, generateLightTiles_m, InitialResampling_m, TemporalResampling_m, SpatialResampling_m,
-        EvaluateFinalSamples_m, FinalShading_m, light_data, light_uv, light_inv_pdf, reservoirs, prev_reservoirs,
-        final_samples, neighborOffsets, light_tile_count, light_tile_size, env_map, occ_map, pos_map, normal_map,
-        depth_map, diffuse_map, roughness_specular, ray_dir_map, prev_occ_map, prev_normal_depth, prev_brdf_map,
-        prev_ray_dir, motionVectors, color, random_offset=random_offset, max_bounce=max_bounce, hooks=hooks,
-        overlap=overlap, shard=_shard, prepared=prepared, normalize=True,
-        indirect_done=denoise_indirect if split_denoise else None, lighting=lighting)
+    split_denoise = gb_depth is None and batched_denoise and shard is None
+    loop_args = (make_sampleable_m, generateLightTiles_m, InitialResampling_m, TemporalResampling_m, SpatialResampling_m,
+                 EvaluateFinalSamples_m, FinalShading_m, light_data, light_uv, light_inv_pdf)
+    loop_kw = dict(random_offset=random_offset, max_bounce=max_bounce, hooks=hooks, overlap=overlap, normalize=True,
+                   lighting=lighting)
+    if shard is None:
+        (total_color, total_color_1, total_diff_light, total_spec_light, total_diff_light_1, total_spec_light_1,
+         total_indirect_light, mFrameIndex) = restir_di_with_pt(
+            use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_worker, spp, framedim_x, framedim_y, *loop_args,
+            reservoirs, prev_reservoirs, final_samples, neighborOffsets, light_tile_count, light_tile_size, env_map, occ_map,
+            pos_map, normal_map, depth_map, diffuse_map, roughness_specular, ray_dir_map, prev_occ_map, prev_normal_depth,
+            prev_brdf_map, prev_ray_dir, motionVectors, color, prepared=prepared,
+            indirect_done=denoise_indirect if split_denoise else None, **loop_kw)
+    else:
+        # Row-band rendering (dist.RowBandShard).  The [N, k] maps are row-major, so the rows this rank reads
+        # -- its band and the halo around it -- are one contiguous slice of every tensor: the spp loop runs on the slices
+        # as on a frame of their own (every per-pixel stream shrinks with the band), the row offset keeps the random
+        # streams those of the full frame, the pixel lists are restricted to the band (light tiles and temporal reuse:
+        # band + 30 rows, see restir_di_with_pt) and after every spatial pass the halo rows are received from their owners.
+        # The six accumulated images of all bands are then gathered and denoised at full frame, exactly as on one GPU.
+        view = shard.view()
+        a0, a1 = shard.active
+        cut = lambda t: None if t is None else (tuple(cut(x) for x in t) if isinstance(t, (tuple, list))
+                                                else t[a0 * framedim_x:a1 * framedim_x])
+        with slangpy.row_offset(a0), slangpy.active_rows(view.rows[0], view.rows[1], framedim_x):
+            band = restir_di_with_pt(
+                use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_worker, spp, framedim_x, a1 - a0, *loop_args,
+                cut(reservoirs), cut(prev_reservoirs), cut(final_samples), neighborOffsets, light_tile_count,
+                light_tile_size, env_map, cut(occ_map), cut(pos_map), cut(normal_map), cut(depth_map), cut(diffuse_map),
+                cut(roughness_specular), cut(ray_dir_map), None, None, None, None, motionVectors, color,
+                prepared=cut(prepared), shard=view, **loop_kw)
+        mFrameIndex = band[7]
+        (total_color, total_color_1, total_diff_light, total_spec_light, total_diff_light_1,
+         total_spec_light_1) = shard.gather_bands([t.detach() for t in band[0:6]], row0=a0)
     # `total / mFrameIndex` of all six sums (:505-515) has happened inside (normalize=True)
     combined_color_indirect = early["combined"] if split_denoise else total_diff_light_1 + total_spec_light_1
 

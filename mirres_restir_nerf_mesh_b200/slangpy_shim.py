@@ -148,23 +148,23 @@ class trace_blocks:
     driver wraps the launches of its critical chain, which it issues on a high-priority stream, so that they get a full
     grid while the background chains keep the small default."""
 
-    def __init__(self, any_blocks=0, closest_blocks=0):
-        self.values = (int(any_blocks), int(closest_blocks))
+    def __init__(self, any_blocks=0, closest_blocks=0, mixed_blocks=0):
+        self.values = (int(any_blocks), int(closest_blocks), int(mixed_blocks))
         self.saved = None
 
     def __enter__(self):
         k = get_kernels()
+        keys = (k.TUNE_ANY_BLOCKS, k.TUNE_CLOSEST_BLOCKS, k.TUNE_MIXED_BLOCKS)
         # 0 = "no opinion": the caller's own tuning (set through the public set_tuning) stays in force
-        self.saved = (k.get_tuning(k.TUNE_ANY_BLOCKS), k.get_tuning(k.TUNE_CLOSEST_BLOCKS))
-        if self.values[0] > 0:
-            k.set_tuning(k.TUNE_ANY_BLOCKS, self.values[0])
-        if self.values[1] > 0:
-            k.set_tuning(k.TUNE_CLOSEST_BLOCKS, self.values[1])
+        self.saved = tuple(k.get_tuning(key) for key in keys)
+        for key, v, old in zip(keys, self.values, self.saved):
+            if v > 0 and old == 0:
+                k.set_tuning(key, v)
 
     def __exit__(self, *a):
         k = get_kernels()
-        k.set_tuning(k.TUNE_ANY_BLOCKS, self.saved[0])
-        k.set_tuning(k.TUNE_CLOSEST_BLOCKS, self.saved[1])
+        for key, old in zip((k.TUNE_ANY_BLOCKS, k.TUNE_CLOSEST_BLOCKS, k.TUNE_MIXED_BLOCKS), self.saved):
+            k.set_tuning(key, old)
 
 
 def prepare_workspace(occ_map):
@@ -185,11 +185,36 @@ def workspace(device, n_pixels):
         _WORKSPACES[key] = ws
         if _FRAME_OFFSET.get(str(device)) is not None:
             _frame_word(ws).copy_(_FRAME_OFFSET[str(device)])
+    if _ROW_OFFSET[-1] != getattr(ws, "_mirres_row_offset", 0):
+        # stream-ordered, like the frame offset: the launches that follow see the new value
+        _row_word(ws).fill_(_ROW_OFFSET[-1])
+        ws._mirres_row_offset = _ROW_OFFSET[-1]
     return ws
 
 
 FRAME_OFFSET_BYTES = 32  # MIRRES_WORKSPACE_FRAME_OFFSET_BYTES
+ROW_OFFSET_BYTES = 36    # MIRRES_WORKSPACE_ROW_OFFSET_BYTES
 _FRAME_OFFSET = {}
+_ROW_OFFSET = [0]
+
+
+def _row_word(ws):
+    return ws[ROW_OFFSET_BYTES:ROW_OFFSET_BYTES + 4].view(torch.int32)
+
+
+class row_offset:
+    """Inside the block the frames handed to the kernels are row bands of a larger frame that start at row `y0`: every
+    workspace used inside gets y0 as its row offset (include/mirres_b200.h), so pixels draw the random streams of their
+    position in the full frame.  Workspaces are keyed by frame size; one that is used again outside the block is reset."""
+
+    def __init__(self, y0):
+        self.y0 = int(y0)
+
+    def __enter__(self):
+        _ROW_OFFSET.append(self.y0)
+
+    def __exit__(self, *a):
+        _ROW_OFFSET.pop()
 
 
 def _frame_word(ws):

@@ -1,6 +1,8 @@
 """Manual multi-GPU check of the rendering partition (BASELINE config 3 shape): the C2 scene at 800 x 800, forward only,
-cut into row bands over the ranks (dist.RowBandShard: 31-row halo, reservoir exchange after every spatial pass, NCCL).
-Rank 0 also renders the whole frame alone and compares: the assembled image must be bit-identical.
+cut into row bands of equal foreground-pixel count over the ranks (dist.RowBandShard: every rank runs the spp loop on the
+slice of the maps that holds its band and halo, receives 31 halo rows of the reservoirs point to point after every spatial
+pass over NCCL; the accumulated images are gathered before the denoiser).  Rank 0 also renders the whole frame alone and
+compares: all six output images must be bit-identical.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/check_rows_sharded.py [spp] [C3|C5]
 """
@@ -44,14 +46,18 @@ def main(spp, cfg_name="C3"):
                                        shard=shard)
 
     with torch.no_grad():
-        shard = D.RowBandShard(W, H)
+        ro, rd = synth.camera_rays_torch(W, H, pose)
+        worker.update_mesh(vert, tri)
+        occ0 = torch.empty(n, 1, device=dev)
+        k.gbuffer_primary(worker.packed, ro, rd, occ0, torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev),
+                          torch.empty(n, 1, device=dev), ws=slangpy_shim.workspace(dev, n))
+        shard = D.RowBandShard(W, H, bounds=D.balanced_bounds(occ0, W, H, world))
         for it in range(2):
             dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            outs = render(shard)
-            full = shard.gather_image(outs[0])
+            outs = render(shard)  # full-frame on every rank
             e1.record()
             torch.cuda.synchronize()
             ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -59,13 +65,13 @@ def main(spp, cfg_name="C3"):
         if rank == 0:
             torch.cuda.synchronize()
             e0.record()
-            want = render(None)[0]
+            want = render(None)
             e1.record()
             torch.cuda.synchronize()
-            same = bool(torch.equal(full, want))
+            same = all(bool(torch.equal(a, b)) for a, b in zip(outs, want))
             print(cfg_name + " row bands over %d GPUs: %dx%d spp %d forward: %.1f ms (max over ranks, incl. reservoir exchange), "
-                  "%.3e samples/s; one GPU alone: %.1f ms; assembled image bit-identical: %s"
-                  % (world, W, H, spp, float(ms), n * spp / (float(ms) * 1e-3), e0.elapsed_time(e1), same))
+                  "%.3e samples/s; one GPU alone: %.1f ms; bands %s; all six images bit-identical: %s"
+                  % (world, W, H, spp, float(ms), n * spp / (float(ms) * 1e-3), e0.elapsed_time(e1), shard.bounds, same))
             assert same
     dist.barrier()
     dist.destroy_process_group()
