@@ -276,4 +276,33 @@ MR_HD float mr_pow8f(float x)
     return x4 * x4;
 }
 
+/*
+ * TEST-ONLY flavour (never compiled into the product): -DMR_FPMATH_LIBM redirects the functions above to the C library,
+ * and the oracle is then built with -ffp-contract=fast -mfma.  That is the closest stand-in available here for the
+ * numerics of the reference's real binary (slangc -> nvcc: FMA contraction on, libdevice transcendentals, pow() for the
+ * Fresnel / falloff powers), which cannot be built in this environment.  tools/numerics_sensitivity.py runs the oracle in
+ * both flavours on the same inputs and reports which integer decisions flip and how far the float outputs move
+ * (profiles/numerics_sensitivity.json): a bound on what "parity unpinned" can hide.
+ */
+#if defined(MR_FPMATH_LIBM) && !defined(__CUDACC__)
+static inline float mr_libm_sinf(float x) { return sinf(x); }
+static inline float mr_libm_cosf(float x) { return cosf(x); }
+static inline void mr_libm_sincosf(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
+static inline float mr_libm_acosf(float x) { return acosf(x); }
+static inline float mr_libm_atan2f(float y, float x) { return atan2f(y, x); }
+static inline float mr_libm_expf(float x) { return expf(x); }
+static inline float mr_libm_pow5f(float x) { return powf(x, 5.0f); }
+static inline float mr_libm_pow8f(float x) { return powf(x, 8.0f); }
+static inline float mr_libm_pow128f(float x) { return powf(x, 128.0f); }
+#define mr_sinf mr_libm_sinf
+#define mr_cosf mr_libm_cosf
+#define mr_sincosf mr_libm_sincosf
+#define mr_acosf mr_libm_acosf
+#define mr_atan2f mr_libm_atan2f
+#define mr_expf mr_libm_expf
+#define mr_pow5f mr_libm_pow5f
+#define mr_pow8f mr_libm_pow8f
+#define mr_pow128f mr_libm_pow128f
+#endif
+
 #endif /* MIRRES_FPMATH_H */

@@ -37,6 +37,32 @@ def lib():
     return _LIB
 
 
+class flavour:
+    """`with flavour("fast"):` runs the oracle built with FMA contraction and C-library transcendentals (make fast; see
+    include/mirres_fpmath.h) inside the block -- the sensitivity study's stand-in for the reference binary's numerics.
+    The contract flavour is restored on exit."""
+
+    def __init__(self, name):
+        assert name in ("contract", "fast")
+        self.name = name
+
+    def __enter__(self):
+        global _LIB
+        self.saved = _LIB
+        if self.name == "fast":
+            so = os.path.join(_HERE, "libmirres_oracle_fast.so")
+            subprocess.check_call(["make", "-C", _HERE, "-s", "fast"])
+            _LIB = ctypes.CDLL(so)
+        else:
+            _LIB = None
+            lib()
+        return self
+
+    def __exit__(self, *a):
+        global _LIB
+        _LIB = self.saved
+
+
 def _p(a):
     if a is None:
         return None
