@@ -179,7 +179,8 @@ def _config(args, cfg):
                 "; G-buffer normals = auto_normals -> interpolation -> prepare_shading_normal, gradient to vertex "
                 "positions" if getattr(args, "mesh_normals", False) else ""),
             "l2": "256 MiB flush between timed steps",
-            "parallelism": "one view per rank, 1 NCCL allreduce of env+vertex+texture grads per step"}
+            "parallelism": "one view per rank; per step the NCCL all-reduce of the env | vertex | texture gradient buffer "
+                           "(12 MB), issued inside the step in two parts"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -269,18 +270,23 @@ def run_gpu(args):
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     # the inputs of a step: mesh, envmap, camera pose (rays are generated on the device from the pose, as the reference's
     # get_rays does)
-    host = dict(vert=pin(vert_np), tri=pin(tri_np), env=pin(env_np), pose=pin(pose_np))
+    # what changes from step to step comes from the host: vertex positions, envmap, camera pose.  The index buffer of the
+    # mesh is static in stage 1 (nerf/renderer.py:967-975 moves vertices, never re-meshes): it is uploaded once
+    host = dict(vert=pin(vert_np), env=pin(env_np), pose=pin(pose_np))
     device_in = {k: v.to(dev) for k, v in host.items()}
-    worker = R.restirbvhWorker(device_in["vert"], device_in["tri"])
+    tri_dev = torch.from_numpy(np.ascontiguousarray(tri_np)).to(dev)
+    worker = R.restirbvhWorker(device_in["vert"], tri_dev)
     mat = synth.ProceduralMaterial(0.0)
     mods = R.load_m_for_restir(W, H, device=dev, max_bounce=mb)
     V, ne = vert_np.shape[0], env_np.size
+    ar_stream = torch.cuda.Stream() if world > 1 else None
+    collective_in_step = [world > 1 and not args.allreduce_after]
     target = torch.full((n, 3), 0.5, device=dev)
     flat_grad = torch.zeros(ne + V * 3 + V * 5, device=dev)  # env | vertex-normal | vertex-texture (kd, rough, metal)
     opts = dict(overlap=not args.no_overlap)
     bvh_stream = torch.cuda.Stream()
 
-    def full_step(vert, tri, env, pose):
+    def full_step(vert, env, pose, tri=tri_dev):
         """One stage-1 training step of one view: LBVH rebuild (nerf/renderer.py:975), camera rays, G-buffer, ReSTIR +
         path tracer, denoise + composite, loss, backward into env / normals / kd / ks, scatter to vertices and vertex
         texture."""
@@ -329,16 +335,24 @@ def run_gpu(args):
         # gradients leave the path as grad_env [He,We,3] and dense per-pixel grads; the latter are scattered to vertices /
         # vertex texture here (the reference: nvdiffrast / tcnn backward), everything lands in ONE flat buffer
         flat_grad[:ne].copy_(env_l.grad.reshape(-1))
+        if collective_in_step[0]:
+            # the per-step collective, part 1: the envmap segment is final here; its all-reduce runs beside the vertex scatters
+            ar_stream.wait_stream(cur)
+            with torch.cuda.stream(ar_stream):
+                dist.all_reduce(flat_grad[:ne])
         if args.mesh_normals:
             flat_grad[ne:ne + 3 * V].copy_(vert_l.grad.reshape(-1))  # d loss / d vertex positions through the normals
         else:
             pk.interpolate_bwd(normal.grad, prim, bary, tri, flat_grad[ne:ne + 3 * V].view(V, 3))
         pk.interpolate_bwd(torch.cat((kd.grad, rs.grad), dim=1), prim, bary, tri, flat_grad[ne + 3 * V:].view(V, 5))
+        if collective_in_step[0]:
+            dist.all_reduce(flat_grad[ne:])  # part 2: vertex-normal and vertex-texture segments
+            cur.wait_stream(ar_stream)
         return loss.detach(), flat_grad
 
     def finish():
-        if world > 1:
-            dist.all_reduce(flat_grad)  # the per-step collective: texture, envmap and vertex gradients
+        if world > 1 and not collective_in_step[0]:
+            dist.all_reduce(flat_grad)  # the per-step collective after the step: texture, envmap and vertex gradients
 
     for _ in range(max(args.warmup, 3)):
         full_step(**device_in)
@@ -346,7 +360,16 @@ def run_gpu(args):
     torch.cuda.synchronize()
     captured = None
     if not args.no_graph:
-        captured = CapturedStep(full_step, device_in, warmup=1)
+        try:
+            captured = CapturedStep(full_step, device_in, warmup=1)  # NCCL all-reduces of the step are captured with it
+        except Exception:
+            if not collective_in_step[0]:
+                raise
+            # a collective that cannot be captured on this stack: one all-reduce after the replay instead (every rank
+            # takes the same branch: capture fails or succeeds on all of them alike)
+            torch.cuda.synchronize()
+            collective_in_step[0] = False
+            captured = CapturedStep(full_step, device_in, warmup=1)
 
     def run_step(from_host):
         if captured is not None:
@@ -401,6 +424,8 @@ def run_gpu(args):
     # per-kernel device times: an eager pass with the chains serialised (events bracket every C-ABI call on the stream
     # it is launched on; with the two chains overlapped the brackets of concurrent kernels would not be comparable)
     opts["overlap"] = False
+    in_step = collective_in_step[0]
+    collective_in_step[0] = False  # rank 0 runs this pass alone
     per_kernel, launches = {}, 0
     if rank == 0:
         full_step(**device_in)
@@ -444,6 +469,8 @@ def run_gpu(args):
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": _config(args, cfg),
+                "collective": None if world == 1 else ("2 all-reduces captured in the step's graph (envmap segment beside the vertex "
+                                                       "scatters, then the vertex segments)" if in_step else "1 all-reduce after the step"),
                 "execution": ("CUDA graph replay of the whole step" if captured is not None else "eager") +
                              (", concurrent schedule (reuse chain, initial candidates, shading and the indirect chains "
                               "on their own streams)" if not args.no_overlap else ""),
@@ -470,8 +497,7 @@ def run_gpu(args):
                                     "sample": "CPU oracle (OpenMP, all host cores): LBVH rebuild + forward spp loop of the same %dx%d frame, 2 repetitions; no G-buffer, denoiser or backward" % (crop, crop)}
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        _leave(torch, dist, captured)
 
 
 def run_render(args):
@@ -647,8 +673,24 @@ def run_render(args):
                                               "forward, no G-buffer or denoiser" % (_oracle_spp(args, cfg), cfg["W"], cfg["H"])}
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        _leave(torch, dist, captured)
+
+
+def _leave(torch, dist, captured):
+    """End of a multi-rank run.  A CUDA graph that captured NCCL work keeps the communicator busy: it is released before
+    the process group goes away, and a rank that still cannot tear the group down within its barrier leaves anyway (the
+    JSON line is out by then)."""
+    sys.stdout.flush()
+    if captured is not None:
+        captured.graph.reset()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = threading.Timer(20.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    dist.destroy_process_group()
+    t.cancel()
 
 
 def step_algorithmic_bytes(cfg_name, cfg, spp, n_foreground=None):
@@ -738,6 +780,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--uniform-bands", action="store_true", help="render mode: bands of equal height instead of equal foreground")
     ap.add_argument("--no-overlap", action="store_true", help="direct and indirect chains on one stream")
+    ap.add_argument("--allreduce-after", action="store_true",
+                    help="one all-reduce after the step instead of two inside it (envmap segment beside the vertex scatters)")
     ap.add_argument("--mesh-normals", action="store_true",
                     help="G-buffer normals through the reference's chain (auto_normals -> interpolation -> "
                          "prepare_shading_normal); the vertex segment of the gradient buffer then holds d loss / d vertex "

@@ -139,6 +139,11 @@ int mirres_light_tiles(const float *env_tex, int W, int H, const float *pdf_, co
  */
 #define MIRRES_WORKSPACE_FRAME_OFFSET_BYTES 32
 #define MIRRES_WORKSPACE_ROW_OFFSET_BYTES 36
+/* Error word: set to 1 by a ray-casting entry point whose traversal had to DROP a stack entry because a ray's stack was
+ * full (64 entries, the reference's unchecked depth, helperDi.slang:136): results of that launch may miss a subtree.
+ * Entry points cannot return it (they never synchronise); the caller reads the word when it synchronises anyway and
+ * clears it.  The library never clears it. */
+#define MIRRES_WORKSPACE_ERROR_BYTES 48
 size_t mirres_workspace_bytes(int n_pixels);
 int mirres_workspace_prepare(const float *occ, int n_pixels, void *workspace, size_t workspace_bytes, void *stream);
 

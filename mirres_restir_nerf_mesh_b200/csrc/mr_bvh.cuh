@@ -145,6 +145,11 @@ MR_DEV void pack_item(const PackParams &p, int gid)
     p.nodes[gid] = n;
 }
 
+// Depth of the traversal stacks: the reference's 64 (helperDi.slang:136), which it never checks.  Here a push beyond the
+// 64th entry is DROPPED instead of written out of bounds, and the queue tracers raise the workspace's error word
+// (MIRRES_WORKSPACE_ERROR_BYTES, include/mirres_b200.h) so that the caller can tell that a launch lost a subtree.  The deepest
+// stack of the BASELINE scenes is 22 entries (profiles/oracle_counters_*.json); only adversarial meshes (thousands of
+// triangles with one Morton code) reach 64.
 #define MR_STACK 64
 
 struct Ray {
@@ -270,7 +275,7 @@ MR_DEV bool any_hit(const BvhView &bvh, float3 origin, float3 dir, TraceStats *s
 #pragma unroll
         for (int k = 3; k >= 0; --k) {
             if (fminf(t_max, w.tf[k]) > w.tn[k]) {
-                if (have) stack[sp++] = next;
+                if (have && sp < MR_STACK) stack[sp++] = next; // (a 65th deferred entry is dropped: see MR_STACK)
                 next = w.ref[k];
                 have = true;
             }
@@ -343,7 +348,7 @@ MR_DEV bool closest_hit(const BvhView &bvh, float3 origin, float3 dir, Hit &out,
 #pragma unroll
         for (int k = 3; k >= 0; --k) {
             if (fminf(closest, w.tf[k]) > w.tn[k]) {
-                if (have) {
+                if (have && sp < MR_STACK) {
                     stack_ref[sp] = next;
                     stack_t[sp] = next_t;
                     ++sp;

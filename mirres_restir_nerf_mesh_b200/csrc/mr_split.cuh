@@ -53,6 +53,7 @@ struct SplitRecT {
     int fin_any[MR_SPLIT_LANES];
     int pending[MR_SPLIT_LANES];       // live tasks of the ray
     int nlog[MR_SPLIT_LANES];          // hits appended (> MR_SPLIT_LOG: overflow)
+    int overflow;                      // some task of this warp dropped a stack entry (MR_STACK)
     SplitLogEntry log[MR_SPLIT_LANES][CAP_];
 };
 typedef SplitRecT<MR_SPLIT_LOG> SplitRec;
@@ -118,9 +119,13 @@ MR_DEV bool task_step(const BvhView &bvh, CTask &T, int *__restrict__ stack_ref,
         for (int k = 3; k >= 0; --k) {
             if (fminf(bound, w.tf[k]) > w.tn[k]) {
                 if (got) {
-                    stack_ref[T.sp] = next;
-                    stack_t[T.sp] = next_t;
-                    ++T.sp;
+                    if (T.sp < MR_STACK) {
+                        stack_ref[T.sp] = next;
+                        stack_t[T.sp] = next_t;
+                        ++T.sp;
+                    } else {
+                        rec.overflow = 1; // dropped, never written out of bounds; the worker reports it (MR_STACK)
+                    }
                 }
                 next = w.ref[k];
                 next_t = w.tn[k];

@@ -42,6 +42,9 @@ namespace mr {
 // a frame of its own (the [N, k] maps are row-major, so a band is a contiguous slice of every tensor) and sets this word
 // to the band's first row: every pixel then draws the random numbers it draws in the full frame.  Zero = plain behaviour.
 #define MR_CTR_ROW_OFFSET 9
+// [12] error word: set to 1 by a queue tracer that had to drop a traversal-stack entry (MR_STACK); never cleared by the
+// library (the caller zero-fills the workspace once and may inspect / clear the word whenever it synchronises)
+#define MR_CTR_ERROR 12
 // [16], [17] sizes of the two lists of paths that are still alive (the path kernels ping-pong between them), [18], [19]
 // the signatures of the calls those lists were written for (see bounce_item in shade.cu; a kernel reads one word and
 // writes the other); cleared by mirres_workspace_prepare

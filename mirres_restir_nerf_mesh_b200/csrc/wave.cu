@@ -138,6 +138,7 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
     bool found = false;     // this lane has just resolved its ray with a hit
     bool exhausted = false; // warp-uniform: the queue has been drained
     bool shared = false;    // warp-uniform: some ray of this warp is being walked by more than one lane
+    bool overflow = false;  // this lane dropped a stack entry (MR_STACK)
     Ray r;
     r.o = r.d = r.inv = f3(0.f);
     for (;;) {
@@ -221,7 +222,8 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
                 for (int k = 3; k >= 0; --k) {
                     if (fminf(1e7f, w.tf[k]) > w.tn[k]) {
                         if (got) {
-                            stack[sp++] = next;
+                            if (sp < MR_STACK) stack[sp++] = next;
+                            else overflow = true;
                         }
                         next = w.ref[k];
                         got = true;
@@ -258,6 +260,7 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
         found = false;
         __syncwarp();
     }
+    if (overflow) ws.counters[MR_CTR_ERROR] = 1;
 }
 
 // Closest-hit: same refill scheme and the reference's visit order (closest_hit in mr_bvh.cuh); lanes that the queue
@@ -305,6 +308,7 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
     rec.pending[lane] = 0;
     rec.nlog[lane] = 0;
     rec.bound[lane] = 1e7f;
+    if (lane == 0) rec.overflow = 0;
     __syncwarp();
     for (;;) {
         // ---- refill from the queue: a lane whose previous ray still has tasks in flight keeps its record
@@ -440,6 +444,7 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
             __syncwarp();
         }
     }
+    if (lane == 0 && rec.overflow) ws.counters[MR_CTR_ERROR] = 1;
 }
 
 // small queues: give every warp a few rays and let stealing spread each of them over the lanes
@@ -644,6 +649,7 @@ static void closest_split_simulate(const BvhView &bvh, const float *org, const f
     bool have[MR_SPLIT_LANES];
     unsigned int rng = seed * 2654435761u + 12345u;
     auto rnd = [&]() { rng = 1664525u * rng + 1013904223u; return rng >> 8; };
+    rec.overflow = 0;
     for (int l = 0; l < lanes; ++l) { have[l] = false; rec.pending[l] = 0; rec.nlog[l] = 0; rec.bound[l] = 1e7f; }
     int next_ray = 0;
     long steals = 0, restarts = 0, logged = 0;

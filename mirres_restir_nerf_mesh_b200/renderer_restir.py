@@ -654,8 +654,10 @@ def prepare_lighting(make_sampleable_m, generateLightTiles_m, light_data, light_
     for i in range(R):
         GenerateLightTiles(generateLightTiles_m, None, env_map, *dist, width, height,
                            random_offset + TOTAL_RIS_PASSES * i, *tiles[i], light_tile_count, light_tile_size)
+    # the dict is valid for ONE loop over exactly this state of the envmap: an in-place optimiser step keeps data_ptr but
+    # bumps the tensor's version counter
     return dict(env_map=env_map, dist=dist, tiles=tiles, ready=R, random_offset=random_offset, spp=int(spp),
-                env_ptr=env_map_init.data_ptr(), **extra)
+                env_ptr=env_map_init.data_ptr(), env_version=env_map_init._version, consumed=False, **extra)
 
 
 # =====================================================================================================================
@@ -702,8 +704,11 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     # autograd, in place, which wants tensors of their own)
     names = ("color", "diff", "spec", "color_1", "diff_1", "spec_1")
     if lighting is not None and not (lighting["random_offset"] == random_offset and lighting["spp"] == spp and
-                                     lighting["env_ptr"] == env_map_init.data_ptr()):
-        lighting = None  # prepared for another call
+                                     lighting["env_ptr"] == env_map_init.data_ptr() and
+                                     lighting.get("env_version") == env_map_init._version and not lighting.get("consumed")):
+        lighting = None  # prepared for another call, for an older state of the envmap, or already used by a loop
+    if lighting is not None:
+        lighting["consumed"] = True
     # blocks zero-filled by prepare_lighting(frame_pixels=n); they are consumed (popped): a second loop on the same
     # `lighting` allocates its own
     early = lighting if (overlap and lighting is not None and lighting.get("frame_pixels") == n and

@@ -15,6 +15,7 @@ Every kernel name of SURVEY.md section 2.1 is served by the C ABI of libmirres_b
 (see INTEGRATION.md).  Kernels the reference never calls (SURVEY.md 2.1 "dead Slang kernels") raise AttributeError.
 """
 import os
+import threading
 
 import torch
 
@@ -83,7 +84,20 @@ def packed_bvh(info, aabb, vert, tri):
 
 
 _WORKSPACES = {}
-_WS_TAG = ["main"]
+
+
+class _Context(threading.local):
+    """Launch context of the calling host thread (the `with` blocks below push and pop here): each thread that drives a
+    renderer has its own, so two threads on different streams do not see each other's workspace tags or row restrictions."""
+
+    def __init__(self):
+        self.ws_tag = ["main"]
+        self.skip_prepare = [False]
+        self.active_rows = [None]
+        self.row_offset = [0]
+
+
+_CTX = _Context()
 
 
 class workspace_tag:
@@ -95,14 +109,12 @@ class workspace_tag:
         self.tag = tag
 
     def __enter__(self):
-        _WS_TAG.append(self.tag)
+        _CTX.ws_tag.append(self.tag)
 
     def __exit__(self, *a):
-        _WS_TAG.pop()
+        _CTX.ws_tag.pop()
 
 
-_SKIP_PREPARE = [False]
-_ACTIVE_ROWS = [None]
 
 
 class active_rows:
@@ -114,14 +126,14 @@ class active_rows:
         self.rows = (int(y0), int(y1), int(fx))
 
     def __enter__(self):
-        _ACTIVE_ROWS.append(self.rows)
+        _CTX.active_rows.append(self.rows)
 
     def __exit__(self, *a):
-        _ACTIVE_ROWS.pop()
+        _CTX.active_rows.pop()
 
 
 def _band_occ(occ):
-    rows = _ACTIVE_ROWS[-1]
+    rows = _CTX.active_rows[-1]
     if rows is None:
         return occ
     y0, y1, fx = rows
@@ -137,10 +149,10 @@ class workspace_prepared:
     driver has already done it with prepare_workspace for the same occupancy map)."""
 
     def __enter__(self):
-        _SKIP_PREPARE.append(True)
+        _CTX.skip_prepare.append(True)
 
     def __exit__(self, *a):
-        _SKIP_PREPARE.pop()
+        _CTX.skip_prepare.pop()
 
 
 class trace_blocks:
@@ -175,7 +187,9 @@ def prepare_workspace(occ_map):
 
 def workspace(device, n_pixels):
     """Wavefront workspace (include/mirres_b200.h) for frames of n_pixels on `device`, allocated once and reused."""
-    key = (str(device), int(n_pixels), _WS_TAG[-1])
+    # one set of workspaces per host thread: two threads that drive renderers of the same frame size on different
+    # streams must not share ray queues and pixel lists (the library's tuning is per thread as well)
+    key = (_device_key(device), int(n_pixels), _CTX.ws_tag[-1], threading.get_ident())
     ws = _WORKSPACES.get(key)
     if ws is None:
         nbytes = get_kernels().workspace_bytes(n_pixels)
@@ -183,23 +197,41 @@ def workspace(device, n_pixels):
         off = (-buf.data_ptr()) % 256  # CUDA allocations are already 512-byte aligned; host ones are not
         ws = buf[off:off + nbytes]
         _WORKSPACES[key] = ws
-        if _FRAME_OFFSET.get(str(device)) is not None:
-            _frame_word(ws).copy_(_FRAME_OFFSET[str(device)])
-    if _ROW_OFFSET[-1] != getattr(ws, "_mirres_row_offset", 0):
+        if _FRAME_OFFSET.get(_device_key(device)) is not None:
+            _frame_word(ws).copy_(_FRAME_OFFSET[_device_key(device)])
+    if _CTX.row_offset[-1] != getattr(ws, "_mirres_row_offset", 0):
         # stream-ordered, like the frame offset: the launches that follow see the new value
-        _row_word(ws).fill_(_ROW_OFFSET[-1])
-        ws._mirres_row_offset = _ROW_OFFSET[-1]
+        _row_word(ws).fill_(_CTX.row_offset[-1])
+        ws._mirres_row_offset = _CTX.row_offset[-1]
     return ws
 
 
 FRAME_OFFSET_BYTES = 32  # MIRRES_WORKSPACE_FRAME_OFFSET_BYTES
-ROW_OFFSET_BYTES = 36    # MIRRES_WORKSPACE_ROW_OFFSET_BYTES
+ROW_OFFSET_BYTES = 36    # MIRRES_WORKSPACE_CTX.row_offset_BYTES
 _FRAME_OFFSET = {}
-_ROW_OFFSET = [0]
 
 
 def _row_word(ws):
     return ws[ROW_OFFSET_BYTES:ROW_OFFSET_BYTES + 4].view(torch.int32)
+
+
+ERROR_BYTES = 48  # MIRRES_WORKSPACE_ERROR_BYTES
+
+
+def check_workspaces(device=None, clear=True):
+    """Synchronises and raises if a ray-casting launch since the last check had to drop a traversal-stack entry (a mesh
+    whose LBVH is deeper than the reference's 64-entry stack: the reference itself has undefined behaviour there)."""
+    bad = []
+    for key, ws in _WORKSPACES.items():
+        if device is not None and key[0] != _device_key(device):
+            continue
+        word = ws[ERROR_BYTES:ERROR_BYTES + 4].view(torch.int32)
+        if int(word.item()) != 0:
+            bad.append(key)
+            if clear:
+                word.zero_()
+    if bad:
+        raise RuntimeError("traversal stack overflow (more than 64 deferred nodes on one ray) in workspaces %r" % (bad,))
 
 
 class row_offset:
@@ -211,18 +243,26 @@ class row_offset:
         self.y0 = int(y0)
 
     def __enter__(self):
-        _ROW_OFFSET.append(self.y0)
+        _CTX.row_offset.append(self.y0)
 
     def __exit__(self, *a):
-        _ROW_OFFSET.pop()
+        _CTX.row_offset.pop()
 
 
 def _frame_word(ws):
     return ws[FRAME_OFFSET_BYTES:FRAME_OFFSET_BYTES + 4].view(torch.int32)
 
 
+def _device_key(device):
+    """'cuda', 'cuda:0' and torch.device('cuda', 0) name the same device: indexed form, current device when no index."""
+    d = torch.device(device)
+    if d.type == "cuda" and d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
+    return str(d)
+
+
 def _frame_offset_tensor(device):
-    dev = str(torch.device(device)) if not isinstance(device, str) else device
+    dev = _device_key(device)
     cur = _FRAME_OFFSET.get(dev)
     if cur is None:
         cur = _FRAME_OFFSET[dev] = torch.zeros(1, dtype=torch.int32, device=device)
@@ -233,10 +273,10 @@ def set_frame_offset(device, value):
     """Adds `value` to the frame index of every subsequent launch on `device` (all workspaces), stream-ordered and
     without touching any launch argument -- which is what lets a captured CUDA graph be replayed with fresh random
     streams.  0 restores the reference schedule."""
-    dev = str(torch.device(device)) if not isinstance(device, str) else device
+    dev = _device_key(device)
     cur = _frame_offset_tensor(device)
     cur.fill_(int(value) & 0x7FFFFFFF)
-    for key, ws in _WORKSPACES.items():
+    for key, ws in list(_WORKSPACES.items()):
         if key[0] == dev:
             _frame_word(ws).copy_(cur)
 
@@ -327,7 +367,7 @@ def _InitialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reser
     # first kernel of every spp iteration that sees the primary occupancy: (re)build the foreground-pixel list here
     occ = _c(occ_map)
     ws = workspace(occ.device, occ.shape[0])
-    if not _SKIP_PREPARE[-1]:
+    if not _CTX.skip_prepare[-1]:
         get_kernels().workspace_prepare(_band_occ(occ), ws)
     get_kernels().initial_resampling(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), _c(pos_map),
                                      _reservoir(reservoirs), _c(env_tex), int(env_width), int(env_height),
@@ -402,7 +442,7 @@ def _final_shading_bwd(m, finalSample, env_tex, env_width, env_height, framedim_
 def _new_dir(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, frameIndex, bounce_count, framedim_x, framedim_y, occ_map,
              pos_map, normal, ray_dir, prd, diffuse_map, linearRoughness_specular_map, new_pos_map, new_ray_d,
              new_occ_map, new_normal):
-    if _WS_TAG[-1] != "main" and int(bounce_count) == 0:
+    if _CTX.ws_tag[-1] != "main" and int(bounce_count) == 0:
         # a chain with its own workspace builds its own foreground-pixel list from the primary occupancy
         get_kernels().workspace_prepare(_band_occ(_c(occ_map)), workspace(prd.device, prd.shape[0]))
     get_kernels().bounce_first(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), int(frameIndex), int(bounce_count),
