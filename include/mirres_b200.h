@@ -46,6 +46,7 @@ int mirres_abi_version(void);
 #define MIRRES_TUNE_CLOSEST_BLOCKS 1
 #define MIRRES_TUNE_MIXED_BLOCKS 2
 #define MIRRES_TUNE_CLOSEST_SPLIT 3
+#define MIRRES_TUNE_ANY_TOP 4 /* 1: boolean-ray walkers read the first five wide levels of the tree from shared memory */
 #define MIRRES_TUNE_COUNT_ 8
 int mirres_set_tuning(int key, int value);
 int mirres_get_tuning(int key); /* current value of `key` for the calling thread (0 = default), or MIRRES_ERR_SHAPE */

@@ -706,7 +706,7 @@ extern "C" {
 int mirres_abi_version(void) { return MIRRES_ABI_VERSION; }
 
 size_t mirres_bvh_scratch_bytes(int F) { return F < 1 ? 0 : carve(nullptr, F, nullptr); }
-size_t mirres_bvh_packed_node_bytes(int F) { return F < 1 ? 0 : sizeof(PackedNode) * (size_t)(F > 1 ? F - 1 : 1); }
+size_t mirres_bvh_packed_node_bytes(int F) { return F < 1 ? 0 : MR_TOP_BYTES + sizeof(PackedNode) * (size_t)(F > 1 ? F - 1 : 1); }
 size_t mirres_bvh_packed_tri_bytes(int F) { return F < 1 ? 0 : sizeof(PackedTri) * (size_t)F; }
 
 // Nine launches (round 1: twenty): init | scene extent | codes + digit histograms | 3 sort passes | leaf records, leaf
@@ -735,10 +735,7 @@ int mirres_bvh_build(const float *vert, int V, const int *tri, int F, int *info,
                                                  pack ? (PackedTri *)packed_tris : nullptr, s.tb, s.state + SS_LEAVES_DONE);
     if (F > 1) k_hierarchy<<<(F - 1 + 255) / 256, 256, 0, st>>>(F, s.keys[1], info, aabb, s.tb);
     MR_CUDA_CHECK_LAUNCH();
-    if (pack) {
-        PackParams pp = {F, info, aabb, vert, tri, (PackedNode *)packed_nodes, nullptr};
-        return foreach_item<PackParams, pack_item, 256>(pp, F > 1 ? F - 1 : 1, st);
-    }
+    if (pack) return pack_traversal(F, info, aabb, vert, tri, packed_nodes, nullptr, st);
     return 0;
 }
 

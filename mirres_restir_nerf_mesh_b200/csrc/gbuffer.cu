@@ -472,7 +472,7 @@ int mirres_gbuffer_primary(const void *packed_nodes, const void *packed_tris, co
     if (vnormal && !tri) return MIRRES_ERR_NULL;
     if (n < 0) return MIRRES_ERR_SHAPE;
     if (n == 0) return 0;
-    GbufParams p = {{(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris}, org, dir, vnormal, tri, occ, pos, normal, depth, prim, bary, geom_normal};
+    GbufParams p = {bvh_view(packed_nodes, packed_tris), org, dir, vnormal, tri, occ, pos, normal, depth, prim, bary, geom_normal};
     cudaStream_t st = (cudaStream_t)stream;
     if (!workspace) return foreach_item<GbufParams, gbuffer_item, 128>(p, n, st);
     if ((uintptr_t)workspace & 255) return MIRRES_ERR_ALIGN;

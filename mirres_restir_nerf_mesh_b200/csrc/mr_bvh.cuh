@@ -69,10 +69,35 @@ struct alignas(32) PackedTri {
 MR_DEV int ref_node(int ref) { return ref & MR_REF_NODE_MASK; }       // ref >= 0 only
 MR_DEV int ref_missing(int ref) { return (ref >> 28) & 3; }           // unused trailing entries of the referenced record
 
+// The first wide levels of the tree as a table of their own, in front of the node array (north-star item "top BVH levels
+// staged in shared memory"): entry 0 is the root record, the children follow breadth first; references between table
+// entries carry MR_REF_TOP and the table slot instead of a node index, so a walker that has copied the table into shared
+// memory follows them without touching global memory.  Five wide levels = ten binary levels: at most 1 + 4 + 16 + 64 + 256
+// records, 43 KB.  Walkers that do not stage the table start at node 0 and never meet a table reference.
+#define MR_REF_TOP 0x08000000
+#define MR_TOP_LEVELS 5
+#define MR_TOP_MAX 341
+struct alignas(32) TopTable {
+    int count;      // records in use (0: no table, e.g. host-check flavour)
+    int pad[31];
+    Rec32 rec[MR_TOP_MAX * 4];
+};
+#define MR_TOP_BYTES ((size_t)sizeof(TopTable))
+
 struct BvhView {
     const PackedNode *__restrict__ nodes; // [max(F-1,1)]
     const PackedTri *__restrict__ tris;   // [F], leaf (sorted-Morton) order
+    const TopTable *__restrict__ top;     // in front of the nodes in the packed buffer
 };
+// the packed node buffer of the C ABI: [TopTable][PackedNode x max(F-1,1)]
+static inline BvhView bvh_view(const void *packed_nodes, const void *packed_tris)
+{
+    BvhView v;
+    v.top = (const TopTable *)packed_nodes;
+    v.nodes = (const PackedNode *)((const char *)packed_nodes + MR_TOP_BYTES);
+    v.tris = (const PackedTri *)packed_tris;
+    return v;
+}
 
 // ---- building the traversal records from the reference-layout tensors ---------------------------------
 struct PackParams {
@@ -151,6 +176,11 @@ MR_DEV void pack_item(const PackParams &p, int gid)
 // stack of the BASELINE scenes is 22 entries (profiles/oracle_counters_*.json); only adversarial meshes (thousands of
 // triangles with one Morton code) reach 64.
 #define MR_STACK 64
+
+// traversal records + top table from reference-layout tensors (trace.cu); packed_tris may be null when the caller has
+// written the triangle records itself
+int pack_traversal(int F, const int *info, const float *aabb, const float *vert, const int *tri, void *packed_nodes,
+                   void *packed_tris, cudaStream_t st);
 
 struct Ray {
     float3 o, d, inv;

@@ -219,7 +219,10 @@ MR_DEV void temporal_px(const TemporalParams &p, int a)
     float u0 = rnd(sg), u1 = rnd(sg);
     float mvx = p.motion ? MR_LDG(p.motion + 2 * i) : 0.f, mvy = p.motion ? MR_LDG(p.motion + 2 * i + 1) : 0.f;
     int ppx = to_int((float)px + mvx * (float)(uint32_t)p.fx + (u0 * 1.f - 0.f));
-    int ppy = to_int((float)py + mvy * (float)(uint32_t)p.fy + (u1 * 1.f - 0.f));
+    // the jittered row is rounded at the magnitude of the FULL frame's row number (int(pixel + u) rounds up to the next
+    // pixel for large coordinates), then brought back into the rows this launch was handed
+    const uint32_t gy = row_of(p.ws, py);
+    int ppy = to_int((float)gy + mvy * (float)(uint32_t)p.fy + (u1 * 1.f - 0.f)) - (int)(gy - py);
     if (ppx >= p.fx || ppx < 0 || ppy >= p.fy || ppy < 0) return;
     const size_t pi = (size_t)ppy * p.fx + ppx;
     if (MR_LDG(p.prev_g.occ + pi) < 0.1f) return;
@@ -695,7 +698,7 @@ int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris,
     InitialParams p;
     int rc = ws_open(p.ws, n, workspace, workspace_bytes);
     if (rc) return rc;
-    p.bvh = {(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris};
+    p.bvh = bvh_view(packed_nodes, packed_tris);
     p.env = {env_tex, env_w, env_h, pdf_, nullptr, mpdf_, nullptr};
     p.g = {occ, normal_depth, brdf_map, ray_dir};
     p.pos_map = pos_map;
@@ -756,7 +759,7 @@ int mirres_spatial_resampling(const void *packed_nodes, const void *packed_tris,
     SpatialParams p;
     int rc = ws_open(p.ws, n, workspace, workspace_bytes);
     if (rc) return rc;
-    p.bvh = {(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris};
+    p.bvh = bvh_view(packed_nodes, packed_tris);
     p.env = {env_tex, env_w, env_h, nullptr, nullptr, nullptr, nullptr};
     p.g = {occ, normal_depth, brdf_map, ray_dir};
     p.pos_map = pos_map;
@@ -781,7 +784,7 @@ int mirres_final_visibility(const void *packed_nodes, const void *packed_tris, c
     VisParams p;
     int rc = ws_open(p.ws, n, workspace, workspace_bytes);
     if (rc) return rc;
-    p.bvh = {(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris};
+    p.bvh = bvh_view(packed_nodes, packed_tris);
     p.res_ld = res_ld; p.pos_map = pos_map; p.vis = vis_map; p.n = n;
     queue_reset(p.ws, st);
     if ((rc = foreach_item<VisParams, final_visibility_gen_px, 256>(p, n, st))) return rc;

@@ -650,7 +650,7 @@ static int fill_bounce(BounceParams &p, const void *packed_nodes, const void *pa
     const int n = fx * fy;
     if (workspace_bytes < workspace_carve(nullptr, n, nullptr)) return MIRRES_ERR_SCRATCH;
     workspace_carve(&p.ws, n, (char *)workspace);
-    p.bvh = {(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris};
+    p.bvh = bvh_view(packed_nodes, packed_tris);
     p.frame = frame_index; p.bounce_count = bounce_count; p.max_bounce = max_bounce; p.fx = fx; p.fy = fy;
     p.occ = occ; p.pos_map = pos_map; p.normal = normal; p.ray_dir = ray_dir; p.prd = prd; p.kd = diffuse_map; p.rm = rough_metal;
     p.new_pos = new_pos; p.new_ray_d = new_ray_d; p.new_occ = new_occ; p.new_normal = new_normal;

@@ -48,6 +48,59 @@ MR_DEV void trace_any_item(const TraceParams &p, int idx)
     if (p.visits) { p.visits[2 * i] = st.nodes; p.visits[2 * i + 1] = st.tris; }
 }
 
+#if !defined(MR_HOST_CHECK)
+// breadth-first copy of the first MR_TOP_LEVELS wide levels into the table in front of the node array; references from a
+// table entry to a table entry are rewritten to MR_REF_TOP | slot (see TopTable)
+__global__ void __launch_bounds__(256) k_top_table(const PackedNode *__restrict__ nodes, TopTable *top)
+{
+    __shared__ int idx[MR_TOP_MAX];
+    __shared__ int count;
+    if (threadIdx.x == 0) {
+        idx[0] = 0;
+        count = 1;
+    }
+    __syncthreads();
+    const float inf = __int_as_float(0x7f800000);
+    int start = 0;
+    for (int level = 0; level < MR_TOP_LEVELS; ++level) {
+        const int end = count;
+        __syncthreads();
+        for (int w = threadIdx.x; w < (end - start) * 4; w += 256) {
+            const int s = start + (w >> 2), k = w & 3;
+            Rec32 e = nodes[idx[s]].e[k];
+            int ref = __float_as_int(e.v[6]);
+            const bool used = !(e.v[0] == inf); // unused entries hold an empty box
+            if (level < MR_TOP_LEVELS - 1 && used && ref >= 0) {
+                const int c = atomicAdd(&count, 1);
+                idx[c] = ref_node(ref);
+                e.v[6] = __int_as_float(MR_REF_TOP | c | (ref & 0x30000000));
+            }
+            top->rec[s * 4 + k] = e;
+        }
+        __syncthreads();
+        start = end;
+    }
+    if (threadIdx.x == 0) top->count = count;
+}
+#endif
+
+int pack_traversal(int F, const int *info, const float *aabb, const float *vert, const int *tri, void *packed_nodes,
+                   void *packed_tris, cudaStream_t st)
+{
+    TopTable *top = (TopTable *)packed_nodes;
+    PackedNode *nodes = (PackedNode *)((char *)packed_nodes + MR_TOP_BYTES);
+    PackParams pp = {F, info, aabb, vert, tri, nodes, (PackedTri *)packed_tris};
+    int rc = foreach_item<PackParams, pack_item, 256>(pp, packed_tris ? F : (F > 1 ? F - 1 : 1), st);
+    if (rc) return rc;
+#if defined(MR_HOST_CHECK)
+    top->count = 0;
+#else
+    k_top_table<<<1, 256, 0, st>>>(nodes, top);
+    MR_CUDA_CHECK_LAUNCH();
+#endif
+    return 0;
+}
+
 } // namespace mr
 
 using namespace mr;
@@ -60,7 +113,7 @@ int mirres_trace_closest(const void *packed_nodes, const void *packed_tris, cons
     if (!packed_nodes || !packed_tris || !org || !dir || !hit) return MIRRES_ERR_NULL;
     if (n < 0) return MIRRES_ERR_SHAPE;
     if (n == 0) return 0;
-    TraceParams p = {{(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris}, org, dir, hit, t, pos, normal, prim, visits};
+    TraceParams p = {bvh_view(packed_nodes, packed_tris), org, dir, hit, t, pos, normal, prim, visits};
     return foreach_item<TraceParams, trace_closest_item, 128>(p, n, (cudaStream_t)stream);
 }
 
@@ -70,7 +123,7 @@ int mirres_trace_any(const void *packed_nodes, const void *packed_tris, const fl
     if (!packed_nodes || !packed_tris || !org || !dir || !hit) return MIRRES_ERR_NULL;
     if (n < 0) return MIRRES_ERR_SHAPE;
     if (n == 0) return 0;
-    TraceParams p = {{(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris}, org, dir, hit, nullptr, nullptr, nullptr, nullptr, visits};
+    TraceParams p = {bvh_view(packed_nodes, packed_tris), org, dir, hit, nullptr, nullptr, nullptr, nullptr, visits};
     return foreach_item<TraceParams, trace_any_item, 128>(p, n, (cudaStream_t)stream);
 }
 
@@ -81,8 +134,7 @@ int mirres_bvh_pack(const int *info, const float *aabb, const float *vert, const
     if (!info || !aabb || !vert || !tri || !packed_nodes || !packed_tris) return MIRRES_ERR_NULL;
     if (F < 1) return MIRRES_ERR_SHAPE;
     if (((uintptr_t)packed_nodes & 31) || ((uintptr_t)packed_tris & 31)) return MIRRES_ERR_ALIGN;
-    PackParams pp = {F, info, aabb, vert, tri, (PackedNode *)packed_nodes, (PackedTri *)packed_tris};
-    return foreach_item<PackParams, pack_item, 256>(pp, F, (cudaStream_t)stream);
+    return pack_traversal(F, info, aabb, vert, tri, packed_nodes, packed_tris, (cudaStream_t)stream);
 }
 
 } // extern "C"

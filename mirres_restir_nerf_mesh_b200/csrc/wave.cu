@@ -123,7 +123,9 @@ __global__ void __launch_bounds__(CP_BLOCK) k_compact_write(const float *__restr
 // is reached) the idle lanes take over the OLDEST deferred subtree of busy lanes.  bvh_hit's boolean result is the OR over
 // all leaf tests (mr_bvh.cuh), so walking the subtrees of one ray on several lanes returns the same flag while the
 // longest ray of a launch stops being a serial chain of ~10^3 dependent L2 loads.
-__device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Workspace &ws, int grab)
+// TOP: the first wide levels of the tree are read from `s_top`, the block's shared-memory copy of bvh.top (see TopTable)
+template <bool TOP>
+__device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Workspace &ws, int grab, const Rec32 *s_top)
 {
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lane = threadIdx.x & 31u;
@@ -158,7 +160,7 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
                     r = make_ray(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z));
                     slot = __float_as_int(o.w);
                     sp = bot = 0;
-                    cur = 0;
+                    cur = TOP ? MR_REF_TOP : 0; // table slot 0 = the root record
                     have = true;
                 }
             }
@@ -209,11 +211,15 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
             if (!have) break;
             // load phase common to both record kinds, so that node lanes and leaf lanes of a diverged warp wait for
             // their L2 round trip at the same time
-            const Rec32 *rec = ref_address(bvh, cur);
-            const Rec32 e0 = load_rec(rec), e1 = load_rec(rec + 1);
+            const bool in_top = TOP && cur >= 0 && (cur & MR_REF_TOP) != 0;
+            const Rec32 *rec = in_top ? s_top + 4 * (cur & 0x1ff) : ref_address(bvh, cur);
+            Rec32 e0, e1;
+            if (in_top) { e0 = rec[0]; e1 = rec[1]; }
+            else { e0 = load_rec(rec); e1 = load_rec(rec + 1); }
             if (cur >= 0) {
                 Rec32 e2, e3;
-                load_tail(rec, ref_missing(cur), e2, e3); // trailing sectors only when the reference says they are in use
+                if (in_top) { e2 = rec[2]; e3 = rec[3]; }
+                else load_tail(rec, ref_missing(cur), e2, e3); // trailing sectors only when the reference says they are in use
                 WideHit w;
                 wide_slabs(r, e0, e1, e2, e3, w);
                 int next = 0;
@@ -455,9 +461,18 @@ __device__ __forceinline__ int grab_limit(int total, int warps)
 
 #define MR_TRACE_WARPS (MR_TRACE_BLOCK / 32)
 
+template <bool TOP>
 __global__ void __launch_bounds__(MR_TRACE_BLOCK) k_trace_any_persistent(BvhView bvh, Workspace ws)
 {
-    trace_any_worker(bvh, ws, grab_limit(ws.counters[MR_CTR_ANY_SIZE], gridDim.x * MR_TRACE_WARPS));
+    __shared__ Rec32 s_top[TOP ? MR_TOP_MAX * 4 : 1];
+    if (TOP) {
+        const int n4 = bvh.top->count * 8; // float4 words of the records in use
+        const float4 *src = reinterpret_cast<const float4 *>(bvh.top->rec);
+        float4 *dst = reinterpret_cast<float4 *>(s_top);
+        for (int i = threadIdx.x; i < n4; i += MR_TRACE_BLOCK) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
+    trace_any_worker<TOP>(bvh, ws, grab_limit(ws.counters[MR_CTR_ANY_SIZE], gridDim.x * MR_TRACE_WARPS), s_top);
 }
 // SPLIT: idle lanes walk deferred subtrees of their warp's closest-hit rays (mr_split.cuh); the hit logs live in shared
 // memory, 4.9 KB per warp.  The walker without splitting needs 0.9 KB per warp.
@@ -480,7 +495,7 @@ __global__ void __launch_bounds__(MR_TRACE_BLOCK, 4) k_trace_mixed_persistent(Bv
     const int w = threadIdx.x >> 5;
     const int warps = gridDim.x * (MR_TRACE_WARPS / 2);
     if (w < MR_TRACE_WARPS / 2) {
-        trace_any_worker(bvh, ws, grab_limit(ws.counters[MR_CTR_ANY_SIZE], warps));
+        trace_any_worker<false>(bvh, ws, grab_limit(ws.counters[MR_CTR_ANY_SIZE], warps), nullptr);
     } else {
         const int grab = SPLIT ? grab_limit(ws.counters[MR_CTR_CLOSEST_SIZE], warps) : 32;
         trace_closest_worker<SPLIT>(bvh, ws, recs[w - MR_TRACE_WARPS / 2], grab);
@@ -501,7 +516,7 @@ void queue_reset(const Workspace &ws, cudaStream_t st)
 // what the tracers need to know about a device, looked up once per device (not per process)
 struct DeviceInfo {
     std::atomic<int> ready;
-    int sm_count, occ_any, occ_closest, occ_closest_split, occ_mixed, occ_mixed_split;
+    int sm_count, occ_any, occ_any_top, occ_closest, occ_closest_split, occ_mixed, occ_mixed_split;
 };
 #define MR_MAX_DEVICES 64
 static DeviceInfo g_devices[MR_MAX_DEVICES];
@@ -523,7 +538,8 @@ static const DeviceInfo &device_info()
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, MR_TRACE_BLOCK, 0);
                 return o < 1 ? 1 : o;
             };
-            d.occ_any = occ(k_trace_any_persistent);
+            d.occ_any = occ(k_trace_any_persistent<false>);
+            d.occ_any_top = occ(k_trace_any_persistent<true>);
             d.occ_closest = occ(k_trace_closest_persistent<false>);
             d.occ_closest_split = occ(k_trace_closest_persistent<true>);
             d.occ_mixed = occ(k_trace_mixed_persistent<false>);
@@ -552,7 +568,8 @@ int trace_queues(const BvhView &bvh, const Workspace &ws, bool any, bool closest
     (void)sm_count;
     const DeviceInfo &d = device_info();
     const bool split = t_tune[MIRRES_TUNE_CLOSEST_SPLIT] != 2; // 0 = default (on), 1 = on, 2 = off
-    const int any_blocks = min(t_tune[MIRRES_TUNE_ANY_BLOCKS] > 0 ? t_tune[MIRRES_TUNE_ANY_BLOCKS] : 3, d.occ_any);
+    const bool top = t_tune[MIRRES_TUNE_ANY_TOP] == 1; // default off: measured, see profiles/README.md
+    const int any_blocks = min(t_tune[MIRRES_TUNE_ANY_BLOCKS] > 0 ? t_tune[MIRRES_TUNE_ANY_BLOCKS] : 3, top ? d.occ_any_top : d.occ_any);
     const int closest_blocks = min(t_tune[MIRRES_TUNE_CLOSEST_BLOCKS] > 0 ? t_tune[MIRRES_TUNE_CLOSEST_BLOCKS] : 2,
                                    split ? d.occ_closest_split : d.occ_closest);
     const int mixed_blocks = min(t_tune[MIRRES_TUNE_MIXED_BLOCKS] > 0 ? t_tune[MIRRES_TUNE_MIXED_BLOCKS] : 4,
@@ -562,7 +579,8 @@ int trace_queues(const BvhView &bvh, const Workspace &ws, bool any, bool closest
         if (split) k_trace_mixed_persistent<true><<<g_mixed, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
         else k_trace_mixed_persistent<false><<<g_mixed, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
     } else if (any) {
-        k_trace_any_persistent<<<g_any, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+        if (top) k_trace_any_persistent<true><<<g_any, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
+        else k_trace_any_persistent<false><<<g_any, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
     } else if (closest) {
         if (split) k_trace_closest_persistent<true><<<g_closest, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
         else k_trace_closest_persistent<false><<<g_closest, MR_TRACE_BLOCK, 0, st>>>(bvh, ws);
@@ -733,7 +751,7 @@ extern "C" int mirres_test_closest_split(const void *packed_nodes, const void *p
 {
     if (!packed_nodes || !packed_tris || !org || !dir || !hit) return MIRRES_ERR_NULL;
     if (n < 0 || lanes < 1 || lanes > MR_SPLIT_LANES) return MIRRES_ERR_SHAPE;
-    BvhView bvh = {(const PackedNode *)packed_nodes, (const PackedTri *)packed_tris};
+    BvhView bvh = bvh_view(packed_nodes, packed_tris);
     if (cap == 1) closest_split_simulate<1>(bvh, org, dir, n, lanes, seed, hit, t, pos, normal, prim, stats);
     else if (cap == 2) closest_split_simulate<2>(bvh, org, dir, n, lanes, seed, hit, t, pos, normal, prim, stats);
     else closest_split_simulate<MR_SPLIT_LOG>(bvh, org, dir, n, lanes, seed, hit, t, pos, normal, prim, stats);

@@ -65,7 +65,7 @@ class Kernels:
         return ctypes.c_uint(int(x) & 0xFFFFFFFF)
 
     # -- tuning ------------------------------------------------------------------------------------------------
-    TUNE_ANY_BLOCKS, TUNE_CLOSEST_BLOCKS, TUNE_MIXED_BLOCKS, TUNE_CLOSEST_SPLIT = 0, 1, 2, 3
+    TUNE_ANY_BLOCKS, TUNE_CLOSEST_BLOCKS, TUNE_MIXED_BLOCKS, TUNE_CLOSEST_SPLIT, TUNE_ANY_TOP = 0, 1, 2, 3, 4
 
     def get_tuning(self, key):
         v = self.lib.mirres_get_tuning(int(key))

@@ -32,7 +32,7 @@ class HostKernels(_kernels.Kernels):
         super().__init__(lib=lib, require_cuda=False)
 
     def bvh_sizes(self, F):
-        return (0, 128 * max(F - 1, 1), 64 * F)
+        return (0, 128 + 341 * 128 + 128 * max(F - 1, 1), 64 * F)  # top table + wide nodes, packed triangles
 
 
 _K = None

@@ -82,3 +82,47 @@ def test_row_band_sharding_is_bit_identical(tmp_path, world, overlap, balanced):
     for i, w in enumerate(want):
         assert np.array_equal(got["arr_%d" % i], w.numpy(), equal_nan=True), i
     assert (got["flat"] == float(sum(range(1, world + 1)))).all()
+
+
+def test_temporal_pass_on_a_row_slice_rounds_like_the_full_frame():
+    """A band of a TALL frame handed to the temporal pass as a frame of its own (with the row offset) must pick the same
+    previous pixel as the full-frame launch: `int(pixel + u)` is rounded at the magnitude of the row number (SURVEY.md
+    quirk 8), so a pass that jittered band-local row numbers would differ in a few pixels per million -- too few for the
+    small frames of the multi-process tests above, enough to break bit-identity at 2048 rows (seen on 2 B200s)."""
+    import hostcheck as H
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim, synth
+    k = H.activate()
+    try:
+        fx, fy, y0, y1 = 32, 70000, 65500, 65600   # rows near 2^16: float spacing 2^-7, one jitter in ~128 rounds up
+        n = fx * fy
+        g = torch.Generator().manual_seed(1)
+        env = H.t(np.ascontiguousarray(synth.envmap(16, 32)[::-1].reshape(-1, 3)))
+        rnd = lambda *s: torch.rand(*s, generator=g)
+        nrm = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=1)
+        maps = dict(occ=torch.ones(n, 1), nd=torch.cat((nrm, 2.0 + 0.01 * rnd(n, 1)), 1).contiguous(), brdf=torch.cat((rnd(n, 1), torch.zeros(n, 1), 0.1 + rnd(n, 1)), 1).contiguous(),
+                    ray=-nrm.clone())
+
+        def reservoirs():
+            ld = torch.cat((torch.ones(n, 1), rnd(n, 2)), 1).contiguous()
+            return [ld, rnd(n, 1), torch.randint(1, 5, (n, 1), generator=g, dtype=torch.int32), rnd(n, 1)]
+        cur, prev = reservoirs(), reservoirs()
+
+        def run(rows):
+            a, b = rows
+            cut = lambda t: t[a * fx:b * fx].clone()
+            res = [cut(t) for t in cur]
+            m = {k_: cut(v) for k_, v in maps.items()}
+            with slangpy_shim.row_offset(a), slangpy_shim.active_rows(y0 - a, y1 - a, fx):
+                ws = slangpy_shim.workspace(torch.device("cpu"), (b - a) * fx)
+                slangpy_shim.prepare_workspace(m["occ"])
+                k.temporal_resampling(res, [cut(t) for t in prev], env, 32, 16, fx, b - a, 77, m["occ"], m["nd"], m["brdf"], m["ray"],
+                                      m["occ"], m["nd"], m["brdf"], m["ray"], ws)
+            return [t[(y0 - a) * fx:(y1 - a) * fx] for t in res]
+
+        full, band = run((0, fy)), run((y0 - 31, y1 + 31))
+        moved = sum(int((f != c[y0 * fx:y1 * fx]).any(dim=1).sum()) for f, c in zip(full[:1], cur[:1]))
+        assert moved > 100  # the pass did something
+        for f, b_ in zip(full, band):
+            assert torch.equal(f, b_)
+    finally:
+        slangpy_shim.set_kernels(None)
