@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     lib = _lib.bind(ctypes.CDLL(lib_path))
     assert lib.mirres_abi_version() == 1
     assert lib.mirres_bvh_scratch_bytes(0) == 0
-    assert lib.mirres_bvh_packed_node_bytes(500000) == 128 * 499999
+    assert lib.mirres_bvh_packed_node_bytes(500000) == 128 + 341 * 128 + 128 * 499999  # top table + wide records
     assert lib.mirres_bvh_packed_tri_bytes(500000) == 64 * 500000
     assert lib.mirres_bvh_scratch_bytes(500000) > 500000 * 6 * 4
 
