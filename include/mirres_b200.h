@@ -140,6 +140,11 @@ int mirres_light_tiles(const float *env_tex, int W, int H, const float *pdf_, co
  */
 #define MIRRES_WORKSPACE_FRAME_OFFSET_BYTES 32
 #define MIRRES_WORKSPACE_ROW_OFFSET_BYTES 36
+/* Band of the spatial pass: two words [lo, hi) at MIRRES_WORKSPACE_BAND_BYTES.  With hi > lo, mirres_spatial_resampling
+ * resamples only the listed pixels of rows [lo, hi) of the frame it is handed; the other listed pixels publish their
+ * reservoir sample for those rows to reuse and keep a zero reservoir in the output (row-band rendering: the pass reads
+ * neighbours up to 30 rows beyond the band).  hi <= lo (the zero-filled default): every listed pixel. */
+#define MIRRES_WORKSPACE_BAND_BYTES 40
 /* Error word: set to 1 by a ray-casting entry point whose traversal had to DROP a stack entry because a ray's stack was
  * full (64 entries, the reference's unchecked depth, helperDi.slang:136): results of that launch may miss a subtree.
  * Entry points cannot return it (they never synchronise); the caller reads the word when it synchronises anyway and

@@ -170,12 +170,16 @@ MR_DEV void pack_item(const PackParams &p, int gid)
     p.nodes[gid] = n;
 }
 
-// Depth of the traversal stacks: the reference's 64 (helperDi.slang:136), which it never checks.  Here a push beyond the
-// 64th entry is DROPPED instead of written out of bounds, and the queue tracers raise the workspace's error word
+// Depth of the traversal stacks: the reference's 64 (helperDi.slang:136), which it never checks.  Here the arrays carry
+// MR_STACK_SLACK spare entries -- a visit of a wide record defers at most three -- and after every visit a stack that
+// has grown beyond 64 is cut back: entries are DROPPED instead of written out of bounds (one compare per visit; a
+// compare per push cost the boolean-ray walker 9 registers and 8 % of its speed), and the queue tracers raise the
+// workspace's error word
 // (MIRRES_WORKSPACE_ERROR_BYTES, include/mirres_b200.h) so that the caller can tell that a launch lost a subtree.  The deepest
 // stack of the BASELINE scenes is 22 entries (profiles/oracle_counters_*.json); only adversarial meshes (thousands of
 // triangles with one Morton code) reach 64.
 #define MR_STACK 64
+#define MR_STACK_SLACK 4
 
 // traversal records + top table from reference-layout tensors (trace.cu); packed_tris may be null when the caller has
 // written the triangle records itself
@@ -293,19 +297,20 @@ MR_DEV bool any_hit(const BvhView &bvh, float3 origin, float3 dir, TraceStats *s
 {
     Ray r = make_ray(origin, dir);
     const float t_max = 1e7f;
-    int stack[MR_STACK];
+    int stack[MR_STACK + MR_STACK_SLACK];
     int sp = 0;
     int node = 0;
     for (;;) {
         WideHit w;
         wide_fetch(r, bvh.nodes, node, w);
         if (STATS) st->nodes += 1;
+        if (sp > MR_STACK) sp = MR_STACK; // see MR_STACK
         int next = 0;
         bool have = false;
 #pragma unroll
         for (int k = 3; k >= 0; --k) {
             if (fminf(t_max, w.tf[k]) > w.tn[k]) {
-                if (have && sp < MR_STACK) stack[sp++] = next; // (a 65th deferred entry is dropped: see MR_STACK)
+                if (have) stack[sp++] = next;
                 next = w.ref[k];
                 have = true;
             }
@@ -363,14 +368,15 @@ MR_DEV bool closest_hit(const BvhView &bvh, float3 origin, float3 dir, Hit &out,
     float closest = 1e7f;
     bool any = false;
     int best_slot = -1;
-    int stack_ref[MR_STACK];
-    float stack_t[MR_STACK];
+    int stack_ref[MR_STACK + MR_STACK_SLACK];
+    float stack_t[MR_STACK + MR_STACK_SLACK];
     int sp = 0;
     int node = 0;
     for (;;) {
         WideHit w;
         wide_fetch(r, bvh.nodes, node, w);
         if (STATS) st->nodes += 1;
+        if (sp > MR_STACK) sp = MR_STACK; // see MR_STACK
         int next = 0;
         float next_t = 0.f;
         bool have = false;
@@ -378,7 +384,7 @@ MR_DEV bool closest_hit(const BvhView &bvh, float3 origin, float3 dir, Hit &out,
 #pragma unroll
         for (int k = 3; k >= 0; --k) {
             if (fminf(closest, w.tf[k]) > w.tn[k]) {
-                if (have && sp < MR_STACK) {
+                if (have) {
                     stack_ref[sp] = next;
                     stack_t[sp] = next_t;
                     ++sp;

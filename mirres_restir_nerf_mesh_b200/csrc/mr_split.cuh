@@ -119,18 +119,18 @@ MR_DEV bool task_step(const BvhView &bvh, CTask &T, int *__restrict__ stack_ref,
         for (int k = 3; k >= 0; --k) {
             if (fminf(bound, w.tf[k]) > w.tn[k]) {
                 if (got) {
-                    if (T.sp < MR_STACK) {
-                        stack_ref[T.sp] = next;
-                        stack_t[T.sp] = next_t;
-                        ++T.sp;
-                    } else {
-                        rec.overflow = 1; // dropped, never written out of bounds; the worker reports it (MR_STACK)
-                    }
+                    stack_ref[T.sp] = next;
+                    stack_t[T.sp] = next_t;
+                    ++T.sp;
                 }
                 next = w.ref[k];
                 next_t = w.tn[k];
                 got = true;
             }
+        }
+        if (T.sp > MR_STACK) { // at most three entries were deferred into the slack of the arrays: dropped and reported
+            T.sp = MR_STACK;
+            rec.overflow = 1;
         }
         if (got) {
             T.cur = next;

@@ -42,6 +42,11 @@ namespace mr {
 // a frame of its own (the [N, k] maps are row-major, so a band is a contiguous slice of every tensor) and sets this word
 // to the band's first row: every pixel then draws the random numbers it draws in the full frame.  Zero = plain behaviour.
 #define MR_CTR_ROW_OFFSET 9
+// [10], [11] band of rows [lo, hi) of the frame handed in that the SPATIAL pass resamples; pixels of the list outside it
+// only publish their sample for the band's pixels to reuse (row-band rendering: the pass reads neighbours up to 30 rows
+// beyond the band).  hi <= lo (the zero-filled default) = every listed pixel.  Written by the caller.
+#define MR_CTR_BAND_LO 10
+#define MR_CTR_BAND_HI 11
 // [12] error word: set to 1 by a queue tracer that had to drop a traversal-stack entry (MR_STACK); never cleared by the
 // library (the caller zero-fills the workspace once and may inspect / clear the word whenever it synchronises)
 #define MR_CTR_ERROR 12
@@ -93,6 +98,11 @@ static inline size_t workspace_carve(Workspace *w, int N, char *base)
     return off;
 }
 
+MR_DEV bool in_band(const Workspace &w, unsigned int py)
+{
+    const int lo = w.counters[MR_CTR_BAND_LO], hi = w.counters[MR_CTR_BAND_HI];
+    return hi <= lo || ((int)py >= lo && (int)py < hi);
+}
 MR_DEV unsigned int row_of(const Workspace &w, unsigned int py) { return py + (unsigned int)w.counters[MR_CTR_ROW_OFFSET]; }
 MR_DEV unsigned int frame_of(const Workspace &w, unsigned int frame_index) { return frame_index + (unsigned int)w.counters[MR_CTR_FRAME_OFFSET]; }
 

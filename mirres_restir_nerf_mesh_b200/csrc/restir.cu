@@ -264,10 +264,6 @@ struct SpatialParams {
     Workspace ws;
 };
 
-// marks the per-pixel cache entries the gen pass of THIS launch has written (entries of pixels that are not on the launch's
-// pixel list keep an older mark and are evaluated by the resolve pass itself)
-MR_DEV int spatial_cache_tag(const SpatialParams &p) { return (int)(frame_of(p.ws, p.frame) | 0x80000000u); }
-
 MR_DEV bool spatial_neighbor(const SpatialParams &p, uint32_t px, uint32_t py, uint32_t startIndex, uint32_t k, size_t &n)
 {
     const uint32_t ni = (startIndex + k) & (p.offset_count - 1u);
@@ -333,7 +329,11 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
     // neighbour needs as well (candAtOwn of the pairwise MIS)
     const float own_target = target_pdf(ris_surface(N, load3(p.g.ray_dir, i), load3(p.g.brdf, i)), cLe, cL);
     p.ws.lcache[2 * i] = make_float4(cLe.x, cLe.y, cLe.z, own_target);
-    p.ws.lcache[2 * i + 1] = make_float4(cL.x, cL.y, cL.z, bits_float(spatial_cache_tag(p)));
+    p.ws.lcache[2 * i + 1] = make_float4(cL.x, cL.y, cL.z, 0.f);
+    // a pixel outside the band of rows this launch resamples (row-band rendering, MR_CTR_BAND_LO) is on the list only
+    // for the entry above -- the band's pixels read it when they pick this one as a neighbour: it queues no ray (it stays
+    // in the warp's votes below) and the resolve pass skips it
+    const bool band = in_band(p.ws, py);
     const float3 cur_pos = load3(p.pos_map, i);
     const size_t base = (size_t)a * MR_MAX_RAYS_PER_PIXEL;
 #pragma unroll
@@ -341,6 +341,7 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
         if (ok[k]) ok[k] = neighbor_ok(N, nd.w, make_float3(nnd[k].x, nnd[k].y, nnd[k].z), nnd[k].w);
         if (ok[k]) ok[k] = nM[k] != 0;
         if (ok[k]) ok[k] = !(nocc[k] < 0.1f);
+        ok[k] = ok[k] && band;
     }
 #if defined(__CUDA_ARCH__)
     const unsigned int lane = threadIdx.x & 31u;
@@ -393,6 +394,7 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
     const int idx = p.ws.active[a];
     const size_t i = (size_t)idx;
     const uint32_t px = (uint32_t)(idx % p.fx), py = (uint32_t)(idx / p.fx);
+    if (!in_band(p.ws, py)) return;
     uint32_t sg = seed_of(px, row_of(p.ws, py), frame_of(p.ws, p.frame));
     float4 nd = load_nd(p.g.normal_depth, i);
     const float3 N = make_float3(nd.x, nd.y, nd.z);
@@ -415,14 +417,7 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
         const Reservoir nr = res_load(p.prev, n);
         const RisSurface nb_s = ris_surface(nN, load3(p.g.ray_dir, n), load3(p.g.brdf, n));
         ++validNeighbors;
-        float4 n0 = p.ws.lcache[2 * n], n1 = p.ws.lcache[2 * n + 1]; // light_of(nr.ld): n is a foreground pixel
-        if (float_bits(n1.w) != spatial_cache_tag(p)) {
-            // the neighbour is not on this launch's pixel list (a halo row of a band, dist.py): evaluate its entry here
-            float3 le, l;
-            light_of(p.env, nr.ld.y, nr.ld.z, le, l);
-            n0 = make_float4(le.x, le.y, le.z, target_pdf(nb_s, le, l));
-            n1 = make_float4(l.x, l.y, l.z, 0.f);
-        }
+        const float4 n0 = p.ws.lcache[2 * n], n1 = p.ws.lcache[2 * n + 1]; // light_of(nr.ld): n is on the pixel list
         const float3 nLe = make_float3(n0.x, n0.y, n0.z), nL = make_float3(n1.x, n1.y, n1.z);
         const bool canonical_hit = p.ws.hit[base + 2 * k] == MR_HIT_HIT;
         const bool candidate_hit = p.ws.hit[base + 2 * k + 1] == MR_HIT_HIT;

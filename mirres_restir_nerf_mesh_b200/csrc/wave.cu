@@ -132,7 +132,7 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
     const unsigned int lt_mask = (1u << lane) - 1u;
     const int total = ws.counters[MR_CTR_ANY_SIZE];
     int *ticket = ws.counters + MR_CTR_ANY_TICKET;
-    int stack[MR_STACK];
+    int stack[MR_STACK + MR_STACK_SLACK];
     int sp = 0, bot = 0;   // live entries: [bot, sp)
     int cur = 0;           // node reference being processed: >= 0 internal, < 0 leaf
     int slot = -1;
@@ -228,12 +228,15 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
                 for (int k = 3; k >= 0; --k) {
                     if (fminf(1e7f, w.tf[k]) > w.tn[k]) {
                         if (got) {
-                            if (sp < MR_STACK) stack[sp++] = next;
-                            else overflow = true;
+                            stack[sp++] = next;
                         }
                         next = w.ref[k];
                         got = true;
                     }
+                }
+                if (sp > MR_STACK) { // a visit defers at most three entries: the array has that much slack (MR_STACK)
+                    sp = MR_STACK;
+                    overflow = true;
                 }
                 if (got) {
                     cur = next;
@@ -296,8 +299,8 @@ __device__ __forceinline__ void trace_closest_worker(const BvhView &bvh, const W
     const int total = ws.counters[MR_CTR_CLOSEST_SIZE];
     int *ticket = ws.counters + MR_CTR_CLOSEST_TICKET;
     CTask T;
-    int stack_ref[MR_STACK];
-    float stack_t[MR_STACK];
+    int stack_ref[MR_STACK + MR_STACK_SLACK];
+    float stack_t[MR_STACK + MR_STACK_SLACK];
     T.r.o = T.r.d = T.r.inv = f3(0.f);
     T.slot = -1;
     T.home = (int)lane;
@@ -662,8 +665,8 @@ static void closest_split_simulate(const BvhView &bvh, const float *org, const f
 {
     SplitRecT<CAP> rec;
     CTask T[MR_SPLIT_LANES];
-    static thread_local int stack_ref[MR_SPLIT_LANES][MR_STACK];
-    static thread_local float stack_t[MR_SPLIT_LANES][MR_STACK];
+    static thread_local int stack_ref[MR_SPLIT_LANES][MR_STACK + MR_STACK_SLACK];
+    static thread_local float stack_t[MR_SPLIT_LANES][MR_STACK + MR_STACK_SLACK];
     bool have[MR_SPLIT_LANES];
     unsigned int rng = seed * 2654435761u + 12345u;
     auto rnd = [&]() { rng = 1664525u * rng + 1013904223u; return rng >> 8; };

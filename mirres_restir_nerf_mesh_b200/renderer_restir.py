@@ -693,6 +693,11 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     def rows_wide():
         return slangpy.active_rows(shard.wide[0], shard.wide[1], framedim_x) if shard is not None else contextlib.nullcontext()
 
+    def band_only():
+        # the spatial pass runs on the wide list (the pixels around the band publish the samples the band reuses) and
+        # resamples the band's rows
+        return slangpy.spatial_band(shard.rows[0], shard.rows[1]) if shard is not None else contextlib.nullcontext()
+
     def zeros(*shape):
         return torch.zeros(shape, dtype=torch.float, device=dev)
 
@@ -893,11 +898,8 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         # fork first: the chains' own foreground lists are then built beside the reuse chain's, not after it
         for st in [st_s, st_i] + st_init + ([main_stream] if main_stream is not caller_stream else []):
             st.wait_stream(caller_stream)
-        with _on(main_stream):
+        with _on(main_stream), rows_wide():  # the reuse chain's list: temporal reuse covers it, spatial reuse its band rows
             slangpy.prepare_workspace(occ_map)
-            if shard is not None:
-                with slangpy.workspace_tag("temporal"), rows_wide():
-                    slangpy.prepare_workspace(occ_map)
         for r in range(R):
             with _on(st_init[r]), slangpy.workspace_tag("initial%d" % r), rows_wide():
                 slangpy.prepare_workspace(occ_map)
@@ -937,14 +939,13 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             ris_pass = 3
             with _on(main_stream):
                 if i > 0:
-                    with slangpy.workspace_tag("temporal") if shard is not None else contextlib.nullcontext():
-                        TemporalResampling(TemporalResampling_m, X[r], S[(i - 1) % 2], env_map, width, height, framedim_x,
-                                           framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map,
-                                           prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
+                    TemporalResampling(TemporalResampling_m, X[r], S[(i - 1) % 2], env_map, width, height, framedim_x,
+                                       framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map,
+                                       prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
                     ris_pass += 1
                 if i >= 2:
                     main_stream.wait_event(copy_done[i - 2])  # S[i % 2] was last read by the copy of iteration i - 2
-                with slangpy.trace_blocks(any_blocks=CRITICAL_ANY_BLOCKS):
+                with slangpy.trace_blocks(any_blocks=CRITICAL_ANY_BLOCKS), band_only():
                     worker.SpatialResampling_(SpatialResampling_m, pos_map, S[i % 2], X[r], neighborOffsets, env_map,
                                               width, height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth,
                                               brdf_map, ray_dir_map)
@@ -1030,13 +1031,13 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                                    prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
                 ris_pass += 1
             reservoirs, prev_reservoirs = prev_reservoirs, reservoirs
-            if shard is not None:
-                slangpy.prepare_workspace(occ_map)  # from here on the band's own rows only
-            worker.SpatialResampling_(SpatialResampling_m, pos_map, reservoirs, prev_reservoirs, neighborOffsets, env_map,
-                                      width, height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth,
-                                      brdf_map, ray_dir_map)
+            with band_only():
+                worker.SpatialResampling_(SpatialResampling_m, pos_map, reservoirs, prev_reservoirs, neighborOffsets,
+                                          env_map, width, height, framedim_x, framedim_y, base + ris_pass, occ_map,
+                                          normal_depth, brdf_map, ray_dir_map)
             ris_pass += 1
             if shard is not None:
+                slangpy.prepare_workspace(occ_map)  # from here on the band's own rows only
                 # the temporal pass of the next iteration reads finished reservoirs up to 31 rows outside this rank's
                 # band: those rows take their owners' values
                 shard.exchange(reservoirs)

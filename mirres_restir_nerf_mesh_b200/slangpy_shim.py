@@ -95,6 +95,7 @@ class _Context(threading.local):
         self.skip_prepare = [False]
         self.active_rows = [None]
         self.row_offset = [0]
+        self.band = [(0, 0)]
 
 
 _CTX = _Context()
@@ -199,6 +200,9 @@ def workspace(device, n_pixels):
         _WORKSPACES[key] = ws
         if _FRAME_OFFSET.get(_device_key(device)) is not None:
             _frame_word(ws).copy_(_FRAME_OFFSET[_device_key(device)])
+    if _CTX.band[-1] != getattr(ws, "_mirres_band", (0, 0)):
+        ws[BAND_BYTES:BAND_BYTES + 8].view(torch.int32).copy_(_band_tensor(ws.device, _CTX.band[-1]))
+        ws._mirres_band = _CTX.band[-1]
     if _CTX.row_offset[-1] != getattr(ws, "_mirres_row_offset", 0):
         # stream-ordered, like the frame offset: the launches that follow see the new value
         _row_word(ws).fill_(_CTX.row_offset[-1])
@@ -216,6 +220,33 @@ def _row_word(ws):
 
 
 ERROR_BYTES = 48  # MIRRES_WORKSPACE_ERROR_BYTES
+BAND_BYTES = 40   # MIRRES_WORKSPACE_BAND_BYTES: two words, rows [lo, hi)
+_BAND_TENSORS = {}
+
+
+def _band_tensor(device, band):
+    """Device-resident copy of a (lo, hi) pair, made once per value: writing the words of a workspace is then a
+    device-to-device copy, which a CUDA graph capture records like any other launch."""
+    key = (str(device), band)
+    t = _BAND_TENSORS.get(key)
+    if t is None:
+        t = _BAND_TENSORS[key] = torch.tensor(band, dtype=torch.int32, device=device)
+    return t
+
+
+class spatial_band:
+    """Inside the block the spatial pass resamples rows [lo, hi) of the frame it is handed only; the other pixels of its
+    list just publish their samples for those rows to reuse (include/mirres_b200.h, MIRRES_WORKSPACE_BAND_BYTES)."""
+
+    def __init__(self, lo, hi):
+        self.band = (int(lo), int(hi))
+
+    def __enter__(self):
+        _CTX.band.append(self.band)
+
+    def __exit__(self, *a):
+        _CTX.band.pop()
+
 
 
 def check_workspaces(device=None, clear=True):
