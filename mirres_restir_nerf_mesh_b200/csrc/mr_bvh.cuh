@@ -108,10 +108,12 @@ struct PackParams {
     const int *__restrict__ tri;    // [F,3]
     PackedNode *__restrict__ nodes;
     PackedTri *__restrict__ tris;
+    TopTable *__restrict__ top; // its record count is cleared here; k_top_table fills the table when it is wanted
 };
 MR_DEV void pack_item(const PackParams &p, int gid)
 {
     const int F = p.F, LEAF = F - 1;
+    if (gid == 0 && p.top) p.top->count = 0;
     if (p.tris) { // null: the caller has written the triangle records itself (mirres_bvh_build does, with the leaf records)
         int prim = MR_LDG(p.info + 3 * (size_t)(LEAF + gid) + 2);
         int i0 = MR_LDG(p.tri + 3 * (size_t)prim), i1 = MR_LDG(p.tri + 3 * (size_t)prim + 1), i2 = MR_LDG(p.tri + 3 * (size_t)prim + 2);
@@ -183,6 +185,7 @@ MR_DEV void pack_item(const PackParams &p, int gid)
 
 // traversal records + top table from reference-layout tensors (trace.cu); packed_tris may be null when the caller has
 // written the triangle records itself
+int tuning_value(int key); // wave.cu: the calling thread's mirres_set_tuning value
 int pack_traversal(int F, const int *info, const float *aabb, const float *vert, const int *tri, void *packed_nodes,
                    void *packed_tris, cudaStream_t st);
 

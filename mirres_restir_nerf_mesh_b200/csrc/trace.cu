@@ -89,14 +89,16 @@ int pack_traversal(int F, const int *info, const float *aabb, const float *vert,
 {
     TopTable *top = (TopTable *)packed_nodes;
     PackedNode *nodes = (PackedNode *)((char *)packed_nodes + MR_TOP_BYTES);
-    PackParams pp = {F, info, aabb, vert, tri, nodes, (PackedTri *)packed_tris};
+    PackParams pp = {F, info, aabb, vert, tri, nodes, (PackedTri *)packed_tris, top};
     int rc = foreach_item<PackParams, pack_item, 256>(pp, packed_tris ? F : (F > 1 ? F - 1 : 1), st);
     if (rc) return rc;
-#if defined(MR_HOST_CHECK)
-    top->count = 0;
-#else
-    k_top_table<<<1, 256, 0, st>>>(nodes, top);
-    MR_CUDA_CHECK_LAUNCH();
+#if !defined(MR_HOST_CHECK)
+    // the table is built only for callers that have switched the staged walker on (it is off by default: measured slower,
+    // profiles/README.md); an empty table makes that walker start at the root record in global memory
+    if (tuning_value(MIRRES_TUNE_ANY_TOP) == 1) {
+        k_top_table<<<1, 256, 0, st>>>(nodes, top);
+        MR_CUDA_CHECK_LAUNCH();
+    }
 #endif
     return 0;
 }

@@ -160,7 +160,7 @@ __device__ __forceinline__ void trace_any_worker(const BvhView &bvh, const Works
                     r = make_ray(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z));
                     slot = __float_as_int(o.w);
                     sp = bot = 0;
-                    cur = TOP ? MR_REF_TOP : 0; // table slot 0 = the root record
+                    cur = (TOP && s_top) ? MR_REF_TOP : 0; // table slot 0 = the root record
                     have = true;
                 }
             }
@@ -468,14 +468,15 @@ template <bool TOP>
 __global__ void __launch_bounds__(MR_TRACE_BLOCK) k_trace_any_persistent(BvhView bvh, Workspace ws)
 {
     __shared__ Rec32 s_top[TOP ? MR_TOP_MAX * 4 : 1];
+    const int n_top = TOP ? bvh.top->count : 0;
     if (TOP) {
-        const int n4 = bvh.top->count * 8; // float4 words of the records in use
+        const int n4 = n_top * 8; // float4 words of the records in use
         const float4 *src = reinterpret_cast<const float4 *>(bvh.top->rec);
         float4 *dst = reinterpret_cast<float4 *>(s_top);
         for (int i = threadIdx.x; i < n4; i += MR_TRACE_BLOCK) dst[i] = __ldg(src + i);
         __syncthreads();
     }
-    trace_any_worker<TOP>(bvh, ws, grab_limit(ws.counters[MR_CTR_ANY_SIZE], gridDim.x * MR_TRACE_WARPS), s_top);
+    trace_any_worker<TOP>(bvh, ws, grab_limit(ws.counters[MR_CTR_ANY_SIZE], gridDim.x * MR_TRACE_WARPS), n_top > 0 ? s_top : nullptr);
 }
 // SPLIT: idle lanes walk deferred subtrees of their warp's closest-hit rays (mr_split.cuh); the hit logs live in shared
 // memory, 4.9 KB per warp.  The walker without splitting needs 0.9 KB per warp.
@@ -509,6 +510,8 @@ __global__ void __launch_bounds__(MR_TRACE_BLOCK, 4) k_trace_mixed_persistent(Bv
 // Launch-shape tuning (mirres_set_tuning): values are per HOST THREAD, so two threads that drive different streams do
 // not see each other's settings; 0 = library default.  Results never depend on them.
 static thread_local int t_tune[MIRRES_TUNE_COUNT_] = {0};
+
+int tuning_value(int key) { return key >= 0 && key < MIRRES_TUNE_COUNT_ ? t_tune[key] : 0; }
 
 void queue_reset(const Workspace &ws, cudaStream_t st)
 {
