@@ -905,6 +905,10 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                 slangpy.prepare_workspace(occ_map)
         with _on(st_s), slangpy.workspace_tag("shade"):
             slangpy.prepare_workspace(occ_map)
+        # ... and so are the indirect chains' lists: once per loop, not once per iteration (three launches each)
+        for c in chains:
+            with _on(c["stream"]), slangpy.workspace_tag(c["tag"]):
+                slangpy.prepare_workspace(occ_map)
         ev = lambda stream: (lambda e: (e.record(stream), e)[1])(torch.cuda.Event() if pos_map.is_cuda else _NullEvent())
         init_done, spatial_done, copy_done = {}, {}, {}
         passes, direct_outs = [], []
@@ -921,7 +925,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             base = random_offset + TOTAL_RIS_PASSES * i
             first_indirect_pass = 4 if i == 0 else 5
             c = chains[i % len(chains)]
-            with _on(c["stream"]), slangpy.workspace_tag(c["tag"]), slangpy.trace_blocks(
+            with _on(c["stream"]), slangpy.workspace_tag(c["tag"]), slangpy.workspace_prepared(), slangpy.trace_blocks(
                     closest_blocks=BACKGROUND_CLOSEST_BLOCKS, mixed_blocks=BACKGROUND_MIXED_BLOCKS):
                 indirect_chain(i, first_indirect_pass, c)
             r = i % R

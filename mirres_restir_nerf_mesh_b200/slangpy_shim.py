@@ -473,8 +473,9 @@ def _final_shading_bwd(m, finalSample, env_tex, env_width, env_height, framedim_
 def _new_dir(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, frameIndex, bounce_count, framedim_x, framedim_y, occ_map,
              pos_map, normal, ray_dir, prd, diffuse_map, linearRoughness_specular_map, new_pos_map, new_ray_d,
              new_occ_map, new_normal):
-    if _CTX.ws_tag[-1] != "main" and int(bounce_count) == 0:
-        # a chain with its own workspace builds its own foreground-pixel list from the primary occupancy
+    if _CTX.ws_tag[-1] != "main" and int(bounce_count) == 0 and not _CTX.skip_prepare[-1]:
+        # a chain with its own workspace builds its own foreground-pixel list from the primary occupancy (unless the
+        # driver has done so once for the whole loop: workspace_prepared)
         get_kernels().workspace_prepare(_band_occ(_c(occ_map)), workspace(prd.device, prd.shape[0]))
     get_kernels().bounce_first(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), int(frameIndex), int(bounce_count),
                                m.define("MAX_Bounce", 2), int(framedim_x), int(framedim_y), _c(occ_map), _c(pos_map),
