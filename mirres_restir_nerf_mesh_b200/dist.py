@@ -99,28 +99,20 @@ class RowBandShard:
 
     def exchange(self, tensors, row0=0):
         """In place: the halo rows of every [rows * fx, k] tensor (rows of the frame from `row0` on; the whole frame by
-        default) take their owners' values.  Per peer ONE message carries the rows of all tensors (32-bit words, fp32 and
-        int32 alike); a rank talks to the ranks whose bands touch its halo only."""
+        default) take their owners' values.  A band of rows is a contiguous piece of each tensor, so the rows travel
+        straight from and into the tensors -- no staging copies: per exchange ONE group of point-to-point operations,
+        and a rank talks only to the ranks whose bands touch its halo."""
         tensors = list(tensors)
         if self.world == 1 or not (self.recv_plan or self.send_plan):
             return
-        views = self._row_views(tensors, row0)
-        ops, recvs = [], []
+        views = [t.view(t.shape[0] // self.fx, -1) for t in tensors]  # [rows, fx * k], any 32-bit dtype
+        ops = []
         for q, (y0, y1) in self.send_plan:
-            buf = torch.cat([v[y0 - row0:y1 - row0] for v in views], dim=1).contiguous()
-            ops.append(dist.P2POp(dist.isend, buf, self._peer(q), self.group))
+            ops += [dist.P2POp(dist.isend, v[y0 - row0:y1 - row0], self._peer(q), self.group) for v in views]
         for q, (y0, y1) in self.recv_plan:
-            buf = torch.empty((y1 - y0, sum(v.shape[1] for v in views)), dtype=torch.float32, device=views[0].device)
-            ops.append(dist.P2POp(dist.irecv, buf, self._peer(q), self.group))
-            recvs.append((y0 - row0, y1 - row0, buf))
+            ops += [dist.P2POp(dist.irecv, v[y0 - row0:y1 - row0], self._peer(q), self.group) for v in views]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-        for y0, y1, buf in recvs:
-            c0 = 0
-            for v in views:
-                c1 = c0 + v.shape[1]
-                v[y0:y1].copy_(buf[:, c0:c1])
-                c0 = c1
 
     def gather_bands(self, images, row0=0):
         """Full-frame copies of fp32 images of which every rank holds its own band (tensors [rows * fx, k] that start at
