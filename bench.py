@@ -552,6 +552,21 @@ def run_render(args):
         bounds = D.balanced_bounds(occ0, W, H, world, min_rows=1) if not args.uniform_bands else D.uniform_bounds(H, world)
         n_fg = int((occ0 >= 0.1).sum().item())
     shard = D.RowBandShard(W, H, rank=rank, world=world, bounds=bounds)
+    if args.emulate:
+        # diagnostics on ONE GPU: the work of rank R of W ranks, halo exchange and gather left out (images are wrong,
+        # timings are what that rank would spend outside communication) -- for timelines of a band at sizes that
+        # otherwise need W GPUs
+        r_, w_ = (int(x) for x in args.emulate.split("/"))
+        b_ = D.balanced_bounds(occ0, W, H, w_, min_rows=1)
+
+        class _Alone(D.RowBandShard):
+            def exchange(self, tensors, row0=0):
+                pass
+
+            def gather_bands(self, images, row0=0):
+                full = [torch.zeros((self.fy * self.fx, im.shape[1]), device=im.device) for im in images]
+                return full
+        shard = _Alone(W, H, rank=r_, world=w_, bounds=b_)
 
     def frame(vert, tri, env, pose):
         with torch.no_grad():
@@ -583,6 +598,8 @@ def run_render(args):
         src = {k: v.to(dev, non_blocking=True) for k, v in host.items()} if from_host else device_in
         return frame(**src)
 
+    if args.timeline:
+        _timeline(torch, lambda _: run_step(False), args.timeline)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     image_host = torch.empty((n, 3), dtype=torch.float32).pin_memory()
 
@@ -778,6 +795,7 @@ def main():
     ap.add_argument("--spp", type=int, default=None, help="render mode: override the configuration's spp")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--emulate", default=None, help="render mode diagnostics: R/W = time the band of rank R of W on one GPU, no communication")
     ap.add_argument("--uniform-bands", action="store_true", help="render mode: bands of equal height instead of equal foreground")
     ap.add_argument("--no-overlap", action="store_true", help="direct and indirect chains on one stream")
     ap.add_argument("--allreduce-after", action="store_true",

@@ -58,9 +58,16 @@ int mirres_get_tuning(int key); /* current value of `key` for the calling thread
  *   info [2F-1,3] i32 (left, right, primitive; leaf <=> left == right == 0), aabb [2F-1,6] f32 (min xyz, max xyz),
  *   internal nodes [0,F-2] (root 0), leaves [F-1,2F-2] in sorted-Morton order  (renderer_restir.py:61-64).
  * packed_nodes / packed_tris (optional, both or neither): traversal records consumed by every ray-casting
- * entry point below; sizes from mirres_bvh_packed_{node,tri}_bytes, 32-byte aligned (256-bit loads).
+ * entry point below; sizes from mirres_bvh_packed_{node,tri}_bytes, 32-byte aligned (256-bit loads).  Opaque to the
+ * caller.  (packed_nodes = a table of the first five wide levels, 43 KB, followed by one 128-byte record per internal
+ * node: the boxes of its up to four grandchildren in the reference's visit order; packed_tris = one 64-byte record
+ * per leaf in sorted-Morton order: v0 | primitive, e1, e2.)
+ * The build is nine stream-ordered launches and never synchronises.  Morton codes are 30-bit (lbvh_morton_codes.slang:
+ * 24-44): the stable sort runs three 10-bit passes.
  * sorted_codes (optional) [F,2] i32: (Morton code, element index) after the stable sort (renderer_restir.py:48-57).
- * scratch: mirres_bvh_scratch_bytes(F) bytes, 256-byte aligned.
+ * scratch: mirres_bvh_scratch_bytes(F) bytes, 256-byte aligned; contents need not be preserved or cleared between calls
+ * (the build's first launch initialises what it needs).  The sort passes wait on counters inside it: scratch must not
+ * be written by anything else while a build is in flight.
  */
 size_t mirres_bvh_scratch_bytes(int F);
 size_t mirres_bvh_packed_node_bytes(int F);
