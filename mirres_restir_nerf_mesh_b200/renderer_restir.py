@@ -1119,7 +1119,7 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
                                                      framedim_x, framedim_y, occ_map, (combined, diff_1, spec_1),
                                                      normal_map.detach(), pos_map.detach())
 
-    split_denoise = gb_depth is None and batched_denoise and shard is None
+    split_denoise = gb_depth is None and batched_denoise
     loop_args = (make_sampleable_m, generateLightTiles_m, InitialResampling_m, TemporalResampling_m, SpatialResampling_m,
                  EvaluateFinalSamples_m, FinalShading_m, light_data, light_uv, light_inv_pdf)
     loop_kw = dict(random_offset=random_offset, max_bounce=max_bounce, hooks=hooks, overlap=overlap, normalize=True,
@@ -1153,6 +1153,8 @@ def run_restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, gb_dept
         mFrameIndex = band[7]
         (total_color, total_color_1, total_diff_light, total_spec_light, total_diff_light_1,
          total_spec_light_1) = shard.gather_bands([t.detach() for t in band[0:6]], row0=a0)
+        if split_denoise:
+            denoise_indirect(total_color_1, total_diff_light_1, total_spec_light_1)  # at full frame, after the gather
     # `total / mFrameIndex` of all six sums (:505-515) has happened inside (normalize=True)
     combined_color_indirect = early["combined"] if split_denoise else total_diff_light_1 + total_spec_light_1
 
