@@ -552,21 +552,7 @@ def run_render(args):
         bounds = D.balanced_bounds(occ0, W, H, world, min_rows=1) if not args.uniform_bands else D.uniform_bounds(H, world)
         n_fg = int((occ0 >= 0.1).sum().item())
     shard = D.RowBandShard(W, H, rank=rank, world=world, bounds=bounds)
-    if args.emulate:
-        # diagnostics on ONE GPU: the work of rank R of W ranks, halo exchange and gather left out (images are wrong,
-        # timings are what that rank would spend outside communication) -- for timelines of a band at sizes that
-        # otherwise need W GPUs
-        r_, w_ = (int(x) for x in args.emulate.split("/"))
-        b_ = D.balanced_bounds(occ0, W, H, w_, min_rows=1)
-
-        class _Alone(D.RowBandShard):
-            def exchange(self, tensors, row0=0):
-                pass
-
-            def gather_bands(self, images, row0=0):
-                full = [torch.zeros((self.fy * self.fx, im.shape[1]), device=im.device) for im in images]
-                return full
-        shard = _Alone(W, H, rank=r_, world=w_, bounds=b_)
+    spp_full = spp
 
     def frame(vert, tri, env, pose):
         with torch.no_grad():
@@ -576,6 +562,52 @@ def run_render(args):
                                            None, None, None, None, W, H, spp, 2, 2, 2.0, 0.1, 0.001, random_offset=1234,
                                            max_bounce=mb, shard=shard, overlap=not args.no_overlap)
         return outs[0]
+
+
+    class _Alone(D.RowBandShard):  # a band without its neighbours: what a rank spends outside communication
+        def exchange(self, tensors, row0=0):
+            pass
+
+        def gather_bands(self, images, row0=0):
+            return [torch.zeros((self.fy * self.fx, im.shape[1]), device=im.device) for im in images]
+
+    if world > 1 and not args.uniform_bands and args.rebalance > 0:
+        # foreground counts do not see that some regions cast longer rays: every rank times a few iterations of ITS band
+        # alone (no exchange: the values are wrong, the cost is right), the times are all-gathered and the bands cut again
+        # into pieces of equal measured cost.  Part of the per-view setup (a few frames' worth of iterations), like the
+        # partition itself.
+        for _ in range(args.rebalance):
+            shard = _Alone(W, H, rank=rank, world=world, bounds=bounds)
+            took = {}
+            from mirres_restir_nerf_mesh_b200.graphed import CapturedStep
+            for spp in (3, 9):
+                # timed as graph replays: eager launches of a band this small are bound by the host, not by the GPU
+                cap = CapturedStep(frame, device_in, warmup=1)
+                cap.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                cap.replay()
+                cap.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                took[spp] = e0.elapsed_time(e1) / 2
+                cap.graph.reset()
+                del cap
+            # six iterations of the band; the per-frame part (LBVH, G-buffer, denoiser) is the same on every rank and drops out
+            mine = torch.tensor([took[9] - took[3]], device=dev, dtype=torch.float64)
+            allt = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allt, mine)
+            bounds = D.rebalanced_bounds(bounds, [max(float(t), 1e-3) for t in allt])
+        spp = spp_full
+        shard = D.RowBandShard(W, H, rank=rank, world=world, bounds=bounds)
+    if args.emulate:
+        # diagnostics on ONE GPU: the work of rank R of W ranks, halo exchange and gather left out (images are wrong,
+        # timings are what that rank would spend outside communication) -- for timelines of a band at sizes that
+        # otherwise need W GPUs
+        r_, w_ = (int(x) for x in args.emulate.split("/"))
+        b_ = [int(x) for x in args.emulate_bounds.split(",")] if args.emulate_bounds else D.balanced_bounds(occ0, W, H, w_, min_rows=1)
+        shard = _Alone(W, H, rank=r_, world=w_, bounds=b_)
 
     for _ in range(2):
         frame(**device_in)
@@ -796,6 +828,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--emulate", default=None, help="render mode diagnostics: R/W = time the band of rank R of W on one GPU, no communication")
+    ap.add_argument("--emulate-bounds", default=None, help="with --emulate: comma-separated band boundaries instead of the computed ones")
+    ap.add_argument("--rebalance", type=int, default=2, help="render mode, N > 1: rounds of re-cutting the bands by measured cost")
     ap.add_argument("--uniform-bands", action="store_true", help="render mode: bands of equal height instead of equal foreground")
     ap.add_argument("--no-overlap", action="store_true", help="direct and indirect chains on one stream")
     ap.add_argument("--allreduce-after", action="store_true",

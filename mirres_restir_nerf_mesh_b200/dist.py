@@ -64,6 +64,27 @@ def balanced_bounds(occ_map, framedim_x, framedim_y, world, min_rows=1, area_wei
     return bounds
 
 
+def rebalanced_bounds(bounds, seconds, min_rows=1):
+    """New boundaries from the time every rank needed for ITS band (any unit): the cost of a row is taken as constant
+    inside a band, and the rows [bounds[0], bounds[-1]) are cut again into pieces of equal cost.  Foreground counts do
+    not see that some regions cast longer rays than others; one or two rounds of this do."""
+    world = len(bounds) - 1
+    dens = []
+    for r in range(world):
+        rows = max(bounds[r + 1] - bounds[r], 1)
+        dens += [float(seconds[r]) / rows] * (bounds[r + 1] - bounds[r])
+    cum = torch.cumsum(torch.tensor(dens, dtype=torch.float64), 0)
+    total = float(cum[-1])
+    out = [bounds[0]]
+    for r in range(1, world):
+        y = bounds[0] + int(torch.searchsorted(cum, torch.tensor(total * r / world, dtype=torch.float64)).item()) + 1
+        y = max(y, out[-1] + min_rows)
+        y = min(y, bounds[-1] - (world - r) * min_rows)
+        out.append(y)
+    out.append(bounds[-1])
+    return out
+
+
 class RowBandShard:
     def __init__(self, framedim_x, framedim_y, rank=None, world=None, group=None, halo=HALO_ROWS, bounds=None):
         self.group = group
