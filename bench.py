@@ -808,8 +808,16 @@ def roofline(cfg_name, cfg, per_kernel, steps, peak, peak_kind, n_foreground=Non
     alg += 36 * c.get("nodes_per_launch", 0) + 48 * c.get("tris_per_launch", 0)
     dur = ms / count * 1e-3
     achieved = alg / dur / 1e9 if alg else None
+    # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of
+    # this command, written by tools/final_round.sh together with the commit it was taken at
+    traffic, traffic_source = c.get("dram_bytes_per_launch"), c.get("dram_bytes_source")
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_%s.json" % cfg_name)
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        if t.get("entry_point") == name:
+            traffic, traffic_source = t.get("dram_bytes_per_launch"), "%s (commit %s)" % (t.get("source"), t.get("commit"))
     return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-            "frac": (achieved / peak) if achieved else None, "traffic": c.get("dram_bytes_per_launch"),
+            "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_source,
             "launch_ms": ms / count, "launches_timed": count, "alg_bytes_per_launch": alg,
             "share_of_step": ms / steps / max(sum(v[0] for v in per_kernel.values()) / steps, 1e-9)}
 

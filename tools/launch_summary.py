@@ -6,7 +6,7 @@ import sys
 
 
 def main(path, out=None, step=None):
-    """step = k: only the launches of the k-th step of the run (a step starts at mr::k_elements, the first kernel of the
+    """step = k: only the launches of the k-th step of the run (a step starts at mr::k_build_init (round 1: mr::k_elements), the first kernel of the
     LBVH rebuild); bench.py's default run is 3 eager warm-ups, 1 capture warm-up, W graph replays, K timed replays, ..."""
     rows = list(csv.reader(open(path)))
     hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
@@ -15,7 +15,7 @@ def main(path, out=None, step=None):
     agg = collections.OrderedDict()
     body = rows[hdr + 1:]
     if step is not None:
-        starts = [i for i, r in enumerate(body) if len(r) > ki and "k_elements" in r[ki]] + [len(body)]
+        starts = [i for i, r in enumerate(body) if len(r) > ki and ("k_build_init" in r[ki] or "k_elements" in r[ki])] + [len(body)]
         body = body[starts[step]:starts[step + 1]]
         path = "%s [step %d of %d]" % (path, step, len(starts) - 1)
     for r in body:
