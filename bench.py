@@ -189,7 +189,7 @@ def _config(args, cfg):
 class ProfiledKernels:
     """Wraps Kernels: counts launches and (optionally) brackets every ABI call with CUDA events on the launching
     stream, so per-kernel device time is measured live inside the timed region."""
-    LAUNCHES = {"bvh_build": 19, "env_build_distribution": 2, "eaw_bwd": 2, "workspace_prepare": 3, "initial_resampling": 3,
+    LAUNCHES = {"bvh_build": 9, "env_build_distribution": 2, "eaw_bwd": 2, "workspace_prepare": 3, "initial_resampling": 3,
                 "spatial_resampling": 3, "final_visibility": 3, "bounce_first": 4, "bounce_shade": 4}
 
     def __init__(self, inner, torch):
