@@ -146,6 +146,8 @@ MR_DEV bool task_step(const BvhView &bvh, CTask &T, int *__restrict__ stack_ref,
                 if (t <= T.closest) T.best = leaf;
                 T.closest = fminf(t, T.closest);
                 T.any = true;
+                // (unsynchronised on purpose: a later task that reads this word while it changes sees the old or the new
+                // distance, both valid bounds for it; compute-sanitizer racecheck reports exactly this pair as a warning)
                 rec.bound[T.home] = T.closest;
                 bound = T.closest;
             } else {
