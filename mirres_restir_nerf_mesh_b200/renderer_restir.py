@@ -876,8 +876,8 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         # candidates depend on the G-buffer and the envmap alone, and final visibility / evaluation / shading only
         # consume the finished spatial reservoirs, so the three stages run on three streams:
         #     I: tiles(i) -> initial(i) -> X[i % 2]
-        #     M: temporal(X[i % 2], prev = S[(i-1) % 2]) -> spatial(X[i % 2] -> S[i % 2])          (the critical path)
-        #     S: B <- S[i % 2]; visibility(B); evaluate(B); shade; running sums
+        #     M: temporal(X[i % R], prev = S[(i-1) % 3]) -> spatial(X[i % R] -> S[i % 3])          (the critical path)
+        #     S: B <- S[i % 3]; visibility(B); evaluate(B); shade; running sums
         # B is ONE buffer shared by all iterations, so the autograd Functions keep saving aliases of buffers that later
         # iterations overwrite, exactly like the reference's two-buffer ping-pong.  Arithmetic, frame
         # indices and accumulation order are those of the sequential schedule; only the enqueue order differs.
@@ -889,7 +889,11 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         # the first iteration's candidates gate the whole reuse chain, the later ones have slack
         st_init = [_side_stream(dev, MAX_INDIRECT_CHAINS + 1 + r, -2 if r == 0 else -1) for r in range(R)]
         X = tuple(_reservoir_set(n, dev, False) for _ in range(R))  # both passes write every pixel
-        S = (_reservoir_set(n, dev, False), _reservoir_set(n, dev, False))
+        # a ring of three finished-reservoir sets: with two, spatial(i) had to wait until the shading stream had copied
+        # S(i - 2) away, and a shading stream that lags (its visibility trace shares the SMs with everything else) stalled
+        # the reuse chain for ~70 us per iteration (timeline of one band of an 8-way C5 render, profiles/README.md)
+        NS = 3
+        S = tuple(_reservoir_set(n, dev, False) for _ in range(NS))
         tiles = lighting["tiles"] if lighting is not None else [(light_data, light_uv, light_inv_pdf)] + [
             (torch.empty_like(light_data), torch.empty_like(light_uv), torch.empty_like(light_inv_pdf))
             for _ in range(R - 1)]
@@ -943,26 +947,26 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             ris_pass = 3
             with _on(main_stream):
                 if i > 0:
-                    TemporalResampling(TemporalResampling_m, X[r], S[(i - 1) % 2], env_map, width, height, framedim_x,
+                    TemporalResampling(TemporalResampling_m, X[r], S[(i - 1) % NS], env_map, width, height, framedim_x,
                                        framedim_y, base + ris_pass, occ_map, normal_depth, brdf_map, ray_dir_map,
                                        prev_occ_map, prev_normal_depth, prev_brdf_map, prev_ray_dir, motionVectors)
                     ris_pass += 1
-                if i >= 2:
-                    main_stream.wait_event(copy_done[i - 2])  # S[i % 2] was last read by the copy of iteration i - 2
+                if i >= NS:
+                    main_stream.wait_event(copy_done[i - NS])  # S[i % NS] was last read by the copy of iteration i - NS
                 with slangpy.trace_blocks(any_blocks=CRITICAL_ANY_BLOCKS), band_only():
-                    worker.SpatialResampling_(SpatialResampling_m, pos_map, S[i % 2], X[r], neighborOffsets, env_map,
+                    worker.SpatialResampling_(SpatialResampling_m, pos_map, S[i % NS], X[r], neighborOffsets, env_map,
                                               width, height, framedim_x, framedim_y, base + ris_pass, occ_map, normal_depth,
                                               brdf_map, ray_dir_map)
                 if shard is not None:
                     # row bands: the halo rows this rank reads in the next iteration (through its temporal pass) take their
                     # owners' values; the collective is ordered on the reuse chain's stream
-                    shard.exchange(S[i % 2])
+                    shard.exchange(S[i % NS])
             ris_pass += 1
             assert ris_pass == first_indirect_pass
             spatial_done[i] = ev(main_stream)
             with _on(st_s), slangpy.workspace_tag("shade"):
                 st_s.wait_event(spatial_done[i])
-                for dst_t, src_t in zip(B, S[i % 2]):
+                for dst_t, src_t in zip(B, S[i % NS]):
                     dst_t.data.copy_(src_t)  # raw overwrite, invisible to autograd like the reference's kernels
                 copy_done[i] = ev(st_s)
                 worker.EvaluateFinalSamples_get_vis(EvaluateFinalSamples_m, pos_map, B, framedim_x, framedim_y,
