@@ -440,14 +440,33 @@ def run_gpu(args):
         per_kernel, launches = pk.per_kernel_ms(), pk.launches // k_steps
 
     tms = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
-    per_rank = None
+    per_rank = per_rank_alone = None
     if world > 1:
-        # every rank's own time beside the maximum: the ranks render different views, so imbalance between views and the
-        # cost of the collective can be told apart
+        # every rank's own time beside the maximum.  The in-step all-reduce makes the ranks wait for one another, so these
+        # come out equal; what tells the imbalance between views from the cost of the collective is the second set: the
+        # same step WITHOUT the collective, every rank for itself (outside the reported timing)
         allt = [torch.empty_like(tms) for _ in range(world)]
         dist.all_gather(allt, tms)
         per_rank = [[round(float(t[0]) / args.steps, 4), round(float(t[1]) / args.steps, 4)] for t in allt]
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        if in_step and captured is not None:
+            alone = CapturedStep(full_step, device_in, warmup=1)  # collective_in_step is off by now: no NCCL in this graph
+            alone.replay()
+            t_alone = 0.0
+            for _ in range(max(args.steps // 2, 3)):
+                flush.fill_(1.0)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                alone.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                t_alone += e0.elapsed_time(e1)
+            mine = torch.tensor([t_alone / max(args.steps // 2, 3)], device=dev, dtype=torch.float64)
+            alla = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(alla, mine)
+            per_rank_alone = [round(float(t), 4) for t in alla]
+            alone.graph.reset()
     ms_dev, ms_e2e = float(tms[0]), float(tms[1])
     samples = n * spp * world * args.steps
     value = samples / (ms_dev * 1e-3)
@@ -488,6 +507,8 @@ def run_gpu(args):
                 "kernel_ms_per_step": {k: round(v[0] / 2, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])}}
         if per_rank is not None:
             line["per_rank_ms_per_step"] = {"device": [t[0] for t in per_rank], "e2e": [t[1] for t in per_rank]}
+            if per_rank_alone is not None:
+                line["per_rank_ms_per_step"]["device_without_collective"] = per_rank_alone
         if world == 1 and not args.no_cpu_baseline:
             crop = cfg["W"]
             s, dt, _ = oracle_sample(args.config, crop, spp)

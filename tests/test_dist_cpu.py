@@ -126,3 +126,28 @@ def test_temporal_pass_on_a_row_slice_rounds_like_the_full_frame():
             assert torch.equal(f, b_)
     finally:
         slangpy_shim.set_kernels(None)
+
+
+@pytest.mark.parametrize("world,balanced", [(2, False), (3, True)])
+def test_bands_as_threads_of_one_process(world, balanced):
+    """The virtual ranks as host threads (tests/band_threads.py) over the host-check kernels: per-thread workspaces and launch
+    context, slices, row offset and band words; same bit-identity as the multi-process runs."""
+    import band_threads as BT
+    import hostcheck as H
+    import parity as P
+    from mirres_restir_nerf_mesh_b200 import dist as D, slangpy_shim
+    H.activate()
+    try:
+        sc = P.scene("T2", 0.4)
+        w = H.OracleBvhWorker(H.t(sc["vert"]), H.t(sc["tri"]))
+        w.update_mesh(H.t(sc["vert"]), H.t(sc["tri"]))
+        want = BT.render(sc, w, "cpu")
+        bounds = D.balanced_bounds(torch.from_numpy(sc["gbuffer"]["occ_map"]), sc["W"], sc["H"], world) if balanced \
+            else D.uniform_bounds(sc["H"], world)
+        outs, errors = BT.render_in_threads(sc, w, "cpu", world, bounds)
+        assert not errors, errors
+        for r in range(world):
+            for a, b in zip(outs[r], want):
+                assert torch.equal(a, b) or bool(((a == b) | (a.isnan() & b.isnan())).all())
+    finally:
+        slangpy_shim.set_kernels(None)

@@ -167,3 +167,26 @@ def test_normal_ao_gpu(kernels, oracle):
     ao = torch.full((n, 3), 7.0, device=DEV)
     kernels.normal_ao(sc["W"], sc["H"], torch.zeros(n, 1, device=DEV), tt(g["normal_map"]), ao)
     assert np.array_equal(ao.cpu().numpy(), oracle.normal_ao(sc["W"], sc["H"], np.zeros((n, 1), np.float32), g["normal_map"]))
+
+
+@pytest.mark.parametrize("name,world,balanced,spp", [("T2", 2, False, 3), ("T2", 3, True, 5), ("C1", 4, True, 3)])
+def test_row_bands_on_one_gpu_are_bit_identical(kernels, name, world, balanced, spp):
+    """Row-band rendering with the ranks as host threads on cuda:0 (tests/band_threads.py): every virtual rank
+    runs the spp loop on the slice of the maps that holds its band and halo, on its own stream, with the concurrent schedule;
+    halo rows and the final gather are tensor copies behind a barrier.  All six outputs must equal the single render bit for
+    bit -- row offset of the random streams, jittered row of temporal reuse, band words of the spatial pass, alive lists
+    and split tracers on band-sized queues, and two host threads driving the library at once."""
+    import band_threads as BT
+    from mirres_restir_nerf_mesh_b200 import dist as D
+    sc = P.scene(name, 0.3)
+    w = make_worker(sc)
+    want = BT.render(sc, w, DEV, spp=spp)
+    torch.cuda.synchronize()
+    occ = tt(sc["gbuffer"]["occ_map"])
+    bounds = D.balanced_bounds(occ, sc["W"], sc["H"], world) if balanced else D.uniform_bounds(sc["H"], world)
+    outs, errors = BT.render_in_threads(sc, w, DEV, world, bounds, spp=spp)
+    torch.cuda.synchronize()
+    assert not errors, errors
+    for r in range(world):
+        for a, b in zip(outs[r], want):
+            assert torch.equal(a, b), (r, (a != b).sum().item())
