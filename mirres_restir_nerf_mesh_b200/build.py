@@ -19,7 +19,7 @@ HOSTCHECK_LIB = os.path.join(HERE, "..", "tests", "_build", "libmirres_hostcheck
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-          "-ccbin", "/usr/bin/g++"]
+          "-ccbin", "/usr/bin/g++"] + os.environ.get("MIRRES_NVCC_DEFINES", "").split()  # -D... for tuning experiments only
 
 
 def _stale(target, deps):

@@ -226,7 +226,9 @@ __global__ void __launch_bounds__(256) k_morton_hist(const float *__restrict__ v
 #define RS_PASSES 3
 #define RS_THREADS 512
 #define RS_WARPS (RS_THREADS / 32)
+#ifndef RS_ROUNDS
 #define RS_ROUNDS 8
+#endif
 #define RS_TILE (RS_THREADS * RS_ROUNDS) // 4096 keys
 #define RS_FLAG 0x80000000u
 

@@ -114,7 +114,9 @@ __global__ void __launch_bounds__(CP_BLOCK) k_compact_write(const float *__restr
 // Warps pull rays from a dense queue with one atomic per refill; a lane whose ray terminates (first hit, or stack empty)
 // is refilled at the next check point, so the SIMD lanes stay busy although path lengths vary by > 10x.
 #define MR_TRACE_BLOCK 256
+#ifndef MR_TRACE_STEPS
 #define MR_TRACE_STEPS 6
+#endif
 #define MR_TRACE_STEPS_SHARED 4
 #define MR_SPLIT_ROUNDS 4
 #define MR_TRACE_STEPS_SPLIT 3

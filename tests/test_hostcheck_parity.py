@@ -256,3 +256,31 @@ def test_cross_bilateral_denoiser(oracle):
                                    random_offset=5)
     outs[0].sum().backward()
     assert all(torch.isfinite(o).all() for o in outs) and kd.grad.abs().sum() > 0
+
+
+def test_path_kernels_without_alive_lists_give_the_same_images():
+    """The path kernels walk the list of paths that are still alive when the workspace carries the signature of the
+    call sequence, and all foreground pixels (with the reference's stop-flag test) otherwise.  Both must give the same
+    result: the driver's normal run against a run whose kernels wipe the signature before every shaded vertex."""
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim
+    sc = P.scene("T2", 0.4)
+    ref = P.oracle_run(sc, max_bounce=3)
+    got = P.product_run(sc, _worker(sc), "cpu", ref["prepared"], max_bounce=3)
+    assert P.compare(ref, got) == []
+
+    class NoLists(H.HostKernels):
+        wiped = 0
+
+        def bounce_shade(self, *a, **kw):
+            ws = kw["ws"] if "ws" in kw else a[-1]  # the workspace is the last argument of Kernels.bounce_shade
+            ws[72:80].view(torch.int32).zero_()  # MR_CTR_ALIVE_SIG words: a foreign signature -> fallback to all foreground pixels
+            NoLists.wiped += 1
+            return super().bounce_shade(*a, **kw)
+
+    slangpy_shim.set_kernels(NoLists())
+    try:
+        got2 = P.product_run(sc, _worker(sc), "cpu", ref["prepared"], max_bounce=3)
+    finally:
+        H.activate()
+    assert NoLists.wiped == sc["cfg"]["spp"] * 3
+    assert P.compare(ref, got2) == []
