@@ -445,6 +445,11 @@ __global__ void __launch_bounds__(1024) k_leaves(int F, const unsigned int *__re
 {
     __shared__ float4 s_lo[64], s_hi[64];
     __shared__ unsigned int s_last;
+    // the block's leaf records are two contiguous pieces of the output (1024 x 12 bytes of info, 1024 x 24 bytes of boxes):
+    // they are staged here and written out as one coalesced stream each instead of nine strided 4-byte stores per thread
+    // (ncu: the kernel was throttled by its store queue)
+    __shared__ int s_info[1024 * 3];
+    __shared__ float s_box[1024 * 6];
     const int gid = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     Box6 b;
     box_empty(b);
@@ -457,12 +462,11 @@ __global__ void __launch_bounds__(1024) k_leaves(int F, const unsigned int *__re
         } else {
             tri_box(vert, tri, e, lo, hi);
         }
-        const size_t nd = (size_t)(F - 1 + gid);
-        info[3 * nd] = 0; info[3 * nd + 1] = 0; info[3 * nd + 2] = e;
+        s_info[3 * threadIdx.x] = 0; s_info[3 * threadIdx.x + 1] = 0; s_info[3 * threadIdx.x + 2] = e;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { aabb[6 * nd + k] = lo[k]; aabb[6 * nd + 3 + k] = hi[k]; b.mn[k] = lo[k]; b.mx[k] = hi[k]; }
+        for (int k = 0; k < 3; ++k) { s_box[6 * threadIdx.x + k] = lo[k]; s_box[6 * threadIdx.x + 3 + k] = hi[k]; b.mn[k] = lo[k]; b.mx[k] = hi[k]; }
         box_store(tb.lv[0] + 2 * (size_t)gid, b);
-        if (sorted_pairs) { sorted_pairs[2 * (size_t)gid] = (int)__ldg(codes + gid); sorted_pairs[2 * (size_t)gid + 1] = e; }
+        if (sorted_pairs) *reinterpret_cast<int2 *>(sorted_pairs + 2 * (size_t)gid) = make_int2((int)__ldg(codes + gid), e);
         if (ptris) {
             const int i0 = __ldg(tri + 3 * (size_t)e), i1 = __ldg(tri + 3 * (size_t)e + 1), i2 = __ldg(tri + 3 * (size_t)e + 2);
             const float3 v0 = load3(vert, (size_t)i0), v1 = load3(vert, (size_t)i1), v2 = load3(vert, (size_t)i2);
@@ -473,6 +477,14 @@ __global__ void __launch_bounds__(1024) k_leaves(int F, const unsigned int *__re
             q[2] = make_float4(e2.x, e2.y, e2.z, 0.f);
             q[3] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    }
+    __syncthreads();
+    {
+        const int first = blockIdx.x * 1024, count = min(1024, F - first);
+        int *gi = info + 3 * (size_t)(F - 1 + first);
+        float *gb = aabb + 6 * (size_t)(F - 1 + first);
+        for (int k = threadIdx.x; k < 3 * count; k += 1024) gi[k] = s_info[k];
+        for (int k = threadIdx.x; k < 6 * count; k += 1024) gb[k] = s_box[k];
     }
     // groups of 4 and 16 inside the warp (a butterfly step k leaves every lane with the union of its aligned 2^k group)
     box_xor_step(b, 1);
