@@ -13,8 +13,10 @@ a rank therefore runs
 and after every spatial pass it receives the 31 rows above and below its band from the ranks that own them -- 24 bytes
 per pixel, 0.6 MB per boundary at 800 px width -- point to point, nothing else travels inside the loop.
 (Recomputing the halo locally is not enough: temporal reuse makes the dependency cone grow by 30 px per iteration.)
-RNG streams are keyed on global pixel coordinates and the maps stay full-frame (only the lists of processed pixels are
-restricted), so every reservoir a rank computes or receives is bit-identical to the single-GPU one.  After the loop the
+The `[N, k]` maps are row-major, so the rows a rank touches are one contiguous slice of every tensor: the spp loop runs
+on the slices as on a frame of their own, and the workspace's row-offset word keeps the random streams (keyed on pixel
+coordinates) those of the full frame, so every reservoir a rank computes or receives is bit-identical to the single-GPU
+one.  After the loop the
 six accumulated images of the bands are all-gathered and denoised / composited at full frame on every rank, exactly as
 on one GPU.  The BVH, the envmap distribution and the light tiles are rebuilt identically on every rank.
 
