@@ -151,3 +151,32 @@ def test_bands_as_threads_of_one_process(world, balanced):
                 assert torch.equal(a, b) or bool(((a == b) | (a.isnan() & b.isnan())).all())
     finally:
         slangpy_shim.set_kernels(None)
+
+
+def test_band_boundaries():
+    """balanced_bounds / rebalanced_bounds / RowBandShard plans on a synthetic occupancy: equal cost per band, rows of pure
+    background outside every band, point-to-point plans symmetric (what a rank sends is what its peer expects)."""
+    from mirres_restir_nerf_mesh_b200 import dist as D
+    fx, fy = 64, 200
+    occ = torch.zeros(fy, fx)
+    occ[40:160, 10:50] = 1.0
+    occ[90:110, :] = 1.0  # a dense stripe: bands must get thinner there
+    b = D.balanced_bounds(occ.reshape(-1, 1), fx, fy, 4)
+    assert b[0] == 40 and b[-1] == 160 and all(y1 > y0 for y0, y1 in zip(b, b[1:]))
+    cost = lambda y0, y1: float(occ[y0:y1].sum()) + D.AREA_WEIGHT * fx * (y1 - y0)
+    costs = [cost(y0, y1) for y0, y1 in zip(b, b[1:])]
+    assert max(costs) < 1.15 * sum(costs) / 4
+    assert min(y1 - y0 for y0, y1 in zip(b, b[1:])) < max(y1 - y0 for y0, y1 in zip(b, b[1:]))
+    assert D.balanced_bounds(occ.reshape(-1, 1), fx, fy, 4, clip=False)[0] == 0
+    assert D.balanced_bounds(torch.zeros(fy * fx, 1), fx, fy, 4) == D.uniform_bounds(fy, 4)
+    # measured cost says band 0 is twice as expensive per row: it must shrink, the total range must stay
+    r = D.rebalanced_bounds(b, [2.0, 1.0, 1.0, 1.0])
+    assert r[0] == b[0] and r[-1] == b[-1] and r[1] - r[0] < b[1] - b[0]
+    shards = [D.RowBandShard(fx, fy, rank=q, world=4, bounds=b) for q in range(4)]
+    for s in shards:
+        assert s.first_row <= s.active[0] <= s.wide[0] <= s.rows[0] and s.rows[1] <= s.wide[1] <= s.active[1] <= s.last_row
+        for q, rows in s.send_plan:
+            assert (s.rank, rows) in shards[q].recv_plan
+        for q, rows in s.recv_plan:
+            assert (s.rank, rows) in shards[q].send_plan
+        assert s.halo_bytes() == sum(y1 - y0 for _, (y0, y1) in s.recv_plan) * fx * 24
