@@ -450,6 +450,7 @@ def run_gpu(args):
         per_rank = [[round(float(t[0]) / args.steps, 4), round(float(t[1]) / args.steps, 4)] for t in allt]
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         if in_step and captured is not None:
+            opts["overlap"] = not args.no_overlap  # (the per-kernel pass above had serialised the chains)
             alone = CapturedStep(full_step, device_in, warmup=1)  # collective_in_step is off by now: no NCCL in this graph
             alone.replay()
             t_alone = 0.0
