@@ -138,6 +138,14 @@ MR_DEV float ris_brdf(const RisSurface &s, float3 L)
     const float INV_PI = 0.31830988f;
     const float NdotV = s.NdotV;
     float NdotL = saturate(dot(s.N, L));
+    if (s.ks_w < 1e-8f) {
+        // No specular weight (the reference's default material, --me_max 0): F is the constant 0 below, so the specular
+        // term is max(0, D G 0 / (4 N.V)) = +0 whatever D and G are (both finite and non-negative for alpha >= 1e-4; a
+        // 0 / 0 at N.V = 0 is a NaN that max() drops), and the result is the lerp of +0 and the diffuse term: the same
+        // bits without the half vector, the NDF and the shadowing term (a quarter of a candidate's instructions).
+        const float diffuse0 = NdotL * INV_PI;
+        return NdotL > 0.f ? lerpf(0.f, diffuse0, s.mix) : 0.f;
+    }
     float3 H = normalize(s.V + L);
     float NdotH = saturate(dot(s.N, H));
     float LdotH = saturate(dot(L, H));
