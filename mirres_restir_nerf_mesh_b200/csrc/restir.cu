@@ -343,15 +343,32 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
         if (ok[k]) ok[k] = !(nocc[k] < 0.1f);
         ok[k] = ok[k] && band;
     }
+    // A visibility only ever MULTIPLIES a target density in the resolve pass (candAtCur *= vis(own surface -> neighbour's
+    // light), canonAtNb *= vis(neighbour's surface -> own light), SpatialResampling.slang:262-284), and that density is
+    // max(0, lum * brdf) with brdf = 0 unless N.L > 0.  A ray whose light lies at or below the horizon of the surface
+    // it starts from therefore multiplies +0: it is not cast, its slot reads "unoccluded", the product is the same +0.
+    bool cast0[MR_MAX_NEIGHBORS], cast1[MR_MAX_NEIGHBORS];
+    float3 nLk[MR_MAX_NEIGHBORS];
+#pragma unroll
+    for (uint32_t k = 0; k < MR_MAX_NEIGHBORS; ++k) {
+        nLk[k] = f3(0.f);
+        cast0[k] = cast1[k] = false;
+        if (ok[k]) {
+            nLk[k] = oct_decode(nld[k].y, nld[k].z);
+            cast0[k] = dot(N, nLk[k]) > 0.f;
+            cast1[k] = dot(make_float3(nnd[k].x, nnd[k].y, nnd[k].z), cL) > 0.f;
+        }
+    }
 #if defined(__CUDA_ARCH__)
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    unsigned int okm[MR_MAX_NEIGHBORS];
+    unsigned int m0[MR_MAX_NEIGHBORS], m1[MR_MAX_NEIGHBORS];
     int total = 0;
 #pragma unroll
     for (uint32_t k = 0; k < MR_MAX_NEIGHBORS; ++k) {
-        okm[k] = __ballot_sync(act, ok[k]);
-        total += 2 * __popc(okm[k]);
+        m0[k] = __ballot_sync(act, cast0[k]);
+        m1[k] = __ballot_sync(act, cast1[k]);
+        total += __popc(m0[k]) + __popc(m1[k]);
     }
     int q0 = 0;
     const int leader = __ffs(act) - 1;
@@ -360,25 +377,25 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
 #pragma unroll
     for (uint32_t k = 0; k < MR_MAX_NEIGHBORS; ++k) {
         if (k < p.neighbor_count) {
-            const int cnt = __popc(okm[k]);
             if (ok[k]) {
-                const int rank = __popc(okm[k] & lt_mask);
-                const float3 nL = oct_decode(nld[k].y, nld[k].z);
-                queue_ray_at(p.ws, q0 + rank, base + 2 * k, cur_pos + VIS_NEAR * nL, nL);
-                queue_ray_at(p.ws, q0 + cnt + rank, base + 2 * k + 1, npos[k] + VIS_NEAR * cL, cL);
+                if (cast0[k]) queue_ray_at(p.ws, q0 + __popc(m0[k] & lt_mask), base + 2 * k, cur_pos + VIS_NEAR * nLk[k], nLk[k]);
+                else p.ws.hit[base + 2 * k] = MR_HIT_MISS;
+                if (cast1[k]) queue_ray_at(p.ws, q0 + __popc(m0[k]) + __popc(m1[k] & lt_mask), base + 2 * k + 1, npos[k] + VIS_NEAR * cL, cL);
+                else p.ws.hit[base + 2 * k + 1] = MR_HIT_MISS;
             } else {
                 queue_empty(p.ws, base + 2 * k);
                 queue_empty(p.ws, base + 2 * k + 1);
             }
-            q0 += 2 * cnt;
+            q0 += __popc(m0[k]) + __popc(m1[k]);
         }
     }
 #else
     for (uint32_t k = 0; k < p.neighbor_count; ++k) {
         if (ok[k]) {
-            const float3 nL = oct_decode(nld[k].y, nld[k].z);
-            queue_ray(p.ws, base + 2 * k, cur_pos + VIS_NEAR * nL, nL);
-            queue_ray(p.ws, base + 2 * k + 1, npos[k] + VIS_NEAR * cL, cL);
+            if (cast0[k]) queue_ray(p.ws, base + 2 * k, cur_pos + VIS_NEAR * nLk[k], nLk[k]);
+            else p.ws.hit[base + 2 * k] = MR_HIT_MISS;
+            if (cast1[k]) queue_ray(p.ws, base + 2 * k + 1, npos[k] + VIS_NEAR * cL, cL);
+            else p.ws.hit[base + 2 * k + 1] = MR_HIT_MISS;
         } else {
             queue_empty(p.ws, base + 2 * k);
             queue_empty(p.ws, base + 2 * k + 1);
