@@ -300,7 +300,7 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
     bool ok[MR_MAX_NEIGHBORS];
     float4 nnd[MR_MAX_NEIGHBORS];
     int nM[MR_MAX_NEIGHBORS];
-    float nocc[MR_MAX_NEIGHBORS];
+    float nocc[MR_MAX_NEIGHBORS], nw[MR_MAX_NEIGHBORS];
     float3 nld[MR_MAX_NEIGHBORS], npos[MR_MAX_NEIGHBORS];
 #pragma unroll
     for (uint32_t k = 0; k < MR_MAX_NEIGHBORS; ++k) {
@@ -311,11 +311,12 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
     for (uint32_t k = 0; k < MR_MAX_NEIGHBORS; ++k) {
         nnd[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         nM[k] = 0;
-        nocc[k] = 0.f;
+        nocc[k] = nw[k] = 0.f;
         nld[k] = npos[k] = f3(0.f);
         if (ok[k]) {
             nnd[k] = load_nd(p.g.normal_depth, nb[k]);
             nM[k] = MR_LDG(p.prev.M + nb[k]);
+            nw[k] = MR_LDG(p.prev.w + nb[k]);
             nocc[k] = MR_LDG(p.g.occ + nb[k]);
             nld[k] = load3(p.prev.ld, nb[k]);
             npos[k] = load3(p.pos_map, nb[k]);
@@ -347,6 +348,13 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
     // light), canonAtNb *= vis(neighbour's surface -> own light), SpatialResampling.slang:262-284), and that density is
     // max(0, lum * brdf) with brdf = 0 unless N.L > 0.  A ray whose light lies at or below the horizon of the surface
     // it starts from therefore multiplies +0: it is not cast, its slot reads "unoccluded", the product is the same +0.
+    // Likewise the products only reach the result through weights that carry the reservoir weight W as a factor:
+    //   candAtCur  -> sampleWeight = candAtCur * W_neighbour * m0   (and m_factor, which feeds st.M, overwritten at the end)
+    //   canonAtNb  -> m1 -> canonical sample weight = p-hat * W_own * canonicalWeight
+    // A reservoir whose sample was found occluded carries W = 0 exactly (InitialResampling.slang:258-270), the weight is
+    // then +0 for either visibility and a zero weight is never selected (u * wSum < 0 is false): the ray towards a
+    // neighbour's dead sample and, for a pixel whose own sample is dead, all rays towards its own light are not cast.
+    const float cur_w = MR_LDG(p.prev.w + i);
     bool cast0[MR_MAX_NEIGHBORS], cast1[MR_MAX_NEIGHBORS];
     float3 nLk[MR_MAX_NEIGHBORS];
 #pragma unroll
@@ -355,8 +363,8 @@ MR_DEV void spatial_gen_px(const SpatialParams &p, int a)
         cast0[k] = cast1[k] = false;
         if (ok[k]) {
             nLk[k] = oct_decode(nld[k].y, nld[k].z);
-            cast0[k] = dot(N, nLk[k]) > 0.f;
-            cast1[k] = dot(make_float3(nnd[k].x, nnd[k].y, nnd[k].z), cL) > 0.f;
+            cast0[k] = dot(N, nLk[k]) > 0.f && nw[k] != 0.f;
+            cast1[k] = dot(make_float3(nnd[k].x, nnd[k].y, nnd[k].z), cL) > 0.f && cur_w != 0.f;
         }
     }
 #if defined(__CUDA_ARCH__)
