@@ -484,7 +484,7 @@ def run_gpu(args):
         pk.gbuffer_primary(worker.packed, ro_c, rd_c, occ_c, pos_c, nrm_c, depth_c, ws=slangpy_shim.workspace(dev, n))
         n_fg = int((occ_c >= 0.1).sum().item())
         roof = roofline(args.config, cfg, per_kernel, 2, peak, "measured" if peaks else "fallback", n_fg)
-        step_alg_all, step_alg = step_algorithmic_bytes(args.config, cfg, spp, n_fg)
+        step_alg_all, step_alg, step_alg_ref = step_algorithmic_bytes(args.config, cfg, spp, n_fg)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -504,7 +504,9 @@ def run_gpu(args):
                     "peak": peak, "unit": "GB/s", "frac": step_alg / (ms_dev / args.steps * 1e-3) / 1e9 / peak,
                     "foreground_pixels": n_fg, "frame_pixels": n,
                     "alg_bytes_per_step_all_pixels": step_alg_all,
-                    "frac_all_pixels": step_alg_all / (ms_dev / args.steps * 1e-3) / 1e9 / peak},
+                    "frac_all_pixels": step_alg_all / (ms_dev / args.steps * 1e-3) / 1e9 / peak,
+                    # traversal bytes of ALL the reference's rays, including those the product proves dead and skips
+                    "frac_reference_rays": step_alg_ref / (ms_dev / args.steps * 1e-3) / 1e9 / peak},
                 "kernel_ms_per_step": {k: round(v[0] / 2, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])}}
         if per_rank is not None:
             line["per_rank_ms_per_step"] = {"device": [t[0] for t in per_rank], "e2e": [t[1] for t in per_rank]}
@@ -773,17 +775,20 @@ def step_algorithmic_bytes(cfg_name, cfg, spp, n_foreground=None):
     traversal term is the oracle's exact node / triangle count and is the same in both."""
     path = os.path.join(ROOT, "profiles", "oracle_counters_%s.json" % cfg_name)
     if not os.path.exists(path):
-        return None, None
+        return None, None, None
     c = json.load(open(path))
     n = cfg["W"] * cfg["H"]
-    trav = c["per_sample"]["B_alg_traversal_bytes"] * n * spp
+    # rays whose result cannot reach the output (tools/oracle_counters.py: "dead product" rays of the spatial pass) are
+    # not cast by the product and are not charged
+    trav = c["per_sample"].get("B_alg_traversal_bytes_cast", c["per_sample"]["B_alg_traversal_bytes"]) * n * spp
     per_px = 872 + 1040 * (spp - 1) + 280 * spp
     build = 424 * c["triangles"]
     if n_foreground is None:
         n_foreground = int(round(c.get("hit_fraction", 1.0) * n))
     stages = (9 + 2) * spp + (spp - 1)  # 9 forward stage entries (+ temporal for i > 0) + 2 backward per iteration
     fg = n_foreground * per_px + (n - n_foreground) * 4 * stages
-    return trav + n * per_px + build, trav + fg + build
+    trav_ref = c["per_sample"]["B_alg_traversal_bytes"] * n * spp
+    return trav + n * per_px + build, trav + fg + build, trav_ref + fg + build
 
 
 def _timeline(torch, step, path):
@@ -827,7 +832,12 @@ def roofline(cfg_name, cfg, per_kernel, steps, peak, peak_kind, n_foreground=Non
         alg = screen * n_foreground + 4 * (n - n_foreground)
     else:
         alg = screen * n
-    alg += 36 * c.get("nodes_per_launch", 0) + 48 * c.get("tris_per_launch", 0)
+    screen_bytes = alg
+    # node pops and triangle tests of the rays the product CASTS (the oracle's count without the reference's rays whose
+    # result cannot reach the output, see tools/oracle_counters.py); the same figure over all the reference's rays is
+    # reported beside it as frac_reference_rays
+    alg += 36 * c.get("cast_nodes_per_launch", c.get("nodes_per_launch", 0)) + 48 * c.get("cast_tris_per_launch", c.get("tris_per_launch", 0))
+    alg_ref = screen_bytes + 36 * c.get("nodes_per_launch", 0) + 48 * c.get("tris_per_launch", 0)
     dur = ms / count * 1e-3
     achieved = alg / dur / 1e9 if alg else None
     # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of
@@ -841,6 +851,7 @@ def roofline(cfg_name, cfg, per_kernel, steps, peak, peak_kind, n_foreground=Non
     return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_source,
             "launch_ms": ms / count, "launches_timed": count, "alg_bytes_per_launch": alg,
+            "frac_reference_rays": alg_ref / dur / 1e9 / peak if alg_ref else None,
             "share_of_step": ms / steps / max(sum(v[0] for v in per_kernel.values()) / steps, 1e-9)}
 
 

@@ -89,7 +89,7 @@ def threads_in_use():
 
 
 def new_counters():
-    return np.zeros(9, dtype=np.int64)
+    return np.zeros(12, dtype=np.int64)
 
 
 def fpmath(op, x, y=None):

@@ -123,7 +123,11 @@ void merge_counters(long long *dst, const TraceCounters &a, const TraceCounters 
 extern "C" {
 
 // counters (optional, accumulated): [0..3] shadow rays nodes_ref,tris_ref,nodes_any,tris_any;
-// [4..5] closest rays nodes,tris; [6] max stack; [7] #shadow rays; [8] #closest rays.
+// [4..5] closest rays nodes,tris; [6] max stack; [7] #shadow rays; [8] #closest rays;
+// [9..11] (spatial pass only) nodes_any, tris_any, #rays of the shadow rays whose result cannot reach the output: the
+// visibility multiplies a target density that is +0 because the light is not above the horizon of the surface the ray
+// leaves, or only feeds a weight that has the W = 0 of a dead reservoir as a factor.  They are part of [0..3] / [7];
+// bench.py subtracts them when it charges the product (which does not cast them) with algorithmic bytes.
 
 // InitialResampling.slang:151-295
 int orc_initial_resampling(const int *info, const float *aabb, const float *vert, const int *tri, const float *pos_map,
@@ -280,8 +284,8 @@ int orc_spatial_resampling(const int *info, const float *aabb, const float *vert
     const uint32_t mask = (uint32_t)offset_count - 1;
 #pragma omp parallel
     {
-        TraceCounters tcs = {0, 0, 0, 0, 0}, tcc = {0, 0, 0, 0, 0};
-        long long nrays = 0;
+        TraceCounters tcs = {0, 0, 0, 0, 0}, tcc = {0, 0, 0, 0, 0}, tcd = {0, 0, 0, 0, 0};
+        long long nrays = 0, ndead = 0;
 #pragma omp for schedule(dynamic, 256)
         for (int idx = 0; idx < fx * fy; ++idx) {
             const uint32_t px = (uint32_t)(idx % fx), py = (uint32_t)(idx / fx);
@@ -320,8 +324,10 @@ int orc_spatial_resampling(const int *info, const float *aabb, const float *vert
                 get_light_info(e, mk2(nr.light_data.y, nr.light_data.z), nLe, nL);
                 f3 neighbor_pos = ld3(pos_map, nidx);
                 nrays += 2;
-                bool canonical_hit = shadow_ray(b, curr_pos, nL, &tcs);
-                bool candidate_hit = shadow_ray(b, neighbor_pos, cL, &tcs);
+                const bool dead0 = !(dot(N, nL) > 0.f) || nr.weight == 0.f, dead1 = !(dot(nN, cL) > 0.f) || cur.weight == 0.f;
+                ndead += (dead0 ? 1 : 0) + (dead1 ? 1 : 0);
+                bool canonical_hit = shadow_ray(b, curr_pos, nL, dead0 ? &tcd : &tcs);
+                bool candidate_hit = shadow_ray(b, neighbor_pos, cL, dead1 ? &tcd : &tcs);
                 float candidateVisibility = candidate_hit ? 0.f : 1.0f;
                 float canonicalVisibility = canonical_hit ? 0.f : 1.0f;
                 // streamingResampleStepMisUnbiased res.slang:173-213
@@ -355,9 +361,16 @@ int orc_spatial_resampling(const int *info, const float *aabb, const float *vert
             store_res(R, i, st);
         }
         merge_counters(counters, tcs, tcc);
+        merge_counters(counters, tcd, TraceCounters{0, 0, 0, 0, 0});
         if (counters) {
 #pragma omp atomic
             counters[7] += nrays;
+#pragma omp atomic
+            counters[9] += tcd.nodes_any;
+#pragma omp atomic
+            counters[10] += tcd.tris_any;
+#pragma omp atomic
+            counters[11] += ndead;
         }
     }
     return 0;

@@ -38,7 +38,7 @@ def main(name):
     out = {"config": name, "frame": [W, H], "spp_measured": spp, "triangles": int(f.shape[0]), "hit_fraction": float(hit.mean()),
            "oracle_seconds": dt, "max_stack_depth": int(max(c[6] for c in per.values())),
            "primary_rays": {"nodes_per_ray": prim_ctr[0] / len(ro), "tris_per_ray": prim_ctr[1] / len(ro)}}
-    tot_n = tot_t = tot_rays = 0
+    tot_n = tot_t = tot_rays = dead_n = dead_t = dead_rays = 0
     for k, c in per.items():
         L = launches[k]
         # contract: shadow rays counted with first-hit exit (c[2], c[3]); closest rays under the reference DFS (c[4], c[5])
@@ -47,12 +47,22 @@ def main(name):
                   "nodes_per_launch": nodes / L, "tris_per_launch": tris / L,
                   "reference_schedule_nodes_per_launch": int(c[0] + c[4]) / L,
                   "reference_schedule_tris_per_launch": int(c[1] + c[5]) / L}
+        # rays of the reference whose result cannot reach the output (oracle/orc_kernels.cpp, counters 9..11); the product
+        # does not cast them, so the figures bench.py charges IT with leave them out
+        out[k]["dead_product_rays_per_launch"] = c[11] / L
+        out[k]["cast_nodes_per_launch"] = (nodes - int(c[9])) / L
+        out[k]["cast_tris_per_launch"] = (tris - int(c[10])) / L
         tot_n += nodes
         tot_t += tris
         tot_rays += int(c[7] + c[8])
+        dead_n += int(c[9])
+        dead_t += int(c[10])
+        dead_rays += int(c[11])
     samples = W * H * spp
     out["per_sample"] = {"rays": tot_rays / samples, "V_n": tot_n / samples, "V_t": tot_t / samples,
-                         "B_alg_traversal_bytes": (36 * tot_n + 48 * tot_t) / samples}
+                         "B_alg_traversal_bytes": (36 * tot_n + 48 * tot_t) / samples,
+                         "rays_cast": (tot_rays - dead_rays) / samples,
+                         "B_alg_traversal_bytes_cast": (36 * (tot_n - dead_n) + 48 * (tot_t - dead_t)) / samples}
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     path = os.path.join(ROOT, "profiles", "oracle_counters_%s.json" % name)
     json.dump(out, open(path, "w"), indent=1)
