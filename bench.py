@@ -284,26 +284,30 @@ def run_gpu(args):
     target = torch.full((n, 3), 0.5, device=dev)
     flat_grad = torch.zeros(ne + V * 3 + V * 5, device=dev)  # env | vertex-normal | vertex-texture (kd, rough, metal)
     opts = dict(overlap=not args.no_overlap)
-    bvh_stream = torch.cuda.Stream()
+    bvh_stream, light_stream = torch.cuda.Stream(), torch.cuda.Stream()
 
     def full_step(vert, env, pose, tri=tri_dev):
         """One stage-1 training step of one view: LBVH rebuild (nerf/renderer.py:975), camera rays, G-buffer, ReSTIR +
         path tracer, denoise + composite, loss, backward into env / normals / kd / ks, scatter to vertices and vertex
         texture."""
-        # the LBVH rebuild runs beside everything that does not need it: camera rays, the environment distribution and
-        # the light tiles of the spp loop
+        # three independent preambles side by side: the LBVH rebuild; the camera rays (a chain of ~20 small torch kernels,
+        # 180 us -- with the lighting behind them on one stream they, not the rebuild, decided when the primary rays
+        # could start, profiles/r8z_timeline_graph_replay.txt); the environment distribution + the light tiles of the
+        # first spp iterations, which nothing needs before the spp loop
         cur = torch.cuda.current_stream()
         flat_grad.zero_()  # early: the fill has left the serial tail of the step by the time the scatters need it
         bvh_stream.wait_stream(cur)
+        light_stream.wait_stream(cur)
         with torch.cuda.stream(bvh_stream):
             worker.update_mesh(vert, tri)
+        with torch.cuda.stream(light_stream):
+            env_l = env.detach().clone().requires_grad_(True)
+            lighting = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env_l, spp, 1234 + 17 * rank,
+                                          frame_pixels=n)
         rays_o, rays_d = synth.camera_rays_torch(W, H, pose)
         if args.mesh_normals:
             vert_l = vert.detach().clone().requires_grad_(True)
             vnrm, _ = MU.auto_normals(vert_l, tri)  # beside the LBVH build
-        env_l = env.detach().clone().requires_grad_(True)
-        lighting = R.prepare_lighting(mods[0], mods[1], mods[8], mods[9], mods[10], env_l, spp, 1234 + 17 * rank,
-                                      frame_pixels=n)
         cur.wait_stream(bvh_stream)
         occ, depth = torch.empty(n, 1, device=dev), torch.empty(n, 1, device=dev)
         pos, nrm = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
@@ -327,6 +331,7 @@ def run_gpu(args):
         kd, rs = mat.gbuffer_materials(pos, occ)   # stand-in for the tiny-cuda-nn material MLP (out of scope)
         kd.requires_grad_(True)
         rs.requires_grad_(True)
+        cur.wait_stream(light_stream)
         outs = R.run_restir_di_with_pt(False, 1, 1, 1, mat, None, worker, *mods, env_l, occ, normal, depth, kd, rs, rays_d,
                                        pos, None, None, None, None, W, H, spp, 2, 2, 2.0, 0.1, 0.001,
                                        random_offset=1234 + 17 * rank, max_bounce=mb, lighting=lighting, **opts)

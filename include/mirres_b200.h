@@ -194,6 +194,21 @@ int mirres_spatial_resampling(const void *packed_nodes, const void *packed_tris,
                               int neighbor_count, float gather_radius, void *workspace, size_t workspace_bytes, void *stream);
 int mirres_final_visibility(const void *packed_nodes, const void *packed_tris, const float *res_ld, int fx, int fy,
                             const float *pos_map, float *vis_map, void *workspace, size_t workspace_bytes, void *stream);
+/* Visibility tags (optional; off until set, per host thread like mirres_set_tuning).  One byte per pixel beside a
+ * reservoir set: 1 = the stored sample has already been found UNOCCLUDED from this pixel by the very ray
+ * mirres_final_visibility would cast for it (origin pos_map + 0.01 L, direction L, same tree); 0 = not known.  Every
+ * sample a pixel ends up with has a provenance that says so: mirres_initial_resampling keeps a candidate only if that ray
+ * missed (InitialResampling.slang:255-270); mirres_spatial_resampling selects a neighbour's sample only with a positive
+ * weight, i.e. after slot 2k -- the same ray -- missed (SpatialResampling.slang:262-266); a pixel's own sample carried
+ * through a pass keeps its tag; a history sample keeps it when mirres_temporal_resampling takes it from the same pixel
+ * of a previous reservoir that belongs to the SAME pos_map and tree (the spp loop of one frame,
+ * nerf/renderer_restir.py:314-459), and loses it otherwise.  mirres_final_visibility then casts rays only for samples
+ * tagged 0; vis_map is bit-identical either way (the skipped rays are repetitions of rays that missed).
+ *   res_tag   [N] bytes: the tag of the reservoir set the next pass WRITES (initial: out; temporal: in / out; spatial: out)
+ *             or, for mirres_final_visibility, of the set it reads
+ *   prev_tag  [N] bytes or NULL: the tag of the prev_* set of the temporal / spatial pass (NULL = nothing known)
+ * The caller keeps the tags beside its reservoir sets and passes (NULL, NULL) when it has none: tags are never inferred. */
+int mirres_set_visibility_tags(unsigned char *res_tag, const unsigned char *prev_tag);
 int mirres_eval_final_fwd(const float *res_ld, const float *res_pdf, const int *res_M, const float *res_w,
                           const float *env_tex, int env_w, int env_h, int fx, int fy, float *fs_dir, float *fs_dist,
                           float *fs_Li, const float *vis_map, void *stream);

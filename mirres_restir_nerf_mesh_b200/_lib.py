@@ -37,6 +37,7 @@ SIGNATURES = {
     "mirres_temporal_resampling": "pppp" + "pppp" + "pii" + "iiu" + "pppp" + "pppp" + "p" + "i" + "pz" + "p",
     "mirres_spatial_resampling": "ppp" + "pppp" + "pppp" + "p" + "pii" + "iiu" + "pppp" + "iif" + "pz" + "p",
     "mirres_final_visibility": "pppiipp" + "pz" + "p",
+    "mirres_set_visibility_tags": "pp",
     "mirres_eval_final_fwd": "pppp" + "pii" + "ii" + "ppp" + "p" + "p",
     "mirres_eval_final_bwd": "pppp" + "ii" + "ii" + "ppp" + "p",
     "mirres_final_shading_fwd": "ppp" + "pii" + "ii" + "ppppp" + "ppp" + "p",

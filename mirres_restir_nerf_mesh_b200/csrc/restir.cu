@@ -115,6 +115,7 @@ struct InitialParams {
     int fx, fy;
     unsigned int frame;
     unsigned int tile_count, tile_size, screen_tile, n_light, n_brdf;
+    unsigned char *vis_tag; // optional, see mirres_set_visibility_tags
     Workspace ws;
 };
 
@@ -178,6 +179,9 @@ MR_DEV void initial_gen_px(const InitialParams &p, int a)
     } else {
         queue_empty(p.ws, (size_t)a);
     }
+    // the sample that survives this pass has been seen unoccluded from this pixel (the resolve pass takes the tag back
+    // together with the sample when the ray hits)
+    if (p.vis_tag) p.vis_tag[i] = st.ld.x > 0.1f ? 1 : 0;
     st.weight = st.weight > 0.f ? (st.wsum / st.M) / st.weight : 0.f;
     st.M = 1.f;
     res_store(p.res, i, st);
@@ -193,6 +197,7 @@ MR_DEV void initial_resolve_px(const InitialParams &p, int a)
     p.res.pdf[i] = 0.f;
     p.res.M[i] = 1;
     p.res.w[i] = 0.f;
+    if (p.vis_tag) p.vis_tag[i] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -205,6 +210,8 @@ struct TemporalParams {
     int fx, fy;
     unsigned int frame;
     unsigned int max_history;
+    unsigned char *vis_tag;            // optional: tag of res (in / out)
+    const unsigned char *prev_vis_tag; // optional: tag of prev, valid for the SAME pos_map and BVH as this frame's
     Workspace ws;
 };
 
@@ -246,6 +253,9 @@ MR_DEV void temporal_px(const TemporalParams &p, int a)
     float normalization = (usedPrev ? prevPdf : currentPdf) / ((float)cur.M * currentPdf + (float)prev.M * prevPdf);
     st.weight = st.weight > 0.f ? (st.wsum * normalization) / st.weight : 0.f;
     res_store(p.res, i, st);
+    // a history sample brings its tag along only if it comes from this very pixel (same position, same ray); the
+    // pixel's own sample keeps the tag it has
+    if (p.vis_tag && usedPrev) p.vis_tag[i] = (p.prev_vis_tag && pi == i) ? p.prev_vis_tag[pi] : 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -261,6 +271,8 @@ struct SpatialParams {
     unsigned int frame;
     unsigned int offset_count, neighbor_count;
     float radius;
+    unsigned char *vis_tag;            // optional: tag of res (out)
+    const unsigned char *prev_vis_tag; // optional: tag of prev
     Workspace ws;
 };
 
@@ -432,6 +444,7 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
     const float currentTargetPdf = c0.w; // target_pdf(cur_s, cLe, cL), from the gen pass
     st.canonical = 1.f;
     uint32_t validNeighbors = 1;
+    unsigned char tag = 0; // of the sample selected so far
     const size_t base = (size_t)a * MR_MAX_RAYS_PER_PIXEL;
     for (uint32_t k = 0; k < p.neighbor_count; ++k) {
         if (p.ws.hit[base + 2 * k] == MR_HIT_NONE) continue;
@@ -461,17 +474,23 @@ MR_DEV void spatial_resolve_px(const SpatialParams &p, int a)
         st.M += (float)nr.M * fminf(m_factor(candAtOwn, candAtCur), m_factor(canonAtNb, currentTargetPdf));
         st.wsum += sampleWeight;
         st.canonical += m1;
-        if (rnd(sg) * st.wsum < sampleWeight) { st.ld = nr.ld; st.pdf = nr.pdf; st.weight = candAtCur; }
+        // a neighbour's sample is only ever selected with a positive weight, i.e. with candAtCur > 0: slot 2k was cast
+        // from this pixel's position towards that sample and came back unoccluded
+        if (rnd(sg) * st.wsum < sampleWeight) { st.ld = nr.ld; st.pdf = nr.pdf; st.weight = candAtCur; tag = 1; }
     }
     {
         float sampleWeight = currentTargetPdf * cur.w * st.canonical;
         st.M += (float)cur.M;
         st.wsum += sampleWeight;
-        if (rnd(sg) * st.wsum < sampleWeight) { st.ld = cur.ld; st.pdf = cur.pdf; st.weight = currentTargetPdf; }
+        if (rnd(sg) * st.wsum < sampleWeight) {
+            st.ld = cur.ld; st.pdf = cur.pdf; st.weight = currentTargetPdf;
+            tag = p.prev_vis_tag ? p.prev_vis_tag[i] : 0;
+        }
     }
     st.M = (float)cur.M;
     st.weight = st.weight > 0.f ? (st.wsum / (float)validNeighbors) / st.weight : 0.f;
     res_store(p.res, i, st);
+    if (p.vis_tag) p.vis_tag[i] = tag;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -481,6 +500,7 @@ struct VisParams {
     const float *__restrict__ pos_map;
     float *__restrict__ vis;
     int n;
+    const unsigned char *vis_tag; // optional: 1 = the stored sample is known to be unoccluded from this pixel
     Workspace ws;
 };
 // thread t: vis[t] = 1 for every pixel (EvaluateFinalSamples.slang:103); the first n_active threads also queue a ray
@@ -490,7 +510,9 @@ MR_DEV void final_visibility_gen_px(const VisParams &p, int t)
     if (t >= p.ws.counters[0]) return;
     const size_t i = (size_t)p.ws.active[t];
     float3 ld = load3(p.res_ld, i);
-    if (ld.x > 0.1f) {
+    // a sample tagged 1 has already been through THIS ray (same origin pos + 0.01 L, same direction, same tree) in the
+    // pass that selected it and was not occluded: vis stays 1 without a second cast
+    if (ld.x > 0.1f && !(p.vis_tag && p.vis_tag[i] == 1)) {
         float3 L = oct_decode(ld.y, ld.z);
         queue_ray(p.ws, (size_t)t, load3(p.pos_map, i) + VIS_NEAR * L, L);
     } else {
@@ -699,6 +721,16 @@ static void res_zero_all(const ResView &r, int n, const Workspace &ws, cudaStrea
     zero_regions_async(z, st);
 }
 
+// visibility tags of the calling host thread (mirres_set_visibility_tags): consumed by the four passes below
+static thread_local unsigned char *t_vis_tag = nullptr;
+static thread_local const unsigned char *t_prev_vis_tag = nullptr;
+int mirres_set_visibility_tags(unsigned char *res_tag, const unsigned char *prev_tag)
+{
+    t_vis_tag = res_tag;
+    t_prev_vis_tag = prev_tag;
+    return 0;
+}
+
 int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris, const float *pos_map, float *res_ld,
                               float *res_pdf, int *res_M, float *res_w, const float *env_tex, int env_w, int env_h,
                               int fx, int fy, unsigned int frame_index, const float *occ, const float *normal_depth,
@@ -728,6 +760,7 @@ int mirres_initial_resampling(const void *packed_nodes, const void *packed_tris,
     p.light_cache = (const float4 *)light_cache;
     p.fx = fx; p.fy = fy; p.frame = frame_index;
     p.tile_count = tile_count; p.tile_size = tile_size; p.screen_tile = screen_tile; p.n_light = n_light; p.n_brdf = n_brdf;
+    p.vis_tag = t_vis_tag;
     res_zero_all(p.res, n, p.ws, st); // background pixels (InitialResampling.slang:166-176) + queue_reset
     if ((rc = foreach_item<InitialParams, initial_gen_px, 128>(p, n, st))) return rc;
     if ((rc = trace_queues(p.bvh, p.ws, true, false, device_sm_count(), st))) return rc;
@@ -756,6 +789,7 @@ int mirres_temporal_resampling(float *res_ld, float *res_pdf, int *res_M, float 
     p.prev = {prev_ld, prev_pdf, prev_M, prev_w};
     p.motion = motion;
     p.fx = fx; p.fy = fy; p.frame = frame_index; p.max_history = max_history;
+    p.vis_tag = t_vis_tag; p.prev_vis_tag = t_prev_vis_tag;
     return foreach_item<TemporalParams, temporal_px, 128>(p, fx * fy, (cudaStream_t)stream);
 }
 
@@ -788,6 +822,7 @@ int mirres_spatial_resampling(const void *packed_nodes, const void *packed_tris,
     p.offsets = neighbor_offsets;
     p.fx = fx; p.fy = fy; p.frame = frame_index;
     p.offset_count = offset_count; p.neighbor_count = neighbor_count; p.radius = gather_radius;
+    p.vis_tag = t_vis_tag; p.prev_vis_tag = t_prev_vis_tag;
     res_zero_all(p.res, n, p.ws, st); // background pixels (SpatialResampling.slang:192-201) + queue_reset
     if ((rc = foreach_item<SpatialParams, spatial_gen_px, 128>(p, n, st))) return rc;
     if ((rc = trace_queues(p.bvh, p.ws, true, false, device_sm_count(), st))) return rc;
@@ -806,6 +841,7 @@ int mirres_final_visibility(const void *packed_nodes, const void *packed_tris, c
     if (rc) return rc;
     p.bvh = bvh_view(packed_nodes, packed_tris);
     p.res_ld = res_ld; p.pos_map = pos_map; p.vis = vis_map; p.n = n;
+    p.vis_tag = t_vis_tag;
     queue_reset(p.ws, st);
     if ((rc = foreach_item<VisParams, final_visibility_gen_px, 256>(p, n, st))) return rc;
     if ((rc = trace_queues(p.bvh, p.ws, true, false, device_sm_count(), st))) return rc;

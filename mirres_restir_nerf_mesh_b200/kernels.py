@@ -169,39 +169,71 @@ class Kernels:
     def _res(self, r):
         return (self._f(r[0]), self._f(r[1]), self._i(r[2]), self._f(r[3]))
 
+    class _Tags:
+        """mirres_set_visibility_tags around ONE pass (include/mirres_b200.h): the tags are per-call arguments here, the
+        library's thread-local setting never outlives the call."""
+
+        def __init__(self, k, n, res_tag, prev_tag):
+            self.k, self.on = k, (res_tag is not None or prev_tag is not None)
+            for t in (res_tag, prev_tag):
+                if t is not None and t.numel() != n:
+                    raise AbiError("visibility tag: expected %d bytes, got %d" % (n, t.numel()))
+            self.args = (k._p(res_tag, torch.uint8, True), k._p(prev_tag, torch.uint8, True))
+
+        def __enter__(self):
+            if self.on:
+                self.k._check(self.k.lib.mirres_set_visibility_tags(*self.args), "mirres_set_visibility_tags")
+
+        def __exit__(self, *a):
+            if self.on:
+                self.k.lib.mirres_set_visibility_tags(None, None)
+
     def initial_resampling(self, packed, pos_map, res, env_tex, W, H, fx, fy, frame_index, occ, normal_depth, brdf_map,
                            ray_dir, pdf_, mpdf_, light_data, light_pdf, ws, tile_count=128, tile_size=1024, screen_tile=8,
-                           n_light=32, n_brdf=1, light_cache=None):
-        rc = self.lib.mirres_initial_resampling(self._p(packed[0]), self._p(packed[1]), self._f(pos_map), *self._res(res),
+                           n_light=32, n_brdf=1, light_cache=None, vis_tag=None):
+        with self._Tags(self, fx * fy, vis_tag, None):
+            rc = self._initial_resampling(packed, pos_map, res, env_tex, W, H, fx, fy, frame_index, occ, normal_depth,
+                                          brdf_map, ray_dir, pdf_, mpdf_, light_data, light_pdf, ws, tile_count, tile_size,
+                                          screen_tile, n_light, n_brdf, light_cache)
+        self._check(rc, "mirres_initial_resampling")
+
+    def _initial_resampling(self, packed, pos_map, res, env_tex, W, H, fx, fy, frame_index, occ, normal_depth, brdf_map,
+                            ray_dir, pdf_, mpdf_, light_data, light_pdf, ws, tile_count, tile_size, screen_tile, n_light,
+                            n_brdf, light_cache):
+        return self.lib.mirres_initial_resampling(self._p(packed[0]), self._p(packed[1]), self._f(pos_map), *self._res(res),
                                                 self._f(env_tex), W, H, fx, fy, self._u32(frame_index), self._f(occ),
                                                 self._f(normal_depth), self._f(brdf_map), self._f(ray_dir), self._f(pdf_),
                                                 self._f(mpdf_), self._f(light_data), self._f(light_pdf),
                                                 self._f(light_cache, True), tile_count,
                                                 tile_size, screen_tile, n_light, n_brdf, *self._ws(ws), self._stream())
-        self._check(rc, "mirres_initial_resampling")
 
     def temporal_resampling(self, res, prev, env_tex, W, H, fx, fy, frame_index, occ, normal_depth, brdf_map, ray_dir,
-                            prev_occ, prev_normal_depth, prev_brdf_map, prev_ray_dir, ws, motion=None, max_history=20):
-        rc = self.lib.mirres_temporal_resampling(*self._res(res), *self._res(prev), self._f(env_tex), W, H, fx, fy,
-                                                 self._u32(frame_index), self._f(occ), self._f(normal_depth),
-                                                 self._f(brdf_map), self._f(ray_dir), self._f(prev_occ),
-                                                 self._f(prev_normal_depth), self._f(prev_brdf_map),
-                                                 self._f(prev_ray_dir), self._f(motion, True), max_history,
-                                                 *self._ws(ws), self._stream())
+                            prev_occ, prev_normal_depth, prev_brdf_map, prev_ray_dir, ws, motion=None, max_history=20,
+                            vis_tag=None, prev_vis_tag=None):
+        with self._Tags(self, fx * fy, vis_tag, prev_vis_tag):
+            rc = self.lib.mirres_temporal_resampling(*self._res(res), *self._res(prev), self._f(env_tex), W, H, fx, fy,
+                                                     self._u32(frame_index), self._f(occ), self._f(normal_depth),
+                                                     self._f(brdf_map), self._f(ray_dir), self._f(prev_occ),
+                                                     self._f(prev_normal_depth), self._f(prev_brdf_map),
+                                                     self._f(prev_ray_dir), self._f(motion, True), max_history,
+                                                     *self._ws(ws), self._stream())
         self._check(rc, "mirres_temporal_resampling")
 
     def spatial_resampling(self, packed, pos_map, res, prev, neighbor_offsets, env_tex, W, H, fx, fy, frame_index, occ,
-                           normal_depth, brdf_map, ray_dir, ws, offset_count=8192, neighbor_count=5, gather_radius=30.0):
-        rc = self.lib.mirres_spatial_resampling(self._p(packed[0]), self._p(packed[1]), self._f(pos_map), *self._res(res),
-                                                *self._res(prev), self._f(neighbor_offsets), self._f(env_tex), W, H, fx,
-                                                fy, self._u32(frame_index), self._f(occ), self._f(normal_depth),
-                                                self._f(brdf_map), self._f(ray_dir), offset_count, neighbor_count,
-                                                float(gather_radius), *self._ws(ws), self._stream())
+                           normal_depth, brdf_map, ray_dir, ws, offset_count=8192, neighbor_count=5, gather_radius=30.0,
+                           vis_tag=None, prev_vis_tag=None):
+        with self._Tags(self, fx * fy, vis_tag, prev_vis_tag):
+            rc = self.lib.mirres_spatial_resampling(self._p(packed[0]), self._p(packed[1]), self._f(pos_map),
+                                                    *self._res(res), *self._res(prev), self._f(neighbor_offsets),
+                                                    self._f(env_tex), W, H, fx, fy, self._u32(frame_index), self._f(occ),
+                                                    self._f(normal_depth), self._f(brdf_map), self._f(ray_dir), offset_count,
+                                                    neighbor_count, float(gather_radius), *self._ws(ws), self._stream())
         self._check(rc, "mirres_spatial_resampling")
 
-    def final_visibility(self, packed, res_ld, fx, fy, pos_map, vis_map, ws):
-        rc = self.lib.mirres_final_visibility(self._p(packed[0]), self._p(packed[1]), self._f(res_ld), fx, fy,
-                                              self._f(pos_map), self._f(vis_map), *self._ws(ws), self._stream())
+    def final_visibility(self, packed, res_ld, fx, fy, pos_map, vis_map, ws, vis_tag=None):
+        with self._Tags(self, fx * fy, vis_tag, None):
+            rc = self.lib.mirres_final_visibility(self._p(packed[0]), self._p(packed[1]), self._f(res_ld), fx, fy,
+                                                  self._f(pos_map), self._f(vis_map), *self._ws(ws), self._stream())
         self._check(rc, "mirres_final_visibility")
 
     def eval_final_fwd(self, res, env_tex, W, H, fx, fy, fs_dir, fs_dist, fs_Li, vis_map):

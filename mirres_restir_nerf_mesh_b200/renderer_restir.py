@@ -38,6 +38,9 @@ USE_PRIORITIES = int(_os.environ.get("MIRRES_PRIORITIES", 1))  # stream prioriti
 # a warp the chains have slack, and a small grid leaves the SMs to the reuse chain (C2 step 4.35 -> 4.26 ms)
 BACKGROUND_CLOSEST_BLOCKS = int(_os.environ.get("MIRRES_BACKGROUND_CLOSEST_BLOCKS", 1))
 BACKGROUND_MIXED_BLOCKS = int(_os.environ.get("MIRRES_BACKGROUND_MIXED_BLOCKS", 2))
+# visibility tags beside the loop's reservoir sets (include/mirres_b200.h, mirres_set_visibility_tags): the final
+# visibility pass then only casts the rays whose answer no earlier pass of the same spp loop has already produced
+USE_VIS_TAGS = int(_os.environ.get("MIRRES_VIS_TAGS", 1))
 _SIDE_STREAMS = {}
 
 
@@ -157,6 +160,22 @@ def _reservoir_set(n, device, zero=True):
     make = torch.zeros if zero else torch.empty
     return (make((n, 3), dtype=torch.float, device=device), make((n, 1), dtype=torch.float, device=device),
             make((n, 1), dtype=torch.int, device=device), make((n, 1), dtype=torch.float, device=device))
+
+
+def attach_vis_tags(*sets):
+    """Puts a zeroed visibility tag beside each reservoir set (slangpy.vis_tag finds it).  Only a driver that owns the
+    whole spp loop may do this: the tags are valid as long as every write to the sets goes through the four passes and
+    pos_map / the tree do not change -- restir_di_with_pt attaches them at its start and drops them at its end."""
+    if not USE_VIS_TAGS:
+        return
+    for s in sets:
+        setattr(s[0], slangpy.VIS_TAG, torch.zeros(s[0].shape[0], dtype=torch.uint8, device=s[0].device))
+
+
+def drop_vis_tags(*sets):
+    for s in sets:
+        if hasattr(s[0], slangpy.VIS_TAG):
+            delattr(s[0], slangpy.VIS_TAG)
 
 
 def load_m_for_restir(framedim_x, framedim_y, device='cuda', max_bounce=2):
@@ -894,6 +913,7 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
         # the reuse chain for ~70 us per iteration (timeline of one band of an 8-way C5 render, profiles/README.md)
         NS = 3
         S = tuple(_reservoir_set(n, dev, False) for _ in range(NS))
+        attach_vis_tags(reservoirs, *(X + S))
         tiles = lighting["tiles"] if lighting is not None else [(light_data, light_uv, light_inv_pdf)] + [
             (torch.empty_like(light_data), torch.empty_like(light_uv), torch.empty_like(light_inv_pdf))
             for _ in range(R - 1)]
@@ -968,6 +988,8 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
                 st_s.wait_event(spatial_done[i])
                 for dst_t, src_t in zip(B, S[i % NS]):
                     dst_t.data.copy_(src_t)  # raw overwrite, invisible to autograd like the reference's kernels
+                if slangpy.vis_tag(B) is not None:
+                    slangpy.vis_tag(B).copy_(slangpy.vis_tag(S[i % NS]))
                 copy_done[i] = ev(st_s)
                 worker.EvaluateFinalSamples_get_vis(EvaluateFinalSamples_m, pos_map, B, framedim_x, framedim_y,
                                                     eva_vis_map)
@@ -1018,7 +1040,9 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
             caller_stream.wait_stream(st)
         keepalive.extend(X + S)
         keepalive.extend(tiles)
+        drop_vis_tags(reservoirs)
     else:
+        attach_vis_tags(reservoirs, prev_reservoirs)
         for i in range(spp):
             base = random_offset + TOTAL_RIS_PASSES * frame
             # frame-index schedule of the reference (nerf/renderer_restir.py:314-459): tiles +0 (+1 inside), initial +2,
@@ -1073,9 +1097,11 @@ def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_
     if overlap:
         for c in chains:
             caller_stream.wait_stream(c["stream"])
-    elif normalize:
-        for name in sums:
-            sums[name] = sums[name] / frame
+    else:
+        drop_vis_tags(reservoirs, prev_reservoirs)
+        if normalize:
+            for name in sums:
+                sums[name] = sums[name] / frame
     if indirect_done is not None:
         indirect_done(sums["color_1"], sums["diff_1"], sums["spec_1"])
     keepalive.clear()

@@ -67,6 +67,16 @@ def _final_sample(x):
     return tuple(x)
 
 
+VIS_TAG = "_mirres_vis_tag"
+
+
+def vis_tag(reservoirs):
+    """The visibility tag a driver has put beside a reservoir set (include/mirres_b200.h, mirres_set_visibility_tags), or
+    None.  It rides on the light_data tensor of the set as an attribute: it exists only where a driver that owns the
+    whole spp loop has attached it (renderer_restir.attach_vis_tags) and goes away with the tensor."""
+    return getattr(_reservoir(reservoirs)[0], VIS_TAG, None)
+
+
 def packed_bvh(info, aabb, vert, tri):
     """Traversal records for reference-layout BVH tensors; cached on the `info` tensor object, which
     restirbvhWorker.update_mesh replaces on every rebuild."""
@@ -407,7 +417,7 @@ def _InitialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reser
                                      m.define("LIGHT_TILE_COUNT", 128), m.define("LIGHT_TILE_SIZE", 1024),
                                      m.define("SCREEN_TILE_SIZE", 8), m.define("INITIAL_LIGHT_SAMPLE_COUNT", 32),
                                      m.define("INITIAL_BRDF_SAMPLE_COUNT", 1),
-                                     light_cache=getattr(light_data, "_mirres_cache", None))
+                                     light_cache=getattr(light_data, "_mirres_cache", None), vis_tag=vis_tag(reservoirs))
 
 
 def _TemporalResampling(m, reservoirs, prevReservoirs, env_tex, env_width, env_height, framedim_x, framedim_y,
@@ -419,7 +429,8 @@ def _TemporalResampling(m, reservoirs, prevReservoirs, env_tex, env_width, env_h
                                       _c(prev_normal_depth), _c(prev_brdf_map), _c(prev_ray_dir),
                                       workspace(occ_map.device, occ_map.shape[0]),
                                       None if motionVectors is None else _c(motionVectors),
-                                      m.define("MAX_HISTORY_LENGTH", 20))
+                                      m.define("MAX_HISTORY_LENGTH", 20), vis_tag=vis_tag(reservoirs),
+                                      prev_vis_tag=vis_tag(prevReservoirs))
 
 
 def _SpatialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reservoirs, prevReservoirs, neighborOffsets,
@@ -430,13 +441,14 @@ def _SpatialResampling(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, pos_map, reser
                                      _c(env_tex), int(env_width), int(env_height), int(framedim_x), int(framedim_y),
                                      int(frameIndex), _c(occ_map), _c(normal_depth), _c(brdf_map), _c(ray_dir),
                                      workspace(occ_map.device, occ_map.shape[0]), m.define("NEIGHBOR_OFFSET_COUNT", 8192), m.define("NEIGHBOR_COUNT", 5),
-                                     float(m.define("GATHER_RADIUS", 30)))
+                                     float(m.define("GATHER_RADIUS", 30)), vis_tag=vis_tag(reservoirs),
+                                     prev_vis_tag=vis_tag(prevReservoirs))
 
 
 def _get_vis(m, g_lbvh_info, g_lbvh_aabb, vert, v_indx, reservoirs, framedim_x, framedim_y, pos_map, vis_map):
     get_kernels().final_visibility(packed_bvh(g_lbvh_info, g_lbvh_aabb, vert, v_indx), _reservoir(reservoirs)[0],
                                    int(framedim_x), int(framedim_y), _c(pos_map), vis_map,
-                                   workspace(vis_map.device, vis_map.shape[0]))
+                                   workspace(vis_map.device, vis_map.shape[0]), vis_tag=vis_tag(reservoirs))
 
 
 def _eval_final_fwd(m, reservoirs, env_tex, env_width, env_height, framedim_x, framedim_y, finalSample, vis_map):

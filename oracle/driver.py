@@ -37,8 +37,12 @@ def prepare_gbuffer(g):
 
 
 def restir_di_with_pt(bvh, env_map, g, spp, fx, fy, random_offset, material, max_bounce=2, tile_count=128,
-                      tile_size=1024, counters=None, snapshots=None):
-    """g: prepared G-buffer dict (prepare_gbuffer).  Returns dict of per-call sums and mFrameIndex."""
+                      tile_size=1024, counters=None, snapshots=None, motion=None):
+    """g: prepared G-buffer dict (prepare_gbuffer).  Returns dict of per-call sums and mFrameIndex.
+    motion: optional [n,2] motion vectors of the temporal pass (the reference passes zeros, renderer_restir.py:487).
+    The sample-provenance tags of orc_kernels.cpp ride along (they change no result): tot["known_final_rays"] counts the
+    final-visibility rays whose answer an earlier pass had produced, tot["provenance_violations"] those of them that
+    were occluded after all (must be 0)."""
     n = fx * fy
     He, We = env_map.shape[0], env_map.shape[1]
     # `counters` may be one array (everything accumulated) or a dict with one array per kernel
@@ -56,6 +60,8 @@ def restir_di_with_pt(bvh, env_map, g, spp, fx, fy, random_offset, material, max
     new_diffuse, new_rs = z3(), np.zeros((n, 2), np.float32)
     vis = np.ones((n, 1), np.float32)
     res, prev = O.new_reservoirs(n), O.new_reservoirs(n)
+    tag_res, tag_prev = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    violations0, known_final = O.provenance_violations(), []
     fs_dir, fs_dist, fs_Li = z3(), z1(), z3()
     occ, nd, brdf, ray, pos = g["occ_map"], g["normal_depth"], g["brdf_map"], g["ray_dir_map"], g["pos_map"]
     normal, kd, rs = g["normal_map"], g["diffuse_map"], g["roughness_specular"]
@@ -66,18 +72,25 @@ def restir_di_with_pt(bvh, env_map, g, spp, fx, fy, random_offset, material, max
         base = random_offset + TOTAL_RIS_PASSES * mFrame
         tiles = O.light_tiles(env, We, He, dist, base + cur, tile_count, tile_size)
         cur += 2
+        O.set_provenance(tag_res, None)
         O.initial_resampling(bvh, pos, res, env, We, He, fx, fy, base + cur, occ, nd, brdf, ray, dist, tiles,
                              tile_count, tile_size, counters=ctr("initial_resampling"))
         cur += 1
         if i > 0:
+            O.set_provenance(tag_res, tag_prev)  # prev: the finished set of the previous iteration, same pos_map and tree
             O.temporal_resampling(res, prev, env, We, He, fx, fy, base + cur, occ, nd, brdf, ray, prev_occ, prev_nd,
-                                  prev_brdf, prev_ray)
+                                  prev_brdf, prev_ray, motion=motion)
             cur += 1
         res, prev = prev, res
+        tag_res, tag_prev = tag_prev, tag_res
+        O.set_provenance(tag_res, tag_prev)
         O.spatial_resampling(bvh, pos, res, prev, offs, env, We, He, fx, fy, base + cur, occ, nd, brdf, ray,
                              counters=ctr("spatial_resampling"))
         cur += 1
+        O.set_provenance(tag_res, None)
         O.final_visibility(bvh, res, fx, fy, pos, vis, counters=ctr("final_visibility"))
+        O.set_provenance(None, None)
+        known_final.append(int(((res[0][:, 0] > 0.1) & (tag_res != 0)).sum()))
         O.eval_final_fwd(res, env, We, He, fx, fy, fs_dir, fs_dist, fs_Li, vis)
         color, cdiff, cspec = O.final_shading_fwd(fs_dir, fs_dist, fs_Li, env, We, He, fx, fy, occ, normal, ray, kd, rs)
         if snapshots is not None:
@@ -106,20 +119,23 @@ def restir_di_with_pt(bvh, env_map, g, spp, fx, fy, random_offset, material, max
             src, dst = dst, src
         mFrame += 1
         res, prev = prev, res
+        tag_res, tag_prev = tag_prev, tag_res
         prev_occ, prev_nd, prev_brdf, prev_ray = occ, nd, brdf, ray
         tot["color"] += color
         tot["diff"] += cdiff
         tot["spec"] += cspec
     tot["mFrameIndex"] = mFrame
+    tot["known_final_rays"] = known_final
+    tot["provenance_violations"] = O.provenance_violations() - violations0
     return tot
 
 
 def run_no_denoise(bvh, env_map, gbuffer, spp, fx, fy, random_offset, material, max_bounce=2, counters=None,
-                   snapshots=None):
+                   snapshots=None, motion=None):
     """run_restir_di_with_pt (renderer_restir.py:473-549) with the denoiser replaced by identity."""
     g = prepare_gbuffer(gbuffer)
     tot = restir_di_with_pt(bvh, env_map, g, spp, fx, fy, random_offset, material, max_bounce, counters=counters,
-                            snapshots=snapshots)
+                            snapshots=snapshots, motion=motion)
     m = np.float32(tot["mFrameIndex"])
     out = {k: (tot[k] / m).astype(np.float32) for k in ("color", "diff", "spec", "color_1", "diff_1", "spec_1")}
     indirect = out["diff_1"] + out["spec_1"]
@@ -129,4 +145,6 @@ def run_no_denoise(bvh, env_map, gbuffer, spp, fx, fy, random_offset, material, 
     out["final"] = np.nan_to_num(final, nan=0.0).astype(np.float32)
     out["indirect"] = indirect
     out["prepared"] = g
+    out["known_final_rays"] = tot["known_final_rays"]
+    out["provenance_violations"] = tot["provenance_violations"]
     return out

@@ -179,6 +179,17 @@ def _res(r):
     return (_p(r[0]), _p(r[1]), _p(r[2]), _p(r[3]))
 
 
+def set_provenance(res_tag=None, prev_tag=None):
+    """uint8 [n] arrays or None: the sample-provenance tags the next pass records / reads (orc_kernels.cpp)."""
+    lib().orc_set_provenance(_p(res_tag), _p(prev_tag))
+
+
+def provenance_violations():
+    f = lib().orc_provenance_violations
+    f.restype = ctypes.c_longlong
+    return int(f())
+
+
 def initial_resampling(bvh, pos_map, res, env_tex, W, H, fx, fy, frame_index, occ, normal_depth, brdf_map, ray_dir,
                        dist, tiles, tile_count=128, tile_size=1024, screen_tile=8, n_light=32, n_brdf=1,
                        counters=None):

@@ -120,7 +120,19 @@ void merge_counters(long long *dst, const TraceCounters &a, const TraceCounters 
 
 } // namespace
 
+// Sample provenance (test infrastructure for the product's visibility tags, include/mirres_b200.h
+// mirres_set_visibility_tags): one byte per pixel beside a reservoir set, 1 = the stored sample has been through the
+// final-visibility ray of this pixel in an earlier pass and was not occluded.  The oracle only RECORDS it -- results do
+// not depend on it -- so that (a) orc_final_visibility can check the claim "tagged => unoccluded" on every tagged ray
+// (g_tag_violations) and (b) the node / triangle counters can tell the rays whose answer was known ([9..11]).
+static unsigned char *g_res_tag = nullptr;
+static const unsigned char *g_prev_tag = nullptr;
+static long long g_tag_violations = 0;
+
 extern "C" {
+
+void orc_set_provenance(unsigned char *res_tag, const unsigned char *prev_tag) { g_res_tag = res_tag; g_prev_tag = prev_tag; }
+long long orc_provenance_violations() { return g_tag_violations; }
 
 // counters (optional, accumulated): [0..3] shadow rays nodes_ref,tris_ref,nodes_any,tris_any;
 // [4..5] closest rays nodes,tris; [6] max stack; [7] #shadow rays; [8] #closest rays;
@@ -196,6 +208,7 @@ int orc_initial_resampling(const int *info, const float *aabb, const float *vert
                 ++nrays;
                 if (shadow_ray(b, ld3(pos_map, i), L, &tcs)) st = empty_ris();
             }
+            if (g_res_tag) g_res_tag[i] = st.light_data.x > 0.1f ? 1 : 0; // what is left has passed its ray
             st.weight = st.weight > 0.f ? (st.weightSum / st.M) / st.weight : 0.f;
             st.M = 1.f;
             store_res(R, i, st);
@@ -265,6 +278,7 @@ int orc_temporal_resampling(float *res_ld, float *res_pdf, int *res_M, float *re
         float normalization = (usedPrev ? prevPdf : currentPdf) / ((float)cur.M * currentPdf + (float)prev.M * prevPdf);
         st.weight = st.weight > 0.f ? (st.weightSum * normalization) / st.weight : 0.f;
         store_res(R, i, st);
+        if (g_res_tag && usedPrev) g_res_tag[i] = (g_prev_tag && pi == i) ? g_prev_tag[pi] : 0;
     }
     return 0;
 }
@@ -305,6 +319,7 @@ int orc_spatial_resampling(const int *info, const float *aabb, const float *vert
             f3 curr_pos = ld3(pos_map, i);
             st.canonicalWeight = 1.f;
             uint32_t validNeighbors = 1;
+            unsigned char tag = 0;
             for (uint32_t k = 0; k < (uint32_t)neighbor_count; ++k) {
                 uint32_t ni = (startIndex + k) & mask; // getNextNeighborPixel :32-39
                 int npx = (int)px + f2i(neighborOffsets[2 * (size_t)ni] * gather_radius);
@@ -347,6 +362,7 @@ int orc_spatial_resampling(const int *info, const float *aabb, const float *vert
                 st.canonicalWeight += m1;
                 bool sel = next1d(sg) * st.weightSum < sampleWeight;
                 if (sel) { st.light_data = nr.light_data; st.inv_pdf = nr.light_pdf; st.weight = candidateTargetPdfAtOther; }
+                if (sel) tag = canonical_hit ? 2 : 1; // 2 cannot happen (a hit zeroes the weight); orc_final_visibility would flag it
             }
             // streamingResampleFinalizeMis res.slang:215-232
             {
@@ -355,7 +371,9 @@ int orc_spatial_resampling(const int *info, const float *aabb, const float *vert
                 st.weightSum += sampleWeight;
                 bool sel = next1d(sg) * st.weightSum < sampleWeight;
                 if (sel) { st.light_data = cur.light_data; st.inv_pdf = cur.light_pdf; st.weight = currentTargetPdf; }
+                if (sel) tag = g_prev_tag ? g_prev_tag[i] : 0;
             }
+            if (g_res_tag) g_res_tag[i] = tag;
             st.M = (float)cur.M;
             st.weight = st.weight > 0.f ? (st.weightSum / (float)validNeighbors) / st.weight : 0.f;
             store_res(R, i, st);
@@ -383,8 +401,8 @@ int orc_final_visibility(const int *info, const float *aabb, const float *vert, 
     Bvh b = {info, aabb, vert, tri};
 #pragma omp parallel
     {
-        TraceCounters tcs = {0, 0, 0, 0, 0}, tcc = {0, 0, 0, 0, 0};
-        long long nrays = 0;
+        TraceCounters tcs = {0, 0, 0, 0, 0}, tcc = {0, 0, 0, 0, 0}, tcd = {0, 0, 0, 0, 0};
+        long long nrays = 0, nknown = 0, bad = 0;
 #pragma omp for schedule(dynamic, 256)
         for (int idx = 0; idx < fx * fy; ++idx) {
             const size_t i = (size_t)idx;
@@ -393,13 +411,25 @@ int orc_final_visibility(const int *info, const float *aabb, const float *vert, 
             if (ld.x > 0.1f) {
                 f3 L = oct_decode(mk2(ld.y, ld.z));
                 ++nrays;
-                vis_map[i] = shadow_ray(b, ld3(pos_map, i), L, &tcs) ? 0.0f : 1.0f;
+                const bool known = g_res_tag && g_res_tag[i] != 0;
+                const bool hit = shadow_ray(b, ld3(pos_map, i), L, known ? &tcd : &tcs);
+                vis_map[i] = hit ? 0.0f : 1.0f;
+                if (known) { ++nknown; if (hit || g_res_tag[i] != 1) ++bad; }
             }
         }
         merge_counters(counters, tcs, tcc);
+        merge_counters(counters, tcd, TraceCounters{0, 0, 0, 0, 0});
+#pragma omp atomic
+        g_tag_violations += bad;
         if (counters) {
 #pragma omp atomic
             counters[7] += nrays;
+#pragma omp atomic
+            counters[9] += tcd.nodes_any;
+#pragma omp atomic
+            counters[10] += tcd.tris_any;
+#pragma omp atomic
+            counters[11] += nknown;
         }
     }
     return 0;

@@ -22,20 +22,21 @@ def scene(name, metallic=0.0, view=0):
                 hit=hit, t=t, pos=pos, nrm=nrm, prim=prim)
 
 
-def oracle_run(sc, random_offset=4242, spp=None, max_bounce=None):
+def oracle_run(sc, random_offset=4242, spp=None, max_bounce=None, motion=None):
     cfg = sc["cfg"]
     snaps = []
     counters = O.new_counters()
     ref = D.run_no_denoise(sc["bvh"], sc["env"], sc["gbuffer"], spp or cfg["spp"], sc["W"], sc["H"], random_offset,
                            lambda p: synth.material(p, sc["metallic"]), max_bounce=max_bounce or cfg["max_bounce"],
-                           snapshots=snaps, counters=counters)
+                           snapshots=snaps, counters=counters, motion=motion)
     ref["snapshots"] = snaps
     ref["counters"] = counters
     return ref
 
 
-def product_run(sc, worker, device, ref_prepared, random_offset=4242, spp=None, max_bounce=None):
-    """worker: a restirbvhWorker (already holding the BVH) on `device`."""
+def product_run(sc, worker, device, ref_prepared, random_offset=4242, spp=None, max_bounce=None, motion=None):
+    """worker: a restirbvhWorker (already holding the BVH) on `device`.  Runs the sequential schedule (hooks); each
+    snapshot also records how many rays the final-visibility pass of its iteration queued ("final_rays")."""
     cfg = sc["cfg"]
     spp = spp or cfg["spp"]
     mb = max_bounce or cfg["max_bounce"]
@@ -52,6 +53,11 @@ def product_run(sc, worker, device, ref_prepared, random_offset=4242, spp=None, 
     def hook(kind, i, d):
         if kind == "direct":
             mine.append({k: snap(v) for k, v in d.items()})
+            # the boolean-ray queue size of the workspace the sequential schedule uses: the final-visibility pass was the
+            # last to fill it (word MR_CTR_ANY_SIZE = 2 of the counter block at the start of the workspace)
+            from mirres_restir_nerf_mesh_b200 import slangpy_shim
+            ws = slangpy_shim.workspace(dev, W * Hh)
+            mine[-1]["final_rays"] = int(ws[:16].cpu().view(torch.int32)[2])
         else:
             mine[-1]["bounce%d" % i[1]] = {k: snap(v) for k, v in d.items()}
 
@@ -59,7 +65,8 @@ def product_run(sc, worker, device, ref_prepared, random_offset=4242, spp=None, 
         outs = R.restir_di_with_pt(False, 1, 1, 1, synth.ProceduralMaterial(sc["metallic"]), worker, spp, W, Hh,
                                    *mods[:7], *mods[8:], tt(sc["env"]), g["occ_map"], g["pos_map"], g["normal_map"],
                                    g["depth_map"], g["diffuse_map"], g["roughness_specular"],
-                                   tt(ref_prepared["ray_dir_map"]), None, None, None, None, None, None,
+                                   tt(ref_prepared["ray_dir_map"]), None, None, None, None,
+                                   None if motion is None else tt(motion), None,
                                    random_offset=random_offset, max_bounce=mb, hooks=hook)
     return dict(snapshots=mine, totals=[o.cpu().numpy() if torch.is_tensor(o) else o for o in outs], spp=spp, mb=mb)
 

@@ -1,0 +1,76 @@
+"""Visibility tags (include/mirres_b200.h, mirres_set_visibility_tags): the final-visibility pass skips the rays whose
+answer an earlier pass of the same spp loop has produced.  Three checks, all on the CPU:
+  * the oracle records the same provenance beside its reservoirs and traces EVERY final ray anyway: a tagged ray that
+    turns out occluded is a violation of the claim the product relies on (must be 0), with and without motion vectors;
+  * the product (host flavour of the kernel source) with tags on, with tags off and the oracle agree bit for bit;
+  * with tags on the pass queues exactly the rays the oracle counts as unknown."""
+import numpy as np
+import pytest
+
+import hostcheck as H
+import parity as P
+from mirres_restir_nerf_mesh_b200 import renderer_restir as R
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _bind_hostcheck():
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim
+    H.activate()
+    yield
+    slangpy_shim.set_kernels(None)
+
+
+def _worker(sc):
+    w = H.OracleBvhWorker(H.t(sc["vert"]), H.t(sc["tri"]))
+    w.update_mesh(H.t(sc["vert"]), H.t(sc["tri"]))
+    return w
+
+
+def _motion(sc, dx, dy):
+    """constant motion vectors, in frame fractions as TemporalResampling.slang:52-56 reads them"""
+    n = sc["W"] * sc["H"]
+    m = np.empty((n, 2), np.float32)
+    m[:, 0], m[:, 1] = dx / sc["W"], dy / sc["H"]
+    return m
+
+
+def _run(sc, tags, ref, **kw):
+    old = R.USE_VIS_TAGS
+    R.USE_VIS_TAGS = int(tags)
+    try:
+        return P.product_run(sc, _worker(sc), "cpu", ref["prepared"], **kw)
+    finally:
+        R.USE_VIS_TAGS = old
+
+
+@pytest.mark.parametrize("name,metallic,spp,shift", [("T1", 0.0, 4, None), ("T2", 0.4, 4, None), ("C1", 0.0, 3, None),
+                                                     ("T1", 0.0, 4, (3, -2)), ("C1", 0.4, 3, (-5, 1)), ("T2", 0.0, 5, (0.6, 0.6))])
+def test_tags_change_nothing_but_the_ray_count(name, metallic, spp, shift):
+    sc = P.scene(name, metallic)
+    motion = None if shift is None else _motion(sc, *shift)
+    ref = P.oracle_run(sc, spp=spp, motion=motion)
+    assert ref["provenance_violations"] == 0
+    on = _run(sc, True, ref, spp=spp, motion=motion)
+    off = _run(sc, False, ref, spp=spp, motion=motion)
+    assert P.compare(ref, on) == []
+    assert P.compare(ref, off) == []
+    valid = [int((s["res"][0][:, 0] > 0.1).sum()) for s in ref["snapshots"]]
+    assert [s["final_rays"] for s in off["snapshots"]] == valid                   # the reference casts one ray per valid sample
+    unknown = [v - k for v, k in zip(valid, ref["known_final_rays"])]
+    assert [s["final_rays"] for s in on["snapshots"]] == unknown                  # the product only the unknown ones
+    assert unknown[0] == 0                                                        # first iteration: every sample has passed its ray
+    if shift is None:
+        assert sum(unknown) <= 1e-3 * sum(valid)                                  # history comes from the same pixel
+    else:
+        assert 0 < sum(unknown) < sum(valid)                                      # history from another pixel: not known
+
+
+def test_history_from_another_pixel_can_be_occluded():
+    """the case the tags must NOT cover: a history sample taken from another pixel has never been tested from here, and
+    some of them are occluded (vis = 0) -- the scene / shift are chosen so that this happens"""
+    sc = P.scene("T2", 0.0)
+    ref = P.oracle_run(sc, spp=6, motion=_motion(sc, 7, 5))
+    occluded = sum(int((s["vis"] == 0).sum()) for s in ref["snapshots"])
+    assert occluded > 0 and ref["provenance_violations"] == 0
+    on = _run(sc, True, ref, spp=6, motion=_motion(sc, 7, 5))
+    assert P.compare(ref, on) == []
