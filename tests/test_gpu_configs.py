@@ -190,3 +190,34 @@ def test_row_bands_on_one_gpu_are_bit_identical(kernels, name, world, balanced, 
     for r in range(world):
         for a, b in zip(outs[r], want):
             assert torch.equal(a, b), (r, (a != b).sum().item())
+
+
+@pytest.mark.parametrize("shift", [None, (3.0, -2.0)])
+def test_visibility_tags_cast_only_unknown_rays(kernels, oracle, shift):
+    """Visibility tags on the GPU (tests/test_vis_tags_cpu.py has the CPU side): every tensor of the loop equals the
+    oracle's -- which traces every final-visibility ray -- while the pass queues exactly the rays the oracle's provenance
+    count calls unknown; with tags off it queues one ray per valid sample."""
+    sc = P.scene("C1", 0.4)
+    motion = None
+    if shift is not None:
+        motion = np.empty((sc["W"] * sc["H"], 2), np.float32)
+        motion[:, 0], motion[:, 1] = shift[0] / sc["W"], shift[1] / sc["H"]
+    ref = P.oracle_run(sc, spp=4, motion=motion)
+    assert ref["provenance_violations"] == 0
+    w = make_worker(sc)
+    valid = [int((s["res"][0][:, 0] > 0.1).sum()) for s in ref["snapshots"]]
+    unknown = [v - k for v, k in zip(valid, ref["known_final_rays"])]
+    old = R.USE_VIS_TAGS
+    try:
+        for tags, want in ((1, unknown), (0, valid)):
+            R.USE_VIS_TAGS = tags
+            got = P.product_run(sc, w, DEV, ref["prepared"], spp=4, motion=motion)
+            assert P.compare(ref, got, rtol=FWD_RTOL) == []
+            assert P.compare(ref, got) == []
+            assert [s["final_rays"] for s in got["snapshots"]] == want
+    finally:
+        R.USE_VIS_TAGS = old
+    if shift is None:
+        assert sum(unknown) <= 1e-3 * sum(valid)      # history comes from the same pixel: (almost) nothing left to cast
+    else:
+        assert 0 < sum(unknown) < sum(valid)          # history from another pixel has never been tested from here
