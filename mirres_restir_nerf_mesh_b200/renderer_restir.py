@@ -169,13 +169,32 @@ def attach_vis_tags(*sets):
     if not USE_VIS_TAGS:
         return
     for s in sets:
-        setattr(s[0], slangpy.VIS_TAG, torch.zeros(s[0].shape[0], dtype=torch.uint8, device=s[0].device))
+        ld = slangpy._reservoir(s)[0]  # (a set may also be the reference's dict form)
+        setattr(ld, slangpy.VIS_TAG, torch.zeros(ld.shape[0], dtype=torch.uint8, device=ld.device))
 
 
 def drop_vis_tags(*sets):
     for s in sets:
-        if hasattr(s[0], slangpy.VIS_TAG):
-            delattr(s[0], slangpy.VIS_TAG)
+        ld = slangpy._reservoir(s)[0]
+        if hasattr(ld, slangpy.VIS_TAG):
+            delattr(ld, slangpy.VIS_TAG)
+
+
+def _no_tags_left_behind(fn):
+    """The caller's reservoir sets never leave the spp loop with a tag on them, whichever way the loop ends: a tag that
+    outlived its loop would vouch for samples it knows nothing about."""
+    import functools
+    import inspect
+    sig = inspect.signature(fn)
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        try:
+            return fn(*a, **k)
+        finally:
+            args = sig.bind(*a, **k).arguments
+            drop_vis_tags(*[args[n] for n in ("reservoirs", "prev_reservoirs") if args.get(n) is not None])
+    return wrapper
 
 
 def load_m_for_restir(framedim_x, framedim_y, device='cuda', max_bounce=2):
@@ -682,6 +701,7 @@ def prepare_lighting(make_sampleable_m, generateLightTiles_m, light_data, light_
 # =====================================================================================================================
 # the spp loop
 # =====================================================================================================================
+@_no_tags_left_behind
 def restir_di_with_pt(use_scale, scale_x, scale_y, scale_z, mlp_mat, bvh_restir_worker, spp, framedim_x, framedim_y,
                       make_sampleable_m, generateLightTiles_m, InitialResampling_m, TemporalResampling_m,
                       SpatialResampling_m, EvaluateFinalSamples_m, FinalShading_m, light_data, light_uv, light_inv_pdf,

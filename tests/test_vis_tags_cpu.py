@@ -74,3 +74,34 @@ def test_history_from_another_pixel_can_be_occluded():
     assert occluded > 0 and ref["provenance_violations"] == 0
     on = _run(sc, True, ref, spp=6, motion=_motion(sc, 7, 5))
     assert P.compare(ref, on) == []
+
+
+def test_no_tag_outlives_its_loop():
+    """the caller's reservoir sets carry no tag after the loop, also when the loop dies half way"""
+    import torch
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim
+    sc = P.scene("T0", 0.0)
+    ref = P.oracle_run(sc, spp=2)
+    W, Hh = sc["W"], sc["H"]
+    mods = R.load_m_for_restir(W, Hh, device=torch.device("cpu"), max_bounce=2)
+    res, prev = mods[11], mods[12]  # reservoirs, prev_reservoirs of the 17-tuple
+    assert slangpy_shim.vis_tag(res) is None
+
+    def run(hook):
+        g = {k: H.t(v) for k, v in sc["gbuffer"].items()}
+        with torch.no_grad():
+            R.restir_di_with_pt(False, 1, 1, 1, None, _worker(sc), 2, W, Hh, *mods[:7], *mods[8:], H.t(sc["env"]),
+                                g["occ_map"], g["pos_map"], g["normal_map"], g["depth_map"], g["diffuse_map"],
+                                g["roughness_specular"], H.t(ref["prepared"]["ray_dir_map"]), None, None, None, None, None,
+                                None, random_offset=1, max_bounce=2, hooks=hook)
+
+    seen = []
+
+    def boom(kind, i, d):
+        seen.append(slangpy_shim.vis_tag(d["reservoirs"]) is not None if kind == "direct" else None)
+        raise RuntimeError("stop here")
+
+    with pytest.raises(RuntimeError):
+        run(boom)
+    assert seen == [True]                                  # the tags were on inside the loop ...
+    assert slangpy_shim.vis_tag(res) is None and slangpy_shim.vis_tag(prev) is None   # ... and are gone after it
