@@ -857,6 +857,10 @@ def roofline(cfg_name, cfg, per_kernel, steps, peak, peak_kind, n_foreground=Non
             "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_source,
             "launch_ms": ms / count, "launches_timed": count, "alg_bytes_per_launch": alg,
             "frac_reference_rays": alg_ref / dur / 1e9 / peak if alg_ref else None,
+            "accounting": "achieved = S_screen * foreground pixels + 36 B per node pop + 48 B per triangle test of the rays this "
+                          "kernel CASTS (oracle count, profiles/oracle_counters_<cfg>.json: cast_*), per launch, / launch_ms; "
+                          "frac_reference_rays charges every ray the reference casts, including the ones the product proves "
+                          "dead or already answered and skips",
             "share_of_step": ms / steps / max(sum(v[0] for v in per_kernel.values()) / steps, 1e-9)}
 
 
