@@ -105,3 +105,36 @@ def test_no_tag_outlives_its_loop():
         run(boom)
     assert seen == [True]                                  # the tags were on inside the loop ...
     assert slangpy_shim.vis_tag(res) is None and slangpy_shim.vis_tag(prev) is None   # ... and are gone after it
+
+
+@pytest.mark.parametrize("name,metallic", [("T2", 0.0), ("C1", 0.4)])
+def test_roofline_charges_exactly_the_rays_the_spatial_pass_casts(name, metallic):
+    """bench.py charges the spatial pass with the oracle's node / triangle counts WITHOUT the rays the oracle classifies as
+    unable to reach the output (orc_kernels.cpp, counters 9..11).  That classification must be the product's: one spatial
+    pass launched on the oracle's own inputs queues exactly (rays - dead) rays, and produces the oracle's reservoirs."""
+    import numpy as np
+    import torch
+    from oracle import oracle as O, driver as D
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim, synth
+    sc = P.scene(name, metallic)
+    per, snaps = {}, []
+    D.run_no_denoise(sc["bvh"], sc["env"], sc["gbuffer"], 1, sc["W"], sc["H"], 4242, lambda p: synth.material(p, metallic),
+                     max_bounce=1, counters=per, snapshots=snaps)
+    c = per["spatial_resampling"]
+    rays, dead = int(c[7]), int(c[11])
+    assert 0 < dead < rays
+    g = D.prepare_gbuffer(sc["gbuffer"])
+    W, Hh, n = sc["W"], sc["H"], sc["W"] * sc["H"]
+    env = np.ascontiguousarray(sc["env"][::-1].reshape(-1, 3), np.float32)
+    offs = (O.neighbor_offsets(8192).reshape(-1, 2) / np.float32(127)).astype(np.float32)
+    k, w = H.kernels(), _worker(sc)
+    ws = slangpy_shim.workspace("cpu", n)
+    k.workspace_prepare(H.t(g["occ_map"]), ws)
+    prev = [H.t(a.copy()) for a in snaps[0]["prev"]]
+    res = [torch.zeros_like(a) for a in prev]
+    k.spatial_resampling(w.packed, H.t(g["pos_map"]), res, prev, H.t(offs), H.t(env), sc["env"].shape[1], sc["env"].shape[0],
+                         W, Hh, 4242 + 3, H.t(g["occ_map"]), H.t(g["normal_depth"]), H.t(g["brdf_map"]),
+                         H.t(g["ray_dir_map"]), ws)
+    assert int(ws[:16].view(torch.int32)[2]) == rays - dead
+    for a, b in zip(res, snaps[0]["res"]):
+        assert np.array_equal(a.numpy().reshape(-1), b.reshape(-1))
