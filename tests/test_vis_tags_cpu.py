@@ -27,10 +27,16 @@ def _worker(sc):
 
 
 def _motion(sc, dx, dy):
-    """constant motion vectors, in frame fractions as TemporalResampling.slang:52-56 reads them"""
+    """motion vectors in frame fractions as TemporalResampling.slang:52-56 reads them: constant, or (dx = "random")
+    independent per pixel within +-dy pixels, so that some pixels find their history at home and others do not"""
     n = sc["W"] * sc["H"]
     m = np.empty((n, 2), np.float32)
-    m[:, 0], m[:, 1] = dx / sc["W"], dy / sc["H"]
+    if dx == "random":
+        r = np.random.default_rng(5).uniform(-dy, dy, size=(n, 2))
+        r[::3] = 0.0                                   # a third of the pixels keep their place exactly
+        m[:, 0], m[:, 1] = r[:, 0] / sc["W"], r[:, 1] / sc["H"]
+    else:
+        m[:, 0], m[:, 1] = dx / sc["W"], dy / sc["H"]
     return m
 
 
@@ -44,7 +50,8 @@ def _run(sc, tags, ref, **kw):
 
 
 @pytest.mark.parametrize("name,metallic,spp,shift", [("T1", 0.0, 4, None), ("T2", 0.4, 4, None), ("C1", 0.0, 3, None),
-                                                     ("T1", 0.0, 4, (3, -2)), ("C1", 0.4, 3, (-5, 1)), ("T2", 0.0, 5, (0.6, 0.6))])
+                                                     ("T1", 0.0, 4, (3, -2)), ("C1", 0.4, 3, (-5, 1)), ("T2", 0.0, 5, (0.6, 0.6)),
+                                                     ("T2", 0.4, 6, ("random", 1.5)), ("C1", 0.0, 4, ("random", 0.7))])
 def test_tags_change_nothing_but_the_ray_count(name, metallic, spp, shift):
     sc = P.scene(name, metallic)
     motion = None if shift is None else _motion(sc, *shift)
