@@ -180,3 +180,70 @@ def test_band_boundaries():
         for q, rows in s.recv_plan:
             assert (s.rank, rows) in shards[q].send_plan
         assert s.halo_bytes() == sum(y1 - y0 for _, (y0, y1) in s.recv_plan) * fx * 24
+
+
+# ---- view-parallel training (BASELINE config 4): one view per rank, the flat gradient buffer summed -------------
+def _view_gradients(view):
+    """forward + backward of one view of the small scene through the product driver (host flavour): the envmap gradient
+    and the per-pixel gradients scattered to the vertices, as bench.py's step lays them out in ONE flat buffer"""
+    import hostcheck as H
+    import parity as P
+    from mirres_restir_nerf_mesh_b200 import renderer_restir as R, synth
+    sc = P.scene("T0", 0.3, view=view)
+    W, Hh = sc["W"], sc["H"]
+    w = H.OracleBvhWorker(H.t(sc["vert"]), H.t(sc["tri"]))
+    w.update_mesh(H.t(sc["vert"]), H.t(sc["tri"]))
+    mods = R.load_m_for_restir(W, Hh, device="cpu")
+    g = {k: H.t(v) for k, v in sc["gbuffer"].items()}
+    env = H.t(sc["env"]).requires_grad_(True)
+    normal = g["normal_map"].clone().requires_grad_(True)
+    outs = R.run_restir_di_with_pt(False, 1, 1, 1, synth.ProceduralMaterial(sc["metallic"]), None, w, *mods, env,
+                                   g["occ_map"], normal, g["depth_map"], g["diffuse_map"], g["roughness_specular"],
+                                   g["ray_dir_map"], g["pos_map"], None, None, None, None, W, Hh, 2, DENOISE_ITER, STEP, *PHI,
+                                   random_offset=31 + 17 * view)
+    torch.nn.functional.mse_loss(outs[0], torch.full_like(outs[0], 0.5)).backward()
+    # per-pixel normal gradients land on the vertices of the triangle the pixel sees (here: its first vertex)
+    V = sc["vert"].shape[0]
+    vgrad = torch.zeros(V, 3)
+    hit = torch.from_numpy(sc["hit"] > 0)
+    first_vertex = torch.from_numpy(sc["tri"][np.maximum(sc["prim"], 0), 0].astype(np.int64))
+    vgrad.index_add_(0, first_vertex[hit], normal.grad[hit])
+    return torch.cat((env.grad.reshape(-1), vgrad.reshape(-1)))
+
+
+def _train_worker(rank, world, port, out_dir):
+    for p in (os.path.dirname(HERE), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import hostcheck as H
+    from mirres_restir_nerf_mesh_b200 import dist as D
+    H.activate()
+    flat = _view_gradients(view=7 * rank)
+    ne = flat.numel() // 2  # (any split point will do: the two parts are independent all-reduces)
+    # the step's collective in the two parts bench.py issues: the envmap segment first, the vertex segments after it
+    D.allreduce_gradients(flat[:ne])
+    D.allreduce_gradients(flat[ne:])
+    if rank == 0:
+        np.save(os.path.join(out_dir, "flat.npy"), flat.numpy())
+    dist.destroy_process_group()
+
+
+def test_view_parallel_training_step_sums_the_gradients_of_all_views(tmp_path):
+    """world 2 over gloo: each rank renders ITS view forward + backward, the flat gradient buffer is all-reduced in two
+    parts; the result equals the sum of the two views' buffers computed in one process (to fp32 addition order: two
+    addends, so exactly)."""
+    world, port = 2, 29731 + os.getpid() % 200
+    mp.spawn(_train_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(os.path.join(str(tmp_path), "flat.npy"))
+    import hostcheck as H
+    from mirres_restir_nerf_mesh_b200 import slangpy_shim
+    H.activate()
+    try:
+        want = (_view_gradients(0) + _view_gradients(7)).numpy()
+    finally:
+        slangpy_shim.set_kernels(None)
+    assert np.abs(want).sum() > 0
+    assert np.array_equal(got, want)
