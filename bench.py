@@ -189,8 +189,10 @@ def _config(args, cfg):
 class ProfiledKernels:
     """Wraps Kernels: counts launches and (optionally) brackets every ABI call with CUDA events on the launching
     stream, so per-kernel device time is measured live inside the timed region."""
-    LAUNCHES = {"bvh_build": 9, "env_build_distribution": 2, "eaw_bwd": 2, "workspace_prepare": 3, "initial_resampling": 3,
-                "spatial_resampling": 3, "final_visibility": 3, "bounce_first": 4, "bounce_shade": 4}
+    # kernels per entry point (ray-casting entry points: zero fill / queue reset + gen + tracer + resolve, the bounces a
+    # prologue before them); checked against the ncu launch list of a step (profiles/r9z_launches.csv.gz: 193 mr:: launches)
+    LAUNCHES = {"bvh_build": 9, "env_build_distribution": 2, "eaw_bwd": 2, "workspace_prepare": 3, "initial_resampling": 4,
+                "spatial_resampling": 4, "final_visibility": 4, "bounce_first": 5, "bounce_shade": 5, "gbuffer_primary": 4}
 
     def __init__(self, inner, torch):
         self._inner, self._torch = inner, torch
