@@ -498,6 +498,7 @@ def run_gpu(args):
                 "config": _config(args, cfg),
                 "collective": None if world == 1 else ("2 all-reduces captured in the step's graph (envmap segment beside the vertex "
                                                        "scatters, then the vertex segments)" if in_step else "1 all-reduce after the step"),
+                "exact_prunings": exact_prunings(),
                 "execution": ("CUDA graph replay of the whole step" if captured is not None else "eager") +
                              (", concurrent schedule (reuse chain, initial candidates, shading and the indirect chains "
                               "on their own streams)" if not args.no_overlap else ""),
@@ -733,6 +734,7 @@ def run_render(args):
         line = {"metric": METRIC, "value": samples / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(args, cfg),
+                "exact_prunings": exact_prunings(),
                 "execution": ("CUDA graph replay of the whole frame (halo exchange and gather captured with it)"
                               if captured is not None else "eager launches" + (" (graph capture failed: %s)" % why_eager if why_eager else "")) +
                              (", concurrent schedule" if not args.no_overlap else ""),
@@ -771,6 +773,18 @@ def _leave(torch, dist, captured):
     t.start()
     dist.destroy_process_group()
     t.cancel()
+
+
+def exact_prunings():
+    """What the product does not compute although the reference does, because the result cannot change the output (all
+    bit-exact against the oracle, which computes and traces everything).  Nothing is cached across steps:
+    every step rebuilds the tree, zeroes its tags and resamples from scratch."""
+    from mirres_restir_nerf_mesh_b200 import renderer_restir as R
+    return ["RIS target function: specular term not evaluated when the specular weight is 0 (it is multiplied by F = 0)",
+            "spatial pass: visibility rays that multiply a zero target density (light not above the start surface's horizon) "
+            "or only feed a weight with W = 0 are not cast",
+            "final visibility: rays whose answer an earlier pass of the same spp loop produced are not cast (visibility tags: %s; "
+            "MIRRES_VIS_TAGS=0 switches them off)" % ("on" if R.USE_VIS_TAGS else "off")]
 
 
 def step_algorithmic_bytes(cfg_name, cfg, spp, n_foreground=None):
