@@ -9,7 +9,10 @@ What is asserted (tools/numerics_sensitivity.py computes it, profiles/numerics_s
     default material (metallic 0), 99.9 % of the pixels by < 4e-5;
   * with a metallic material the GGX lobe of near-mirror pixels amplifies rounding (cancellation in (a^2 - 1) cos^2 + 1):
     99.9 % of the pixels stay within 5e-3, which is the honest size of the gap a 1e-4 claim against the real binary would
-    have to survive there.
+    have to survive there;
+  * the gradients that leave the path (float64 backward oracle on each flavour's own forward state, same upstream weights)
+    move by < 1e-3 of their scale -- the north-star gradient tolerance -- for the default material, 99.9 % of the pixels
+    by < 1e-4; with the metallic material the same near-mirror pixels reach a few 1e-3.
 """
 import os
 import sys
@@ -38,3 +41,9 @@ def test_reference_like_numerics_stay_within_tolerance(oracle, name, metallic):
             assert it["direct_colour_rel_err"]["p999"] < 5e-3
     # the spp average is the same estimator either way: its mean moves by rounding, not by bias
     assert c["images"]["final"]["rel_diff_of_mean"] < 1e-4
+    g = c["gradients_last_pass"]
+    for k in ("normal", "kd", "rough_metal"):
+        assert g[k]["scale"] > 0
+        assert g[k]["p999_err_over_scale"] < (1e-4 if metallic == 0.0 else 2e-3), (k, g[k])
+        assert g[k]["max_err_over_scale"] < (1e-3 if metallic == 0.0 else 2e-2), (k, g[k])
+    assert g["env"]["max_err_over_scale"] < 2e-3 and g["env"]["rel_diff_of_sum"] < 1e-4, g["env"]

@@ -22,7 +22,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import oracle as O, driver as D  # noqa: E402
+from oracle import oracle as O, driver as D, backward as BW  # noqa: E402
 from mirres_restir_nerf_mesh_b200 import synth  # noqa: E402
 
 
@@ -44,6 +44,17 @@ def run(name, spp=None, random_offset=4242, metallic=0.0):
 def relerr(a, b, floor=1e-6):
     a, b = a.astype(np.float64), b.astype(np.float64)
     return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+def gradients(snap, g, env_shape, weights):
+    """Gradients that leave the path for ONE shading pass, from the float64 backward oracle evaluated on a
+    flavour's own forward state: d loss / d (normal, kd, roughness-metallic) per pixel and the envmap scatter, for
+    loss = sum(color * weights)."""
+    gN, gK, gR, gL = BW.final_shading_grads(snap["fs_dir"], snap["fs_dist"], snap["fs_Li"], g["occ_map"], g["normal_map"],
+                                            g["ray_dir_map"], g["diffuse_map"], g["roughness_specular"], weights,
+                                            np.zeros_like(weights), np.zeros_like(weights))
+    gE = BW.eval_final_grad_env(snap["res"][0], snap["res"][3], snap["vis"], gL.astype(np.float32), env_shape[1], env_shape[0])
+    return {"normal": gN, "kd": gK, "rough_metal": gR, "env": gE}
 
 
 def compare(name, spp=None, metallic=0.0):
@@ -85,6 +96,29 @@ def compare(name, spp=None, metallic=0.0):
                     "direct_colour_rel_err": {"max": float(col_err.max()) if col_err.size else 0.0,
                                               "p999": float(np.quantile(col_err, 0.999)) if col_err.size else 0.0}})
     rep["iterations"] = its
+    # gradients of the last shading pass under both flavours' forward states (same upstream weights).  Per-pixel
+    # gradients are compared where the decisions agree; the envmap gradient is a scatter over texels, compared as a
+    # whole (a flipped selection moves its contribution to another texel) relative to its largest entry.
+    gA_in = D.prepare_gbuffer(A["g"])
+    cfg = synth.CONFIGS[name]
+    env_shape = synth.envmap(*cfg["env"]).shape
+    rng = np.random.default_rng(3)
+    wts = rng.uniform(0.5, 1.5, size=(len(fg), 3)).astype(np.float32)
+    ga = gradients(A["snaps"][-1], gA_in, env_shape, wts)
+    gb = gradients(snapsB[-1], gA_in, env_shape, wts)
+    sa, sb = A["snaps"][-1], snapsB[-1]
+    agree = fg & (np.abs(sa["res"][0] - sb["res"][0]).max(axis=1) <= 1e-6) & (sa["vis"][:, 0] == sb["vis"][:, 0])
+    grads = {}
+    for k in ("normal", "kd", "rough_metal"):
+        scale = np.abs(ga[k]).max()
+        d = np.abs(ga[k][agree] - gb[k][agree]).max(axis=1) / max(scale, 1e-30)
+        grads[k] = {"max_err_over_scale": float(d.max()) if d.size else 0.0,
+                    "p999_err_over_scale": float(np.quantile(d, 0.999)) if d.size else 0.0, "scale": float(scale)}
+    scale = np.abs(ga["env"]).max()
+    grads["env"] = {"max_err_over_scale": float(np.abs(ga["env"] - gb["env"]).max() / max(scale, 1e-30)),
+                    "rel_diff_of_sum": float(abs(ga["env"].sum() - gb["env"].sum()) / max(abs(ga["env"].sum()), 1e-30)),
+                    "scale": float(scale), "note": "includes the pixels whose decisions flipped"}
+    rep["gradients_last_pass"] = grads
     img = {}
     for k in ("color", "color_1", "final"):
         a, b = A["out"][k][fg].astype(np.float64), outB[k][fg].astype(np.float64)
@@ -107,7 +141,8 @@ def main(names):
               "| tile flips:", it["light_tile_texel_flips"], "| selection flips: %d of %d" % (it["reservoir_selection_flips"], c["foreground_pixels"]),
               "| vis flips:", it["visibility_flips"], "| Li max rel err %.2e" % it["Li_rel_err"]["max"],
               "| colour max rel err %.2e (p99.9 %.2e)" % (it["direct_colour_rel_err"]["max"], it["direct_colour_rel_err"]["p999"]),
-              "| image mean rel diff %.2e" % c["images"]["final"]["rel_diff_of_mean"])
+              "| image mean rel diff %.2e" % c["images"]["final"]["rel_diff_of_mean"],
+              "| grads (err / scale): " + ", ".join("%s %.1e" % (k, v["max_err_over_scale"]) for k, v in c["gradients_last_pass"].items()))
 
 
 if __name__ == "__main__":
